@@ -1,0 +1,286 @@
+// General three-pass path: any box size (mixed radix 2/3/4/5/8 + generic prime radix).
+//   g1: z pencils, real-to-complex (two real rows per complex transform), mean subtracted on load
+//   g2: y transform in place on the half spectrum, tiles of contiguous k_z
+//   g3: x transform fused with |delta_k|^2 and the bin histogram (spectrum is never written back)
+// HBM traffic 4N + 32 N_h bytes per spectrum.  The fused two-pass kernels (ps21_fused.cu) replace it
+// for the power-of-two shapes of the benchmark configurations.
+#include "ps21_internal.cuh"
+#include "../../include/ps21.h"
+
+namespace ps21 {
+
+// ---------------------------------------------------------------------------------------------
+// LUT: bin index of every half-spectrum mode, natural layout [x][y][kz]
+// ---------------------------------------------------------------------------------------------
+__global__ void k_general_lut(uint16_t* __restrict__ lut, unsigned long long* __restrict__ counts, int n0, int n1,
+                              int nz, int nh, const double* __restrict__ k0sq, const double* __restrict__ k1sq,
+                              const double* __restrict__ k2sq, const double* __restrict__ edges, int nbins,
+                              int mode, int ig_kperp, int ig_kpar, int ig_k0, int y_zero) {
+    const long long total = (long long)n0 * n1 * nh;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        const int kz = (int)(i % nh);
+        const int y = (int)((i / nh) % n1);
+        const int x = (int)(i / ((long long)nh * n1));
+        int w = (kz == 0 || (2 * kz == nz)) ? 1 : 2;
+        const bool perp0 = (x == 0 && y == y_zero);
+        if (ig_kperp && perp0) w = 0;
+        if (ig_kpar && kz == 0) w = 0;
+        if (ig_k0 && perp0 && kz == 0) w = 0;
+        int b;
+        if (mode == PS21_MODE_SPHERICAL) {
+            b = digitize_mode(k0sq[x], k1sq[y], k2sq[kz], edges, nbins);
+        } else {
+            b = digitize_mode(k0sq[x], k1sq[y], 0.0, edges, nbins);
+            if (b >= 0) b = b * nh + kz;
+        }
+        uint16_t v = kDiscard;
+        if (b >= 0 && w > 0) {
+            v = (uint16_t)b;
+            atomicAdd(&counts[b], (unsigned long long)w);
+        }
+        lut[i] = v;
+    }
+}
+
+int general_build_lut(ps21_plan* p, int chunk, const double* d_k0sq, const double* d_k1sq, const double* d_k2sq,
+                      const double* d_edges, cudaStream_t st) {
+    const ChunkDev& c = p->chunks[chunk];
+    const long long total = (long long)p->n0 * p->n1 * c.nh;
+    int grid = (int)((total + 255) / 256);
+    if (grid > 4096) grid = 4096;
+    // y index of the "k_perp = 0" line exactly as the reference writes it: shifted [n0//2, n0//2, :]
+    int y_zero = ((p->n0 / 2 - p->n1 / 2) % p->n1 + p->n1) % p->n1;
+    PS21_LAUNCH(k_general_lut, dim3(grid), dim3(256), 0, st, p->d_lut[chunk],
+                (unsigned long long*)(p->d_counts + c.out_off), p->n0, p->n1, c.nz, c.nh, d_k0sq, d_k1sq, d_k2sq,
+                d_edges, p->nbins, p->mode, p->ig_kperp, p->ig_kpar, p->ig_k0, y_zero);
+    PS21_CUDA(cudaGetLastError());
+    return PS21_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Offset estimate: mean of the x = 0 slab of every chunk (fixed-order reduction -> deterministic).
+// Any constant close to the mean works: subtracting it changes only the k = 0 coefficient, which is
+// restored in fp64 by the finalize kernel when that mode is binned at all.
+// ---------------------------------------------------------------------------------------------
+__global__ void k_slab_mean(const float* __restrict__ boxes, long long batch_stride, int n1, int n2_total,
+                            const ChunkDev* __restrict__ chunks, int nchunks, float* __restrict__ means) {
+    __shared__ double red[256];
+    const int box = blockIdx.x / nchunks;
+    const int c = blockIdx.x % nchunks;
+    const ChunkDev ch = chunks[c];
+    const float* src = boxes + (long long)box * batch_stride + ch.start;
+    double acc = 0.0;
+    const int total = n1 * ch.nz;
+    for (int i = threadIdx.x; i < total; i += blockDim.x) {
+        const int y = i / ch.nz, z = i % ch.nz;
+        acc += (double)src[(long long)y * n2_total + z];
+    }
+    red[threadIdx.x] = acc;
+    __syncthreads();
+    for (int s = blockDim.x / 2; s > 0; s >>= 1) {
+        if ((int)threadIdx.x < s) red[threadIdx.x] += red[threadIdx.x + s];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) means[(long long)box * nchunks + c] = (float)(red[0] / (double)total);
+}
+
+int launch_slab_mean(ps21_plan* p, const float* d_boxes, long long batch_stride, long long batch, cudaStream_t st) {
+    PS21_LAUNCH(k_slab_mean, dim3((unsigned)(batch * p->nchunks)), dim3(256), 0, st, d_boxes, batch_stride, p->n1,
+                p->n2_total, p->d_chunks, p->nchunks, p->d_means);
+    PS21_CUDA(cudaGetLastError());
+    p->launches_last++;
+    return PS21_OK;
+}
+
+// item -> (box, chunk) for a shape whose chunk-id list is `ids[0..nper)`
+struct ItemMap {
+    const int* ids;
+    int nper;
+    long long item0;
+};
+__device__ __forceinline__ void item_to_box_chunk(const ItemMap& m, long long local, long long& box, int& chunk) {
+    const long long it = m.item0 + local;
+    box = it / m.nper;
+    chunk = m.ids[it % m.nper];
+}
+
+// ---------------------------------------------------------------------------------------------
+// g1: z pass.  CTA = `cols` complex columns = 2*cols consecutive (x,y) rows of one spectrum.
+// ---------------------------------------------------------------------------------------------
+__global__ void k_general_zpass(const float* __restrict__ boxes, long long batch_stride, int n2_total, int nrows,
+                                ItemMap im, const ChunkDev* __restrict__ chunks, int nchunks,
+                                const float* __restrict__ means, float2* __restrict__ scratch,
+                                long long spec_elems, FftFactors fz, const float2* __restrict__ tw, int cols) {
+    PS21_DYN_SMEM(float2, smem);
+    const int nz = fz.n;
+    const int nh = nz / 2 + 1;
+    const int ld = cols | 1;
+    float2* A = smem;
+    float2* B = smem + (size_t)nz * ld;
+    long long box;
+    int cid;
+    item_to_box_chunk(im, blockIdx.y, box, cid);
+    const ChunkDev ch = chunks[cid];
+    const float mean = means[box * nchunks + cid];
+    const int row0 = blockIdx.x * 2 * cols;
+    const float* src = boxes + box * batch_stride + ch.start;
+    float* Af = reinterpret_cast<float*>(A);
+    for (int i = threadIdx.x; i < 2 * cols * nz; i += blockDim.x) {
+        const int rr = i / nz, z = i % nz;
+        const int row = row0 + rr;
+        float v = 0.f;
+        if (row < nrows) v = src[(long long)row * n2_total + z] - mean;
+        Af[2 * (z * ld + (rr >> 1)) + (rr & 1)] = v;
+    }
+    __syncthreads();
+    const float2* R = column_fft(A, B, fz, ld, cols, tw);
+    float2* dst = scratch + (long long)blockIdx.y * spec_elems;
+    for (int i = threadIdx.x; i < 2 * cols * nh; i += blockDim.x) {
+        const int rr = i / nh, k = i % nh;
+        const int row = row0 + rr;
+        if (row >= nrows) continue;
+        const int col = rr >> 1;
+        const float2 Z = R[k * ld + col];
+        const int kc = (k == 0) ? 0 : nz - k;
+        const float2 Zc = R[kc * ld + col];
+        float2 o;
+        if ((rr & 1) == 0) {  // even row: (Z + conj(Z*))/2
+            o.x = 0.5f * (Z.x + Zc.x);
+            o.y = 0.5f * (Z.y - Zc.y);
+        } else {  // odd row: (Z - conj(Z*)) / (2i)
+            o.x = 0.5f * (Z.y + Zc.y);
+            o.y = -0.5f * (Z.x - Zc.x);
+        }
+        dst[(long long)row * nh + k] = o;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// g2: y pass, in place.  CTA = fixed x, `tile` consecutive k_z.
+// ---------------------------------------------------------------------------------------------
+__global__ void k_general_ypass(float2* __restrict__ scratch, long long spec_elems, int n1, int nh, FftFactors fy,
+                                const float2* __restrict__ tw, int tile) {
+    PS21_DYN_SMEM(float2, smem);
+    const int ntile = (nh + tile - 1) / tile;
+    const int x = blockIdx.x / ntile;
+    const int k0 = (blockIdx.x % ntile) * tile;
+    const int cols = min(tile, nh - k0);
+    const int ld = tile | 1;
+    float2* A = smem;
+    float2* B = smem + (size_t)n1 * ld;
+    float2* base = scratch + (long long)blockIdx.y * spec_elems + (long long)x * n1 * nh + k0;
+    for (int i = threadIdx.x; i < n1 * cols; i += blockDim.x) {
+        const int y = i / cols, t = i % cols;
+        A[y * ld + t] = base[(long long)y * nh + t];
+    }
+    __syncthreads();
+    const float2* R = column_fft(A, B, fy, ld, cols, tw);
+    for (int i = threadIdx.x; i < n1 * cols; i += blockDim.x) {
+        const int y = i / cols, t = i % cols;
+        base[(long long)y * nh + t] = R[y * ld + t];
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// g3: x pass + |delta_k|^2 + histogram.  CTA (slot s of spectrum) loops over tiles of `tile`
+// consecutive (k_y,k_z) columns; fp64 bins privatised in shared memory; one flush per CTA into its
+// own partial-sum slot (no global atomics -> the cross-CTA reduction order is fixed).
+// ---------------------------------------------------------------------------------------------
+__global__ void k_general_xpass_bin(const float2* __restrict__ scratch, long long spec_elems, int n0, int n1,
+                                    int nh, int nz, FftFactors fx, const float2* __restrict__ tw, int tile,
+                                    ItemMap im, const ChunkDev* __restrict__ chunks,
+                                    const uint16_t* const* __restrict__ luts, double* __restrict__ partials,
+                                    long long out_per_box, int slots_max, float2* __restrict__ dc, int nchunks) {
+    PS21_DYN_SMEM(float2, smem);
+    long long box;
+    int cid;
+    item_to_box_chunk(im, blockIdx.y, box, cid);
+    const ChunkDev ch = chunks[cid];
+    const uint16_t* __restrict__ lut = luts[cid];
+    const int ld = tile | 1;
+    float2* A = smem;
+    float2* B = smem + (size_t)n0 * ld;
+    double* bins = reinterpret_cast<double*>(smem + 2 * (size_t)n0 * ld);
+    for (int i = threadIdx.x; i < ch.nbins_out; i += blockDim.x) bins[i] = 0.0;
+    const long long plane = (long long)n1 * nh;
+    const long long ntiles = (plane + tile - 1) / tile;
+    const float2* base = scratch + (long long)blockIdx.y * spec_elems;
+    for (long long tl = blockIdx.x; tl < ntiles; tl += gridDim.x) {
+        const long long m0 = tl * tile;
+        const int cols = (int)min((long long)tile, plane - m0);
+        __syncthreads();
+        for (int i = threadIdx.x; i < n0 * cols; i += blockDim.x) {
+            const int x = i / cols, t = i % cols;
+            A[x * ld + t] = base[(long long)x * plane + m0 + t];
+        }
+        __syncthreads();
+        const float2* R = column_fft(A, B, fx, ld, cols, tw);
+        for (int i = threadIdx.x; i < n0 * cols; i += blockDim.x) {
+            const int x = i / cols, t = i % cols;
+            const long long m = m0 + t;
+            const float2 v = R[x * ld + t];
+            if (x == 0 && m == 0) dc[box * nchunks + cid] = v;
+            const uint16_t b = lut[(long long)x * plane + m];
+            if (b != kDiscard) {
+                const int kz = (int)(m % nh);
+                const float w = (kz == 0 || 2 * kz == nz) ? 1.f : 2.f;
+                const float pw = w * (v.x * v.x + v.y * v.y);
+                atomicAdd(&bins[b], (double)pw);
+            }
+        }
+    }
+    __syncthreads();
+    double* out = partials + (box * slots_max + blockIdx.x) * out_per_box + ch.out_off;
+    for (int i = threadIdx.x; i < ch.nbins_out; i += blockDim.x) out[i] = bins[i];
+}
+
+int general_init() {
+#ifndef PS21_EMU
+    const int big = 220 * 1024;
+    PS21_CUDA(cudaFuncSetAttribute(k_general_zpass, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+    PS21_CUDA(cudaFuncSetAttribute(k_general_ypass, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+    PS21_CUDA(cudaFuncSetAttribute(k_general_xpass_bin, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+#endif
+    return PS21_OK;
+}
+
+static size_t fft_smem_bytes(int n, int tile) { return 2 * (size_t)n * (tile | 1) * sizeof(float2); }
+
+int general_forward(ps21_plan* p, ShapePlan& sp, const float* d_boxes, long long batch_stride, long long item0,
+                    long long nitems, cudaStream_t st) {
+    const int n0 = p->n0, n1 = p->n1;
+    const long long spec_elems = (long long)n0 * n1 * sp.nh;
+    ItemMap im{sp.d_chunks, (int)sp.chunks.size(), item0};
+    const int nrows = n0 * n1;
+    {
+        ProfScope ps(p, KK_PASS1, st);
+        dim3 grid((nrows + 2 * sp.g1_cols - 1) / (2 * sp.g1_cols), (unsigned)nitems);
+        PS21_LAUNCH(k_general_zpass, grid, dim3(256), fft_smem_bytes(sp.nz, sp.g1_cols), st, d_boxes, batch_stride,
+                    p->n2_total, nrows, im, p->d_chunks, p->nchunks, p->d_means, p->d_scratch, spec_elems, sp.fz,
+                    sp.tw_z, sp.g1_cols);
+        PS21_CUDA(cudaGetLastError());
+    }
+    {
+        ProfScope ps(p, KK_PASS_MID, st);
+        const int ntile = (sp.nh + sp.g2_tile - 1) / sp.g2_tile;
+        dim3 grid(n0 * ntile, (unsigned)nitems);
+        PS21_LAUNCH(k_general_ypass, grid, dim3(256), fft_smem_bytes(n1, sp.g2_tile), st, p->d_scratch, spec_elems,
+                    n1, sp.nh, sp.fy, sp.tw_y, sp.g2_tile);
+        PS21_CUDA(cudaGetLastError());
+    }
+    {
+        ProfScope ps(p, KK_PASS_BIN, st);
+        const int nb_out = p->chunks[sp.chunks[0]].nbins_out;
+        dim3 grid(sp.g3_slots, (unsigned)nitems);
+        size_t smem = fft_smem_bytes(n0, sp.g3_tile) + (size_t)nb_out * sizeof(double);
+        PS21_LAUNCH(k_general_xpass_bin, grid, dim3(256), smem, st, p->d_scratch, spec_elems, n0, n1, sp.nh, sp.nz,
+                    sp.fx, sp.tw_x, sp.g3_tile, im, p->d_chunks, (const uint16_t* const*)p->d_lut_table,
+                    p->d_partials, p->out_per_box, p->slots_max, p->d_dc, p->nchunks);
+        PS21_CUDA(cudaGetLastError());
+    }
+    p->launches_last += 3;
+    return PS21_OK;
+}
+
+}  // namespace ps21

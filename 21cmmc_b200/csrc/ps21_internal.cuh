@@ -1,0 +1,161 @@
+// Internal declarations shared by the translation units of libps21.so.
+#pragma once
+
+#ifdef PS21_EMU
+#include "cuda_emu.h"  // tests/emu: host emulation of the CUDA subset used by the general path (tests only)
+#else
+#include <cuda_runtime.h>
+#endif
+
+#include <cstdint>
+#include <string>
+#include <vector>
+
+#include "fft_smem.cuh"
+
+#ifndef PS21_EMU
+// dynamic shared memory of a kernel, typed view
+#define PS21_DYN_SMEM(type, name)                                         \
+    extern __shared__ __align__(16) unsigned char ps21_dyn_smem_raw[];    \
+    type* name = reinterpret_cast<type*>(ps21_dyn_smem_raw)
+#endif
+
+#ifdef PS21_EMU
+#define PS21_LAUNCH(kernel, grid, block, smem, stream, ...) \
+    ps21emu::launch((grid), (block), (smem), [&]() { kernel(__VA_ARGS__); })
+#else
+#define PS21_LAUNCH(kernel, grid, block, smem, stream, ...) kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__)
+#endif
+
+namespace ps21 {
+
+constexpr int kMaxBinsSmem = 8192;     // fp64 bins held in shared memory by the binning kernels
+constexpr uint16_t kDiscard = 0xFFFF;  // LUT value: mode carries zero weight or lies outside the edges
+
+// One chunk (= one spectrum) of a box.
+struct ChunkDev {
+    int start;            // first slice on axis 2
+    int nz;               // slices
+    int nh;               // nz/2 + 1
+    int shape;            // index into the plan's shape table
+    int nbins_out;        // nbins (spherical) or nbins*nh (cylindrical)
+    int dc_bin;           // output bin that holds the k=0 mode, or -1
+    long long out_off;    // offset of this chunk in a box's power record
+    int nslots;           // partial-sum slots written per spectrum by the binning kernel of its path
+    double norm;          // V / N^2
+    double ncells;        // N = n0*n1*nz
+};
+
+// Per distinct chunk length.
+struct ShapePlan {
+    int nz = 0, nh = 0;
+    int path = 0;  // PS21_PATH_GENERAL / PS21_PATH_FUSED
+    FftFactors fz{}, fy{}, fx{};
+    float2* tw_z = nullptr;  // device twiddle tables exp(-2 pi i q / n)
+    float2* tw_y = nullptr;
+    float2* tw_x = nullptr;
+    std::vector<int> chunks;      // chunk ids with this length
+    int* d_chunks = nullptr;      // same on device
+    // general path tiling
+    int g1_cols = 0;   // complex columns (= row pairs) per CTA in the z pass
+    int g2_tile = 0;   // k_z columns per CTA in the y pass
+    int g3_tile = 0;   // (k_y,k_z) columns per CTA in the x pass
+    int g3_slots = 0;  // CTAs per spectrum in the x pass (= partial-sum slots)
+    // fused path (ps21_fused.cu)
+    void* fused = nullptr;
+};
+
+struct DataTables {
+    int nsets = 0;
+    double* d_data = nullptr;    // [nsets][out_per_box]
+    double* d_noise2 = nullptr;  // [nsets][out_per_box] noise^2
+    uint8_t* d_mask = nullptr;   // [nsets][out_per_box]
+    double model_uncertainty = 0.15;
+    int error_on_model = 1;
+};
+
+}  // namespace ps21
+
+struct ps21_plan {
+    int n0 = 0, n1 = 0, n2_total = 0, nchunks = 0, nbins = 0, mode = 0, device = 0, path_req = 0;
+    int ig_kperp = 0, ig_kpar = 0, ig_k0 = 0;
+    long long out_per_box = 0;
+    long long alg_bytes_per_box = 0;
+    long long workspace_cap = 0;
+    int slots_max = 0;
+    std::vector<ps21::ChunkDev> chunks;
+    std::vector<ps21::ShapePlan> shapes;
+    ps21::ChunkDev* d_chunks = nullptr;
+    // per chunk LUT: bin index of every half-spectrum mode, layout defined by the path of its shape
+    std::vector<uint16_t*> d_lut;  // [nchunks]
+    uint16_t** d_lut_table = nullptr;  // the same pointers in device memory
+    std::vector<long long> h_counts;
+    long long* d_counts = nullptr;   // [out_per_box]
+    double* d_kfac = nullptr;        // [out_per_box] k^3 / (2 pi^2)  (spherical only)
+    // workspace
+    float2* d_scratch = nullptr;
+    long long scratch_elems = 0;
+    double* d_partials = nullptr;    // [batch][out_per_box][slots_max]
+    float* d_means = nullptr;        // [batch][nchunks]
+    float2* d_dc = nullptr;          // [batch][nchunks] DC Fourier coefficient of the mean-subtracted chunk
+    long long batch_cap = 0;
+    double* d_power_tmp = nullptr;   // [batch][out_per_box] when the caller passes no power buffer
+    ps21::DataTables data;
+    long long launches_last = 0;
+    // optional per-kernel timing with CUDA events on the launching stream (ps21_plan_profile)
+    bool profiling = false;
+    struct ProfRec { int kind; void* e0; void* e1; };
+    std::vector<ProfRec> prof;
+    // host staging (ps21_*_host)
+    float* d_stage[2] = {nullptr, nullptr};
+    long long stage_boxes = 0;
+    void* stage_stream[2] = {nullptr, nullptr};
+    void* stage_event[2] = {nullptr, nullptr};
+};
+
+namespace ps21 {
+enum KernelKind { KK_MEAN = 0, KK_PASS1 = 1, KK_PASS_MID = 2, KK_PASS_BIN = 3, KK_FINALIZE = 4, KK_COUNT = 5 };
+// RAII: records an event pair around the launches issued in its scope when profiling is on
+struct ProfScope {
+    ps21_plan* p; cudaStream_t st; int idx = -1;
+    ProfScope(ps21_plan* plan, int kind, cudaStream_t s);
+    ~ProfScope();
+};
+void set_error(const std::string& msg);
+int cuda_fail(cudaError_t e, const char* what);
+#define PS21_CUDA(call)                                        \
+    do {                                                       \
+        cudaError_t _e = (call);                               \
+        if (_e != cudaSuccess) return ps21::cuda_fail(_e, #call); \
+    } while (0)
+
+// general path (ps21_general.cu)
+int general_build_lut(ps21_plan* p, int chunk, const double* d_k0sq, const double* d_k1sq, const double* d_k2sq,
+                      const double* d_edges, cudaStream_t st);
+int general_init();
+int launch_slab_mean(ps21_plan* p, const float* d_boxes, long long batch_stride, long long batch, cudaStream_t st);
+int general_forward(ps21_plan* p, ShapePlan& sp, const float* d_boxes, long long batch_stride, long long item0,
+                    long long nitems, cudaStream_t st);
+
+// fused path (ps21_fused.cu); returns 0 and sets sp.fused when the shape is supported
+int fused_try_setup(ps21_plan* p, ShapePlan& sp);
+void fused_destroy(ShapePlan& sp);
+int fused_build_lut(ps21_plan* p, int chunk, const double* d_k0sq, const double* d_k1sq, const double* d_k2sq,
+                    const double* d_edges, cudaStream_t st);
+int fused_forward(ps21_plan* p, ShapePlan& sp, const float* d_boxes, long long batch_stride, long long item0,
+                  long long nitems, cudaStream_t st);
+long long fused_scratch_elems(const ShapePlan& sp, int n0, int n1);
+
+// exact fp64 digitisation shared by both LUT builders: np.digitize(sqrt((a+b)+c), edges) - 1, or -1
+__device__ __forceinline__ int digitize_mode(double a, double b, double c, const double* __restrict__ edges,
+                                             int nbins) {
+    const double kmag = __dsqrt_rn(__dadd_rn(__dadd_rn(a, b), c));
+    // number of edges <= kmag (upper bound), edges ascending
+    int lo = 0, hi = nbins + 1;
+    while (lo < hi) {
+        int mid = (lo + hi) >> 1;
+        if (edges[mid] <= kmag) lo = mid + 1; else hi = mid;
+    }
+    return (lo >= 1 && lo <= nbins) ? lo - 1 : -1;
+}
+}  // namespace ps21

@@ -1,0 +1,710 @@
+// Plan management, finalize / likelihood kernels and the extern "C" entry points of include/ps21.h.
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <map>
+
+#include "ps21_internal.cuh"
+#include "../../include/ps21.h"
+
+namespace ps21 {
+
+static thread_local std::string g_err;
+void set_error(const std::string& msg) { g_err = msg; }
+int cuda_fail(cudaError_t e, const char* what) {
+    g_err = std::string("CUDA error: ") + cudaGetErrorString(e) + " in " + what;
+    return PS21_ERR_CUDA;
+}
+ProfScope::ProfScope(ps21_plan* plan, int kind, cudaStream_t s) : p(plan), st(s) {
+#ifndef PS21_EMU
+    if (!p->profiling) return;
+    cudaEvent_t a, b;
+    if (cudaEventCreate(&a) != cudaSuccess || cudaEventCreate(&b) != cudaSuccess) return;
+    cudaEventRecord(a, st);
+    idx = (int)p->prof.size();
+    p->prof.push_back({kind, (void*)a, (void*)b});
+#endif
+}
+ProfScope::~ProfScope() {
+#ifndef PS21_EMU
+    if (idx >= 0) cudaEventRecord((cudaEvent_t)p->prof[idx].e1, st);
+#endif
+}
+
+static int invalid(const std::string& msg) {
+    g_err = msg;
+    return PS21_ERR_INVALID;
+}
+
+static FftFactors factorize(int n) {
+    FftFactors f{};
+    f.n = n;
+    int m = n, ns = 0;
+    auto take = [&](int r) {
+        while (m % r == 0 && ns < 14) {
+            f.radix[ns++] = r;
+            m /= r;
+        }
+    };
+    take(8);
+    take(4);
+    take(2);
+    take(3);
+    take(5);
+    for (int pr = 7; m > 1 && ns < 14; pr += 2) take(pr);
+    f.nstages = ns;
+    if (m != 1) f.nstages = -1;
+    return f;
+}
+
+static int upload_twiddles(int n, float2** out) {
+    std::vector<float2> tw(n);
+    for (int q = 0; q < n; ++q) {
+        const double a = -2.0 * M_PI * (double)q / (double)n;
+        tw[q] = make_float2((float)std::cos(a), (float)std::sin(a));
+    }
+    PS21_CUDA(cudaMalloc((void**)out, sizeof(float2) * n));
+    PS21_CUDA(cudaMemcpy(*out, tw.data(), sizeof(float2) * n, cudaMemcpyHostToDevice));
+    return PS21_OK;
+}
+
+static int pick_tile(int n, size_t extra) {
+    const int cand[5] = {16, 8, 4, 2, 1};
+    for (size_t budget : {(size_t)100 * 1024, (size_t)220 * 1024})
+        for (int t : cand)
+            if (2 * (size_t)n * (t | 1) * sizeof(float2) + extra <= budget) return t;
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// finalize: partial sums -> power -> Delta^2 -> chi^2   (likelihood.py:863/:652 and :584-604)
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ double chi2_term(double delta, double data, double noise2, double mu, int err_on_model) {
+    const double mod = mu * (err_on_model ? delta : data);
+    const double d = delta - data;
+    return d * d / (mod * mod + noise2);
+}
+
+__global__ void k_finalize(const double* __restrict__ partials, int slots_max, long long out_per_box,
+                           const ChunkDev* __restrict__ chunks, int nchunks, const long long* __restrict__ counts,
+                           const double* __restrict__ kfac, const float* __restrict__ means,
+                           const float2* __restrict__ dc, double* __restrict__ power, double* __restrict__ delta,
+                           double* __restrict__ lnl, const double* __restrict__ data,
+                           const double* __restrict__ noise2, const uint8_t* __restrict__ mask, int nsets,
+                           double mu, int err_on_model) {
+    PS21_DYN_SMEM(double, sdelta);
+    const long long box = blockIdx.x;
+    for (long long i = threadIdx.x; i < out_per_box; i += blockDim.x) {
+        int c = 0;
+        while (c + 1 < nchunks && chunks[c + 1].out_off <= i) ++c;
+        const ChunkDev ch = chunks[c];
+        double s = 0.0;
+        for (int sl = 0; sl < ch.nslots; ++sl) s += partials[(box * slots_max + sl) * out_per_box + i];
+        if (ch.dc_bin >= 0 && ch.out_off + ch.dc_bin == i) {
+            // restore the k=0 power removed by the offset subtraction: |F'(0) + N c|^2 - |F'(0)|^2
+            const float2 f0 = dc[box * nchunks + c];
+            const double shift = ch.ncells * (double)means[box * nchunks + c];
+            const double full = (double)f0.x + shift;
+            s += full * full - (double)f0.x * (double)f0.x;
+        }
+        const double pw = s / (double)counts[i] * ch.norm;  // 0/0 -> NaN for empty bins, as the reference
+        if (power) power[box * out_per_box + i] = pw;
+        if (kfac) {
+            const double d = pw * kfac[i];
+            if (delta) delta[box * out_per_box + i] = d;
+            if (lnl) sdelta[i] = d;
+        }
+    }
+    if (lnl) {
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            const long long set = box % nsets;
+            double total = 0.0;
+            for (int c = 0; c < nchunks; ++c) {
+                const ChunkDev ch = chunks[c];
+                double cs = 0.0;
+                for (int b = 0; b < ch.nbins_out; ++b) {
+                    const long long i = ch.out_off + b;
+                    const long long j = set * out_per_box + i;
+                    if (mask[j]) cs += chi2_term(sdelta[i], data[j], noise2[j], mu, err_on_model);
+                }
+                total += -0.5 * cs;
+            }
+            lnl[box] = total;
+        }
+    }
+}
+
+__global__ void k_lnl_from_delta(const double* __restrict__ delta, long long out_per_box,
+                                 const ChunkDev* __restrict__ chunks, int nchunks, double* __restrict__ lnl,
+                                 const double* __restrict__ data, const double* __restrict__ noise2,
+                                 const uint8_t* __restrict__ mask, int nsets, double mu, int err_on_model,
+                                 long long batch) {
+    const long long box = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (box >= batch) return;
+    const long long set = box % nsets;
+    double total = 0.0;
+    for (int c = 0; c < nchunks; ++c) {
+        const ChunkDev ch = chunks[c];
+        double cs = 0.0;
+        for (int b = 0; b < ch.nbins_out; ++b) {
+            const long long i = ch.out_off + b;
+            const long long j = set * out_per_box + i;
+            if (mask[j]) cs += chi2_term(delta[box * out_per_box + i], data[j], noise2[j], mu, err_on_model);
+        }
+        total += -0.5 * cs;
+    }
+    lnl[box] = total;
+}
+
+__global__ void k_chi2_rows(const double* __restrict__ delta, long long n, long long nrec,
+                            const double* __restrict__ data, const double* __restrict__ noise,
+                            const uint8_t* __restrict__ mask, long long nseg, const long long* __restrict__ seg_len,
+                            double mu, int err_on_model, double* __restrict__ lnl) {
+    const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= nrec) return;
+    double total = 0.0;
+    long long i = 0;
+    for (long long s = 0; s < nseg; ++s) {
+        double cs = 0.0;
+        for (long long e = i + seg_len[s]; i < e; ++i)
+            if (mask[i]) {
+                const double nz = noise ? noise[i] : 0.0;
+                cs += chi2_term(delta[r * n + i], data[i], nz * nz, mu, err_on_model);
+            }
+        total += -0.5 * cs;
+    }
+    lnl[r] = total;
+}
+
+static void free_dev(void* p) {
+    if (p) cudaFree(p);
+}
+
+static int ensure_batch(ps21_plan* p, long long batch) {
+    if (batch <= p->batch_cap) return PS21_OK;
+    free_dev(p->d_partials);
+    free_dev(p->d_means);
+    free_dev(p->d_dc);
+    free_dev(p->d_power_tmp);
+    p->d_partials = nullptr;
+    p->d_means = nullptr;
+    p->d_dc = nullptr;
+    p->d_power_tmp = nullptr;
+    p->batch_cap = 0;
+    PS21_CUDA(cudaMalloc((void**)&p->d_partials, sizeof(double) * batch * p->slots_max * p->out_per_box));
+    PS21_CUDA(cudaMalloc((void**)&p->d_means, sizeof(float) * batch * p->nchunks));
+    PS21_CUDA(cudaMalloc((void**)&p->d_dc, sizeof(float2) * batch * p->nchunks));
+    PS21_CUDA(cudaMemset(p->d_dc, 0, sizeof(float2) * batch * p->nchunks));
+    PS21_CUDA(cudaMalloc((void**)&p->d_power_tmp, sizeof(double) * batch * p->out_per_box));
+    p->batch_cap = batch;
+    return PS21_OK;
+}
+
+// All kernels of one call, asynchronous on `st`.
+static int run_device(ps21_plan* p, const float* d_boxes, long long batch, long long batch_stride, double* d_power,
+                      double* d_delta, double* d_lnl, cudaStream_t st) {
+    if (batch <= 0) return PS21_OK;
+    if (batch_stride < (long long)p->n0 * p->n1 * p->n2_total)
+        return invalid("batch_stride smaller than one box");
+    if (d_lnl && p->data.nsets == 0) {
+        set_error("ps21_set_data must be called before a likelihood evaluation");
+        return PS21_ERR_STATE;
+    }
+    if ((d_lnl || d_delta) && p->mode != PS21_MODE_SPHERICAL)
+        return invalid("Delta^2 / lnL are defined for the spherical mode only");
+    int rc = ensure_batch(p, batch);
+    if (rc) return rc;
+    {
+        ProfScope ps(p, KK_MEAN, st);
+        rc = launch_slab_mean(p, d_boxes, batch_stride, batch, st);
+    }
+    if (rc) return rc;
+    for (auto& sp : p->shapes) {
+        const long long nper = (long long)sp.chunks.size();
+        const long long total = batch * nper;
+        const long long spec = (sp.path == PS21_PATH_FUSED) ? fused_scratch_elems(sp, p->n0, p->n1)
+                                                             : (long long)p->n0 * p->n1 * sp.nh;
+        long long per = p->scratch_elems / spec;
+        if (per < 1) return invalid("internal: scratch smaller than one spectrum");
+        if (per > 32768) per = 32768;
+        for (long long i0 = 0; i0 < total; i0 += per) {
+            const long long n = (total - i0 < per) ? (total - i0) : per;
+            rc = (sp.path == PS21_PATH_FUSED) ? fused_forward(p, sp, d_boxes, batch_stride, i0, n, st)
+                                              : general_forward(p, sp, d_boxes, batch_stride, i0, n, st);
+            if (rc) return rc;
+        }
+    }
+    double* pw = d_power;
+    const bool want_lnl = d_lnl != nullptr;
+    const size_t smem = want_lnl ? sizeof(double) * p->out_per_box : 0;
+    ProfScope psf(p, KK_FINALIZE, st);
+    PS21_LAUNCH(k_finalize, dim3((unsigned)batch), dim3(128), smem, st, p->d_partials, p->slots_max, p->out_per_box,
+                p->d_chunks, p->nchunks, p->d_counts, p->mode == PS21_MODE_SPHERICAL ? p->d_kfac : nullptr,
+                p->d_means, p->d_dc, pw, d_delta, d_lnl, p->data.d_data, p->data.d_noise2, p->data.d_mask,
+                p->data.nsets > 0 ? p->data.nsets : 1, p->data.model_uncertainty, p->data.error_on_model);
+    PS21_CUDA(cudaGetLastError());
+    p->launches_last++;
+    return PS21_OK;
+}
+
+}  // namespace ps21
+
+using namespace ps21;
+
+extern "C" {
+
+const char* ps21_last_error(void) { return g_err.c_str(); }
+int ps21_version(void) { return 100; }
+
+int ps21_plan_destroy(ps21_plan* p) {
+    if (!p) return PS21_OK;
+    cudaSetDevice(p->device);
+    for (auto& sp : p->shapes) {
+        free_dev(sp.tw_z);
+        free_dev(sp.tw_y);
+        free_dev(sp.tw_x);
+        free_dev(sp.d_chunks);
+        fused_destroy(sp);
+    }
+    for (auto* l : p->d_lut) free_dev(l);
+    free_dev(p->d_lut_table);
+    free_dev(p->d_chunks);
+    free_dev(p->d_counts);
+    free_dev(p->d_kfac);
+    free_dev(p->d_scratch);
+    free_dev(p->d_partials);
+    free_dev(p->d_means);
+    free_dev(p->d_dc);
+    free_dev(p->d_power_tmp);
+    free_dev(p->data.d_data);
+    free_dev(p->data.d_noise2);
+    free_dev(p->data.d_mask);
+    for (int i = 0; i < 2; ++i) {
+        free_dev(p->d_stage[i]);
+        if (p->stage_stream[i]) cudaStreamDestroy((cudaStream_t)p->stage_stream[i]);
+        if (p->stage_event[i]) cudaEventDestroy((cudaEvent_t)p->stage_event[i]);
+    }
+    delete p;
+    return PS21_OK;
+}
+
+int ps21_plan_create(const ps21_desc* d, ps21_plan** out) {
+    if (!d || !out) return invalid("null argument");
+    *out = nullptr;
+    if (d->n0 < 1 || d->n1 < 1 || d->n2_total < 1 || d->nchunks < 1 || d->nbins < 1)
+        return invalid("n0, n1, n2_total, nchunks and nbins must be positive");
+    if (!d->chunk_start || !d->chunk_end || !d->volume || !d->k0sq || !d->k1sq || !d->k2sq || !d->edges ||
+        !d->kcentres)
+        return invalid("null array in descriptor");
+    if (d->mode != PS21_MODE_SPHERICAL && d->mode != PS21_MODE_CYLINDRICAL) return invalid("unknown mode");
+    if ((d->ignore_kperp_zero || d->ignore_k_zero) && d->n0 != d->n1)
+        return invalid("ignore_kperp_zero / ignore_k_zero need n0 == n1 (the reference indexes both sky axes "
+                       "with n0//2, likelihood.py:775-780)");
+    PS21_CUDA(cudaSetDevice(d->device));
+    {
+        int irc = general_init();
+        if (irc) return irc;
+    }
+    ps21_plan* p = new ps21_plan();
+    p->n0 = d->n0; p->n1 = d->n1; p->n2_total = d->n2_total; p->nchunks = d->nchunks; p->nbins = d->nbins;
+    p->mode = d->mode; p->device = d->device; p->path_req = d->path;
+    p->ig_kperp = d->ignore_kperp_zero; p->ig_kpar = d->ignore_kpar_zero; p->ig_k0 = d->ignore_k_zero;
+    p->workspace_cap = d->workspace_bytes > 0 ? d->workspace_bytes : (2LL << 30);
+    int rc = PS21_OK;
+    auto fail = [&](int code) {
+        ps21_plan_destroy(p);
+        return code;
+    };
+    // chunks and shapes
+    std::map<int, int> shape_of_nz;
+    long long off = 0, k2off = 0;
+    std::vector<long long> k2offs;
+    for (int c = 0; c < d->nchunks; ++c) {
+        const int s = d->chunk_start[c], e = d->chunk_end[c];
+        if (s < 0 || e <= s || e > d->n2_total) return fail(invalid("bad chunk bounds"));
+        ChunkDev ch{};
+        ch.start = s; ch.nz = e - s; ch.nh = ch.nz / 2 + 1;
+        ch.nbins_out = d->mode == PS21_MODE_SPHERICAL ? d->nbins : d->nbins * ch.nh;
+        if (ch.nbins_out >= (int)kDiscard || ch.nbins_out > kMaxBinsSmem)
+            return fail(invalid("too many output bins per spectrum (limit 8192)"));
+        ch.out_off = off;
+        off += ch.nbins_out;
+        ch.ncells = (double)d->n0 * d->n1 * ch.nz;
+        ch.norm = d->volume[c] / (ch.ncells * ch.ncells);
+        auto it = shape_of_nz.find(ch.nz);
+        if (it == shape_of_nz.end()) {
+            ShapePlan sp;
+            sp.nz = ch.nz; sp.nh = ch.nh;
+            shape_of_nz[ch.nz] = (int)p->shapes.size();
+            ch.shape = (int)p->shapes.size();
+            p->shapes.push_back(sp);
+        } else ch.shape = it->second;
+        p->shapes[ch.shape].chunks.push_back(c);
+        // k = 0 mode: binned only when it has weight and lies inside the edges (linear bins start at 0)
+        ch.dc_bin = -1;
+        if (!d->ignore_kperp_zero && !d->ignore_k_zero && !d->ignore_kpar_zero) {
+            const double* ed = d->edges + (long long)c * (d->nbins + 1);
+            int cnt = 0;
+            for (int j = 0; j <= d->nbins; ++j) cnt += (ed[j] <= 0.0);
+            if (cnt >= 1 && cnt <= d->nbins) ch.dc_bin = (d->mode == PS21_MODE_SPHERICAL) ? cnt - 1 : (cnt - 1) * ch.nh;
+        }
+        p->chunks.push_back(ch);
+        k2offs.push_back(k2off);
+        k2off += ch.nz;
+        p->alg_bytes_per_box += 4LL * d->n0 * d->n1 * ch.nz + 16LL * d->n0 * d->n1 * ch.nh;
+    }
+    p->out_per_box = off;
+    // shapes: factorisations, twiddles, tiling, path
+    long long spec_max = 0;
+    p->slots_max = 1;
+    for (auto& sp : p->shapes) {
+        sp.fz = factorize(sp.nz); sp.fy = factorize(d->n1); sp.fx = factorize(d->n0);
+        if (sp.fz.nstages < 0 || sp.fy.nstages < 0 || sp.fx.nstages < 0)
+            return fail(invalid("axis length has too many prime factors"));
+        if ((rc = upload_twiddles(sp.nz, &sp.tw_z))) return fail(rc);
+        if ((rc = upload_twiddles(d->n1, &sp.tw_y))) return fail(rc);
+        if ((rc = upload_twiddles(d->n0, &sp.tw_x))) return fail(rc);
+        PS21_CUDA(cudaMalloc((void**)&sp.d_chunks, sizeof(int) * sp.chunks.size()));
+        PS21_CUDA(cudaMemcpy(sp.d_chunks, sp.chunks.data(), sizeof(int) * sp.chunks.size(), cudaMemcpyHostToDevice));
+        sp.path = PS21_PATH_GENERAL;
+        if (d->path != PS21_PATH_GENERAL && d->mode == PS21_MODE_SPHERICAL && fused_try_setup(p, sp) == 0)
+            sp.path = PS21_PATH_FUSED;
+        if (d->path == PS21_PATH_FUSED && sp.path != PS21_PATH_FUSED)
+            return fail(invalid("fused path requested but this shape/alignment is not supported by it: " + g_err));
+        const int nb_out = p->chunks[sp.chunks[0]].nbins_out;
+        sp.g1_cols = pick_tile(sp.nz, 0);
+        sp.g2_tile = pick_tile(d->n1, 0);
+        sp.g3_tile = pick_tile(d->n0, sizeof(double) * nb_out);
+        if (!sp.g1_cols || !sp.g2_tile || !sp.g3_tile) return fail(invalid("axis too long for the shared-memory FFT"));
+        const long long ntiles = ((long long)d->n1 * sp.nh + sp.g3_tile - 1) / sp.g3_tile;
+        const long long cap = d->mode == PS21_MODE_SPHERICAL ? 64 : 16;
+        sp.g3_slots = (int)(ntiles < cap ? ntiles : cap);
+        long long spec = (long long)d->n0 * d->n1 * sp.nh;
+        int nslots = sp.g3_slots;
+        if (sp.path == PS21_PATH_FUSED) {
+            spec = fused_scratch_elems(sp, d->n0, d->n1);
+            nslots = p->chunks[sp.chunks[0]].nslots;  // set by fused_try_setup
+        }
+        for (int c : sp.chunks) p->chunks[c].nslots = nslots;
+        if (nslots > p->slots_max) p->slots_max = nslots;
+        if (spec > spec_max) spec_max = spec;
+    }
+    // scratch: as many spectra as fit the cap, at least one
+    {
+        long long n = p->workspace_cap / (spec_max * (long long)sizeof(float2));
+        if (n < 1) n = 1;
+        p->scratch_elems = n * spec_max;
+        if (cudaMalloc((void**)&p->d_scratch, sizeof(float2) * p->scratch_elems) != cudaSuccess) {
+            cudaGetLastError();
+            set_error("cannot allocate half-spectrum scratch");
+            return fail(PS21_ERR_NOMEM);
+        }
+    }
+    PS21_CUDA(cudaMalloc((void**)&p->d_chunks, sizeof(ChunkDev) * p->nchunks));
+    PS21_CUDA(cudaMemcpy(p->d_chunks, p->chunks.data(), sizeof(ChunkDev) * p->nchunks, cudaMemcpyHostToDevice));
+    // k^3/(2 pi^2) at the bin centres (likelihood.py:863, :652)
+    if (d->mode == PS21_MODE_SPHERICAL) {
+        std::vector<double> kf(p->out_per_box);
+        for (int c = 0; c < d->nchunks; ++c)
+            for (int b = 0; b < d->nbins; ++b) {
+                const double k = d->kcentres[(long long)c * d->nbins + b];
+                kf[p->chunks[c].out_off + b] = k * k * k / (2.0 * M_PI * M_PI);
+            }
+        PS21_CUDA(cudaMalloc((void**)&p->d_kfac, sizeof(double) * p->out_per_box));
+        PS21_CUDA(cudaMemcpy(p->d_kfac, kf.data(), sizeof(double) * p->out_per_box, cudaMemcpyHostToDevice));
+    }
+    // LUTs + counts
+    PS21_CUDA(cudaMalloc((void**)&p->d_counts, sizeof(long long) * p->out_per_box));
+    PS21_CUDA(cudaMemset(p->d_counts, 0, sizeof(long long) * p->out_per_box));
+    {
+        double *dk0 = nullptr, *dk1 = nullptr, *dk2 = nullptr, *ded = nullptr;
+        PS21_CUDA(cudaMalloc((void**)&dk0, sizeof(double) * d->n0));
+        PS21_CUDA(cudaMalloc((void**)&dk1, sizeof(double) * d->n1));
+        PS21_CUDA(cudaMalloc((void**)&dk2, sizeof(double) * k2off));
+        PS21_CUDA(cudaMalloc((void**)&ded, sizeof(double) * d->nchunks * (d->nbins + 1)));
+        PS21_CUDA(cudaMemcpy(dk0, d->k0sq, sizeof(double) * d->n0, cudaMemcpyHostToDevice));
+        PS21_CUDA(cudaMemcpy(dk1, d->k1sq, sizeof(double) * d->n1, cudaMemcpyHostToDevice));
+        PS21_CUDA(cudaMemcpy(dk2, d->k2sq, sizeof(double) * k2off, cudaMemcpyHostToDevice));
+        PS21_CUDA(cudaMemcpy(ded, d->edges, sizeof(double) * d->nchunks * (d->nbins + 1), cudaMemcpyHostToDevice));
+        p->d_lut.assign(d->nchunks, nullptr);
+        for (int c = 0; c < d->nchunks && rc == PS21_OK; ++c) {
+            const ShapePlan& sp = p->shapes[p->chunks[c].shape];
+            const long long spec = (sp.path == PS21_PATH_FUSED) ? fused_scratch_elems(sp, d->n0, d->n1)
+                                                                 : (long long)d->n0 * d->n1 * sp.nh;
+            if (cudaMalloc((void**)&p->d_lut[c], sizeof(uint16_t) * spec) != cudaSuccess) {
+                cudaGetLastError();
+                set_error("cannot allocate bin-index table");
+                rc = PS21_ERR_NOMEM;
+                break;
+            }
+            const double* e = ded + (long long)c * (d->nbins + 1);
+            rc = (sp.path == PS21_PATH_FUSED) ? fused_build_lut(p, c, dk0, dk1, dk2 + k2offs[c], e, 0)
+                                              : general_build_lut(p, c, dk0, dk1, dk2 + k2offs[c], e, 0);
+        }
+        cudaError_t se = cudaDeviceSynchronize();
+        free_dev(dk0); free_dev(dk1); free_dev(dk2); free_dev(ded);
+        if (rc) return fail(rc);
+        if (se != cudaSuccess) return fail(cuda_fail(se, "LUT build"));
+    }
+    PS21_CUDA(cudaMalloc((void**)&p->d_lut_table, sizeof(uint16_t*) * d->nchunks));
+    PS21_CUDA(cudaMemcpy(p->d_lut_table, p->d_lut.data(), sizeof(uint16_t*) * d->nchunks, cudaMemcpyHostToDevice));
+    p->h_counts.resize(p->out_per_box);
+    PS21_CUDA(cudaMemcpy(p->h_counts.data(), p->d_counts, sizeof(long long) * p->out_per_box, cudaMemcpyDeviceToHost));
+    *out = p;
+    return PS21_OK;
+}
+
+int ps21_plan_info(const ps21_plan* p, ps21_info* info) {
+    if (!p || !info) return invalid("null argument");
+    info->nshapes = (int)p->shapes.size();
+    info->path_of_chunk0 = p->shapes[p->chunks[0].shape].path;
+    info->out_per_box = p->out_per_box;
+    info->workspace_bytes = p->scratch_elems * (long long)sizeof(float2);
+    info->alg_bytes_per_box = p->alg_bytes_per_box;
+    info->launches_last_call = p->launches_last;
+    info->dominant_ms_last = 0.0;
+    return PS21_OK;
+}
+
+int ps21_plan_set_profiling(ps21_plan* p, int32_t on) {
+    if (!p) return invalid("null argument");
+    p->profiling = on != 0;
+    return PS21_OK;
+}
+
+int ps21_plan_profile(ps21_plan* p, double* ms_by_kind, int64_t* launches_by_kind) {
+    if (!p || !ms_by_kind || !launches_by_kind) return invalid("null argument");
+    for (int k = 0; k < KK_COUNT; ++k) { ms_by_kind[k] = 0.0; launches_by_kind[k] = 0; }
+#ifndef PS21_EMU
+    PS21_CUDA(cudaSetDevice(p->device));
+    for (auto& r : p->prof) {
+        cudaEvent_t a = (cudaEvent_t)r.e0, b = (cudaEvent_t)r.e1;
+        float ms = 0.f;
+        if (cudaEventSynchronize(b) == cudaSuccess && cudaEventElapsedTime(&ms, a, b) == cudaSuccess) {
+            ms_by_kind[r.kind] += ms;
+            launches_by_kind[r.kind] += 1;
+        }
+        cudaEventDestroy(a);
+        cudaEventDestroy(b);
+    }
+#endif
+    p->prof.clear();
+    return PS21_OK;
+}
+
+int ps21_plan_layout(const ps21_plan* p, int64_t* offsets) {
+    if (!p || !offsets) return invalid("null argument");
+    for (int c = 0; c < p->nchunks; ++c) offsets[c] = p->chunks[c].out_off;
+    offsets[p->nchunks] = p->out_per_box;
+    return PS21_OK;
+}
+
+int ps21_plan_counts(const ps21_plan* p, int64_t* counts) {
+    if (!p || !counts) return invalid("null argument");
+    for (long long i = 0; i < p->out_per_box; ++i) counts[i] = p->h_counts[i];
+    return PS21_OK;
+}
+
+int ps21_set_data(ps21_plan* p, int32_t nsets, const double* data, const double* noise, const uint8_t* kmask,
+                  double model_uncertainty, int32_t error_on_model) {
+    if (!p || !data || !kmask || nsets < 1) return invalid("null argument / nsets < 1");
+    if (p->mode != PS21_MODE_SPHERICAL) return invalid("likelihood data need the spherical mode");
+    PS21_CUDA(cudaSetDevice(p->device));
+    free_dev(p->data.d_data); free_dev(p->data.d_noise2); free_dev(p->data.d_mask);
+    p->data = DataTables{};
+    const long long n = (long long)nsets * p->out_per_box;
+    std::vector<double> n2(n, 0.0);
+    if (noise) for (long long i = 0; i < n; ++i) n2[i] = noise[i] * noise[i];
+    PS21_CUDA(cudaMalloc((void**)&p->data.d_data, sizeof(double) * n));
+    PS21_CUDA(cudaMalloc((void**)&p->data.d_noise2, sizeof(double) * n));
+    PS21_CUDA(cudaMalloc((void**)&p->data.d_mask, n));
+    PS21_CUDA(cudaMemcpy(p->data.d_data, data, sizeof(double) * n, cudaMemcpyHostToDevice));
+    PS21_CUDA(cudaMemcpy(p->data.d_noise2, n2.data(), sizeof(double) * n, cudaMemcpyHostToDevice));
+    PS21_CUDA(cudaMemcpy(p->data.d_mask, kmask, n, cudaMemcpyHostToDevice));
+    p->data.nsets = nsets;
+    p->data.model_uncertainty = model_uncertainty;
+    p->data.error_on_model = error_on_model ? 1 : 0;
+    return PS21_OK;
+}
+
+int ps21_power_batched(ps21_plan* p, const float* d_boxes, int64_t batch, int64_t batch_stride, double* d_power,
+                       void* stream) {
+    if (!p || !d_boxes || !d_power) return invalid("null argument");
+    PS21_CUDA(cudaSetDevice(p->device));
+    p->launches_last = 0;
+    return run_device(p, d_boxes, batch, batch_stride, d_power, nullptr, nullptr, (cudaStream_t)stream);
+}
+
+int ps21_lnl_batched(ps21_plan* p, const float* d_boxes, int64_t batch, int64_t batch_stride, double* d_lnl,
+                     double* d_delta, double* d_power, void* stream) {
+    if (!p || !d_boxes || !d_lnl) return invalid("null argument");
+    PS21_CUDA(cudaSetDevice(p->device));
+    p->launches_last = 0;
+    return run_device(p, d_boxes, batch, batch_stride, d_power, d_delta, d_lnl, (cudaStream_t)stream);
+}
+
+// Host-buffer variants: boxes are staged through two device buffers; the copy of slice i+1 overlaps
+// the kernels of slice i.
+static int run_host(ps21_plan* p, const float* h_boxes, long long batch, long long batch_stride, double* h_lnl,
+                    double* h_delta, double* h_power) {
+    PS21_CUDA(cudaSetDevice(p->device));
+    p->launches_last = 0;
+    if (batch <= 0) return PS21_OK;
+    const long long box_elems = (long long)p->n0 * p->n1 * p->n2_total;
+    if (batch_stride < box_elems) return invalid("batch_stride smaller than one box");
+    // slice size: at most 1 GiB per staging buffer, at least one box
+    long long per = (1LL << 30) / (box_elems * 4);
+    if (per < 1) per = 1;
+    if (per > batch) per = batch;
+    if (per > p->stage_boxes) {
+        for (int i = 0; i < 2; ++i) {
+            free_dev(p->d_stage[i]);
+            p->d_stage[i] = nullptr;
+        }
+        p->stage_boxes = 0;
+        for (int i = 0; i < 2; ++i) PS21_CUDA(cudaMalloc((void**)&p->d_stage[i], sizeof(float) * per * box_elems));
+        p->stage_boxes = per;
+    }
+    for (int i = 0; i < 2; ++i) {
+        if (!p->stage_stream[i]) {
+            cudaStream_t s;
+            PS21_CUDA(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+            p->stage_stream[i] = (void*)s;
+        }
+        if (!p->stage_event[i]) {
+            cudaEvent_t e;
+            PS21_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+            p->stage_event[i] = (void*)e;
+        }
+    }
+    cudaStream_t s_copy = (cudaStream_t)p->stage_stream[0], s_comp = (cudaStream_t)p->stage_stream[1];
+    int rc = ensure_batch(p, per);
+    if (rc) return rc;
+    double *d_res_p = nullptr, *d_res_d = nullptr, *d_res_l = nullptr;
+    PS21_CUDA(cudaMalloc((void**)&d_res_p, sizeof(double) * batch * p->out_per_box));
+    if (h_delta) PS21_CUDA(cudaMalloc((void**)&d_res_d, sizeof(double) * batch * p->out_per_box));
+    if (h_lnl) PS21_CUDA(cudaMalloc((void**)&d_res_l, sizeof(double) * batch));
+    // events: [0] = "copy into buffer b done" is recorded per slice on s_copy; compute waits on it.
+    // buffer reuse: copy of slice i+2 waits for the compute of slice i (event recorded on s_comp).
+    cudaEvent_t ev_copy[2], ev_comp[2];
+    for (int i = 0; i < 2; ++i) {
+        cudaEventCreateWithFlags(&ev_copy[i], cudaEventDisableTiming);
+        cudaEventCreateWithFlags(&ev_comp[i], cudaEventDisableTiming);
+    }
+    long long done = 0;
+    int sl = 0;
+    while (done < batch && rc == PS21_OK) {
+        const long long n = (batch - done < per) ? (batch - done) : per;
+        const int b = sl & 1;
+        if (sl >= 2) cudaStreamWaitEvent(s_copy, ev_comp[b], 0);
+        if (batch_stride == box_elems) {
+            cudaMemcpyAsync(p->d_stage[b], h_boxes + done * batch_stride, sizeof(float) * n * box_elems,
+                            cudaMemcpyHostToDevice, s_copy);
+        } else {
+            for (long long i = 0; i < n; ++i)
+                cudaMemcpyAsync(p->d_stage[b] + i * box_elems, h_boxes + (done + i) * batch_stride,
+                                sizeof(float) * box_elems, cudaMemcpyHostToDevice, s_copy);
+        }
+        cudaEventRecord(ev_copy[b], s_copy);
+        cudaStreamWaitEvent(s_comp, ev_copy[b], 0);
+        rc = run_device(p, p->d_stage[b], n, box_elems, d_res_p + done * p->out_per_box,
+                        d_res_d ? d_res_d + done * p->out_per_box : nullptr, d_res_l ? d_res_l + done : nullptr,
+                        s_comp);
+        cudaEventRecord(ev_comp[b], s_comp);
+        done += n;
+        ++sl;
+    }
+    if (rc == PS21_OK) {
+        if (h_power)
+            cudaMemcpyAsync(h_power, d_res_p, sizeof(double) * batch * p->out_per_box, cudaMemcpyDeviceToHost, s_comp);
+        if (h_delta)
+            cudaMemcpyAsync(h_delta, d_res_d, sizeof(double) * batch * p->out_per_box, cudaMemcpyDeviceToHost, s_comp);
+        if (h_lnl) cudaMemcpyAsync(h_lnl, d_res_l, sizeof(double) * batch, cudaMemcpyDeviceToHost, s_comp);
+    }
+    cudaError_t e1 = cudaStreamSynchronize(s_copy);
+    cudaError_t e2 = cudaStreamSynchronize(s_comp);
+    for (int i = 0; i < 2; ++i) {
+        cudaEventDestroy(ev_copy[i]);
+        cudaEventDestroy(ev_comp[i]);
+    }
+    free_dev(d_res_p); free_dev(d_res_d); free_dev(d_res_l);
+    if (rc) return rc;
+    if (e1 != cudaSuccess) return cuda_fail(e1, "host staging copy stream");
+    if (e2 != cudaSuccess) return cuda_fail(e2, "host staging compute stream");
+    return PS21_OK;
+}
+
+int ps21_power_host(ps21_plan* p, const float* h_boxes, int64_t batch, int64_t batch_stride, double* h_power) {
+    if (!p || !h_boxes || !h_power) return invalid("null argument");
+    return run_host(p, h_boxes, batch, batch_stride, nullptr, nullptr, h_power);
+}
+
+int ps21_lnl_host(ps21_plan* p, const float* h_boxes, int64_t batch, int64_t batch_stride, double* h_lnl,
+                  double* h_delta, double* h_power) {
+    if (!p || !h_boxes || !h_lnl) return invalid("null argument");
+    if (p->data.nsets == 0) {
+        set_error("ps21_set_data must be called before a likelihood evaluation");
+        return PS21_ERR_STATE;
+    }
+    return run_host(p, h_boxes, batch, batch_stride, h_lnl, h_delta, h_power);
+}
+
+int ps21_lnl_from_delta(ps21_plan* p, const double* h_delta, int64_t batch, double* h_lnl) {
+    if (!p || !h_delta || !h_lnl) return invalid("null argument");
+    if (p->data.nsets == 0) {
+        set_error("ps21_set_data must be called before a likelihood evaluation");
+        return PS21_ERR_STATE;
+    }
+    PS21_CUDA(cudaSetDevice(p->device));
+    if (batch <= 0) return PS21_OK;
+    double *dd = nullptr, *dl = nullptr;
+    PS21_CUDA(cudaMalloc((void**)&dd, sizeof(double) * batch * p->out_per_box));
+    PS21_CUDA(cudaMalloc((void**)&dl, sizeof(double) * batch));
+    PS21_CUDA(cudaMemcpy(dd, h_delta, sizeof(double) * batch * p->out_per_box, cudaMemcpyHostToDevice));
+    PS21_LAUNCH(k_lnl_from_delta, dim3((unsigned)((batch + 63) / 64)), dim3(64), 0, (cudaStream_t)0, dd,
+                p->out_per_box, p->d_chunks, p->nchunks, dl, p->data.d_data, p->data.d_noise2, p->data.d_mask,
+                p->data.nsets, p->data.model_uncertainty, p->data.error_on_model, (long long)batch);
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaMemcpy(h_lnl, dl, sizeof(double) * batch, cudaMemcpyDeviceToHost);
+    free_dev(dd); free_dev(dl);
+    if (e != cudaSuccess) return cuda_fail(e, "lnl_from_delta");
+    p->launches_last = 1;
+    return PS21_OK;
+}
+
+int ps21_chi2_host(int32_t device, int64_t nrec, int64_t n, const double* delta, const double* data,
+                   const double* noise, const uint8_t* mask, int64_t nseg, const int64_t* seg_len,
+                   double model_uncertainty, int32_t error_on_model, double* lnl) {
+    if (!delta || !data || !mask || !seg_len || !lnl || nrec < 0 || n < 0) return invalid("null argument");
+    long long tot = 0;
+    for (int64_t s = 0; s < nseg; ++s) tot += seg_len[s];
+    if (tot != n) return invalid("segment lengths do not add up to n");
+    if (nrec == 0) return PS21_OK;
+    PS21_CUDA(cudaSetDevice(device));
+    double *dd = nullptr, *da = nullptr, *dn = nullptr, *dl = nullptr;
+    uint8_t* dm = nullptr;
+    long long* ds = nullptr;
+    cudaError_t e = cudaSuccess;
+    auto up = [&](void** dst, const void* src, size_t bytes) {
+        if (e == cudaSuccess) e = cudaMalloc(dst, bytes ? bytes : 1);
+        if (e == cudaSuccess && bytes) e = cudaMemcpy(*dst, src, bytes, cudaMemcpyHostToDevice);
+    };
+    up((void**)&dd, delta, sizeof(double) * nrec * n);
+    up((void**)&da, data, sizeof(double) * n);
+    if (noise) up((void**)&dn, noise, sizeof(double) * n);
+    up((void**)&dm, mask, (size_t)n);
+    up((void**)&ds, seg_len, sizeof(long long) * nseg);
+    if (e == cudaSuccess) e = cudaMalloc((void**)&dl, sizeof(double) * nrec);
+    if (e == cudaSuccess) {
+        PS21_LAUNCH(k_chi2_rows, dim3((unsigned)((nrec + 63) / 64)), dim3(64), 0, (cudaStream_t)0, dd, (long long)n,
+                    (long long)nrec, da, dn, dm, (long long)nseg, ds, model_uncertainty, error_on_model ? 1 : 0, dl);
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaMemcpy(lnl, dl, sizeof(double) * nrec, cudaMemcpyDeviceToHost);
+    free_dev(dd); free_dev(da); free_dev(dn); free_dev(dm); free_dev(ds); free_dev(dl);
+    if (e != cudaSuccess) return cuda_fail(e, "ps21_chi2_host");
+    return PS21_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,490 @@
+"""Power-spectrum likelihoods with the plugin API of src/py21cmmc/likelihood.py, computed on the GPU.
+
+``Likelihood1DPowerCoeval`` / ``Likelihood1DPowerLightcone`` keep the constructor options, ``setup``,
+``reduce_data``, ``computeLikelihood``, ``store`` and the ``compute_power`` staticmethod of the reference
+(likelihood.py:269-892).  Where the reference calls ``powerbox.get_power`` per chunk (:480-488,
+:782-790) these classes call libps21.so through ctypes; there is no CPU fallback.  Two additions:
+
+* ``reduce_data_batch`` / ``likelihood_batch``: many walkers in one device call (batched FFT +
+  binning + chi^2, only scalars and Delta^2 records come back);
+* ``device`` / ``edge_rule`` / ``kernel_path`` constructor options (they take part in ``__eq__`` like every
+  other init argument, core.py:92-122).
+
+Instances hold no device handle (plans live in a per-process cache), so they pickle into pool
+workers and YAML-dump like the reference's.
+"""
+from __future__ import annotations
+
+import logging
+from functools import cached_property
+from io import IOBase
+from os import path, rename
+from pathlib import Path
+
+import numpy as np
+from scipy.interpolate import InterpolatedUnivariateSpline
+
+from . import _capi, binning, core
+from .plan import get_plan
+
+logger = logging.getLogger("21cmFAST")
+np.seterr(invalid="ignore", divide="ignore")  # likelihood.py:22: empty bins are NaN, silently
+
+_DEFAULTS = {"device": None, "edge_rule": "legacy_1.001", "kernel_path": "auto"}
+
+
+def set_defaults(device=None, edge_rule=None, kernel_path=None):
+    """Defaults used by the ``compute_power`` staticmethods (which have no instance to ask)."""
+    if device is not None:
+        _DEFAULTS["device"] = int(device)
+    if edge_rule is not None:
+        if edge_rule not in binning.EDGE_RULES:
+            raise ValueError(f"edge_rule must be one of {binning.EDGE_RULES}")
+        _DEFAULTS["edge_rule"] = edge_rule
+    if kernel_path is not None:
+        _DEFAULTS["kernel_path"] = kernel_path
+
+
+def _device(dev=None):
+    if dev is not None:
+        return int(dev)
+    if _DEFAULTS["device"] is not None:
+        return _DEFAULTS["device"]
+    try:
+        import torch
+
+        if torch.cuda.is_available():
+            return torch.cuda.current_device()
+    except Exception:
+        pass
+    return 0
+
+
+def _is_cuda_tensor(x):
+    return type(x).__module__.startswith("torch") and getattr(x, "is_cuda", False)
+
+
+def _power_records(plan, boxes):
+    """(batch, out_per_box) float64 power for host arrays or CUDA tensors."""
+    if _is_cuda_tensor(boxes):
+        return plan.power_device(boxes).cpu().numpy()
+    return plan.power_host(boxes)
+
+
+class LikelihoodBase(core.ModuleBase):
+    """likelihood.py:40-108."""
+
+    def computeLikelihood(self, model):
+        raise NotImplementedError("The Base likelihood should never be used directly!")
+
+    def reduce_data(self, ctx):
+        raise NotImplementedError("The Base likelihood should never be used directly!")
+
+    def _expose_core_parameters(self):
+        for m in self._cores:
+            for k in ("user_params", "flag_options", "cosmo_params", "astro_params"):
+                if hasattr(m, k):
+                    if hasattr(self, k) and getattr(self, k) != getattr(m, k):
+                        raise ValueError("Setup has detected incompatible input parameter dicts in "
+                                         f"specified cores: {k}")
+                    setattr(self, k, getattr(m, k))
+
+    def setup(self):
+        super().setup()
+        self._expose_core_parameters()
+
+    def get_fiducial_model(self):
+        return self.reduce_data(self.chain.build_model_data())
+
+
+class LikelihoodBaseFile(LikelihoodBase):
+    """Data / noise read from (or, with ``simulate=True``, written to) ``.npz`` files (likelihood.py:111-266)."""
+
+    _ignore_attributes = LikelihoodBase._ignore_attributes + ("simulate",)
+
+    def __init__(self, datafile=None, noisefile=None, simulate=False, use_data=True):
+        super().__init__()
+        self.datafile = [datafile] if isinstance(datafile, (str, IOBase)) else datafile
+        self.noisefile = [noisefile] if isinstance(noisefile, (str, IOBase)) else noisefile
+        self._use_data = use_data
+        self._simulate = simulate
+        self.data = None
+        self.noise = None
+
+    def setup(self):
+        super().setup()
+        if not self._use_data:
+            return
+        if not self._simulate and not self.datafile:
+            raise ValueError("Either an existing datafile has to be specified, or simulate set to True.")
+        simctx = self.chain.simulate_mock() if self._simulate else None
+        self.data = self.reduce_data(simctx) if self._simulate else self._read_data()
+        can_define = hasattr(self, "define_noise") and self._simulate
+        if can_define or self.noisefile:
+            self.noise = self.define_noise(simctx, self.data) if can_define else self._read_noise()
+        if self.datafile and self._simulate:
+            self._write(self.datafile, self.data, "data")
+        if self.noisefile and can_define:
+            self._write(self.noisefile, self.noise, "noise")
+
+    @staticmethod
+    def _load_all(files, kind, hint=""):
+        out = []
+        for fl in files:
+            if not path.exists(fl):
+                raise FileNotFoundError(f"Could not find {kind}file: {fl}. {hint}")
+            out.append(dict(np.load(fl, allow_pickle=True)))
+        return out
+
+    def _read_data(self):
+        return self._load_all(self.datafile, "data", "If you meant to simulate data, set simulate=True.")
+
+    def _read_noise(self):
+        return self._load_all(self.noisefile, "noise") if self.noisefile else None
+
+    @staticmethod
+    def _write(files, records, kind):
+        for fl, d in zip(files, records):
+            if path.exists(fl):
+                logger.warning(f"File {fl} already exists. Moving previous version to {fl}.bk")
+                rename(fl, fl + ".bk")
+            np.savez(fl, **d)
+            logger.info(f"Saved {kind} file: {fl}")
+
+    def _write_data(self):
+        self._write(self.datafile, self.data, "data")
+
+    def _write_noise(self):
+        self._write(self.noisefile, self.noise, "noise")
+
+
+class Likelihood1DPowerCoeval(LikelihoodBaseFile):
+    """Gaussian likelihood on the spherically averaged Delta^2(k) of coeval cubes (likelihood.py:269-682)."""
+
+    required_cores = ((core.CoreCoevalModule,),)
+    _variant = "coeval"
+
+    def __init__(self, n_psbins=None, min_k=0.1, max_k=1.0, logk=True, model_uncertainty=0.15,
+                 error_on_model=True, ignore_kperp_zero=True, ignore_kpar_zero=False, ignore_k_zero=False,
+                 name="", device=None, edge_rule="legacy_1.001", kernel_path="auto", *args, **kwargs):
+        super().__init__(*args, **kwargs)
+        if self.noisefile and self.datafile and len(self.datafile) != len(self.noisefile):
+            raise ValueError("If noisefile or datafile are provided, they should have the same number "
+                             "of files (one for each coeval box)")
+        if edge_rule not in binning.EDGE_RULES:
+            raise ValueError(f"edge_rule must be one of {binning.EDGE_RULES}")
+        self.n_psbins = n_psbins
+        self.min_k = min_k
+        self.max_k = max_k
+        self.logk = logk
+        self.error_on_model = error_on_model
+        self.model_uncertainty = model_uncertainty
+        self.ignore_k_zero = ignore_k_zero
+        self.ignore_kperp_zero = ignore_kperp_zero
+        self.ignore_kpar_zero = ignore_kpar_zero
+        self.name = name
+        self.device = device
+        self.edge_rule = edge_rule
+        self.kernel_path = kernel_path
+
+    # ------------------------------------------------------------------ format checks / setup
+    def _check_data_format(self):
+        for i, d in enumerate(self.data):
+            if "k" not in d or "delta" not in d:
+                raise ValueError(f"datafile #{i + 1} of {len(self.data)} has the wrong format.")
+
+    def _check_noise_format(self):
+        for i, n in enumerate(self.noise):
+            if "k" not in n or "errs" not in n:
+                raise ValueError(f"noisefile #{i + 1} of {len(self.noise)} has the wrong format")
+
+    def _n_expected(self):
+        return len(self.redshift)
+
+    def setup(self):
+        super().setup()
+        if not self._use_data:
+            return
+        what = "redshift" if self._variant == "coeval" else "chunk"
+        if len(self.data) != self._n_expected():
+            raise ValueError(f"There needs to be one dataset (datafile) for each {what}!")
+        if self.noise and len(self.noise) != self._n_expected():
+            raise ValueError(f"There needs to be one dataset (noisefile) for each {what}!")
+        self._check_data_format()
+        if self.noise:
+            self._check_noise_format()
+
+    @cached_property
+    def data_spline(self):
+        return [InterpolatedUnivariateSpline(d["k"], d["delta"], k=1) for d in self.data]
+
+    @cached_property
+    def noise_spline(self):
+        if not self.noise:
+            return None
+        return [InterpolatedUnivariateSpline(n["k"], n["errs"], k=1) for n in self.noise]
+
+    @property
+    def redshift(self):
+        return self.core_primary.redshift
+
+    @cached_property
+    def paired_core(self):
+        paired = [c for c in self._cores if isinstance(c, core.CoreCoevalModule)]
+        if len(paired) > 1:
+            raise ValueError("You've got more than one CoreCoevalModule -- they will overwrite each other!")
+        return paired[0]
+
+    # ------------------------------------------------------------------ the hot path
+    @staticmethod
+    def _plan(shape, bounds, lengths, n_psbins, log_bins, ikperp, ikpar, ik0, device=None, edge_rule=None,
+              kernel_path=None, mode="spherical"):
+        if n_psbins is None:
+            cyl = mode == "cylindrical"
+            nbs = {binning.default_nbins((shape[0], shape[1], b - a), 2 if cyl else 3) for a, b in bounds}
+            if len(nbs) != 1:
+                raise NotImplementedError("n_psbins=None gives different default bin counts for chunks of "
+                                          "different length; pass n_psbins explicitly")
+            n_psbins = nbs.pop()
+        return get_plan(shape, bounds, lengths, int(n_psbins), log_bins, ikperp, ikpar, ik0,
+                        edge_rule or _DEFAULTS["edge_rule"], mode, _device(device),
+                        kernel_path or _DEFAULTS["kernel_path"])
+
+    @staticmethod
+    def compute_power(brightness_temp, L, n_psbins, log_bins=True, ignore_kperp_zero=True,
+                      ignore_kpar_zero=False, ignore_k_zero=False):
+        """Spherically averaged P(k) of one coeval cube: ``[power, k_centres]`` (likelihood.py:433-498)."""
+        shape = tuple(brightness_temp.shape)
+        if len(set(shape)) != 1:
+            raise ValueError("coeval cubes must be cubic (the reference indexes all axes with shape[0]//2)")
+        plan = Likelihood1DPowerCoeval._plan(shape, [(0, shape[2])], [(L, L, L)], n_psbins, log_bins,
+                                             ignore_kperp_zero, ignore_kpar_zero, ignore_k_zero)
+        rec = _power_records(plan, brightness_temp)[0]
+        return [rec.copy(), plan.kcentres[0].copy()]
+
+    def _own_plan(self, shape, bounds, lengths):
+        return self._plan(shape, bounds, lengths, self.n_psbins, self.logk, self.ignore_kperp_zero,
+                          self.ignore_kpar_zero, self.ignore_k_zero, self.device, self.edge_rule, self.kernel_path)
+
+    def _geometry(self, ctx):
+        """(boxes as one stack, plan) for a context.  Coeval: every redshift cube is a 1-chunk box."""
+        cubes = ctx.get("brightness_temp")
+        shape = tuple(cubes[0].shape)
+        L = self.user_params.BOX_LEN
+        plan = self._own_plan(shape, [(0, shape[2])], [(L, L, L)])
+        return cubes, plan
+
+    def _stack(self, cubes):
+        if _is_cuda_tensor(cubes[0]):
+            import torch
+
+            return torch.stack(list(cubes)).contiguous()
+        return np.stack([np.asarray(c, dtype=np.float32) for c in cubes])
+
+    def _models_from_power(self, plan, rec):
+        """rec: (nrec, out_per_box) power -> list over records of {"k","delta"} per chunk (likelihood.py:863)."""
+        out = []
+        for r in rec:
+            m = []
+            for c in range(plan.nchunks):
+                k = plan.kcentres[c].copy()
+                power = plan._chunk_view(r, c)
+                m.append({"k": k, "delta": power * k**3 / (2 * np.pi**2)})
+            out.append(m)
+        return out
+
+    def reduce_data(self, ctx):
+        """One ``{"k", "delta"}`` dict per redshift (likelihood.py:639-654), all cubes in one device call."""
+        cubes, plan = self._geometry(ctx)
+        rec = _power_records(plan, self._stack(cubes))
+        return [m[0] for m in self._models_from_power(plan, rec)]
+
+    def _tables(self, ks):
+        """Data side of computeLikelihood at the given k arrays: (data, noise, mask) lists (likelihood.py:588-597)."""
+        data, noise, mask = [], [], []
+        for i, k in enumerate(ks):
+            sel = np.logical_and(k <= self.max_k, k >= self.min_k)
+            data.append(self.data_spline[i](k))
+            noise.append(self.noise_spline[i](k) if self.noise_spline else np.zeros_like(k))
+            mask.append(sel)
+        return data, noise, mask
+
+    def computeLikelihood(self, model):
+        """ln L of one reduced model (likelihood.py:584-607); the chi^2 runs on the device."""
+        ks = [np.asarray(m["k"], dtype=np.float64) for m in model]
+        data, noise, mask = self._tables(ks)
+        seg = np.array([len(k) for k in ks], dtype=np.int64)
+        delta = np.concatenate([np.asarray(m["delta"], dtype=np.float64) for m in model])
+        lnl = chi2_device(delta[None, :], np.concatenate(data), np.concatenate(noise), np.concatenate(mask), seg,
+                          self.model_uncertainty, self.error_on_model, _device(self.device))[0]
+        logger.debug(f"Likelihood computed: {lnl}")
+        return float(lnl)
+
+    def store(self, model, storage):
+        """Blobs ``k_z{z}`` / ``delta_z{z}`` (likelihood.py:656-664)."""
+        for i, m in enumerate(model):
+            storage.update({k + "_z%s" % self.redshift[i]: v for k, v in m.items()})
+
+    # ------------------------------------------------------------------ batched walkers
+    def _prepare_plan_data(self, plan):
+        ks = [plan.kcentres[0]] * self._n_expected() if self._variant == "coeval" else list(plan.kcentres)
+        data, noise, mask = self._tables(ks)
+        nsets = self._n_expected() if self._variant == "coeval" else 1
+        shape = (nsets, plan.nchunks, plan.nbins)
+        plan.set_data(np.array(data).reshape(shape), np.array(noise).reshape(shape),
+                      np.array(mask, dtype=np.uint8).reshape(shape), self.model_uncertainty, self.error_on_model)
+
+    def reduce_data_batch(self, ctxs):
+        """``[reduce_data(ctx) for ctx in ctxs]`` with a single device call."""
+        return self.likelihood_batch(ctxs, want_lnl=False)[1]
+
+    def likelihood_batch(self, ctxs, want_lnl=True):
+        """(lnL array, list of models) for many contexts: one batched FFT + binning + chi^2 call."""
+        if not ctxs:
+            return np.zeros(0), []
+        stacks, plan = [], None
+        for ctx in ctxs:
+            cubes, plan = self._geometry(ctx)
+            stacks.append(self._stack(cubes))
+        per = stacks[0].shape[0]
+        if _is_cuda_tensor(stacks[0]):
+            import torch
+
+            boxes = torch.cat(stacks)
+        else:
+            boxes = np.concatenate(stacks)
+        if want_lnl:
+            self._prepare_plan_data(plan)
+            if _is_cuda_tensor(boxes):
+                import torch
+
+                delta = torch.empty((boxes.shape[0], plan.out_per_box), dtype=torch.float64, device=boxes.device)
+                lnl = plan.lnl_device(boxes, delta=delta).cpu().numpy()
+                delta = delta.cpu().numpy()
+            else:
+                lnl, delta, _ = plan.lnl_host(boxes, want_delta=True)
+            lnl = lnl.reshape(len(ctxs), per).sum(axis=1)
+            recs = [[{"k": plan.kcentres[c].copy(), "delta": plan._chunk_view(r, c).copy()}
+                     for c in range(plan.nchunks)] for r in delta]
+        else:
+            lnl = None
+            recs = self._models_from_power(plan, _power_records(plan, boxes))
+        models = []
+        for w in range(len(ctxs)):
+            rows = recs[w * per:(w + 1) * per]
+            models.append([r[0] for r in rows] if self._variant == "coeval" else rows[0])
+        return lnl, models
+
+
+class Likelihood1DPowerLightcone(Likelihood1DPowerCoeval):
+    """The same likelihood on a lightcone cut into ``nchunks`` line-of-sight chunks (likelihood.py:685-892)."""
+
+    required_cores = ((core.CoreLightConeModule,),)
+    _variant = "lightcone"
+
+    def __init__(self, *args, datafile="", nchunks=1, **kwargs):
+        super().__init__(*args, **kwargs)
+        self.nchunks = nchunks
+        self.datafile = [datafile] if isinstance(datafile, (str, Path)) else datafile
+
+    def _n_expected(self):
+        return self.nchunks
+
+    def setup(self):
+        LikelihoodBaseFile.setup(self)
+        if not self._use_data:
+            return
+        if len(self.data) != self.nchunks:
+            raise ValueError("There needs to be one dataset (datafile) for each chunk!!")
+        if self.noise and len(self.noise) != self.nchunks:
+            raise ValueError("There needs to be one dataset (noisefile) for each chunk!")
+        self._check_data_format()
+        if self.noise:
+            self._check_noise_format()
+
+    @cached_property
+    def paired_core(self):
+        paired = [c for c in self._cores if isinstance(c, core.CoreLightConeModule) and c.name == self.name]
+        if len(paired) > 1:
+            raise ValueError("You've got more than one CoreLightConeModule with the same name -- "
+                             "they will overwrite each other!")
+        return paired[0]
+
+    @staticmethod
+    def compute_power(box, length, n_psbins, log_bins=True, ignore_kperp_zero=True, ignore_kpar_zero=False,
+                      ignore_k_zero=False):
+        """Spherically averaged P(k) of one lightcone chunk: ``[power, k_centres]`` (likelihood.py:734-800).
+
+        ``box`` may be a non-contiguous view ``bt[:, :, start:end]`` (likelihood.py:855); it is staged as a
+        contiguous (n0, n1, nz) box.
+        """
+        shape = tuple(box.shape)
+        plan = Likelihood1DPowerCoeval._plan(shape, [(0, shape[2])], [tuple(length)], n_psbins, log_bins,
+                                             ignore_kperp_zero, ignore_kpar_zero, ignore_k_zero)
+        if _is_cuda_tensor(box):
+            box = box.contiguous()
+        rec = _power_records(plan, box)[0]
+        return [rec.copy(), plan.kcentres[0].copy()]
+
+    @staticmethod
+    def compute_power_2d(box, length, n_psbins, log_bins=False, ignore_kperp_zero=True, ignore_kpar_zero=False,
+                         ignore_k_zero=False):
+        """Cylindrical P(k_perp, k_par) = ``get_power(..., res_ndim=2)``.
+
+        Returns ``[P2D (n_psbins, nz) in shifted k_par order, k_perp centres, k_par (nz,) shifted]``.
+        """
+        shape = tuple(box.shape)
+        plan = Likelihood1DPowerCoeval._plan(shape, [(0, shape[2])], [tuple(length)], n_psbins, log_bins,
+                                             ignore_kperp_zero, ignore_kpar_zero, ignore_k_zero,
+                                             mode="cylindrical")
+        if _is_cuda_tensor(box):
+            box = box.contiguous()
+        half = plan._chunk_view(_power_records(plan, box)[0], 0)  # (nb, nh)
+        nz = shape[2]
+        f = np.fft.fftshift(np.fft.fftfreq(nz, d=1.0 / nz)).round().astype(int)  # shifted integer frequencies
+        cols = np.minimum(np.abs(f), nz - np.abs(f))
+        kpar = np.fft.fftshift(np.fft.fftfreq(nz, d=float(length[2]) / nz)) * 2 * np.pi
+        return [half[:, cols], plan.kcentres[0].copy(), kpar]
+
+    def _geometry(self, ctx):
+        lc = ctx.get("lightcone")
+        bt = lc.brightness_temp
+        shape = tuple(bt.shape)
+        ci = binning.chunk_indices(lc.n_slices, self.nchunks)
+        # IndexError for too few chunk starts, like the reference loop (likelihood.py:849-851)
+        bounds = [(ci[i], ci[i + 1]) for i in range(self.nchunks)]
+        L = self.user_params.BOX_LEN
+        lengths = [(L, L, (b - a) * lc.cell_size) for a, b in bounds]
+        return [bt], self._own_plan(shape, bounds, lengths)
+
+    def reduce_data(self, ctx):
+        """One ``{"k", "delta"}`` dict per chunk (likelihood.py:833-865), all chunks in one device call."""
+        boxes, plan = self._geometry(ctx)
+        rec = _power_records(plan, self._stack(boxes))
+        return self._models_from_power(plan, rec)[0]
+
+    def store(self, model, storage):
+        """Blobs ``k_{i}`` / ``delta_{i}`` (likelihood.py:867-876)."""
+        for i, m in enumerate(model):
+            storage.update({k + "_%s" % i: v for k, v in m.items()})
+
+
+def chi2_device(delta, data, noise, mask, seg, model_uncertainty, error_on_model, device=0):
+    """-0.5 * sum_seg sum_k (delta-data)^2 / ((mu*delta|data)^2 + noise^2) for every row of ``delta``."""
+    import ctypes as C
+
+    lib = _capi.load()
+    delta = np.ascontiguousarray(delta, dtype=np.float64)
+    nrec, n = delta.shape
+    data = np.ascontiguousarray(data, dtype=np.float64)
+    noise = np.ascontiguousarray(noise, dtype=np.float64)
+    mask = np.ascontiguousarray(mask, dtype=np.uint8)
+    seg = np.ascontiguousarray(seg, dtype=np.int64)
+    out = np.empty(nrec, dtype=np.float64)
+    dp = C.POINTER(C.c_double)
+    _capi.check(lib.ps21_chi2_host(int(device), nrec, n, delta.ctypes.data_as(dp), data.ctypes.data_as(dp),
+                                   noise.ctypes.data_as(dp), mask.ctypes.data_as(C.POINTER(C.c_uint8)),
+                                   len(seg), seg.ctypes.data_as(C.POINTER(C.c_int64)),
+                                   float(model_uncertainty), int(bool(error_on_model)),
+                                   out.ctypes.data_as(dp)))
+    return out

@@ -1,0 +1,107 @@
+// TEST INFRASTRUCTURE ONLY.  Host emulation of the small CUDA subset used by the *general* path of
+// 21cmmc_b200/csrc so that the `-m "not gpu"` test-suite can execute the kernel logic (index maths,
+// FFT stages, binning, plan bookkeeping) against the oracle without a GPU.  One CUDA block at a time;
+// the threads of a block are ucontext fibers, `__syncthreads()` yields to a round-robin scheduler.
+// It is compiled only into tests/emu/libps21_emu.so (g++ -DPS21_EMU); the product library
+// (21cmmc_b200/libps21.so) is built by nvcc for sm_100a and never contains this code.
+#pragma once
+#include <ucontext.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdint>
+#include <cstdlib>
+#include <cstring>
+#include <functional>
+#include <vector>
+
+struct float2 {
+    float x, y;
+};
+static inline float2 make_float2(float x, float y) { return float2{x, y}; }
+struct uint3 {
+    unsigned x, y, z;
+};
+struct dim3 {
+    unsigned x, y, z;
+    dim3(unsigned a = 1, unsigned b = 1, unsigned c = 1) : x(a), y(b), z(c) {}
+};
+
+namespace ps21emu {
+extern uint3 threadIdx, blockIdx;
+extern dim3 blockDim, gridDim;
+extern char* g_dyn_smem;
+void syncthreads();
+void launch(dim3 grid, dim3 block, size_t smem, const std::function<void()>& body);
+}  // namespace ps21emu
+using ps21emu::blockDim;
+using ps21emu::blockIdx;
+using ps21emu::gridDim;
+using ps21emu::threadIdx;
+
+#define __global__
+#define __device__
+#define __host__
+#define __forceinline__ inline
+#define __restrict__
+#define __shared__ static
+#define __syncthreads() ps21emu::syncthreads()
+#define PS21_DYN_SMEM(type, name) type* name = reinterpret_cast<type*>(ps21emu::g_dyn_smem)
+
+template <class T>
+static inline T __ldg(const T* p) { return *p; }
+static inline double __dsqrt_rn(double a) { return std::sqrt(a); }
+static inline double __dadd_rn(double a, double b) { return a + b; }
+template <class T>
+static inline T atomicAdd(T* p, T v) {
+    T old = *p;
+    *p = old + v;
+    return old;
+}
+using std::max;
+using std::min;
+
+// runtime API
+typedef int cudaError_t;
+typedef void* cudaStream_t;
+typedef void* cudaEvent_t;
+enum { cudaSuccess = 0 };
+enum cudaMemcpyKind { cudaMemcpyHostToDevice, cudaMemcpyDeviceToHost, cudaMemcpyDeviceToDevice };
+enum { cudaStreamNonBlocking = 1, cudaEventDisableTiming = 2 };
+static inline const char* cudaGetErrorString(cudaError_t) { return "emu"; }
+static inline cudaError_t cudaGetLastError() { return 0; }
+static inline cudaError_t cudaSetDevice(int) { return 0; }
+static inline cudaError_t cudaDeviceSynchronize() { return 0; }
+static inline cudaError_t cudaMalloc(void** p, size_t n) {
+    *p = std::malloc(n ? n : 1);
+    return *p ? 0 : 2;
+}
+static inline cudaError_t cudaFree(void* p) {
+    std::free(p);
+    return 0;
+}
+static inline cudaError_t cudaMemcpy(void* d, const void* s, size_t n, cudaMemcpyKind) {
+    std::memcpy(d, s, n);
+    return 0;
+}
+static inline cudaError_t cudaMemcpyAsync(void* d, const void* s, size_t n, cudaMemcpyKind, cudaStream_t) {
+    std::memcpy(d, s, n);
+    return 0;
+}
+static inline cudaError_t cudaMemset(void* d, int v, size_t n) {
+    std::memset(d, v, n);
+    return 0;
+}
+static inline cudaError_t cudaStreamCreateWithFlags(cudaStream_t* s, int) {
+    *s = (void*)1;
+    return 0;
+}
+static inline cudaError_t cudaStreamDestroy(cudaStream_t) { return 0; }
+static inline cudaError_t cudaStreamSynchronize(cudaStream_t) { return 0; }
+static inline cudaError_t cudaStreamWaitEvent(cudaStream_t, cudaEvent_t, int) { return 0; }
+static inline cudaError_t cudaEventCreateWithFlags(cudaEvent_t* e, int) {
+    *e = (void*)1;
+    return 0;
+}
+static inline cudaError_t cudaEventRecord(cudaEvent_t, cudaStream_t) { return 0; }
+static inline cudaError_t cudaEventDestroy(cudaEvent_t) { return 0; }

@@ -25,8 +25,9 @@ CASES = {
 def make_box(case, seed=0):
     """float32 box, mean ~20, sigma ~10, from a 64-bit integer hash of the cell index."""
     n = int(np.prod(case["shape"]))
-    i = np.arange(n, dtype=np.uint64) + np.uint64(seed) * np.uint64(0x9E3779B97F4A7C15)
+    off = np.uint64((int(seed) * 0x9E3779B97F4A7C15) % 2**64)
     with np.errstate(over="ignore"):
+        i = np.arange(n, dtype=np.uint64) + off
         x = i * np.uint64(0xD1342543DE82EF95) + np.uint64(0x2545F4914F6CDD1D)
         x ^= x >> np.uint64(32)
         x *= np.uint64(0xDA942042E4DD58B5)

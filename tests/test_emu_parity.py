@@ -1,0 +1,78 @@
+"""CPU parity: the *same* kernel sources as libps21.so (general path), built by g++ against the host
+CUDA emulation in tests/emu, driven through the C ABI and the plugin classes, versus the oracle.
+This checks index maths, FFT stages, binning, plan bookkeeping and the host layer without a GPU; the
+`-m gpu` tests repeat it on the real library."""
+import numpy as np
+import pytest
+
+from tests import parity_cases as PC
+
+
+@pytest.fixture(scope="module")
+def mods():
+    from tests.emu.build_emu import build
+
+    lib = build()
+    import py21cmmc_b200
+    from py21cmmc_b200 import _capi, chain, core, likelihood, plan
+
+    _capi._testing_set_library(lib)
+    yield likelihood, core, chain
+    plan.clear_plans()
+    _capi._testing_set_library(None)
+
+
+@pytest.mark.parametrize("shape,L,nb,log,flags,rule", [
+    ((16, 16, 32), (24.0, 24.0, 48.0), 8, True, (True, False, False), "legacy_1.001"),
+    ((16, 16, 32), (24.0, 24.0, 48.0), 8, False, (False, False, False), "legacy_1.001"),  # DC binned
+    ((12, 12, 37), (18.0, 18.0, 55.5), 6, True, (True, False, False), "legacy_1.001"),   # prime length
+    ((15, 15, 17), (22.5, 22.5, 25.5), 7, True, (True, True, False), "legacy_1.001"),    # odd sizes
+    ((24, 24, 18), (36.0, 36.0, 27.0), 10, False, (True, False, True), "inscribed"),
+    ((10, 10, 14), (15.0, 15.0, 21.0), None, True, (True, False, False), "legacy_1.001"),  # default bins
+])
+def test_compute_power_lightcone(mods, shape, L, nb, log, flags, rule):
+    PC.check_compute_power(mods[0], shape, L, nb, log, flags, rule)
+
+
+def test_compute_power_coeval(mods):
+    PC.check_compute_power(mods[0], (20, 20, 20), 30.0, 9, True, coeval=True)
+    with pytest.raises(ValueError):
+        mods[0].Likelihood1DPowerCoeval.compute_power(np.zeros((8, 8, 6), np.float32), 10.0, 4)
+
+
+def test_lightcone_likelihood_chain(mods):
+    PC.check_lightcone_likelihood(*mods, shape=(16, 16, 48), box_len=24.0, nchunks=3, nb=8, min_k=0.3, max_k=3.0)
+
+
+def test_lightcone_unequal_chunks_linear(mods):
+    # 50 slices / 3 chunks -> 17, 17, 16: two shapes in one plan
+    PC.check_lightcone_likelihood(*mods, shape=(12, 12, 50), box_len=18.0, nchunks=3, nb=6, min_k=0.2, max_k=4.0,
+                                  logk=False)
+
+
+def test_coeval_likelihood_chain(mods):
+    PC.check_coeval_likelihood(*mods, n=12, box_len=18.0, nb=6)
+
+
+def test_cylindrical(mods):
+    PC.check_cylindrical(mods[0], (12, 12, 16), (18.0, 18.0, 24.0), 5)
+    PC.check_cylindrical(mods[0], (10, 10, 9), (15.0, 15.0, 13.5), 4)
+
+
+def test_too_few_slices_raises_like_reference(mods):
+    lk, core, chain = mods
+    with pytest.raises(IndexError):
+        PC.make_lightcone_chain(lk, core, chain, (4, 4, 6), 6.0, nchunks=4, nb=3)
+
+
+def test_lnl_before_data_is_a_state_error(mods):
+    from py21cmmc_b200 import Ps21Error
+    from py21cmmc_b200.plan import PowerPlan
+    from py21cmmc_b200 import _capi
+
+    pl = PowerPlan((8, 8, 8), [(0, 8)], [(12.0, 12.0, 12.0)], 4, library=_capi.LIB_PATH)
+    with pytest.raises(Ps21Error):
+        pl.lnl_host(np.zeros((1, 8, 8, 8), np.float32))
+    with pytest.raises(ValueError):
+        pl.power_host(np.zeros((1, 8, 8, 4), np.float32))
+    pl.close()

@@ -1,0 +1,151 @@
+"""GPU parity (run with -m gpu on a B200): libps21.so through the C ABI / plugin classes vs the oracle.
+
+Small and medium sizes are compared element-wise with oracle/ps_oracle.py (fp64 FFT); the benchmark's
+full-size shape is checked through size-independent properties (Parseval, batch invariance,
+determinism) because the oracle would need minutes there.
+"""
+import os
+
+import numpy as np
+import pytest
+
+from tests import parity_cases as PC
+from tests.helpers import POWER_RTOL, rel_err, synth_box
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+@pytest.fixture(scope="module")
+def mods():
+    import torch
+
+    assert torch.cuda.is_available()
+    import py21cmmc_b200
+    from py21cmmc_b200 import _capi, chain, core, likelihood
+
+    _capi._testing_set_library(None)
+    lib = _capi.load()  # raises if libps21.so is missing: no fallback
+    assert lib.ps21_version() >= 100
+    return likelihood, core, chain
+
+
+@pytest.fixture(params=["general", "auto"])
+def kpath(request, mods):
+    mods[0].set_defaults(kernel_path=request.param)
+    yield request.param
+    mods[0].set_defaults(kernel_path="auto")
+
+
+@pytest.mark.parametrize("shape,L,nb,log,flags,rule", [
+    ((16, 16, 32), (24.0, 24.0, 48.0), 8, True, (True, False, False), "legacy_1.001"),
+    ((16, 16, 32), (24.0, 24.0, 48.0), 8, False, (False, False, False), "legacy_1.001"),
+    ((12, 12, 37), (18.0, 18.0, 55.5), 6, True, (True, False, False), "legacy_1.001"),
+    ((15, 15, 17), (22.5, 22.5, 25.5), 7, True, (True, True, False), "legacy_1.001"),
+    ((24, 24, 18), (36.0, 36.0, 27.0), 10, False, (True, False, True), "inscribed"),
+    ((35, 35, 37), (52.5, 52.5, 55.5), None, True, (True, False, False), "legacy_1.001"),
+    ((50, 50, 50), (75.0, 75.0, 75.0), None, True, (True, False, False), "legacy_1.001"),
+    ((64, 64, 128), (96.0, 96.0, 192.0), 20, True, (True, False, False), "legacy_1.001"),
+    ((128, 128, 256), (192.0, 192.0, 384.0), 20, True, (True, False, False), "legacy_1.001"),  # config 1 chunk
+    ((128, 128, 128), (192.0, 192.0, 192.0), 20, False, (False, False, False), "inscribed"),
+    ((64, 64, 334), (96.0, 96.0, 501.0), 12, True, (True, False, False), "legacy_1.001"),      # 2 x 167
+])
+def test_compute_power_lightcone(mods, kpath, shape, L, nb, log, flags, rule):
+    PC.check_compute_power(mods[0], shape, L, nb, log, flags, rule)
+
+
+def test_golden_vectors(mods, kpath):
+    from tests.golden.make_golden import CASES, make_box
+
+    gold = np.load(os.path.join(GOLD, "oracle_golden.npz"))
+    for name, case in CASES.items():
+        mods[0].set_defaults(edge_rule=case["rule"])
+        try:
+            p, k = mods[0].Likelihood1DPowerLightcone.compute_power(make_box(case), case["L"], case["nb"],
+                                                                    case["log"], *case["flags"])
+        finally:
+            mods[0].set_defaults(edge_rule="legacy_1.001")
+        assert np.array_equal(k, gold[f"{name}_k"])
+        assert rel_err(p, gold[f"{name}_power"]) < POWER_RTOL
+
+
+def test_compute_power_coeval_200(mods, kpath):
+    # config 2 box: 200^3, n_psbins = 20
+    PC.check_compute_power(mods[0], (200, 200, 200), 300.0, 20, True, coeval=True)
+
+
+def test_lightcone_likelihood_chain(mods, kpath):
+    PC.check_lightcone_likelihood(*mods, shape=(32, 32, 128), box_len=48.0, nchunks=4, nb=10, min_k=0.2, max_k=3.0)
+
+
+def test_lightcone_unequal_chunks_linear(mods, kpath):
+    PC.check_lightcone_likelihood(*mods, shape=(20, 20, 100), box_len=30.0, nchunks=3, nb=6, min_k=0.2, max_k=4.0,
+                                  logk=False)
+
+
+def test_config1_lightcone(mods, kpath):
+    # BASELINE config 1: 128 x 128 x 1024, 4 chunks, 20 log bins, 1.5 Mpc cells
+    PC.check_lightcone_likelihood(*mods, shape=(128, 128, 1024), box_len=192.0, nchunks=4, nb=20, min_k=0.1,
+                                  max_k=1.0)
+
+
+def test_coeval_likelihood_chain(mods, kpath):
+    PC.check_coeval_likelihood(*mods, n=40, box_len=60.0, nb=8)
+
+
+def test_cylindrical(mods):
+    PC.check_cylindrical(mods[0], (32, 32, 64), (48.0, 48.0, 96.0), 8)
+    PC.check_cylindrical(mods[0], (20, 20, 9), (30.0, 30.0, 13.5), 4)
+
+
+def test_device_tensor_api_and_determinism(mods, kpath):
+    import torch
+
+    from py21cmmc_b200.plan import get_plan
+
+    shape = (64, 64, 256)
+    L = 96.0
+    bounds = [(0, 128), (128, 256)]
+    plan = get_plan(shape, bounds, [(L, L, 192.0)] * 2, 12, True, True, False, False, "legacy_1.001", "spherical",
+                    torch.cuda.current_device(), kpath)
+    boxes = np.stack([synth_box(shape, s) for s in range(5)])
+    t = torch.from_numpy(boxes).cuda()
+    a = plan.power_device(t).cpu().numpy()
+    b = plan.power_device(t).cpu().numpy()
+    assert np.array_equal(a, b, equal_nan=True), "two runs must agree bitwise (fixed-order reductions)"
+    # batch invariance: each box alone gives the same bits as inside the batch
+    for i in range(5):
+        one = plan.power_device(t[i:i + 1].contiguous()).cpu().numpy()[0]
+        assert np.array_equal(one, a[i], equal_nan=True)
+    # host-buffer entry point == device-buffer entry point
+    h = plan.power_host(boxes)
+    assert np.array_equal(h, a, equal_nan=True)
+
+
+def test_full_size_properties(mods, kpath):
+    """256^2 x 1024 lightcone (the benchmark shape): Parseval + linearity in amplitude."""
+    import torch
+
+    from py21cmmc_b200.plan import get_plan
+
+    shape = (256, 256, 1024)
+    L = 384.0
+    bounds = [(i * 256, (i + 1) * 256) for i in range(4)]
+    dev = torch.cuda.current_device()
+    # linear bins, every mode weighted: sum_b P_b count_b = V/N * sum x^2  (legacy top edge keeps all modes)
+    plan = get_plan(shape, bounds, [(L, L, 384.0)] * 4, 24, False, False, False, False, "legacy_1.001",
+                    "spherical", dev, kpath)
+    g = torch.Generator(device="cuda").manual_seed(1234)
+    box = torch.randn((1,) + shape, generator=g, device="cuda", dtype=torch.float32) * 10 + 20
+    p = plan.power_device(box).cpu().numpy()[0].reshape(4, 24)
+    cnt = plan.counts.reshape(4, 24)
+    assert cnt.sum() == 4 * 256 ** 3
+    V, N = L * L * 384.0, 256 ** 3
+    for c in range(4):
+        chunk = box[0, :, :, c * 256:(c + 1) * 256].double()
+        expect = V / N * float((chunk * chunk).sum())
+        got = float(np.nansum(p[c] * cnt[c]))
+        assert abs(got / expect - 1) < 2e-6
+    # scaling the field by 2 scales every bin by exactly 4 (power-of-two scaling is exact in fp32)
+    p2 = plan.power_device((box * 2).contiguous()).cpu().numpy()[0]
+    assert np.array_equal(p2, 4 * p.ravel(), equal_nan=True)
