@@ -93,18 +93,6 @@ int launch_slab_mean(ps21_plan* p, const float* d_boxes, long long batch_stride,
     return PS21_OK;
 }
 
-// item -> (box, chunk) for a shape whose chunk-id list is `ids[0..nper)`
-struct ItemMap {
-    const int* ids;
-    int nper;
-    long long item0;
-};
-__device__ __forceinline__ void item_to_box_chunk(const ItemMap& m, long long local, long long& box, int& chunk) {
-    const long long it = m.item0 + local;
-    box = it / m.nper;
-    chunk = m.ids[it % m.nper];
-}
-
 // ---------------------------------------------------------------------------------------------
 // g1: z pass.  CTA = `cols` complex columns = 2*cols consecutive (x,y) rows of one spectrum.
 // ---------------------------------------------------------------------------------------------

@@ -146,6 +146,18 @@ int fused_forward(ps21_plan* p, ShapePlan& sp, const float* d_boxes, long long b
                   long long nitems, cudaStream_t st);
 long long fused_scratch_elems(const ShapePlan& sp, int n0, int n1);
 
+// item -> (box, chunk) for a shape whose chunk-id list is `ids[0..nper)`
+struct ItemMap {
+    const int* ids;
+    int nper;
+    long long item0;
+};
+__device__ __forceinline__ void item_to_box_chunk(const ItemMap& m, long long local, long long& box, int& chunk) {
+    const long long it = m.item0 + local;
+    box = it / m.nper;
+    chunk = m.ids[it % m.nper];
+}
+
 // exact fp64 digitisation shared by both LUT builders: np.digitize(sqrt((a+b)+c), edges) - 1, or -1
 __device__ __forceinline__ int digitize_mode(double a, double b, double c, const double* __restrict__ edges,
                                              int nbins) {
