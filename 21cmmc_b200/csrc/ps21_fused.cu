@@ -1,20 +1,543 @@
-// Fused two-pass path for power-of-two shapes (placeholder until the kernels land).
+// Fused two-pass path for the benchmark shape: 256 x 256 sky plane, 256-slice chunks (BASELINE config 3/5).
+//
+// HBM traffic = 4N (read lightcone) + 8N_h (write half spectrum) + 8N_h (read it), the B_alg of SURVEY 8d.
+//
+//   pass 1  k_fused_p1   CTA = one x slab, 4 units (y_lo = 0..3) of 64 z-rows (y = y_lo + 4j) each.
+//                        rows land in shared memory by bulk async copies (TMA, cp.async.bulk + mbarrier);
+//                        z: 256 real -> 128-point complex FFT on the (even,odd) packing, radix 16 x 8,
+//                           in place inside the row, only __syncwarp between stages;
+//                        untangle (real-FFT post-processing) fused into the first y stage;
+//                        y: 64-point FFT over j (radix 8 x 8, in place), times w_256^(y_lo ky_a);
+//                        results go to HBM in tile order so that pass 2 reads one contiguous 64 KB
+//                        block per tile: tile = (ky_a, 8 consecutive k_z), inner [x][y_lo][k_z].
+//   pass 2  k_fused_p2   CTA loops over tiles: one 64 KB bulk copy per tile, 4-point FFT over y_lo and
+//                        256-point FFT over x (radix 4x4, 16, 4; in place, XOR-swizzled 64-byte chunks so
+//                        every stage is bank-conflict free), |delta_k|^2 straight from registers, bin
+//                        index from a byte LUT read coalesced, lane-private fp32 bins in shared memory,
+//                        flushed per tile into fp64 bins in a fixed order (bitwise reproducible), one
+//                        partial-sum record per CTA (no global atomics).
+//
+// All transforms are decimation-in-frequency and in place: a thread writes exactly the locations it
+// read, so no ping-pong buffer and no barrier between the read and the write of a stage.
+#include <cmath>
+
 #include "ps21_internal.cuh"
 #include "../../include/ps21.h"
 
 namespace ps21 {
+namespace fz {
 
-int fused_try_setup(ps21_plan*, ShapePlan&) {
-    set_error("fused path not built");
-    return -1;
+constexpr int NX = 256, NY = 256, NZ = 256;
+constexpr int NHC = NZ / 2;            // 128 complex per packed row
+constexpr int R1 = 64, R2 = 4;         // NY = R1 * R2: pass 1 transforms R1 rows, pass 2 the remaining R2
+constexpr int T = 8;                   // k_z columns per tile (64-byte runs)
+constexpr int ROWLD = 136;             // complex slots per row in pass-1 shared memory (1088 B: bank offset 64 B)
+constexpr int TILE = NX * R2 * T;      // 8192 complex = 64 KB
+constexpr int NT_MAIN = R1 * (NHC / T);  // 1024 tiles with k_z < 128
+constexpr int NTILES = NT_MAIN + R1 / T; // + 8 tiles holding the Nyquist plane (k_z = 128): 1032
+constexpr int SLOTS = 86;              // CTAs per spectrum in pass 2 (12 tiles each)
+constexpr int P1_THREADS = 256;
+constexpr int P2_THREADS = 256;
+constexpr int MAX_BINS = 40;
+static_assert(NTILES % SLOTS == 0, "tiles must divide evenly over the slots");
+static_assert((long long)NTILES * TILE == (long long)NX * NY * (NZ / 2 + 1), "tile order covers the half spectrum exactly");
+
+struct FusedShape {
+    float2* tw256 = nullptr;   // exp(-2 pi i q / 256)
+};
+
+// ------------------------------------------------------------------------------------------------
+// PTX helpers: mbarrier + bulk async copy (TMA, 1-D) global -> shared
+// ------------------------------------------------------------------------------------------------
+#ifndef PS21_EMU
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
 }
-void fused_destroy(ShapePlan&) {}
-int fused_build_lut(ps21_plan*, int, const double*, const double*, const double*, const double*, cudaStream_t) {
-    return PS21_ERR_INVALID;
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
-int fused_forward(ps21_plan*, ShapePlan&, const float*, long long, long long, long long, cudaStream_t) {
-    return PS21_ERR_INVALID;
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t done;
+    const uint32_t addr = smem_u32(bar);
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(addr), "r"(parity)
+            : "memory");
+    } while (!done);
 }
-long long fused_scratch_elems(const ShapePlan&, int, int) { return 0; }
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+#else
+// emulated build (tests only): the bulk copy is a synchronous memcpy; the mbarrier is modelled as
+// {pending bytes, arrived flag, phase bit} packed in its 8 bytes
+struct EmuBar {
+    int pending;
+    unsigned short arrived, phase;
+};
+__device__ __forceinline__ void emu_bar_check(EmuBar* b) {
+    if (b->arrived && b->pending == 0) {
+        b->arrived = 0;
+        b->phase ^= 1;
+    }
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int) { *bar = 0; }
+__device__ __forceinline__ void mbar_fence_init() {}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    EmuBar* b = reinterpret_cast<EmuBar*>(bar);
+    b->pending += (int)bytes;
+    b->arrived = 1;
+    emu_bar_check(b);
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    EmuBar* b = reinterpret_cast<EmuBar*>(bar);
+    while (b->phase == parity) ps21emu::spin_yield();
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    std::memcpy(dst, src, bytes);
+    EmuBar* b = reinterpret_cast<EmuBar*>(bar);
+    b->pending -= (int)bytes;
+    emu_bar_check(b);
+}
+__device__ __forceinline__ void fence_proxy_async() {}
+#endif
+
+// ------------------------------------------------------------------------------------------------
+// layout of the half-spectrum scratch ("tile order")
+// ------------------------------------------------------------------------------------------------
+// 64-byte chunk (x, y_lo) inside a tile; the low bit of y_lo is flipped by bit0(x)^bit2(x) so that the
+// three x stages of pass 2 touch both halves of every 128-byte bank line (conflict free).
+__device__ __forceinline__ int chunk_of(int x, int yl) { return 4 * x + (yl ^ ((x ^ (x >> 2)) & 1)); }
+__device__ __forceinline__ int tile_idx(int x, int yl, int t) { return chunk_of(x, yl) * T + t; }
+// where pass 1 stores the coefficient (x, y_lo, ky_a, kz)
+__device__ __forceinline__ long long scratch_addr(int x, int yl, int kya, int kz) {
+    int tile, t;
+    if (kz < NHC) {
+        tile = kya * (NHC / T) + (kz >> 3);
+        t = kz & 7;
+    } else {
+        tile = NT_MAIN + (kya >> 3);
+        t = kya & 7;
+    }
+    return (long long)tile * TILE + tile_idx(x, yl, t);
+}
+// which Fourier mode the pass-2 output (tile, task, r) is:  task = (m', n', t), r = (ky_b, b')
+__device__ __forceinline__ void p2_mode_of(int tile, int task, int r, int& kx, int& ky, int& kz) {
+    const int t = task & 7, n1 = (task >> 3) & 15, m1 = task >> 7;
+    const int kyb = r >> 2, b1 = r & 3;
+    kx = m1 + 4 * n1 + 64 * b1;
+    int kya;
+    if (tile < NT_MAIN) {
+        kya = tile >> 4;
+        kz = 8 * (tile & 15) + t;
+    } else {
+        kya = 8 * (tile - NT_MAIN) + t;
+        kz = NHC;
+    }
+    ky = kya + R1 * kyb;
+}
+
+// ------------------------------------------------------------------------------------------------
+// LUT (one byte per mode, in pass-2 register order) + counts
+// ------------------------------------------------------------------------------------------------
+__global__ void k_fused_lut(uint8_t* __restrict__ lut, unsigned long long* __restrict__ counts,
+                            const double* __restrict__ k0sq, const double* __restrict__ k1sq,
+                            const double* __restrict__ k2sq, const double* __restrict__ edges, int nbins,
+                            int ig_kperp, int ig_kpar, int ig_k0) {
+    const long long total = (long long)NTILES * TILE;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        const int tile = (int)(i / TILE), e = (int)(i % TILE);
+        int kx, ky, kz;
+        p2_mode_of(tile, e >> 4, e & 15, kx, ky, kz);
+        int w = (kz == 0 || kz == NHC) ? 1 : 2;
+        const bool perp0 = (kx == 0 && ky == 0);
+        if (ig_kperp && perp0) w = 0;
+        if (ig_kpar && kz == 0) w = 0;
+        if (ig_k0 && perp0 && kz == 0) w = 0;
+        const int b = digitize_mode(k0sq[kx], k1sq[ky], k2sq[kz], edges, nbins);
+        uint8_t v = 255;
+        if (b >= 0 && w > 0) {
+            v = (uint8_t)b;
+            atomicAdd(&counts[b], (unsigned long long)w);
+        }
+        lut[i] = v;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// pass 1
+// ------------------------------------------------------------------------------------------------
+// 128-point DIF FFT of one packed row, executed by the 8 threads (t = 0..7) that own the row.
+__device__ __forceinline__ void zfft_row(float2* __restrict__ row, int t, float mean, const float2* __restrict__ tw) {
+    float2 v[16];
+#pragma unroll
+    for (int m = 0; m < 16; ++m) {
+        float2 a = row[t + 8 * m];
+        v[m] = make_float2(a.x - mean, a.y - mean);
+    }
+    small_dft<16>(v);
+#pragma unroll
+    for (int m = 1; m < 16; ++m) v[m] = cmul(v[m], tw[(2 * t * m) & 255]);  // w_128^(t m')
+    __syncwarp();
+#pragma unroll
+    for (int m = 0; m < 16; ++m) row[8 * m + (t ^ (m & 7))] = v[m];  // swizzled inside each group of 8
+    __syncwarp();
+    float2 a[8], b[8];
+    const int m0 = t, m1 = t + 8;
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+        a[u] = row[8 * m0 + (u ^ (m0 & 7))];
+        b[u] = row[8 * m1 + (u ^ (m1 & 7))];
+    }
+    small_dft<8>(a);
+    small_dft<8>(b);
+    __syncwarp();
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {  // C[m' + 16 u'], natural order
+        row[m0 + 16 * u] = a[u];
+        row[m1 + 16 * u] = b[u];
+    }
+}
+
+// untangle of the (even,odd)-packed real FFT for the column pair (p, 128-p), one row
+__device__ __forceinline__ void untangle(float2 ck, float2 cn, float2 w, float2& a1, float2& a2) {
+    const float2 e = make_float2(0.5f * (ck.x + cn.x), 0.5f * (ck.y - cn.y));
+    const float2 o = make_float2(0.5f * (ck.y + cn.y), -0.5f * (ck.x - cn.x));
+    const float2 tw = cmul(w, o);
+    a1 = make_float2(e.x + tw.x, e.y + tw.y);
+    a2 = make_float2(e.x - tw.x, -(e.y - tw.y));
+}
+
+__global__ void __launch_bounds__(P1_THREADS, 3)
+k_fused_p1(const float* __restrict__ boxes, long long batch_stride, int n2_total, ItemMap im,
+           const ChunkDev* __restrict__ chunks, int nchunks, const float* __restrict__ means,
+           float2* __restrict__ scratch, const float2* __restrict__ tw_g) {
+    PS21_DYN_SMEM(float2, buf);                  // [64][ROWLD]
+    float2* tw = buf + R1 * ROWLD;                                       // [256]
+    uint64_t* bar = reinterpret_cast<uint64_t*>(tw + 256);
+    const int tid = threadIdx.x;
+    long long box;
+    int cid;
+    item_to_box_chunk(im, blockIdx.y, box, cid);
+    const ChunkDev ch = chunks[cid];
+    const float mean = means[box * nchunks + cid];
+    const int x = blockIdx.x;
+    const float* src = boxes + box * batch_stride + ch.start + (long long)x * NY * n2_total;
+    float2* dst = scratch + (long long)blockIdx.y * ((long long)NTILES * TILE);
+    tw[tid] = tw_g[tid];
+    if (tid == 0) {
+        mbar_init(bar, 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
+    auto issue = [&](int yl) {  // warp 0: 64 rows of 1 KB each
+        if (tid < 32) {
+            if (tid == 0) mbar_expect_tx(bar, R1 * NZ * 4);
+            __syncwarp();
+            for (int j = tid; j < R1; j += 32)
+                bulk_g2s(buf + j * ROWLD, src + (long long)(yl + R2 * j) * n2_total, NZ * 4, bar);
+        }
+    };
+    issue(0);
+    uint32_t phase = 0;
+    for (int yl = 0; yl < R2; ++yl) {
+        mbar_wait(bar, phase);
+        phase ^= 1;
+        // ---- z: one 128-point FFT per row, 8 threads per row
+        for (int task = tid; task < R1 * 8; task += P1_THREADS) zfft_row(buf + (task >> 3) * ROWLD, task & 7, mean, tw);
+        __syncthreads();
+        // ---- untangle + first y stage (radix 8 over rows u + 8m), in place
+        for (int task = tid; task < 65 * 8; task += P1_THREADS) {
+            int p, u;
+            if (task < 512) {
+                p = task & 63;
+                u = task >> 6;
+            } else {
+                p = 64;
+                u = task - 512;
+            }
+            float2 c1[8], c2[8];
+            const float2 w = tw[p];  // w_256^p
+#pragma unroll
+            for (int m = 0; m < 8; ++m) {
+                const float2* r = buf + (u + 8 * m) * ROWLD;
+                const float2 ck = r[p];
+                if (p == 0) {
+                    c1[m] = make_float2(ck.x + ck.y, 0.f);
+                    c2[m] = make_float2(ck.x - ck.y, 0.f);
+                } else if (p == 64) {
+                    c1[m] = make_float2(ck.x, -ck.y);
+                    c2[m] = make_float2(0.f, 0.f);
+                } else {
+                    untangle(ck, r[NHC - p], w, c1[m], c2[m]);
+                }
+            }
+            small_dft<8>(c1);
+            if (p != 64) small_dft<8>(c2);
+#pragma unroll
+            for (int m = 0; m < 8; ++m) {
+                float2* r = buf + (u + 8 * m) * ROWLD;
+                const float2 f = tw[(4 * u * m) & 255];  // w_64^(u m')
+                r[p] = (m == 0) ? c1[m] : cmul(c1[m], f);
+                if (p != 64) r[NHC - p] = (m == 0) ? c2[m] : cmul(c2[m], f);
+            }
+        }
+        __syncthreads();
+        // ---- second y stage (radix 8 over rows 8m' + u) straight to HBM, times w_256^(y_lo ky_a)
+        for (int task = tid; task < (NHC + 1) * 8; task += P1_THREADS) {
+            const int kz = task % (NHC + 1), m1 = task / (NHC + 1);
+            float2 v[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) v[u] = buf[(8 * m1 + u) * ROWLD + kz];
+            small_dft<8>(v);
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int kya = m1 + 8 * u;
+                const float2 o = (yl == 0) ? v[u] : cmul(v[u], tw[(yl * kya) & 255]);
+                dst[scratch_addr(x, yl, kya, kz)] = o;
+            }
+        }
+        __syncthreads();
+        if (yl + 1 < R2) {
+            if (tid == 0) fence_proxy_async();
+            issue(yl + 1);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// pass 2
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(P2_THREADS, 2)
+k_fused_p2(const float2* __restrict__ scratch, ItemMap im, const ChunkDev* __restrict__ chunks,
+           const uint16_t* const* __restrict__ luts, double* __restrict__ partials, long long out_per_box,
+           int slots_max, float2* __restrict__ dc, int nchunks, const float2* __restrict__ tw_g, int nbins) {
+    PS21_DYN_SMEM(float2, tile);               // [TILE]
+    float2* tw = tile + TILE;                                          // [256]
+    uint64_t* bar = reinterpret_cast<uint64_t*>(tw + 256);
+    double* cbins = reinterpret_cast<double*>(bar + 2);                // [MAX_BINS]
+    float* lbins = reinterpret_cast<float*>(cbins + MAX_BINS);         // [nbins][P2_THREADS]
+    const int tid = threadIdx.x;
+    long long box;
+    int cid;
+    item_to_box_chunk(im, blockIdx.y, box, cid);
+    const ChunkDev ch = chunks[cid];
+    const uint8_t* __restrict__ lut = reinterpret_cast<const uint8_t*>(luts[cid]);
+    const float2* src = scratch + (long long)blockIdx.y * ((long long)NTILES * TILE);
+    tw[tid] = tw_g[tid];
+    for (int i = tid; i < nbins * P2_THREADS; i += P2_THREADS) lbins[i] = 0.f;
+    if (tid < MAX_BINS) cbins[tid] = 0.0;
+    if (tid == 0) {
+        mbar_init(bar, 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
+    int tl = blockIdx.x;
+    if (tid == 0) {
+        mbar_expect_tx(bar, TILE * 8);
+        bulk_g2s(tile, src + (long long)tl * TILE, TILE * 8, bar);
+    }
+    uint32_t phase = 0;
+    for (; tl < NTILES; tl += SLOTS) {
+        mbar_wait(bar, phase);
+        phase ^= 1;
+        // ---- S1: 4-point FFT over y_lo (-> ky_b) x first radix-4 of x (x = xa + 64 m -> m'), twiddle w_256^(xa m')
+        for (int task = tid; task < 512; task += P2_THREADS) {
+            const int t = task & 7, xa = task >> 3;
+            float2 v[4][4];  // [m][yl]
+#pragma unroll
+            for (int m = 0; m < 4; ++m)
+#pragma unroll
+                for (int yl = 0; yl < 4; ++yl) v[m][yl] = tile[tile_idx(xa + 64 * m, yl, t)];
+#pragma unroll
+            for (int m = 0; m < 4; ++m) small_dft<4>(v[m]);
+#pragma unroll
+            for (int yl = 0; yl < 4; ++yl) {
+                float2 c[4] = {v[0][yl], v[1][yl], v[2][yl], v[3][yl]};
+                small_dft<4>(c);
+#pragma unroll
+                for (int m = 0; m < 4; ++m) v[m][yl] = c[m];
+            }
+#pragma unroll
+            for (int m = 0; m < 4; ++m) {
+                const float2 f = tw[(xa * m) & 255];
+#pragma unroll
+                for (int yl = 0; yl < 4; ++yl)
+                    tile[tile_idx(xa + 64 * m, yl, t)] = (m == 0) ? v[m][yl] : cmul(v[m][yl], f);
+            }
+        }
+        __syncthreads();
+        // ---- S2: radix 16 over xa = xb + 4 n inside block m' (-> n'), twiddle w_64^(xb n')
+        for (int task = tid; task < 512; task += P2_THREADS) {
+            const int t = task & 7, xb = (task >> 3) & 3, yl = (task >> 5) & 3, m1 = task >> 7;
+            float2 v[16];
+#pragma unroll
+            for (int n = 0; n < 16; ++n) v[n] = tile[tile_idx(64 * m1 + xb + 4 * n, yl, t)];
+            small_dft<16>(v);
+#pragma unroll
+            for (int n = 0; n < 16; ++n) {
+                const float2 o = (n == 0 || xb == 0) ? v[n] : cmul(v[n], tw[(4 * xb * n) & 255]);
+                tile[tile_idx(64 * m1 + xb + 4 * n, yl, t)] = o;
+            }
+        }
+        __syncthreads();
+        // ---- S3: last radix 4 over xb (-> b'), |delta_k|^2, bins
+        for (int task = tid; task < 512; task += P2_THREADS) {
+            const int t = task & 7, n1 = (task >> 3) & 15, m1 = task >> 7;
+            float pw[16];
+            float2 first = make_float2(0.f, 0.f);
+#pragma unroll
+            for (int yl = 0; yl < 4; ++yl) {
+                float2 c[4];
+#pragma unroll
+                for (int xb = 0; xb < 4; ++xb) c[xb] = tile[tile_idx(64 * m1 + 4 * n1 + xb, yl, t)];
+                small_dft<4>(c);
+                if (yl == 0) first = c[0];
+#pragma unroll
+                for (int b = 0; b < 4; ++b) pw[4 * yl + b] = c[b].x * c[b].x + c[b].y * c[b].y;
+            }
+            if (tl == 0 && task == 0) dc[box * nchunks + cid] = first;
+            const float mult = (tl >= NT_MAIN || ((tl & 15) == 0 && t == 0)) ? 1.f : 2.f;
+            const uint4 lv = *reinterpret_cast<const uint4*>(lut + (long long)tl * TILE + task * 16);
+            const uint32_t w4[4] = {lv.x, lv.y, lv.z, lv.w};
+#pragma unroll
+            for (int r = 0; r < 16; ++r) {
+                const uint32_t b = (w4[r >> 2] >> (8 * (r & 3))) & 255u;
+                if (b != 255u) lbins[b * P2_THREADS + tid] += mult * pw[r];
+            }
+        }
+        __syncthreads();
+        // tile buffer is free: prefetch the next tile while the bins are flushed
+        if (tid == 0 && tl + SLOTS < NTILES) {
+            fence_proxy_async();
+            mbar_expect_tx(bar, TILE * 8);
+            bulk_g2s(tile, src + (long long)(tl + SLOTS) * TILE, TILE * 8, bar);
+        }
+        // ---- flush the lane-private fp32 bins into the CTA's fp64 bins, fixed order
+        {
+            const int warp = tid >> 5, lane = tid & 31;
+            for (int b = warp; b < nbins; b += P2_THREADS / 32) {
+                double acc = 0.0;
+#pragma unroll
+                for (int i = 0; i < P2_THREADS / 32; ++i) {
+                    float* q = lbins + b * P2_THREADS + lane + 32 * i;
+                    acc += (double)*q;
+                    *q = 0.f;
+                }
+#pragma unroll
+                for (int s = 16; s > 0; s >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, s);
+                if (lane == 0) cbins[b] += acc;
+            }
+        }
+        // (the next iteration's barriers order the zeroed lane bins before they are used again)
+    }
+    __syncthreads();
+    double* out = partials + (box * slots_max + blockIdx.x) * out_per_box + ch.out_off;
+    for (int i = tid; i < nbins; i += P2_THREADS) out[i] = cbins[i];
+}
+
+static size_t p1_smem() { return (size_t)R1 * ROWLD * 8 + 256 * 8 + 16; }
+static size_t p2_smem(int nbins) { return (size_t)TILE * 8 + 256 * 8 + 16 + MAX_BINS * 8 + (size_t)nbins * P2_THREADS * 4; }
+
+}  // namespace fz
+
+int fused_try_setup(ps21_plan* p, ShapePlan& sp) {
+    using namespace fz;
+    if (p->n0 != NX || p->n1 != NY || sp.nz != NZ) {
+        set_error("fused path supports 256 x 256 x 256 chunks");
+        return -1;
+    }
+    if (p->mode != PS21_MODE_SPHERICAL || p->nbins > MAX_BINS) {
+        set_error("fused path needs spherical bins and n_psbins <= 40");
+        return -1;
+    }
+    if (p->n2_total % 4 != 0) {
+        set_error("fused path needs n2_total % 4 == 0 (16-byte aligned rows)");
+        return -1;
+    }
+    for (int c : sp.chunks)
+        if (p->chunks[c].start % 4 != 0) {
+            set_error("fused path needs chunk starts that are multiples of 4 slices");
+            return -1;
+        }
+    auto* fs = new FusedShape();
+    std::vector<float2> tw(256);
+    for (int q = 0; q < 256; ++q) {
+        const double a = -2.0 * 3.14159265358979323846 * q / 256.0;
+        tw[q] = make_float2((float)cos(a), (float)sin(a));
+    }
+    if (cudaMalloc((void**)&fs->tw256, sizeof(float2) * 256) != cudaSuccess ||
+        cudaMemcpy(fs->tw256, tw.data(), sizeof(float2) * 256, cudaMemcpyHostToDevice) != cudaSuccess ||
+        cudaFuncSetAttribute(k_fused_p1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p1_smem()) != cudaSuccess ||
+        cudaFuncSetAttribute(k_fused_p2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p2_smem(MAX_BINS)) !=
+            cudaSuccess) {
+        cudaGetLastError();
+        if (fs->tw256) cudaFree(fs->tw256);
+        delete fs;
+        set_error("fused path: device setup failed");
+        return -1;
+    }
+    sp.fused = fs;
+    for (int c : sp.chunks) p->chunks[c].nslots = SLOTS;
+    return 0;
+}
+
+void fused_destroy(ShapePlan& sp) {
+    if (!sp.fused) return;
+    auto* fs = static_cast<fz::FusedShape*>(sp.fused);
+    if (fs->tw256) cudaFree(fs->tw256);
+    delete fs;
+    sp.fused = nullptr;
+}
+
+long long fused_scratch_elems(const ShapePlan&, int, int) { return (long long)fz::NTILES * fz::TILE; }
+
+int fused_build_lut(ps21_plan* p, int chunk, const double* d_k0sq, const double* d_k1sq, const double* d_k2sq,
+                    const double* d_edges, cudaStream_t st) {
+    const ChunkDev& c = p->chunks[chunk];
+    PS21_LAUNCH(fz::k_fused_lut, dim3(PS21_EMU_OR(8, 2048)), dim3(256), 0, st, reinterpret_cast<uint8_t*>(p->d_lut[chunk]),
+                (unsigned long long*)(p->d_counts + c.out_off), d_k0sq, d_k1sq, d_k2sq, d_edges, p->nbins,
+                p->ig_kperp, p->ig_kpar, p->ig_k0);
+    PS21_CUDA(cudaGetLastError());
+    return PS21_OK;
+}
+
+int fused_forward(ps21_plan* p, ShapePlan& sp, const float* d_boxes, long long batch_stride, long long item0,
+                  long long nitems, cudaStream_t st) {
+    using namespace fz;
+    auto* fs = static_cast<FusedShape*>(sp.fused);
+    if ((reinterpret_cast<uintptr_t>(d_boxes) & 15) != 0 || batch_stride % 4 != 0) {
+        set_error("fused path needs 16-byte aligned boxes and batch_stride % 4 == 0");
+        return PS21_ERR_INVALID;
+    }
+    ItemMap im{sp.d_chunks, (int)sp.chunks.size(), item0};
+    {
+        ProfScope ps(p, KK_PASS1, st);
+        PS21_LAUNCH(k_fused_p1, dim3(NX, (unsigned)nitems), dim3(P1_THREADS), p1_smem(), st, d_boxes, batch_stride,
+                    p->n2_total, im, p->d_chunks, p->nchunks, p->d_means, p->d_scratch, fs->tw256);
+        PS21_CUDA(cudaGetLastError());
+    }
+    {
+        ProfScope ps(p, KK_PASS_BIN, st);
+        PS21_LAUNCH(k_fused_p2, dim3(SLOTS, (unsigned)nitems), dim3(P2_THREADS), p2_smem(p->nbins), st, p->d_scratch,
+                    im, p->d_chunks, (const uint16_t* const*)p->d_lut_table, p->d_partials, p->out_per_box,
+                    p->slots_max, p->d_dc, p->nchunks, fs->tw256, p->nbins);
+        PS21_CUDA(cudaGetLastError());
+    }
+    p->launches_last += 2;
+    return PS21_OK;
+}
 
 }  // namespace ps21

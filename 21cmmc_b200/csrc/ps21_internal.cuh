@@ -16,8 +16,14 @@
 #ifndef PS21_EMU
 // dynamic shared memory of a kernel, typed view
 #define PS21_DYN_SMEM(type, name)                                         \
-    extern __shared__ __align__(16) unsigned char ps21_dyn_smem_raw[];    \
+    extern __shared__ __align__(128) unsigned char ps21_dyn_smem_raw[];   \
     type* name = reinterpret_cast<type*>(ps21_dyn_smem_raw)
+#endif
+
+#ifdef PS21_EMU
+#define PS21_EMU_OR(emu, real) (emu)
+#else
+#define PS21_EMU_OR(emu, real) (real)
 #endif
 
 #ifdef PS21_EMU

@@ -22,6 +22,9 @@ static inline float2 make_float2(float x, float y) { return float2{x, y}; }
 struct uint3 {
     unsigned x, y, z;
 };
+struct uint4 {
+    unsigned x, y, z, w;
+};
 struct dim3 {
     unsigned x, y, z;
     dim3(unsigned a = 1, unsigned b = 1, unsigned c = 1) : x(a), y(b), z(c) {}
@@ -32,6 +35,10 @@ extern uint3 threadIdx, blockIdx;
 extern dim3 blockDim, gridDim;
 extern char* g_dyn_smem;
 void syncthreads();
+void syncwarp();
+void spin_yield();  // stay runnable, let the other fibers advance (used by the emulated mbarrier wait)
+unsigned long long* shfl_slot(int tid);
+int linear_tid();
 void launch(dim3 grid, dim3 block, size_t smem, const std::function<void()>& body);
 }  // namespace ps21emu
 using ps21emu::blockDim;
@@ -46,6 +53,26 @@ using ps21emu::threadIdx;
 #define __restrict__
 #define __shared__ static
 #define __syncthreads() ps21emu::syncthreads()
+#define __syncwarp() ps21emu::syncwarp()
+#define __launch_bounds__(...)
+#define __align__(n)
+template <class T>
+static inline T __shfl_xor_sync(unsigned, T v, int lanemask) {
+    static_assert(sizeof(T) <= 8, "shuffle payload");
+    const int me = ps21emu::linear_tid();
+    unsigned long long raw = 0;
+    std::memcpy(&raw, &v, sizeof(T));
+    *ps21emu::shfl_slot(me) = raw;
+    ps21emu::syncwarp();
+    raw = *ps21emu::shfl_slot((me & ~31) | ((me ^ lanemask) & 31));
+    ps21emu::syncwarp();
+    T out;
+    std::memcpy(&out, &raw, sizeof(T));
+    return out;
+}
+enum { cudaFuncAttributeMaxDynamicSharedMemorySize = 8 };
+template <class F>
+static inline int cudaFuncSetAttribute(F, int, int) { return 0; }
 #define PS21_DYN_SMEM(type, name) type* name = reinterpret_cast<type*>(ps21emu::g_dyn_smem)
 
 template <class T>

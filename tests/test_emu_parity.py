@@ -59,6 +59,15 @@ def test_cylindrical(mods):
     PC.check_cylindrical(mods[0], (10, 10, 9), (15.0, 15.0, 13.5), 4)
 
 
+def test_fused_two_pass_kernels_256(mods):
+    """The fused sm_100a kernels (bulk copies modelled as memcpy) on one 256^3 chunk vs the oracle."""
+    mods[0].set_defaults(kernel_path="fused")
+    try:
+        PC.check_compute_power(mods[0], (256, 256, 256), (384.0, 384.0, 384.0), 20, True, seed=5)
+    finally:
+        mods[0].set_defaults(kernel_path="auto")
+
+
 def test_too_few_slices_raises_like_reference(mods):
     lk, core, chain = mods
     with pytest.raises(IndexError):

@@ -54,6 +54,44 @@ def test_compute_power_lightcone(mods, kpath, shape, L, nb, log, flags, rule):
     PC.check_compute_power(mods[0], shape, L, nb, log, flags, rule)
 
 
+@pytest.mark.parametrize("nb,log,flags", [
+    (20, True, (True, False, False)),
+    (24, False, (False, False, False)),   # DC mode binned: exercises the fp64 offset restoration
+    (40, True, (True, True, True)),
+])
+def test_fused_path_vs_oracle_256(mods, nb, log, flags):
+    """256 x 256 x 256 chunk (benchmark chunk shape) through the fused kernels vs the fp64 oracle."""
+    mods[0].set_defaults(kernel_path="fused")
+    try:
+        PC.check_compute_power(mods[0], (256, 256, 256), (384.0, 384.0, 384.0), nb, log, flags, seed=11)
+    finally:
+        mods[0].set_defaults(kernel_path="auto")
+
+
+def test_fused_lightcone_batch_vs_general(mods):
+    """Two 256 x 256 x 512 lightcones (2 chunks each): fused == general path to fp32-FFT accuracy, and the
+    fused path is bitwise reproducible and batch invariant."""
+    import torch
+
+    from py21cmmc_b200.plan import get_plan
+
+    shape = (256, 256, 512)
+    bounds = [(0, 256), (256, 512)]
+    Ls = [(384.0, 384.0, 384.0)] * 2
+    dev = torch.cuda.current_device()
+    pf = get_plan(shape, bounds, Ls, 20, True, True, False, False, "legacy_1.001", "spherical", dev, "fused")
+    pg = get_plan(shape, bounds, Ls, 20, True, True, False, False, "legacy_1.001", "spherical", dev, "general")
+    assert pf.path == "fused" and pg.path == "general"
+    assert np.array_equal(pf.counts, pg.counts)
+    g = torch.Generator(device="cuda").manual_seed(7)
+    boxes = torch.randn((3,) + shape, generator=g, device="cuda", dtype=torch.float32) * 10 + 20
+    a = pf.power_device(boxes).cpu().numpy()
+    b = pg.power_device(boxes).cpu().numpy()
+    assert rel_err(a, b) < 2e-6
+    assert np.array_equal(a, pf.power_device(boxes).cpu().numpy(), equal_nan=True)
+    assert np.array_equal(a[1], pf.power_device(boxes[1:2].contiguous()).cpu().numpy()[0], equal_nan=True)
+
+
 def test_golden_vectors(mods, kpath):
     from tests.golden.make_golden import CASES, make_box
 
