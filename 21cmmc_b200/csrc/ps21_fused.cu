@@ -78,6 +78,24 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
                  : "memory");
 }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+// L2 eviction policies: streamed data must not push the (re-used) bin-index table out of L2
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ void bulk_g2s_hint(void* dst, const void* src, uint32_t bytes, uint64_t* bar, uint64_t pol) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
+            smem_u32(dst)),
+        "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(pol)
+        : "memory");
+}
 
 #else
 // emulated build (tests only): the bulk copy is a synchronous memcpy; the mbarrier is modelled as
@@ -111,6 +129,11 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
     emu_bar_check(b);
 }
 __device__ __forceinline__ void fence_proxy_async() {}
+__device__ __forceinline__ uint64_t l2_policy_evict_first() { return 0; }
+__device__ __forceinline__ uint64_t l2_policy_evict_last() { return 0; }
+__device__ __forceinline__ void bulk_g2s_hint(void* dst, const void* src, uint32_t bytes, uint64_t* bar, uint64_t) {
+    bulk_g2s(dst, src, bytes, bar);
+}
 #endif
 
 // ------------------------------------------------------------------------------------------------
@@ -180,7 +203,7 @@ __global__ void k_fused_lut(uint8_t* __restrict__ lut, unsigned long long* __res
 // pass 1
 // ------------------------------------------------------------------------------------------------
 // 128-point DIF FFT of one packed row, executed by the 8 threads (t = 0..7) that own the row.
-__device__ __forceinline__ void zfft_row(float2* __restrict__ row, int t, float mean, const float2* __restrict__ tw) {
+__device__ __forceinline__ void zfft_row(float2* __restrict__ row, int t, float mean, const float2* __restrict__ twz) {
     float2 v[16];
 #pragma unroll
     for (int m = 0; m < 16; ++m) {
@@ -189,7 +212,7 @@ __device__ __forceinline__ void zfft_row(float2* __restrict__ row, int t, float 
     }
     small_dft<16>(v);
 #pragma unroll
-    for (int m = 1; m < 16; ++m) v[m] = cmul(v[m], tw[(2 * t * m) & 255]);  // w_128^(t m')
+    for (int m = 1; m < 16; ++m) v[m] = cmul(v[m], twz[8 * m + t]);  // w_128^(t m'), lane-contiguous table
     __syncwarp();
 #pragma unroll
     for (int m = 0; m < 16; ++m) row[8 * m + (t ^ (m & 7))] = v[m];  // swizzled inside each group of 8
@@ -224,9 +247,10 @@ __global__ void __launch_bounds__(P1_THREADS, 3)
 k_fused_p1(const float* __restrict__ boxes, long long batch_stride, int n2_total, ItemMap im,
            const ChunkDev* __restrict__ chunks, int nchunks, const float* __restrict__ means,
            float2* __restrict__ scratch, const float2* __restrict__ tw_g) {
-    PS21_DYN_SMEM(float2, buf);                  // [64][ROWLD]
-    float2* tw = buf + R1 * ROWLD;                                       // [256]
-    uint64_t* bar = reinterpret_cast<uint64_t*>(tw + 256);
+    PS21_DYN_SMEM(float2, buf);                                          // [64][ROWLD]
+    float2* tw = buf + R1 * ROWLD;                                       // [256] w_256^q
+    float2* twz = tw + 256;                                              // [16][8] w_128^(t m)
+    uint64_t* bar = reinterpret_cast<uint64_t*>(twz + 128);              // [2]: rows 0..31, rows 32..63
     const int tid = threadIdx.x;
     long long box;
     int cid;
@@ -237,26 +261,56 @@ k_fused_p1(const float* __restrict__ boxes, long long batch_stride, int n2_total
     const float* src = boxes + box * batch_stride + ch.start + (long long)x * NY * n2_total;
     float2* dst = scratch + (long long)blockIdx.y * ((long long)NTILES * TILE);
     tw[tid] = tw_g[tid];
+    if (tid < 128) twz[tid] = tw_g[(2 * (tid & 7) * (tid >> 3)) & 255];
     if (tid == 0) {
         mbar_init(bar, 1);
+        mbar_init(bar + 1, 1);
         mbar_fence_init();
     }
     __syncthreads();
-    auto issue = [&](int yl) {  // warp 0: 64 rows of 1 KB each
+    const uint64_t pol = l2_policy_evict_first();
+    auto issue_half = [&](int yl, int half) {  // warp 0: 32 rows of 1 KB each
         if (tid < 32) {
-            if (tid == 0) mbar_expect_tx(bar, R1 * NZ * 4);
+            if (tid == 0) mbar_expect_tx(bar + half, (R1 / 2) * NZ * 4);
             __syncwarp();
-            for (int j = tid; j < R1; j += 32)
-                bulk_g2s(buf + j * ROWLD, src + (long long)(yl + R2 * j) * n2_total, NZ * 4, bar);
+            const int j = half * (R1 / 2) + tid;
+            bulk_g2s_hint(buf + j * ROWLD, src + (long long)(yl + R2 * j) * n2_total, NZ * 4, bar + half, pol);
         }
     };
-    issue(0);
+    // second y stage for the butterfly groups m1 in [mlo, mlo+4): rows 8*mlo .. 8*mlo+31
+    auto ystage2 = [&](int yl, int mlo) {
+        for (int task = tid; task < 4 * (NHC + 1); task += P1_THREADS) {
+            int kz, m1;
+            if (task < 4 * NHC) {
+                kz = task & (NHC - 1);
+                m1 = mlo + (task >> 7);
+            } else {  // Nyquist column
+                kz = NHC;
+                m1 = mlo + task - 4 * NHC;
+            }
+            float2 v[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) v[u] = buf[(8 * m1 + u) * ROWLD + kz];
+            small_dft<8>(v);
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int kya = m1 + 8 * u;
+                const float2 o = (yl == 0) ? v[u] : cmul(v[u], tw[(yl * kya) & 255]);
+                dst[scratch_addr(x, yl, kya, kz)] = o;
+            }
+        }
+    };
+    issue_half(0, 0);
+    issue_half(0, 1);
     uint32_t phase = 0;
     for (int yl = 0; yl < R2; ++yl) {
+        // ---- z: one 128-point FFT per row, 8 threads per row; rows 0..31 as soon as they have landed
         mbar_wait(bar, phase);
+        for (int task = tid; task < (R1 / 2) * 8; task += P1_THREADS) zfft_row(buf + (task >> 3) * ROWLD, task & 7, mean, twz);
+        mbar_wait(bar + 1, phase);
+        for (int task = tid; task < (R1 / 2) * 8; task += P1_THREADS)
+            zfft_row(buf + (R1 / 2 + (task >> 3)) * ROWLD, task & 7, mean, twz);
         phase ^= 1;
-        // ---- z: one 128-point FFT per row, 8 threads per row
-        for (int task = tid; task < R1 * 8; task += P1_THREADS) zfft_row(buf + (task >> 3) * ROWLD, task & 7, mean, tw);
         __syncthreads();
         // ---- untangle + first y stage (radix 8 over rows u + 8m), in place
         for (int task = tid; task < 65 * 8; task += P1_THREADS) {
@@ -295,24 +349,19 @@ k_fused_p1(const float* __restrict__ boxes, long long batch_stride, int n2_total
             }
         }
         __syncthreads();
-        // ---- second y stage (radix 8 over rows 8m' + u) straight to HBM, times w_256^(y_lo ky_a)
-        for (int task = tid; task < (NHC + 1) * 8; task += P1_THREADS) {
-            const int kz = task % (NHC + 1), m1 = task / (NHC + 1);
-            float2 v[8];
-#pragma unroll
-            for (int u = 0; u < 8; ++u) v[u] = buf[(8 * m1 + u) * ROWLD + kz];
-            small_dft<8>(v);
-#pragma unroll
-            for (int u = 0; u < 8; ++u) {
-                const int kya = m1 + 8 * u;
-                const float2 o = (yl == 0) ? v[u] : cmul(v[u], tw[(yl * kya) & 255]);
-                dst[scratch_addr(x, yl, kya, kz)] = o;
-            }
-        }
+        // ---- second y stage (radix 8 over rows 8m' + u) straight to HBM, times w_256^(y_lo ky_a);
+        //      rows 0..31 are consumed first so that the next unit's first half can start loading early
+        ystage2(yl, 0);
         __syncthreads();
         if (yl + 1 < R2) {
             if (tid == 0) fence_proxy_async();
-            issue(yl + 1);
+            issue_half(yl + 1, 0);
+        }
+        ystage2(yl, 4);
+        __syncthreads();
+        if (yl + 1 < R2) {
+            if (tid == 0) fence_proxy_async();
+            issue_half(yl + 1, 1);
         }
     }
 }
@@ -325,7 +374,8 @@ k_fused_p2(const float2* __restrict__ scratch, ItemMap im, const ChunkDev* __res
            const uint16_t* const* __restrict__ luts, double* __restrict__ partials, long long out_per_box,
            int slots_max, float2* __restrict__ dc, int nchunks, const float2* __restrict__ tw_g, int nbins) {
     PS21_DYN_SMEM(float2, tile);               // [TILE]
-    float2* tw = tile + TILE;                                          // [256]
+    uint8_t* lutb = reinterpret_cast<uint8_t*>(tile + TILE);           // [TILE] bin index of every output of the tile
+    float2* tw = reinterpret_cast<float2*>(lutb + TILE);               // [256]
     uint64_t* bar = reinterpret_cast<uint64_t*>(tw + 256);
     double* cbins = reinterpret_cast<double*>(bar + 2);                // [MAX_BINS]
     float* lbins = reinterpret_cast<float*>(cbins + MAX_BINS);         // [nbins][P2_THREADS]
@@ -345,10 +395,13 @@ k_fused_p2(const float2* __restrict__ scratch, ItemMap im, const ChunkDev* __res
     }
     __syncthreads();
     int tl = blockIdx.x;
-    if (tid == 0) {
-        mbar_expect_tx(bar, TILE * 8);
-        bulk_g2s(tile, src + (long long)tl * TILE, TILE * 8, bar);
-    }
+    const uint64_t pol_stream = l2_policy_evict_first(), pol_keep = l2_policy_evict_last();
+    auto issue_tile = [&](int t_next) {
+        mbar_expect_tx(bar, TILE * 8 + TILE);
+        bulk_g2s_hint(tile, src + (long long)t_next * TILE, TILE * 8, bar, pol_stream);
+        bulk_g2s_hint(lutb, lut + (long long)t_next * TILE, TILE, bar, pol_keep);
+    };
+    if (tid == 0) issue_tile(tl);
     uint32_t phase = 0;
     for (; tl < NTILES; tl += SLOTS) {
         mbar_wait(bar, phase);
@@ -410,7 +463,7 @@ k_fused_p2(const float2* __restrict__ scratch, ItemMap im, const ChunkDev* __res
             }
             if (tl == 0 && task == 0) dc[box * nchunks + cid] = first;
             const float mult = (tl >= NT_MAIN || ((tl & 15) == 0 && t == 0)) ? 1.f : 2.f;
-            const uint4 lv = *reinterpret_cast<const uint4*>(lut + (long long)tl * TILE + task * 16);
+            const uint4 lv = *reinterpret_cast<const uint4*>(lutb + task * 16);
             const uint32_t w4[4] = {lv.x, lv.y, lv.z, lv.w};
 #pragma unroll
             for (int r = 0; r < 16; ++r) {
@@ -422,8 +475,7 @@ k_fused_p2(const float2* __restrict__ scratch, ItemMap im, const ChunkDev* __res
         // tile buffer is free: prefetch the next tile while the bins are flushed
         if (tid == 0 && tl + SLOTS < NTILES) {
             fence_proxy_async();
-            mbar_expect_tx(bar, TILE * 8);
-            bulk_g2s(tile, src + (long long)(tl + SLOTS) * TILE, TILE * 8, bar);
+            issue_tile(tl + SLOTS);
         }
         // ---- flush the lane-private fp32 bins into the CTA's fp64 bins, fixed order
         {
@@ -448,8 +500,10 @@ k_fused_p2(const float2* __restrict__ scratch, ItemMap im, const ChunkDev* __res
     for (int i = tid; i < nbins; i += P2_THREADS) out[i] = cbins[i];
 }
 
-static size_t p1_smem() { return (size_t)R1 * ROWLD * 8 + 256 * 8 + 16; }
-static size_t p2_smem(int nbins) { return (size_t)TILE * 8 + 256 * 8 + 16 + MAX_BINS * 8 + (size_t)nbins * P2_THREADS * 4; }
+static size_t p1_smem() { return (size_t)R1 * ROWLD * 8 + 256 * 8 + 128 * 8 + 16; }
+static size_t p2_smem(int nbins) {
+    return (size_t)TILE * 8 + TILE + 256 * 8 + 16 + MAX_BINS * 8 + (size_t)nbins * P2_THREADS * 4;
+}
 
 }  // namespace fz
 

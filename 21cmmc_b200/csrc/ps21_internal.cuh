@@ -94,6 +94,7 @@ struct ps21_plan {
     ps21::ChunkDev* d_chunks = nullptr;
     // per chunk LUT: bin index of every half-spectrum mode, layout defined by the path of its shape
     std::vector<uint16_t*> d_lut;  // [nchunks]
+    std::vector<char> lut_owned;   // chunks with identical geometry share one table
     uint16_t** d_lut_table = nullptr;  // the same pointers in device memory
     std::vector<long long> h_counts;
     long long* d_counts = nullptr;   // [out_per_box]
@@ -101,6 +102,7 @@ struct ps21_plan {
     // workspace
     float2* d_scratch = nullptr;
     long long scratch_elems = 0;
+    long long spec_max = 0;
     double* d_partials = nullptr;    // [batch][out_per_box][slots_max]
     float* d_means = nullptr;        // [batch][nchunks]
     float2* d_dc = nullptr;          // [batch][nchunks] DC Fourier coefficient of the mean-subtracted chunk

@@ -201,6 +201,20 @@ static int ensure_batch(ps21_plan* p, long long batch) {
     return PS21_OK;
 }
 
+static int ensure_scratch(ps21_plan* p, long long want_elems) {
+    if (p->scratch_elems >= want_elems) return PS21_OK;
+    free_dev(p->d_scratch);
+    p->d_scratch = nullptr;
+    p->scratch_elems = 0;
+    if (cudaMalloc((void**)&p->d_scratch, sizeof(float2) * want_elems) != cudaSuccess) {
+        cudaGetLastError();
+        set_error("cannot allocate half-spectrum scratch");
+        return PS21_ERR_NOMEM;
+    }
+    p->scratch_elems = want_elems;
+    return PS21_OK;
+}
+
 // All kernels of one call, asynchronous on `st`.
 static int run_device(ps21_plan* p, const float* d_boxes, long long batch, long long batch_stride, double* d_power,
                       double* d_delta, double* d_lnl, cudaStream_t st) {
@@ -225,9 +239,12 @@ static int run_device(ps21_plan* p, const float* d_boxes, long long batch, long 
         const long long total = batch * nper;
         const long long spec = (sp.path == PS21_PATH_FUSED) ? fused_scratch_elems(sp, p->n0, p->n1)
                                                              : (long long)p->n0 * p->n1 * sp.nh;
-        long long per = p->scratch_elems / spec;
-        if (per < 1) return invalid("internal: scratch smaller than one spectrum");
+        long long per = p->workspace_cap / (spec * (long long)sizeof(float2));
+        if (per < 1) per = 1;
         if (per > 32768) per = 32768;
+        if (per > total) per = total;
+        rc = ensure_scratch(p, per * spec);
+        if (rc) return rc;
         for (long long i0 = 0; i0 < total; i0 += per) {
             const long long n = (total - i0 < per) ? (total - i0) : per;
             rc = (sp.path == PS21_PATH_FUSED) ? fused_forward(p, sp, d_boxes, batch_stride, i0, n, st)
@@ -267,7 +284,8 @@ int ps21_plan_destroy(ps21_plan* p) {
         free_dev(sp.d_chunks);
         fused_destroy(sp);
     }
-    for (auto* l : p->d_lut) free_dev(l);
+    for (size_t i = 0; i < p->d_lut.size(); ++i)
+        if (i < p->lut_owned.size() && p->lut_owned[i]) free_dev(p->d_lut[i]);
     free_dev(p->d_lut_table);
     free_dev(p->d_chunks);
     free_dev(p->d_counts);
@@ -310,7 +328,7 @@ int ps21_plan_create(const ps21_desc* d, ps21_plan** out) {
     p->n0 = d->n0; p->n1 = d->n1; p->n2_total = d->n2_total; p->nchunks = d->nchunks; p->nbins = d->nbins;
     p->mode = d->mode; p->device = d->device; p->path_req = d->path;
     p->ig_kperp = d->ignore_kperp_zero; p->ig_kpar = d->ignore_kpar_zero; p->ig_k0 = d->ignore_k_zero;
-    p->workspace_cap = d->workspace_bytes > 0 ? d->workspace_bytes : (2LL << 30);
+    p->workspace_cap = d->workspace_bytes > 0 ? d->workspace_bytes : (8LL << 30);
     int rc = PS21_OK;
     auto fail = [&](int code) {
         ps21_plan_destroy(p);
@@ -390,17 +408,8 @@ int ps21_plan_create(const ps21_desc* d, ps21_plan** out) {
         if (nslots > p->slots_max) p->slots_max = nslots;
         if (spec > spec_max) spec_max = spec;
     }
-    // scratch: as many spectra as fit the cap, at least one
-    {
-        long long n = p->workspace_cap / (spec_max * (long long)sizeof(float2));
-        if (n < 1) n = 1;
-        p->scratch_elems = n * spec_max;
-        if (cudaMalloc((void**)&p->d_scratch, sizeof(float2) * p->scratch_elems) != cudaSuccess) {
-            cudaGetLastError();
-            set_error("cannot allocate half-spectrum scratch");
-            return fail(PS21_ERR_NOMEM);
-        }
-    }
+    // scratch grows on demand (ensure_scratch) up to the cap; one spectrum of the largest shape to start with
+    p->spec_max = spec_max;
     PS21_CUDA(cudaMalloc((void**)&p->d_chunks, sizeof(ChunkDev) * p->nchunks));
     PS21_CUDA(cudaMemcpy(p->d_chunks, p->chunks.data(), sizeof(ChunkDev) * p->nchunks, cudaMemcpyHostToDevice));
     // k^3/(2 pi^2) at the bin centres (likelihood.py:863, :652)
@@ -428,8 +437,22 @@ int ps21_plan_create(const ps21_desc* d, ps21_plan** out) {
         PS21_CUDA(cudaMemcpy(dk2, d->k2sq, sizeof(double) * k2off, cudaMemcpyHostToDevice));
         PS21_CUDA(cudaMemcpy(ded, d->edges, sizeof(double) * d->nchunks * (d->nbins + 1), cudaMemcpyHostToDevice));
         p->d_lut.assign(d->nchunks, nullptr);
+        p->lut_owned.assign(d->nchunks, 0);
+        std::vector<int> twin(d->nchunks, -1);
         for (int c = 0; c < d->nchunks && rc == PS21_OK; ++c) {
             const ShapePlan& sp = p->shapes[p->chunks[c].shape];
+            // chunks of equal length, edges and k_z share one table (the usual case: equal-length chunks)
+            for (int o = 0; o < c && twin[c] < 0; ++o)
+                if (p->chunks[o].shape == p->chunks[c].shape && twin[o] < 0 &&
+                    std::memcmp(d->edges + (long long)o * (d->nbins + 1), d->edges + (long long)c * (d->nbins + 1),
+                                sizeof(double) * (d->nbins + 1)) == 0 &&
+                    std::memcmp(d->k2sq + k2offs[o], d->k2sq + k2offs[c], sizeof(double) * p->chunks[c].nz) == 0)
+                    twin[c] = o;
+            if (twin[c] >= 0) {
+                p->d_lut[c] = p->d_lut[twin[c]];
+                continue;
+            }
+            p->lut_owned[c] = 1;
             const long long spec = (sp.path == PS21_PATH_FUSED) ? fused_scratch_elems(sp, d->n0, d->n1)
                                                                  : (long long)d->n0 * d->n1 * sp.nh;
             if (cudaMalloc((void**)&p->d_lut[c], sizeof(uint16_t) * spec) != cudaSuccess) {
@@ -443,6 +466,10 @@ int ps21_plan_create(const ps21_desc* d, ps21_plan** out) {
                                               : general_build_lut(p, c, dk0, dk1, dk2 + k2offs[c], e, 0);
         }
         cudaError_t se = cudaDeviceSynchronize();
+        for (int c = 0; c < d->nchunks && se == cudaSuccess; ++c)
+            if (twin[c] >= 0)
+                se = cudaMemcpy(p->d_counts + p->chunks[c].out_off, p->d_counts + p->chunks[twin[c]].out_off,
+                                sizeof(long long) * p->chunks[c].nbins_out, cudaMemcpyDeviceToDevice);
         free_dev(dk0); free_dev(dk1); free_dev(dk2); free_dev(ded);
         if (rc) return fail(rc);
         if (se != cudaSuccess) return fail(cuda_fail(se, "LUT build"));
