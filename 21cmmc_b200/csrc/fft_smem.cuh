@@ -19,11 +19,50 @@ struct FftFactors {
     int radix[14];
 };
 
+// Complex helpers.  On sm_100 the adds/subs and the twiddle multiplies use the packed fp32x2
+// instructions (FADD2 / FFMA2 / FMUL2, with register-broadcast and lane-swap operand selectors), which
+// halves the instruction count of the butterflies; the emulated test build uses the scalar forms.
+#if defined(__CUDA_ARCH__) && (__CUDA_ARCH__ >= 1000) && !defined(PS21_EMU)
+#define PS21_PACKED_F32X2 1
+#endif
+
 __device__ __forceinline__ float2 cmul(float2 a, float2 b) {
     return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
 }
+#ifdef PS21_PACKED_F32X2
+__device__ __forceinline__ float2 cadd(float2 a, float2 b) { return __fadd2_rn(a, b); }
+__device__ __forceinline__ float2 csub(float2 a, float2 b) { return __fadd2_rn(a, make_float2(-b.x, -b.y)); }
+// a + (-i) b  and  a - (-i) b
+__device__ __forceinline__ float2 cadd_mi(float2 a, float2 b) {
+    return __ffma2_rn(make_float2(b.y, b.x), make_float2(1.f, -1.f), a);
+}
+__device__ __forceinline__ float2 csub_mi(float2 a, float2 b) {
+    return __ffma2_rn(make_float2(b.y, b.x), make_float2(-1.f, 1.f), a);
+}
+// a + s*b, s real
+__device__ __forceinline__ float2 caxpy(float s, float2 b, float2 a) { return __ffma2_rn(b, make_float2(s, s), a); }
+// a * (c - i s)
+__device__ __forceinline__ float2 crot(float2 a, float c, float s) {
+    return __ffma2_rn(make_float2(a.y, a.x), make_float2(s, -s), __fmul2_rn(a, make_float2(c, c)));
+}
+// a * w with the twiddle stored as (w.x, w.y, -w.y, w.x)
+__device__ __forceinline__ float2 cmul_tw(float2 a, float4 w) {
+    return __ffma2_rn(make_float2(a.x, a.x), make_float2(w.x, w.y),
+                      __fmul2_rn(make_float2(a.y, a.y), make_float2(w.z, w.w)));
+}
+#else
 __device__ __forceinline__ float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
 __device__ __forceinline__ float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+__device__ __forceinline__ float2 cadd_mi(float2 a, float2 b) { return make_float2(a.x + b.y, a.y - b.x); }
+__device__ __forceinline__ float2 csub_mi(float2 a, float2 b) { return make_float2(a.x - b.y, a.y + b.x); }
+__device__ __forceinline__ float2 caxpy(float s, float2 b, float2 a) { return make_float2(a.x + s * b.x, a.y + s * b.y); }
+__device__ __forceinline__ float2 crot(float2 a, float c, float s) {
+    return make_float2(c * a.x + s * a.y, c * a.y - s * a.x);
+}
+__device__ __forceinline__ float2 cmul_tw(float2 a, float4 w) {
+    return make_float2(a.x * w.x + a.y * w.z, a.x * w.y + a.y * w.w);
+}
+#endif
 // multiply by -i
 __device__ __forceinline__ float2 cmul_mi(float2 a) { return make_float2(a.y, -a.x); }
 
@@ -42,11 +81,10 @@ __device__ __forceinline__ void small_dft<3>(float2 (&v)[3]) {
     const float c = 0.86602540378443864676f;  // sin(pi/3)
     float2 s = cadd(v[1], v[2]);
     float2 d = csub(v[1], v[2]);
-    float2 m = make_float2(v[0].x - 0.5f * s.x, v[0].y - 0.5f * s.y);
-    float2 jd = make_float2(c * d.y, -c * d.x);  // -i*c*d
+    float2 m = caxpy(-0.5f, s, v[0]);
     v[0] = cadd(v[0], s);
-    v[1] = cadd(m, jd);
-    v[2] = csub(m, jd);
+    v[1] = cadd_mi(m, make_float2(c * d.x, c * d.y));
+    v[2] = csub_mi(m, make_float2(c * d.x, c * d.y));
 }
 
 template <>
@@ -54,11 +92,11 @@ __device__ __forceinline__ void small_dft<4>(float2 (&v)[4]) {
     float2 t0 = cadd(v[0], v[2]);
     float2 t1 = csub(v[0], v[2]);
     float2 t2 = cadd(v[1], v[3]);
-    float2 t3 = cmul_mi(csub(v[1], v[3]));
+    float2 t3 = csub(v[1], v[3]);
     v[0] = cadd(t0, t2);
-    v[1] = cadd(t1, t3);
     v[2] = csub(t0, t2);
-    v[3] = csub(t1, t3);
+    v[1] = cadd_mi(t1, t3);
+    v[3] = csub_mi(t1, t3);
 }
 
 template <>
@@ -69,17 +107,15 @@ __device__ __forceinline__ void small_dft<5>(float2 (&v)[5]) {
     const float s2 = 0.58778525229247312917f;   // sin(4pi/5)
     float2 a1 = cadd(v[1], v[4]), a2 = cadd(v[2], v[3]);
     float2 b1 = csub(v[1], v[4]), b2 = csub(v[2], v[3]);
-    float2 r1 = make_float2(v[0].x + c1 * a1.x + c2 * a2.x, v[0].y + c1 * a1.y + c2 * a2.y);
-    float2 r2 = make_float2(v[0].x + c2 * a1.x + c1 * a2.x, v[0].y + c2 * a1.y + c1 * a2.y);
+    float2 r1 = caxpy(c2, a2, caxpy(c1, a1, v[0]));
+    float2 r2 = caxpy(c1, a2, caxpy(c2, a1, v[0]));
     float2 q1 = make_float2(s1 * b1.x + s2 * b2.x, s1 * b1.y + s2 * b2.y);
     float2 q2 = make_float2(s2 * b1.x - s1 * b2.x, s2 * b1.y - s1 * b2.y);
-    float2 x0 = make_float2(v[0].x + a1.x + a2.x, v[0].y + a1.y + a2.y);
-    float2 jq1 = cmul_mi(q1), jq2 = cmul_mi(q2);
-    v[0] = x0;
-    v[1] = cadd(r1, jq1);
-    v[4] = csub(r1, jq1);
-    v[2] = cadd(r2, jq2);
-    v[3] = csub(r2, jq2);
+    v[0] = cadd(v[0], cadd(a1, a2));
+    v[1] = cadd_mi(r1, q1);
+    v[4] = csub_mi(r1, q1);
+    v[2] = cadd_mi(r2, q2);
+    v[3] = csub_mi(r2, q2);
 }
 
 template <>
@@ -90,17 +126,16 @@ __device__ __forceinline__ void small_dft<8>(float2 (&v)[8]) {
     small_dft<4>(e);
     small_dft<4>(o);
     // w8^1 = (1 - i)/sqrt2, w8^2 = -i, w8^3 = (-1 - i)/sqrt2
-    float2 o1 = make_float2(h * (o[1].x + o[1].y), h * (o[1].y - o[1].x));
-    float2 o2 = cmul_mi(o[2]);
-    float2 o3 = make_float2(h * (o[3].y - o[3].x), -h * (o[3].x + o[3].y));
+    const float2 u1 = cadd_mi(o[1], o[1]);  // (x + y, y - x) = sqrt2 * o1 * w8
+    const float2 u3 = csub_mi(o[3], o[3]);  // (x - y, x + y) = -sqrt2 * o3 * w8^3
     v[0] = cadd(e[0], o[0]);
     v[4] = csub(e[0], o[0]);
-    v[1] = cadd(e[1], o1);
-    v[5] = csub(e[1], o1);
-    v[2] = cadd(e[2], o2);
-    v[6] = csub(e[2], o2);
-    v[3] = cadd(e[3], o3);
-    v[7] = csub(e[3], o3);
+    v[1] = caxpy(h, u1, e[1]);
+    v[5] = caxpy(-h, u1, e[1]);
+    v[2] = cadd_mi(e[2], o[2]);
+    v[6] = csub_mi(e[2], o[2]);
+    v[3] = caxpy(-h, u3, e[3]);
+    v[7] = caxpy(h, u3, e[3]);
 }
 
 // 16-point DFT as 4x4 (used by the fused power-of-two kernels).
@@ -117,28 +152,71 @@ __device__ __forceinline__ void small_dft<16>(float2 (&v)[16]) {
 #pragma unroll
         for (int q = 0; q < 4; ++q) a[j][q] = t[q];
     }
-    // twiddle a[j][q] *= w16^(j*q)
-    // j=1: q=1 w^1, q=2 w^2, q=3 w^3 ; j=2: w^2, w^4, w^6 ; j=3: w^3, w^6, w^9
-    auto w1 = [&](float2 x) { return make_float2(c1 * x.x + s1 * x.y, c1 * x.y - s1 * x.x); };
-    auto w2 = [&](float2 x) { return make_float2(h * (x.x + x.y), h * (x.y - x.x)); };
-    auto w3 = [&](float2 x) { return make_float2(s1 * x.x + c1 * x.y, s1 * x.y - c1 * x.x); };
-    auto w6 = [&](float2 x) { return make_float2(h * (x.y - x.x), -h * (x.x + x.y)); };
-    auto w9 = [&](float2 x) { return make_float2(-c1 * x.x - s1 * x.y, s1 * x.x - c1 * x.y); };
-    a[1][1] = w1(a[1][1]);
-    a[1][2] = w2(a[1][2]);
-    a[1][3] = w3(a[1][3]);
-    a[2][1] = w2(a[2][1]);
-    a[2][2] = cmul_mi(a[2][2]);
-    a[2][3] = w6(a[2][3]);
-    a[3][1] = w3(a[3][1]);
-    a[3][2] = w6(a[3][2]);
-    a[3][3] = w9(a[3][3]);
+    // a[j][q] *= w16^(j q), w16^m = cos(m pi/8) - i sin(m pi/8)
+    a[1][1] = crot(a[1][1], c1, s1);    // w^1
+    a[1][2] = crot(a[1][2], h, h);      // w^2
+    a[1][3] = crot(a[1][3], s1, c1);    // w^3
+    a[2][1] = crot(a[2][1], h, h);      // w^2
+    a[2][2] = cmul_mi(a[2][2]);         // w^4 = -i
+    a[2][3] = crot(a[2][3], -h, h);     // w^6
+    a[3][1] = crot(a[3][1], s1, c1);    // w^3
+    a[3][2] = crot(a[3][2], -h, h);     // w^6
+    a[3][3] = crot(a[3][3], -c1, -s1);  // w^9
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
         float2 t[4] = {a[0][q], a[1][q], a[2][q], a[3][q]};
         small_dft<4>(t);
 #pragma unroll
         for (int p = 0; p < 4; ++p) v[q + 4 * p] = t[p];
+    }
+}
+
+// 32-point DFT as 8x4: i = j + 4 i2, k = q + 8 p;  w32^(ik) = w32^(jq) w4^(jp) w8^(i2 q).
+template <>
+__device__ __forceinline__ void small_dft<32>(float2 (&v)[32]) {
+    // cos / sin of m pi / 16
+    constexpr float C1 = 0.98078528040323044913f, S1 = 0.19509032201612826785f;
+    constexpr float C2 = 0.92387953251128675613f, S2 = 0.38268343236508977173f;
+    constexpr float C3 = 0.83146961230254523708f, S3 = 0.55557023301960222474f;
+    constexpr float H = 0.70710678118654752440f;
+    float2 a[4][8];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        float2 t[8];
+#pragma unroll
+        for (int i2 = 0; i2 < 8; ++i2) t[i2] = v[j + 4 * i2];
+        small_dft<8>(t);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) a[j][q] = t[q];
+    }
+    // a[j][q] *= w32^(j q);  crot(x, cos, sin) multiplies by cos - i sin
+    a[1][1] = crot(a[1][1], C1, S1);    // 1
+    a[1][2] = crot(a[1][2], C2, S2);    // 2
+    a[1][3] = crot(a[1][3], C3, S3);    // 3
+    a[1][4] = crot(a[1][4], H, H);      // 4
+    a[1][5] = crot(a[1][5], S3, C3);    // 5
+    a[1][6] = crot(a[1][6], S2, C2);    // 6
+    a[1][7] = crot(a[1][7], S1, C1);    // 7
+    a[2][1] = crot(a[2][1], C2, S2);    // 2
+    a[2][2] = crot(a[2][2], H, H);      // 4
+    a[2][3] = crot(a[2][3], S2, C2);    // 6
+    a[2][4] = cmul_mi(a[2][4]);         // 8 = -i
+    a[2][5] = crot(a[2][5], -S2, C2);   // 10
+    a[2][6] = crot(a[2][6], -H, H);     // 12
+    a[2][7] = crot(a[2][7], -C2, S2);   // 14
+    a[3][1] = crot(a[3][1], C3, S3);    // 3
+    a[3][2] = crot(a[3][2], S2, C2);    // 6
+    a[3][3] = crot(a[3][3], -S1, C1);   // 9
+    a[3][4] = crot(a[3][4], -H, H);     // 12
+    a[3][5] = crot(a[3][5], -C1, S1);   // 15
+    a[3][6] = crot(a[3][6], -C2, -S2);  // 18
+    a[3][7] = crot(a[3][7], -S3, -C3);  // 21
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+        float2 t[4] = {a[0][q], a[1][q], a[2][q], a[3][q]};
+        small_dft<4>(t);
+#pragma unroll
+        for (int p = 0; p < 4; ++p) v[q + 8 * p] = t[p];
     }
 }
 

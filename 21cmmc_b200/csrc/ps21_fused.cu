@@ -10,10 +10,12 @@
 //                        y: 64-point FFT over j (radix 8 x 8, in place), times w_256^(y_lo ky_a);
 //                        results go to HBM in tile order so that pass 2 reads one contiguous 64 KB
 //                        block per tile: tile = (ky_a, 8 consecutive k_z), inner [x][y_lo][k_z].
-//   pass 2  k_fused_p2   CTA loops over tiles: one 64 KB bulk copy per tile, 4-point FFT over y_lo and
-//                        256-point FFT over x (radix 4x4, 16, 4; in place, XOR-swizzled 64-byte chunks so
-//                        every stage is bank-conflict free), |delta_k|^2 straight from registers, bin
-//                        index from a byte LUT read coalesced, lane-private fp32 bins in shared memory,
+//   pass 2  k_fused_p2   CTA loops over tiles: one 64 KB bulk copy per tile (+ its 8 KB of bin indices),
+//                        4-point FFT over y_lo and 256-point FFT over x in TWO stages of 32 points per
+//                        thread (4x8, then 32; in place, XOR-swizzled 64-byte chunks so both stages are
+//                        bank-conflict free) -- the kernel is bound by shared-memory bandwidth, so every
+//                        stage saved counts; |delta_k|^2 straight from registers, bin index from the
+//                        byte LUT staged next to the tile, lane-private fp32 bins in shared memory,
 //                        flushed per tile into fp64 bins in a fixed order (bitwise reproducible), one
 //                        partial-sum record per CTA (no global atomics).
 //
@@ -43,7 +45,7 @@ static_assert(NTILES % SLOTS == 0, "tiles must divide evenly over the slots");
 static_assert((long long)NTILES * TILE == (long long)NX * NY * (NZ / 2 + 1), "tile order covers the half spectrum exactly");
 
 struct FusedShape {
-    float2* tw256 = nullptr;   // exp(-2 pi i q / 256)
+    float4* tw256 = nullptr;   // w = exp(-2 pi i q / 256) stored as (w.x, w.y, -w.y, w.x) for cmul_tw
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -155,11 +157,10 @@ __device__ __forceinline__ long long scratch_addr(int x, int yl, int kya, int kz
     }
     return (long long)tile * TILE + tile_idx(x, yl, t);
 }
-// which Fourier mode the pass-2 output (tile, task, r) is:  task = (m', n', t), r = (ky_b, b')
+// which Fourier mode the pass-2 output (tile, task, r) is:  task = (m', ky_b, t), r = 0..31 -> kx = m' + 8 r
 __device__ __forceinline__ void p2_mode_of(int tile, int task, int r, int& kx, int& ky, int& kz) {
-    const int t = task & 7, n1 = (task >> 3) & 15, m1 = task >> 7;
-    const int kyb = r >> 2, b1 = r & 3;
-    kx = m1 + 4 * n1 + 64 * b1;
+    const int t = task & 7, kyb = (task >> 3) & 3, m1 = task >> 5;
+    kx = m1 + 8 * r;
     int kya;
     if (tile < NT_MAIN) {
         kya = tile >> 4;
@@ -183,7 +184,7 @@ __global__ void k_fused_lut(uint8_t* __restrict__ lut, unsigned long long* __res
          i += (long long)gridDim.x * blockDim.x) {
         const int tile = (int)(i / TILE), e = (int)(i % TILE);
         int kx, ky, kz;
-        p2_mode_of(tile, e >> 4, e & 15, kx, ky, kz);
+        p2_mode_of(tile, e >> 5, e & 31, kx, ky, kz);
         int w = (kz == 0 || kz == NHC) ? 1 : 2;
         const bool perp0 = (kx == 0 && ky == 0);
         if (ig_kperp && perp0) w = 0;
@@ -203,16 +204,15 @@ __global__ void k_fused_lut(uint8_t* __restrict__ lut, unsigned long long* __res
 // pass 1
 // ------------------------------------------------------------------------------------------------
 // 128-point DIF FFT of one packed row, executed by the 8 threads (t = 0..7) that own the row.
-__device__ __forceinline__ void zfft_row(float2* __restrict__ row, int t, float mean, const float2* __restrict__ twz) {
+__device__ __forceinline__ void zfft_row(float2* __restrict__ row, int t, float mean, const float4* __restrict__ twz) {
     float2 v[16];
 #pragma unroll
     for (int m = 0; m < 16; ++m) {
-        float2 a = row[t + 8 * m];
-        v[m] = make_float2(a.x - mean, a.y - mean);
+        v[m] = csub(row[t + 8 * m], make_float2(mean, mean));
     }
     small_dft<16>(v);
 #pragma unroll
-    for (int m = 1; m < 16; ++m) v[m] = cmul(v[m], twz[8 * m + t]);  // w_128^(t m'), lane-contiguous table
+    for (int m = 1; m < 16; ++m) v[m] = cmul_tw(v[m], twz[8 * m + t]);  // w_128^(t m'), lane-contiguous table
     __syncwarp();
 #pragma unroll
     for (int m = 0; m < 16; ++m) row[8 * m + (t ^ (m & 7))] = v[m];  // swizzled inside each group of 8
@@ -234,23 +234,35 @@ __device__ __forceinline__ void zfft_row(float2* __restrict__ row, int t, float 
     }
 }
 
-// untangle of the (even,odd)-packed real FFT for the column pair (p, 128-p), one row
-__device__ __forceinline__ void untangle(float2 ck, float2 cn, float2 w, float2& a1, float2& a2) {
-    const float2 e = make_float2(0.5f * (ck.x + cn.x), 0.5f * (ck.y - cn.y));
-    const float2 o = make_float2(0.5f * (ck.y + cn.y), -0.5f * (ck.x - cn.x));
-    const float2 tw = cmul(w, o);
-    a1 = make_float2(e.x + tw.x, e.y + tw.y);
-    a2 = make_float2(e.x - tw.x, -(e.y - tw.y));
+// untangle of the (even,odd)-packed real FFT for the column pair (p, 128-p), one row.
+// With E = (C_p + conj C_{N-p})/2 and O = (C_p - conj C_{N-p})/(2i):  A_p = E + w^p O,  A_{N-p} = conj(E - w^p O).
+// `wu` is the table entry of  w_256^p * (-i/2), so that  w^p O = wu * (C_p - conj C_{N-p}).
+__device__ __forceinline__ void untangle(float2 ck, float2 cn, float4 wu, float2& a1, float2& a2) {
+#ifdef PS21_PACKED_F32X2
+    const float2 e2 = __ffma2_rn(cn, make_float2(1.f, -1.f), ck);   // 2E
+    const float2 d = __ffma2_rn(cn, make_float2(-1.f, 1.f), ck);    // C_p - conj C_{N-p}
+    const float2 t = cmul_tw(d, wu);
+    a1 = __ffma2_rn(e2, make_float2(0.5f, 0.5f), t);
+    a2 = __ffma2_rn(e2, make_float2(0.5f, -0.5f), __fmul2_rn(t, make_float2(-1.f, 1.f)));
+#else
+    const float2 e2 = make_float2(ck.x + cn.x, ck.y - cn.y);
+    const float2 d = make_float2(ck.x - cn.x, ck.y + cn.y);
+    const float2 t = cmul_tw(d, wu);
+    a1 = make_float2(0.5f * e2.x + t.x, 0.5f * e2.y + t.y);
+    a2 = make_float2(0.5f * e2.x - t.x, -(0.5f * e2.y - t.y));
+#endif
 }
 
 __global__ void __launch_bounds__(P1_THREADS, 3)
 k_fused_p1(const float* __restrict__ boxes, long long batch_stride, int n2_total, ItemMap im,
            const ChunkDev* __restrict__ chunks, int nchunks, const float* __restrict__ means,
-           float2* __restrict__ scratch, const float2* __restrict__ tw_g) {
+           float2* __restrict__ scratch, const float4* __restrict__ tw_g) {
     PS21_DYN_SMEM(float2, buf);                                          // [64][ROWLD]
-    float2* tw = buf + R1 * ROWLD;                                       // [256] w_256^q
-    float2* twz = tw + 256;                                              // [16][8] w_128^(t m)
-    uint64_t* bar = reinterpret_cast<uint64_t*>(twz + 128);              // [2]: rows 0..31, rows 32..63
+    float4* twz = reinterpret_cast<float4*>(buf + R1 * ROWLD);           // [16][8] w_128^(t m)
+    float4* ty1 = twz + 128;                                             // [8][8]  w_64^(u m)
+    float4* ty2 = ty1 + 64;                                              // [64]    w_256^(y_lo ky_a), per unit
+    float4* twu = ty2 + 64;                                              // [65]    w_256^p * (-i/2)
+    uint64_t* bar = reinterpret_cast<uint64_t*>(twu + 66);               // [2]: rows 0..31, rows 32..63
     const int tid = threadIdx.x;
     long long box;
     int cid;
@@ -260,9 +272,16 @@ k_fused_p1(const float* __restrict__ boxes, long long batch_stride, int n2_total
     const int x = blockIdx.x;
     const float* src = boxes + box * batch_stride + ch.start + (long long)x * NY * n2_total;
     float2* dst = scratch + (long long)blockIdx.y * ((long long)NTILES * TILE);
-    tw[tid] = tw_g[tid];
     if (tid < 128) twz[tid] = tw_g[(2 * (tid & 7) * (tid >> 3)) & 255];
+    if (tid >= 128 && tid < 192) ty1[tid - 128] = tw_g[(4 * ((tid - 128) >> 3) * (tid & 7)) & 255];
+    if (tid >= 192 && tid < 192 + 65) {
+        const float4 w = tw_g[tid - 192];  // (wx, wy, -wy, wx);  w * (-i/2) = (wy/2, -wx/2)
+        twu[tid - 192] = make_float4(0.5f * w.y, -0.5f * w.x, 0.5f * w.x, 0.5f * w.y);
+    }
     if (tid == 0) {
+        twu[64] = make_float4(0.f, 0.f, 0.f, 0.f);  // column 64 is handled separately
+        const float4 w = tw_g[64];
+        twu[64] = make_float4(0.5f * w.y, -0.5f * w.x, 0.5f * w.x, 0.5f * w.y);
         mbar_init(bar, 1);
         mbar_init(bar + 1, 1);
         mbar_fence_init();
@@ -295,7 +314,7 @@ k_fused_p1(const float* __restrict__ boxes, long long batch_stride, int n2_total
 #pragma unroll
             for (int u = 0; u < 8; ++u) {
                 const int kya = m1 + 8 * u;
-                const float2 o = (yl == 0) ? v[u] : cmul(v[u], tw[(yl * kya) & 255]);
+                const float2 o = (yl == 0) ? v[u] : cmul_tw(v[u], ty2[kya]);
                 dst[scratch_addr(x, yl, kya, kz)] = o;
             }
         }
@@ -304,6 +323,7 @@ k_fused_p1(const float* __restrict__ boxes, long long batch_stride, int n2_total
     issue_half(0, 1);
     uint32_t phase = 0;
     for (int yl = 0; yl < R2; ++yl) {
+        if (tid < 64) ty2[tid] = tw_g[(yl * tid) & 255];  // read after the next two barriers
         // ---- z: one 128-point FFT per row, 8 threads per row; rows 0..31 as soon as they have landed
         mbar_wait(bar, phase);
         for (int task = tid; task < (R1 / 2) * 8; task += P1_THREADS) zfft_row(buf + (task >> 3) * ROWLD, task & 7, mean, twz);
@@ -323,7 +343,7 @@ k_fused_p1(const float* __restrict__ boxes, long long batch_stride, int n2_total
                 u = task - 512;
             }
             float2 c1[8], c2[8];
-            const float2 w = tw[p];  // w_256^p
+            const float4 w = twu[p];  // w_256^p * (-i/2)
 #pragma unroll
             for (int m = 0; m < 8; ++m) {
                 const float2* r = buf + (u + 8 * m) * ROWLD;
@@ -343,9 +363,9 @@ k_fused_p1(const float* __restrict__ boxes, long long batch_stride, int n2_total
 #pragma unroll
             for (int m = 0; m < 8; ++m) {
                 float2* r = buf + (u + 8 * m) * ROWLD;
-                const float2 f = tw[(4 * u * m) & 255];  // w_64^(u m')
-                r[p] = (m == 0) ? c1[m] : cmul(c1[m], f);
-                if (p != 64) r[NHC - p] = (m == 0) ? c2[m] : cmul(c2[m], f);
+                const float4 f = ty1[8 * u + m];  // w_64^(u m')
+                r[p] = (m == 0) ? c1[m] : cmul_tw(c1[m], f);
+                if (p != 64) r[NHC - p] = (m == 0) ? c2[m] : cmul_tw(c2[m], f);
             }
         }
         __syncthreads();
@@ -372,10 +392,10 @@ k_fused_p1(const float* __restrict__ boxes, long long batch_stride, int n2_total
 __global__ void __launch_bounds__(P2_THREADS, 2)
 k_fused_p2(const float2* __restrict__ scratch, ItemMap im, const ChunkDev* __restrict__ chunks,
            const uint16_t* const* __restrict__ luts, double* __restrict__ partials, long long out_per_box,
-           int slots_max, float2* __restrict__ dc, int nchunks, const float2* __restrict__ tw_g, int nbins) {
+           int slots_max, float2* __restrict__ dc, int nchunks, const float4* __restrict__ tw_g, int nbins) {
     PS21_DYN_SMEM(float2, tile);               // [TILE]
     uint8_t* lutb = reinterpret_cast<uint8_t*>(tile + TILE);           // [TILE] bin index of every output of the tile
-    float2* tw = reinterpret_cast<float2*>(lutb + TILE);               // [256]
+    float4* tw = reinterpret_cast<float4*>(lutb + TILE);               // [256]
     uint64_t* bar = reinterpret_cast<uint64_t*>(tw + 256);
     double* cbins = reinterpret_cast<double*>(bar + 2);                // [MAX_BINS]
     float* lbins = reinterpret_cast<float*>(cbins + MAX_BINS);         // [nbins][P2_THREADS]
@@ -406,69 +426,55 @@ k_fused_p2(const float2* __restrict__ scratch, ItemMap im, const ChunkDev* __res
     for (; tl < NTILES; tl += SLOTS) {
         mbar_wait(bar, phase);
         phase ^= 1;
-        // ---- S1: 4-point FFT over y_lo (-> ky_b) x first radix-4 of x (x = xa + 64 m -> m'), twiddle w_256^(xa m')
-        for (int task = tid; task < 512; task += P2_THREADS) {
-            const int t = task & 7, xa = task >> 3;
-            float2 v[4][4];  // [m][yl]
+        // ---- S1: 4-point FFT over y_lo (-> ky_b) x radix 8 over x = xa + 32 m (-> m'), twiddle w_256^(xa m');
+        //      one task of 32 points per thread, in place
+        {
+            const int t = tid & 7, xa = tid >> 3;
+            float2 v[8][4];  // [m][yl]
 #pragma unroll
-            for (int m = 0; m < 4; ++m)
+            for (int m = 0; m < 8; ++m)
 #pragma unroll
-                for (int yl = 0; yl < 4; ++yl) v[m][yl] = tile[tile_idx(xa + 64 * m, yl, t)];
+                for (int yl = 0; yl < 4; ++yl) v[m][yl] = tile[tile_idx(xa + 32 * m, yl, t)];
 #pragma unroll
-            for (int m = 0; m < 4; ++m) small_dft<4>(v[m]);
+            for (int m = 0; m < 8; ++m) small_dft<4>(v[m]);
 #pragma unroll
             for (int yl = 0; yl < 4; ++yl) {
-                float2 c[4] = {v[0][yl], v[1][yl], v[2][yl], v[3][yl]};
-                small_dft<4>(c);
+                float2 c[8];
 #pragma unroll
-                for (int m = 0; m < 4; ++m) v[m][yl] = c[m];
+                for (int m = 0; m < 8; ++m) c[m] = v[m][yl];
+                small_dft<8>(c);
+#pragma unroll
+                for (int m = 0; m < 8; ++m) v[m][yl] = c[m];
             }
 #pragma unroll
-            for (int m = 0; m < 4; ++m) {
-                const float2 f = tw[(xa * m) & 255];
+            for (int m = 0; m < 8; ++m) {
+                const float4 f = tw[(xa * m) & 255];
 #pragma unroll
                 for (int yl = 0; yl < 4; ++yl)
-                    tile[tile_idx(xa + 64 * m, yl, t)] = (m == 0) ? v[m][yl] : cmul(v[m][yl], f);
+                    tile[tile_idx(xa + 32 * m, yl, t)] = (m == 0) ? v[m][yl] : cmul_tw(v[m][yl], f);
             }
         }
         __syncthreads();
-        // ---- S2: radix 16 over xa = xb + 4 n inside block m' (-> n'), twiddle w_64^(xb n')
-        for (int task = tid; task < 512; task += P2_THREADS) {
-            const int t = task & 7, xb = (task >> 3) & 3, yl = (task >> 5) & 3, m1 = task >> 7;
-            float2 v[16];
+        // ---- S2: radix 32 over xa inside block m' (-> r, kx = m' + 8 r), |delta_k|^2, bins
+        {
+            const int t = tid & 7, kyb = (tid >> 3) & 3, m1 = tid >> 5;
+            float2 v[32];
 #pragma unroll
-            for (int n = 0; n < 16; ++n) v[n] = tile[tile_idx(64 * m1 + xb + 4 * n, yl, t)];
-            small_dft<16>(v);
-#pragma unroll
-            for (int n = 0; n < 16; ++n) {
-                const float2 o = (n == 0 || xb == 0) ? v[n] : cmul(v[n], tw[(4 * xb * n) & 255]);
-                tile[tile_idx(64 * m1 + xb + 4 * n, yl, t)] = o;
-            }
-        }
-        __syncthreads();
-        // ---- S3: last radix 4 over xb (-> b'), |delta_k|^2, bins
-        for (int task = tid; task < 512; task += P2_THREADS) {
-            const int t = task & 7, n1 = (task >> 3) & 15, m1 = task >> 7;
-            float pw[16];
-            float2 first = make_float2(0.f, 0.f);
-#pragma unroll
-            for (int yl = 0; yl < 4; ++yl) {
-                float2 c[4];
-#pragma unroll
-                for (int xb = 0; xb < 4; ++xb) c[xb] = tile[tile_idx(64 * m1 + 4 * n1 + xb, yl, t)];
-                small_dft<4>(c);
-                if (yl == 0) first = c[0];
-#pragma unroll
-                for (int b = 0; b < 4; ++b) pw[4 * yl + b] = c[b].x * c[b].x + c[b].y * c[b].y;
-            }
-            if (tl == 0 && task == 0) dc[box * nchunks + cid] = first;
+            for (int xa = 0; xa < 32; ++xa) v[xa] = tile[tile_idx(32 * m1 + xa, kyb, t)];
+            small_dft<32>(v);
+            if (tl == 0 && tid == 0) dc[box * nchunks + cid] = v[0];
             const float mult = (tl >= NT_MAIN || ((tl & 15) == 0 && t == 0)) ? 1.f : 2.f;
-            const uint4 lv = *reinterpret_cast<const uint4*>(lutb + task * 16);
-            const uint32_t w4[4] = {lv.x, lv.y, lv.z, lv.w};
+            const uint4* lp = reinterpret_cast<const uint4*>(lutb + tid * 32);
 #pragma unroll
-            for (int r = 0; r < 16; ++r) {
-                const uint32_t b = (w4[r >> 2] >> (8 * (r & 3))) & 255u;
-                if (b != 255u) lbins[b * P2_THREADS + tid] += mult * pw[r];
+            for (int h = 0; h < 2; ++h) {
+                const uint4 lv = lp[h];
+                const uint32_t w4[4] = {lv.x, lv.y, lv.z, lv.w};
+#pragma unroll
+                for (int r = 0; r < 16; ++r) {
+                    const uint32_t b = (w4[r >> 2] >> (8 * (r & 3))) & 255u;
+                    const float2 c = v[16 * h + r];
+                    if (b != 255u) lbins[b * P2_THREADS + tid] += mult * (c.x * c.x + c.y * c.y);
+                }
             }
         }
         __syncthreads();
@@ -500,9 +506,9 @@ k_fused_p2(const float2* __restrict__ scratch, ItemMap im, const ChunkDev* __res
     for (int i = tid; i < nbins; i += P2_THREADS) out[i] = cbins[i];
 }
 
-static size_t p1_smem() { return (size_t)R1 * ROWLD * 8 + 256 * 8 + 128 * 8 + 16; }
+static size_t p1_smem() { return (size_t)R1 * ROWLD * 8 + (128 + 64 + 64 + 66) * 16 + 16; }
 static size_t p2_smem(int nbins) {
-    return (size_t)TILE * 8 + TILE + 256 * 8 + 16 + MAX_BINS * 8 + (size_t)nbins * P2_THREADS * 4;
+    return (size_t)TILE * 8 + TILE + 256 * 16 + 16 + MAX_BINS * 8 + (size_t)nbins * P2_THREADS * 4;
 }
 
 }  // namespace fz
@@ -527,13 +533,14 @@ int fused_try_setup(ps21_plan* p, ShapePlan& sp) {
             return -1;
         }
     auto* fs = new FusedShape();
-    std::vector<float2> tw(256);
+    std::vector<float4> tw(256);
     for (int q = 0; q < 256; ++q) {
         const double a = -2.0 * 3.14159265358979323846 * q / 256.0;
-        tw[q] = make_float2((float)cos(a), (float)sin(a));
+        const float c = (float)cos(a), sn = (float)sin(a);
+        tw[q] = make_float4(c, sn, -sn, c);
     }
-    if (cudaMalloc((void**)&fs->tw256, sizeof(float2) * 256) != cudaSuccess ||
-        cudaMemcpy(fs->tw256, tw.data(), sizeof(float2) * 256, cudaMemcpyHostToDevice) != cudaSuccess ||
+    if (cudaMalloc((void**)&fs->tw256, sizeof(float4) * 256) != cudaSuccess ||
+        cudaMemcpy(fs->tw256, tw.data(), sizeof(float4) * 256, cudaMemcpyHostToDevice) != cudaSuccess ||
         cudaFuncSetAttribute(k_fused_p1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p1_smem()) != cudaSuccess ||
         cudaFuncSetAttribute(k_fused_p2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p2_smem(MAX_BINS)) !=
             cudaSuccess) {

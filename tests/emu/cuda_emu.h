@@ -19,6 +19,10 @@ struct float2 {
     float x, y;
 };
 static inline float2 make_float2(float x, float y) { return float2{x, y}; }
+struct alignas(16) float4 {
+    float x, y, z, w;
+};
+static inline float4 make_float4(float x, float y, float z, float w) { return float4{x, y, z, w}; }
 struct uint3 {
     unsigned x, y, z;
 };
