@@ -50,7 +50,13 @@ __device__ __forceinline__ float2 cmul_tw(float2 a, float4 w) {
     return __ffma2_rn(make_float2(a.x, a.x), make_float2(w.x, w.y),
                       __fmul2_rn(make_float2(a.y, a.y), make_float2(w.z, w.w)));
 }
+// a * w with a plain (w.x, w.y) twiddle: three packed instructions, half the table bytes of cmul_tw
+__device__ __forceinline__ float2 cmul_w2(float2 a, float2 w) {
+    const float2 rot = __fmul2_rn(make_float2(a.y, a.x), make_float2(-1.f, 1.f));  // i*a
+    return __ffma2_rn(rot, make_float2(w.y, w.y), __fmul2_rn(a, make_float2(w.x, w.x)));
+}
 #else
+__device__ __forceinline__ float2 cmul_w2(float2 a, float2 w) { return cmul(a, w); }
 __device__ __forceinline__ float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
 __device__ __forceinline__ float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
 __device__ __forceinline__ float2 cadd_mi(float2 a, float2 b) { return make_float2(a.x + b.y, a.y - b.x); }

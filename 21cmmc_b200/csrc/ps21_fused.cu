@@ -44,6 +44,14 @@ constexpr int MAX_BINS = 40;
 static_assert(NTILES % SLOTS == 0, "tiles must divide evenly over the slots");
 static_assert((long long)NTILES * TILE == (long long)NX * NY * (NZ / 2 + 1), "tile order covers the half spectrum exactly");
 
+// w = exp(-2 pi i q / 256) as (w.x, w.y, -w.y, w.x); read through the constant cache where the index is
+// warp-uniform (the y twiddles of pass 1), which keeps those reads off the shared-memory pipe
+#ifndef PS21_EMU
+__constant__ float4 c_tw256[256];
+#else
+static float4 c_tw256[256];
+#endif
+
 struct FusedShape {
     float4* tw256 = nullptr;   // w = exp(-2 pi i q / 256) stored as (w.x, w.y, -w.y, w.x) for cmul_tw
 };
@@ -141,9 +149,10 @@ __device__ __forceinline__ void bulk_g2s_hint(void* dst, const void* src, uint32
 // ------------------------------------------------------------------------------------------------
 // layout of the half-spectrum scratch ("tile order")
 // ------------------------------------------------------------------------------------------------
-// 64-byte chunk (x, y_lo) inside a tile; the low bit of y_lo is flipped by bit0(x)^bit2(x) so that the
-// three x stages of pass 2 touch both halves of every 128-byte bank line (conflict free).
-__device__ __forceinline__ int chunk_of(int x, int yl) { return 4 * x + (yl ^ ((x ^ (x >> 2)) & 1)); }
+// 64-byte chunk (x, y_lo) inside a tile; the low bit of y_lo is flipped by bit0(x)^bit5(x) so that both
+// x stages of pass 2 (lanes over consecutive x, and over x in steps of 32) touch both halves of every
+// 128-byte bank line (conflict free).
+__device__ __forceinline__ int chunk_of(int x, int yl) { return 4 * x + (yl ^ ((x ^ (x >> 5)) & 1)); }
 __device__ __forceinline__ int tile_idx(int x, int yl, int t) { return chunk_of(x, yl) * T + t; }
 // where pass 1 stores the coefficient (x, y_lo, ky_a, kz)
 __device__ __forceinline__ long long scratch_addr(int x, int yl, int kya, int kz) {
@@ -157,9 +166,10 @@ __device__ __forceinline__ long long scratch_addr(int x, int yl, int kya, int kz
     }
     return (long long)tile * TILE + tile_idx(x, yl, t);
 }
-// which Fourier mode the pass-2 output (tile, task, r) is:  task = (m', ky_b, t), r = 0..31 -> kx = m' + 8 r
+// which Fourier mode the pass-2 output (tile, task, r) is:  r = 0..31 -> kx = m' + 8 r.  The 32 lanes of a
+// warp hold (t, m' & 3): nearly the same |k| for every r, so their bin sequences change at the same r.
 __device__ __forceinline__ void p2_mode_of(int tile, int task, int r, int& kx, int& ky, int& kz) {
-    const int t = task & 7, kyb = (task >> 3) & 3, m1 = task >> 5;
+    const int t = task & 7, m1 = ((task >> 3) & 3) | ((task >> 7) << 2), kyb = (task >> 5) & 3;
     kx = m1 + 8 * r;
     int kya;
     if (tile < NT_MAIN) {
@@ -204,7 +214,7 @@ __global__ void k_fused_lut(uint8_t* __restrict__ lut, unsigned long long* __res
 // pass 1
 // ------------------------------------------------------------------------------------------------
 // 128-point DIF FFT of one packed row, executed by the 8 threads (t = 0..7) that own the row.
-__device__ __forceinline__ void zfft_row(float2* __restrict__ row, int t, float mean, const float4* __restrict__ twz) {
+__device__ __forceinline__ void zfft_row(float2* __restrict__ row, int t, float mean, const float2* __restrict__ twz) {
     float2 v[16];
 #pragma unroll
     for (int m = 0; m < 16; ++m) {
@@ -212,7 +222,7 @@ __device__ __forceinline__ void zfft_row(float2* __restrict__ row, int t, float 
     }
     small_dft<16>(v);
 #pragma unroll
-    for (int m = 1; m < 16; ++m) v[m] = cmul_tw(v[m], twz[8 * m + t]);  // w_128^(t m'), lane-contiguous table
+    for (int m = 1; m < 16; ++m) v[m] = cmul_w2(v[m], twz[8 * m + t]);  // w_128^(t m'), lane-contiguous table
     __syncwarp();
 #pragma unroll
     for (int m = 0; m < 16; ++m) row[8 * m + (t ^ (m & 7))] = v[m];  // swizzled inside each group of 8
@@ -258,10 +268,8 @@ k_fused_p1(const float* __restrict__ boxes, long long batch_stride, int n2_total
            const ChunkDev* __restrict__ chunks, int nchunks, const float* __restrict__ means,
            float2* __restrict__ scratch, const float4* __restrict__ tw_g) {
     PS21_DYN_SMEM(float2, buf);                                          // [64][ROWLD]
-    float4* twz = reinterpret_cast<float4*>(buf + R1 * ROWLD);           // [16][8] w_128^(t m)
-    float4* ty1 = twz + 128;                                             // [8][8]  w_64^(u m)
-    float4* ty2 = ty1 + 64;                                              // [64]    w_256^(y_lo ky_a), per unit
-    float4* twu = ty2 + 64;                                              // [65]    w_256^p * (-i/2)
+    float2* twz = buf + R1 * ROWLD;                                      // [16][8] w_128^(t m)
+    float4* twu = reinterpret_cast<float4*>(twz + 128);                  // [65]    w_256^p * (-i/2)
     uint64_t* bar = reinterpret_cast<uint64_t*>(twu + 66);               // [2]: rows 0..31, rows 32..63
     const int tid = threadIdx.x;
     long long box;
@@ -272,8 +280,10 @@ k_fused_p1(const float* __restrict__ boxes, long long batch_stride, int n2_total
     const int x = blockIdx.x;
     const float* src = boxes + box * batch_stride + ch.start + (long long)x * NY * n2_total;
     float2* dst = scratch + (long long)blockIdx.y * ((long long)NTILES * TILE);
-    if (tid < 128) twz[tid] = tw_g[(2 * (tid & 7) * (tid >> 3)) & 255];
-    if (tid >= 128 && tid < 192) ty1[tid - 128] = tw_g[(4 * ((tid - 128) >> 3) * (tid & 7)) & 255];
+    if (tid < 128) {
+        const float4 w = tw_g[(2 * (tid & 7) * (tid >> 3)) & 255];
+        twz[tid] = make_float2(w.x, w.y);
+    }
     if (tid >= 192 && tid < 192 + 65) {
         const float4 w = tw_g[tid - 192];  // (wx, wy, -wy, wx);  w * (-i/2) = (wy/2, -wx/2)
         twu[tid - 192] = make_float4(0.5f * w.y, -0.5f * w.x, 0.5f * w.x, 0.5f * w.y);
@@ -314,7 +324,7 @@ k_fused_p1(const float* __restrict__ boxes, long long batch_stride, int n2_total
 #pragma unroll
             for (int u = 0; u < 8; ++u) {
                 const int kya = m1 + 8 * u;
-                const float2 o = (yl == 0) ? v[u] : cmul_tw(v[u], ty2[kya]);
+                const float2 o = (yl == 0) ? v[u] : cmul_tw(v[u], c_tw256[(yl * kya) & 255]);  // warp-uniform index
                 dst[scratch_addr(x, yl, kya, kz)] = o;
             }
         }
@@ -323,7 +333,6 @@ k_fused_p1(const float* __restrict__ boxes, long long batch_stride, int n2_total
     issue_half(0, 1);
     uint32_t phase = 0;
     for (int yl = 0; yl < R2; ++yl) {
-        if (tid < 64) ty2[tid] = tw_g[(yl * tid) & 255];  // read after the next two barriers
         // ---- z: one 128-point FFT per row, 8 threads per row; rows 0..31 as soon as they have landed
         mbar_wait(bar, phase);
         for (int task = tid; task < (R1 / 2) * 8; task += P1_THREADS) zfft_row(buf + (task >> 3) * ROWLD, task & 7, mean, twz);
@@ -363,7 +372,7 @@ k_fused_p1(const float* __restrict__ boxes, long long batch_stride, int n2_total
 #pragma unroll
             for (int m = 0; m < 8; ++m) {
                 float2* r = buf + (u + 8 * m) * ROWLD;
-                const float4 f = ty1[8 * u + m];  // w_64^(u m')
+                const float4 f = c_tw256[(4 * u * m) & 255];  // w_64^(u m'), warp-uniform index
                 r[p] = (m == 0) ? c1[m] : cmul_tw(c1[m], f);
                 if (p != 64) r[NHC - p] = (m == 0) ? c2[m] : cmul_tw(c2[m], f);
             }
@@ -455,9 +464,12 @@ k_fused_p2(const float2* __restrict__ scratch, ItemMap im, const ChunkDev* __res
             }
         }
         __syncthreads();
-        // ---- S2: radix 32 over xa inside block m' (-> r, kx = m' + 8 r), |delta_k|^2, bins
+        // ---- S2: radix 32 over xa inside block m' (-> r, kx = m' + 8 r), |delta_k|^2, bins.
+        //      Along r the bin index rises (kx >= 0) and falls again (kx < 0) and the lanes of a warp see
+        //      nearly the same |k|: powers are summed in a register while the bin stays the same and the
+        //      lane-private shared-memory bin is touched only where some lane changes bin (warp vote).
         {
-            const int t = tid & 7, kyb = (tid >> 3) & 3, m1 = tid >> 5;
+            const int t = tid & 7, m1 = ((tid >> 3) & 3) | ((tid >> 7) << 2), kyb = (tid >> 5) & 3;
             float2 v[32];
 #pragma unroll
             for (int xa = 0; xa < 32; ++xa) v[xa] = tile[tile_idx(32 * m1 + xa, kyb, t)];
@@ -465,6 +477,8 @@ k_fused_p2(const float2* __restrict__ scratch, ItemMap im, const ChunkDev* __res
             if (tl == 0 && tid == 0) dc[box * nchunks + cid] = v[0];
             const float mult = (tl >= NT_MAIN || ((tl & 15) == 0 && t == 0)) ? 1.f : 2.f;
             const uint4* lp = reinterpret_cast<const uint4*>(lutb + tid * 32);
+            uint32_t cur = 255u;
+            float acc = 0.f;
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
                 const uint4 lv = lp[h];
@@ -473,9 +487,18 @@ k_fused_p2(const float2* __restrict__ scratch, ItemMap im, const ChunkDev* __res
                 for (int r = 0; r < 16; ++r) {
                     const uint32_t b = (w4[r >> 2] >> (8 * (r & 3))) & 255u;
                     const float2 c = v[16 * h + r];
-                    if (b != 255u) lbins[b * P2_THREADS + tid] += mult * (c.x * c.x + c.y * c.y);
+                    const float pw = c.x * c.x + c.y * c.y;
+                    if (__any_sync(0xffffffffu, b != cur)) {
+                        if (b != cur) {
+                            if (cur != 255u) lbins[cur * P2_THREADS + tid] += mult * acc;
+                            cur = b;
+                            acc = 0.f;
+                        }
+                    }
+                    acc += pw;
                 }
             }
+            if (cur != 255u) lbins[cur * P2_THREADS + tid] += mult * acc;
         }
         __syncthreads();
         // tile buffer is free: prefetch the next tile while the bins are flushed
@@ -506,7 +529,7 @@ k_fused_p2(const float2* __restrict__ scratch, ItemMap im, const ChunkDev* __res
     for (int i = tid; i < nbins; i += P2_THREADS) out[i] = cbins[i];
 }
 
-static size_t p1_smem() { return (size_t)R1 * ROWLD * 8 + (128 + 64 + 64 + 66) * 16 + 16; }
+static size_t p1_smem() { return (size_t)R1 * ROWLD * 8 + 128 * 8 + 66 * 16 + 16; }
 static size_t p2_smem(int nbins) {
     return (size_t)TILE * 8 + TILE + 256 * 16 + 16 + MAX_BINS * 8 + (size_t)nbins * P2_THREADS * 4;
 }
@@ -539,6 +562,16 @@ int fused_try_setup(ps21_plan* p, ShapePlan& sp) {
         const float c = (float)cos(a), sn = (float)sin(a);
         tw[q] = make_float4(c, sn, -sn, c);
     }
+#ifndef PS21_EMU
+    if (cudaMemcpyToSymbol(c_tw256, tw.data(), sizeof(float4) * 256) != cudaSuccess) {
+        cudaGetLastError();
+        delete fs;
+        set_error("fused path: constant table upload failed");
+        return -1;
+    }
+#else
+    std::memcpy(c_tw256, tw.data(), sizeof(float4) * 256);
+#endif
     if (cudaMalloc((void**)&fs->tw256, sizeof(float4) * 256) != cudaSuccess ||
         cudaMemcpy(fs->tw256, tw.data(), sizeof(float4) * 256, cudaMemcpyHostToDevice) != cudaSuccess ||
         cudaFuncSetAttribute(k_fused_p1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p1_smem()) != cudaSuccess ||

@@ -74,6 +74,15 @@ static inline T __shfl_xor_sync(unsigned, T v, int lanemask) {
     std::memcpy(&out, &raw, sizeof(T));
     return out;
 }
+static inline int __any_sync(unsigned, int pred) {
+    const int me = ps21emu::linear_tid();
+    *ps21emu::shfl_slot(me) = pred ? 1ull : 0ull;
+    ps21emu::syncwarp();
+    int any = 0;
+    for (int l = 0; l < 32; ++l) any |= (int)*ps21emu::shfl_slot((me & ~31) | l);
+    ps21emu::syncwarp();
+    return any;
+}
 enum { cudaFuncAttributeMaxDynamicSharedMemorySize = 8 };
 template <class F>
 static inline int cudaFuncSetAttribute(F, int, int) { return 0; }
