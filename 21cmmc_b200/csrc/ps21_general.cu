@@ -204,17 +204,34 @@ __global__ void k_general_xpass_bin(const float2* __restrict__ scratch, long lon
         }
         __syncthreads();
         const float2* R = column_fft(A, B, fx, ld, cols, tw);
-        for (int i = threadIdx.x; i < n0 * cols; i += blockDim.x) {
-            const int x = i / cols, t = i % cols;
-            const long long m = m0 + t;
-            const float2 v = R[x * ld + t];
-            if (x == 0 && m == 0) dc[box * nchunks + cid] = v;
-            const uint16_t b = lut[(long long)x * plane + m];
-            if (b != kDiscard) {
+        // Each thread walks a contiguous k_x segment of one column: the bin index changes rarely along
+        // k_x, so powers are summed in a register and the shared fp64 bin is touched once per run.
+        {
+            const int nseg = blockDim.x / cols;                  // segments per column
+            const int t = threadIdx.x % cols, seg = threadIdx.x / cols;
+            if (seg < nseg) {
+                const int xlen = (n0 + nseg - 1) / nseg;
+                const int x0 = seg * xlen, x1 = min(n0, x0 + xlen);
+                const long long m = m0 + t;
                 const int kz = (int)(m % nh);
                 const float w = (kz == 0 || 2 * kz == nz) ? 1.f : 2.f;
-                const float pw = w * (v.x * v.x + v.y * v.y);
-                atomicAdd(&bins[b], (double)pw);
+                unsigned cur = kDiscard;
+                float acc = 0.f;
+                int run = 0;
+                for (int x = x0; x < x1; ++x) {
+                    const float2 v = R[x * ld + t];
+                    if (x == 0 && m == 0) dc[box * nchunks + cid] = v;
+                    const unsigned b = lut[(long long)x * plane + m];
+                    if (b != cur || run == 32) {  // bounded fp32 run length: at most 32 terms before fp64
+                        if (cur != kDiscard) atomicAdd(&bins[cur], (double)(w * acc));
+                        cur = b;
+                        acc = 0.f;
+                        run = 0;
+                    }
+                    acc += v.x * v.x + v.y * v.y;
+                    ++run;
+                }
+                if (cur != kDiscard) atomicAdd(&bins[cur], (double)(w * acc));
             }
         }
     }
