@@ -13,10 +13,20 @@
 
 namespace ps21 {
 
+// exact n / d for 0 <= n < 65536 by multiply-shift (constants from the host: make_fastdiv in ps21_plan.cu)
+struct FastDiv {
+    unsigned mul, shift;
+};
+__device__ __forceinline__ int fast_div(int n, FastDiv f) {
+    return (int)(((unsigned long long)(unsigned)n * f.mul) >> f.shift);
+}
+
 struct FftFactors {
     int n;
     int nstages;
     int radix[14];
+    FastDiv div_ns[14];  // division by Ns = product of the radices before stage s
+    FastDiv div_nb[14];  // division by n / radix[s]
 };
 
 // Complex helpers.  On sm_100 the adds/subs and the twiddle multiplies use the packed fp32x2
@@ -226,23 +236,26 @@ __device__ __forceinline__ void small_dft<32>(float2 (&v)[32]) {
     }
 }
 
-// One Stockham stage of radix R over `ncols` columns.  Ns = product of the radices already applied.
+// One Stockham stage of radix R over 2^lc columns (lc = log2 of the tile width; ragged tiles still run all
+// columns of the tile -- columns are independent, the surplus ones are never stored).  Ns = product of the
+// radices already applied.  No integer division: the column split is a shift, j % Ns a multiply-shift.
 template <int R>
 __device__ __forceinline__ void stage_radix(const float2* __restrict__ in, float2* __restrict__ out, int n,
-                                            int Ns, int ld, int ncols, const float2* __restrict__ tw) {
+                                            int Ns, FastDiv dns, int ld, int lc, const float2* __restrict__ tw) {
     const int nb = n / R;
     const int tws = n / (Ns * R);
-    for (int task = threadIdx.x; task < nb * ncols; task += blockDim.x) {
-        const int c = task % ncols;
-        const int j = task / ncols;
-        const int k = j % Ns;
+    const int cmask = (1 << lc) - 1;
+    for (int task = threadIdx.x; task < (nb << lc); task += blockDim.x) {
+        const int c = task & cmask;
+        const int j = task >> lc;
+        const int k = j - fast_div(j, dns) * Ns;
         float2 v[R];
 #pragma unroll
         for (int m = 0; m < R; ++m) v[m] = in[(j + m * nb) * ld + c];
         if (Ns > 1) {
             const int step = k * tws;
 #pragma unroll
-            for (int m = 1; m < R; ++m) v[m] = cmul(v[m], __ldg(&tw[m * step]));
+            for (int m = 1; m < R; ++m) v[m] = cmul_w2(v[m], __ldg(&tw[m * step]));
         }
         small_dft<R>(v);
         const int j0 = (j - k) * R + k;
@@ -253,23 +266,24 @@ __device__ __forceinline__ void stage_radix(const float2* __restrict__ in, float
 
 // Any radix p (prime factors > 5, e.g. chunk lengths such as 334 = 2 * 167): one output per task.
 __device__ __forceinline__ void stage_generic(const float2* __restrict__ in, float2* __restrict__ out, int n,
-                                              int Ns, int p, int ld, int ncols,
+                                              int Ns, FastDiv dns, FastDiv dnb, int p, int ld, int lc,
                                               const float2* __restrict__ tw) {
     const int nb = n / p;
     const int tws = n / (Ns * p);
-    for (int task = threadIdx.x; task < n * ncols; task += blockDim.x) {
-        const int c = task % ncols;
-        const int q = task / ncols;
-        const int j = q % nb;
-        const int mo = q / nb;
-        const int k = j % Ns;
+    const int cmask = (1 << lc) - 1;
+    for (int task = threadIdx.x; task < (n << lc); task += blockDim.x) {
+        const int c = task & cmask;
+        const int q = task >> lc;
+        const int mo = fast_div(q, dnb);
+        const int j = q - mo * nb;
+        const int k = j - fast_div(j, dns) * Ns;
         const int step = k * tws;
         float2 acc = make_float2(0.f, 0.f);
         int rot = 0;  // (mi*mo) % p
         for (int mi = 0; mi < p; ++mi) {
             int idx = mi * step + rot * nb;
             if (idx >= n) idx -= n;
-            acc = cadd(acc, cmul(in[(j + mi * nb) * ld + c], __ldg(&tw[idx])));
+            acc = cadd(acc, cmul_w2(in[(j + mi * nb) * ld + c], __ldg(&tw[idx])));
             rot += mo;
             if (rot >= p) rot -= p;
         }
@@ -277,8 +291,8 @@ __device__ __forceinline__ void stage_generic(const float2* __restrict__ in, flo
     }
 }
 
-// Full column FFT.  Returns the buffer that holds the result (a or b).  Ends with __syncthreads().
-__device__ __forceinline__ float2* column_fft(float2* a, float2* b, const FftFactors& f, int ld, int ncols,
+// Full column FFT over 2^lc columns.  Returns the buffer that holds the result (a or b).  Ends with a barrier.
+__device__ __forceinline__ float2* column_fft(float2* a, float2* b, const FftFactors& f, int ld, int lc,
                                               const float2* __restrict__ tw) {
     float2* in = a;
     float2* out = b;
@@ -286,12 +300,13 @@ __device__ __forceinline__ float2* column_fft(float2* a, float2* b, const FftFac
     for (int s = 0; s < f.nstages; ++s) {
         const int r = f.radix[s];
         switch (r) {
-            case 2: stage_radix<2>(in, out, f.n, Ns, ld, ncols, tw); break;
-            case 3: stage_radix<3>(in, out, f.n, Ns, ld, ncols, tw); break;
-            case 4: stage_radix<4>(in, out, f.n, Ns, ld, ncols, tw); break;
-            case 5: stage_radix<5>(in, out, f.n, Ns, ld, ncols, tw); break;
-            case 8: stage_radix<8>(in, out, f.n, Ns, ld, ncols, tw); break;
-            default: stage_generic(in, out, f.n, Ns, r, ld, ncols, tw); break;
+            case 2: stage_radix<2>(in, out, f.n, Ns, f.div_ns[s], ld, lc, tw); break;
+            case 3: stage_radix<3>(in, out, f.n, Ns, f.div_ns[s], ld, lc, tw); break;
+            case 4: stage_radix<4>(in, out, f.n, Ns, f.div_ns[s], ld, lc, tw); break;
+            case 5: stage_radix<5>(in, out, f.n, Ns, f.div_ns[s], ld, lc, tw); break;
+            case 8: stage_radix<8>(in, out, f.n, Ns, f.div_ns[s], ld, lc, tw); break;
+            case 16: stage_radix<16>(in, out, f.n, Ns, f.div_ns[s], ld, lc, tw); break;
+            default: stage_generic(in, out, f.n, Ns, f.div_ns[s], f.div_nb[s], r, ld, lc, tw); break;
         }
         __syncthreads();
         float2* t = in;

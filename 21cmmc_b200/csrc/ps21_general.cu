@@ -99,10 +99,11 @@ int launch_slab_mean(ps21_plan* p, const float* d_boxes, long long batch_stride,
 __global__ void k_general_zpass(const float* __restrict__ boxes, long long batch_stride, int n2_total, int nrows,
                                 ItemMap im, const ChunkDev* __restrict__ chunks, int nchunks,
                                 const float* __restrict__ means, float2* __restrict__ scratch,
-                                long long spec_elems, FftFactors fz, const float2* __restrict__ tw, int cols) {
+                                long long spec_elems, FftFactors fz, const float2* __restrict__ tw, int lc) {
     PS21_DYN_SMEM(float2, smem);
     const int nz = fz.n;
     const int nh = nz / 2 + 1;
+    const int cols = 1 << lc;
     const int ld = cols | 1;
     float2* A = smem;
     float2* B = smem + (size_t)nz * ld;
@@ -114,33 +115,34 @@ __global__ void k_general_zpass(const float* __restrict__ boxes, long long batch
     const int row0 = blockIdx.x * 2 * cols;
     const float* src = boxes + box * batch_stride + ch.start;
     float* Af = reinterpret_cast<float*>(A);
-    for (int i = threadIdx.x; i < 2 * cols * nz; i += blockDim.x) {
-        const int rr = i / nz, z = i % nz;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+    for (int rr = warp; rr < 2 * cols; rr += nwarps) {  // one real row per warp iteration, lanes along z
         const int row = row0 + rr;
-        float v = 0.f;
-        if (row < nrows) v = src[(long long)row * n2_total + z] - mean;
-        Af[2 * (z * ld + (rr >> 1)) + (rr & 1)] = v;
+        const float* r = src + (long long)row * n2_total;
+        const int base = 2 * (rr >> 1) + (rr & 1);
+        for (int z = lane; z < nz; z += 32) Af[2 * z * ld + base] = (row < nrows) ? r[z] - mean : 0.f;
     }
     __syncthreads();
-    const float2* R = column_fft(A, B, fz, ld, cols, tw);
+    const float2* R = column_fft(A, B, fz, ld, lc, tw);
     float2* dst = scratch + (long long)blockIdx.y * spec_elems;
-    for (int i = threadIdx.x; i < 2 * cols * nh; i += blockDim.x) {
-        const int rr = i / nh, k = i % nh;
+    for (int rr = warp; rr < 2 * cols; rr += nwarps) {
         const int row = row0 + rr;
         if (row >= nrows) continue;
         const int col = rr >> 1;
-        const float2 Z = R[k * ld + col];
-        const int kc = (k == 0) ? 0 : nz - k;
-        const float2 Zc = R[kc * ld + col];
-        float2 o;
-        if ((rr & 1) == 0) {  // even row: (Z + conj(Z*))/2
-            o.x = 0.5f * (Z.x + Zc.x);
-            o.y = 0.5f * (Z.y - Zc.y);
-        } else {  // odd row: (Z - conj(Z*)) / (2i)
-            o.x = 0.5f * (Z.y + Zc.y);
-            o.y = -0.5f * (Z.x - Zc.x);
+        float2* o = dst + (long long)row * nh;
+        for (int k = lane; k < nh; k += 32) {
+            const float2 Z = R[k * ld + col];
+            const float2 Zc = R[((k == 0) ? 0 : nz - k) * ld + col];
+            float2 v;
+            if ((rr & 1) == 0) {  // even row: (Z + conj(Z*))/2
+                v.x = 0.5f * (Z.x + Zc.x);
+                v.y = 0.5f * (Z.y - Zc.y);
+            } else {  // odd row: (Z - conj(Z*)) / (2i)
+                v.x = 0.5f * (Z.y + Zc.y);
+                v.y = -0.5f * (Z.x - Zc.x);
+            }
+            o[k] = v;
         }
-        dst[(long long)row * nh + k] = o;
     }
 }
 
@@ -148,25 +150,26 @@ __global__ void k_general_zpass(const float* __restrict__ boxes, long long batch
 // g2: y pass, in place.  CTA = fixed x, `tile` consecutive k_z.
 // ---------------------------------------------------------------------------------------------
 __global__ void k_general_ypass(float2* __restrict__ scratch, long long spec_elems, int n1, int nh, FftFactors fy,
-                                const float2* __restrict__ tw, int tile) {
+                                const float2* __restrict__ tw, int lc) {
     PS21_DYN_SMEM(float2, smem);
-    const int ntile = (nh + tile - 1) / tile;
+    const int tile = 1 << lc;
+    const int ntile = (nh + tile - 1) >> lc;
     const int x = blockIdx.x / ntile;
-    const int k0 = (blockIdx.x % ntile) * tile;
+    const int k0 = (blockIdx.x - x * ntile) << lc;
     const int cols = min(tile, nh - k0);
     const int ld = tile | 1;
     float2* A = smem;
     float2* B = smem + (size_t)n1 * ld;
     float2* base = scratch + (long long)blockIdx.y * spec_elems + (long long)x * n1 * nh + k0;
-    for (int i = threadIdx.x; i < n1 * cols; i += blockDim.x) {
-        const int y = i / cols, t = i % cols;
-        A[y * ld + t] = base[(long long)y * nh + t];
+    for (int i = threadIdx.x; i < (n1 << lc); i += blockDim.x) {
+        const int y = i >> lc, t = i & (tile - 1);
+        A[y * ld + t] = (t < cols) ? base[(long long)y * nh + t] : make_float2(0.f, 0.f);
     }
     __syncthreads();
-    const float2* R = column_fft(A, B, fy, ld, cols, tw);
-    for (int i = threadIdx.x; i < n1 * cols; i += blockDim.x) {
-        const int y = i / cols, t = i % cols;
-        base[(long long)y * nh + t] = R[y * ld + t];
+    const float2* R = column_fft(A, B, fy, ld, lc, tw);
+    for (int i = threadIdx.x; i < (n1 << lc); i += blockDim.x) {
+        const int y = i >> lc, t = i & (tile - 1);
+        if (t < cols) base[(long long)y * nh + t] = R[y * ld + t];
     }
 }
 
@@ -176,7 +179,7 @@ __global__ void k_general_ypass(float2* __restrict__ scratch, long long spec_ele
 // own partial-sum slot (no global atomics -> the cross-CTA reduction order is fixed).
 // ---------------------------------------------------------------------------------------------
 __global__ void k_general_xpass_bin(const float2* __restrict__ scratch, long long spec_elems, int n0, int n1,
-                                    int nh, int nz, FftFactors fx, const float2* __restrict__ tw, int tile,
+                                    int nh, int nz, FftFactors fx, const float2* __restrict__ tw, int lc,
                                     ItemMap im, const ChunkDev* __restrict__ chunks,
                                     const uint16_t* const* __restrict__ luts, double* __restrict__ partials,
                                     long long out_per_box, int slots_max, float2* __restrict__ dc, int nchunks) {
@@ -186,6 +189,7 @@ __global__ void k_general_xpass_bin(const float2* __restrict__ scratch, long lon
     item_to_box_chunk(im, blockIdx.y, box, cid);
     const ChunkDev ch = chunks[cid];
     const uint16_t* __restrict__ lut = luts[cid];
+    const int tile = 1 << lc;
     const int ld = tile | 1;
     float2* A = smem;
     float2* B = smem + (size_t)n0 * ld;
@@ -198,18 +202,18 @@ __global__ void k_general_xpass_bin(const float2* __restrict__ scratch, long lon
         const long long m0 = tl * tile;
         const int cols = (int)min((long long)tile, plane - m0);
         __syncthreads();
-        for (int i = threadIdx.x; i < n0 * cols; i += blockDim.x) {
-            const int x = i / cols, t = i % cols;
-            A[x * ld + t] = base[(long long)x * plane + m0 + t];
+        for (int i = threadIdx.x; i < (n0 << lc); i += blockDim.x) {
+            const int x = i >> lc, t = i & (tile - 1);
+            A[x * ld + t] = (t < cols) ? base[(long long)x * plane + m0 + t] : make_float2(0.f, 0.f);
         }
         __syncthreads();
-        const float2* R = column_fft(A, B, fx, ld, cols, tw);
+        const float2* R = column_fft(A, B, fx, ld, lc, tw);
         // Each thread walks a contiguous k_x segment of one column: the bin index changes rarely along
         // k_x, so powers are summed in a register and the shared fp64 bin is touched once per run.
         {
-            const int nseg = blockDim.x / cols;                  // segments per column
-            const int t = threadIdx.x % cols, seg = threadIdx.x / cols;
-            if (seg < nseg) {
+            const int nseg = blockDim.x >> lc;                   // segments per column
+            const int t = threadIdx.x & (tile - 1), seg = threadIdx.x >> lc;
+            if (t < cols) {
                 const int xlen = (n0 + nseg - 1) / nseg;
                 const int x0 = seg * xlen, x1 = min(n0, x0 + xlen);
                 const long long m = m0 + t;
@@ -250,6 +254,11 @@ int general_init() {
     return PS21_OK;
 }
 
+static int ilog2(int v) {
+    int l = 0;
+    while ((1 << l) < v) ++l;
+    return l;
+}
 static size_t fft_smem_bytes(int n, int tile) { return 2 * (size_t)n * (tile | 1) * sizeof(float2); }
 
 int general_forward(ps21_plan* p, ShapePlan& sp, const float* d_boxes, long long batch_stride, long long item0,
@@ -263,7 +272,7 @@ int general_forward(ps21_plan* p, ShapePlan& sp, const float* d_boxes, long long
         dim3 grid((nrows + 2 * sp.g1_cols - 1) / (2 * sp.g1_cols), (unsigned)nitems);
         PS21_LAUNCH(k_general_zpass, grid, dim3(256), fft_smem_bytes(sp.nz, sp.g1_cols), st, d_boxes, batch_stride,
                     p->n2_total, nrows, im, p->d_chunks, p->nchunks, p->d_means, p->d_scratch, spec_elems, sp.fz,
-                    sp.tw_z, sp.g1_cols);
+                    sp.tw_z, ilog2(sp.g1_cols));
         PS21_CUDA(cudaGetLastError());
     }
     {
@@ -271,7 +280,7 @@ int general_forward(ps21_plan* p, ShapePlan& sp, const float* d_boxes, long long
         const int ntile = (sp.nh + sp.g2_tile - 1) / sp.g2_tile;
         dim3 grid(n0 * ntile, (unsigned)nitems);
         PS21_LAUNCH(k_general_ypass, grid, dim3(256), fft_smem_bytes(n1, sp.g2_tile), st, p->d_scratch, spec_elems,
-                    n1, sp.nh, sp.fy, sp.tw_y, sp.g2_tile);
+                    n1, sp.nh, sp.fy, sp.tw_y, ilog2(sp.g2_tile));
         PS21_CUDA(cudaGetLastError());
     }
     {
@@ -280,7 +289,7 @@ int general_forward(ps21_plan* p, ShapePlan& sp, const float* d_boxes, long long
         dim3 grid(sp.g3_slots, (unsigned)nitems);
         size_t smem = fft_smem_bytes(n0, sp.g3_tile) + (size_t)nb_out * sizeof(double);
         PS21_LAUNCH(k_general_xpass_bin, grid, dim3(256), smem, st, p->d_scratch, spec_elems, n0, n1, sp.nh, sp.nz,
-                    sp.fx, sp.tw_x, sp.g3_tile, im, p->d_chunks, (const uint16_t* const*)p->d_lut_table,
+                    sp.fx, sp.tw_x, ilog2(sp.g3_tile), im, p->d_chunks, (const uint16_t* const*)p->d_lut_table,
                     p->d_partials, p->out_per_box, p->slots_max, p->d_dc, p->nchunks);
         PS21_CUDA(cudaGetLastError());
     }

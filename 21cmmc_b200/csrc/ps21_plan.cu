@@ -36,6 +36,16 @@ static int invalid(const std::string& msg) {
     return PS21_ERR_INVALID;
 }
 
+static FastDiv make_fastdiv(int d) {
+    // q = (n * mul) >> shift is exact for 0 <= n < 2^16, 1 <= d < 2^16 (mul = ceil(2^(16+L) / d), L = ceil(log2 d))
+    int L = 0;
+    while ((1 << L) < d) ++L;
+    FastDiv f;
+    f.shift = 16 + L;
+    f.mul = (unsigned)(((1ull << f.shift) + d - 1) / d);
+    return f;
+}
+
 static FftFactors factorize(int n) {
     FftFactors f{};
     f.n = n;
@@ -46,6 +56,7 @@ static FftFactors factorize(int n) {
             m /= r;
         }
     };
+    take(16);
     take(8);
     take(4);
     take(2);
@@ -53,7 +64,13 @@ static FftFactors factorize(int n) {
     take(5);
     for (int pr = 7; m > 1 && ns < 14; pr += 2) take(pr);
     f.nstages = ns;
-    if (m != 1) f.nstages = -1;
+    if (m != 1 || n >= 65536) f.nstages = -1;
+    int Ns = 1;
+    for (int s = 0; s < ns; ++s) {
+        f.div_ns[s] = make_fastdiv(Ns);
+        f.div_nb[s] = make_fastdiv(n / f.radix[s]);
+        Ns *= f.radix[s];
+    }
     return f;
 }
 
