@@ -103,11 +103,10 @@ struct ps21_plan {
     float2* d_scratch = nullptr;
     long long scratch_elems = 0;
     long long spec_max = 0;
-    double* d_partials = nullptr;    // [batch][out_per_box][slots_max]
+    double* d_partials = nullptr;    // [batch][slots_max][out_per_box]
     float* d_means = nullptr;        // [batch][nchunks]
     float2* d_dc = nullptr;          // [batch][nchunks] DC Fourier coefficient of the mean-subtracted chunk
     long long batch_cap = 0;
-    double* d_power_tmp = nullptr;   // [batch][out_per_box] when the caller passes no power buffer
     ps21::DataTables data;
     long long launches_last = 0;
     // optional per-kernel timing with CUDA events on the launching stream (ps21_plan_profile)
@@ -118,7 +117,6 @@ struct ps21_plan {
     float* d_stage[2] = {nullptr, nullptr};
     long long stage_boxes = 0;
     void* stage_stream[2] = {nullptr, nullptr};
-    void* stage_event[2] = {nullptr, nullptr};
 };
 
 namespace ps21 {

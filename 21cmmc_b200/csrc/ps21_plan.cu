@@ -203,17 +203,14 @@ static int ensure_batch(ps21_plan* p, long long batch) {
     free_dev(p->d_partials);
     free_dev(p->d_means);
     free_dev(p->d_dc);
-    free_dev(p->d_power_tmp);
     p->d_partials = nullptr;
     p->d_means = nullptr;
     p->d_dc = nullptr;
-    p->d_power_tmp = nullptr;
     p->batch_cap = 0;
     PS21_CUDA(cudaMalloc((void**)&p->d_partials, sizeof(double) * batch * p->slots_max * p->out_per_box));
     PS21_CUDA(cudaMalloc((void**)&p->d_means, sizeof(float) * batch * p->nchunks));
     PS21_CUDA(cudaMalloc((void**)&p->d_dc, sizeof(float2) * batch * p->nchunks));
     PS21_CUDA(cudaMemset(p->d_dc, 0, sizeof(float2) * batch * p->nchunks));
-    PS21_CUDA(cudaMalloc((void**)&p->d_power_tmp, sizeof(double) * batch * p->out_per_box));
     p->batch_cap = batch;
     return PS21_OK;
 }
@@ -311,14 +308,12 @@ int ps21_plan_destroy(ps21_plan* p) {
     free_dev(p->d_partials);
     free_dev(p->d_means);
     free_dev(p->d_dc);
-    free_dev(p->d_power_tmp);
     free_dev(p->data.d_data);
     free_dev(p->data.d_noise2);
     free_dev(p->data.d_mask);
     for (int i = 0; i < 2; ++i) {
         free_dev(p->d_stage[i]);
         if (p->stage_stream[i]) cudaStreamDestroy((cudaStream_t)p->stage_stream[i]);
-        if (p->stage_event[i]) cudaEventDestroy((cudaEvent_t)p->stage_event[i]);
     }
     delete p;
     return PS21_OK;
@@ -342,15 +337,19 @@ int ps21_plan_create(const ps21_desc* d, ps21_plan** out) {
         if (irc) return irc;
     }
     ps21_plan* p = new ps21_plan();
+    struct Guard {  // destroys the half-built plan on every early return
+        ps21_plan*& plan;
+        ps21_plan** out;
+        ~Guard() {
+            if (*out == nullptr && plan) ps21_plan_destroy(plan);
+        }
+    } guard{p, out};
     p->n0 = d->n0; p->n1 = d->n1; p->n2_total = d->n2_total; p->nchunks = d->nchunks; p->nbins = d->nbins;
     p->mode = d->mode; p->device = d->device; p->path_req = d->path;
     p->ig_kperp = d->ignore_kperp_zero; p->ig_kpar = d->ignore_kpar_zero; p->ig_k0 = d->ignore_k_zero;
     p->workspace_cap = d->workspace_bytes > 0 ? d->workspace_bytes : (8LL << 30);
     int rc = PS21_OK;
-    auto fail = [&](int code) {
-        ps21_plan_destroy(p);
-        return code;
-    };
+    auto fail = [&](int code) { return code; };  // the guard releases the plan
     // chunks and shapes
     std::map<int, int> shape_of_nz;
     long long off = 0, k2off = 0;
@@ -615,11 +614,6 @@ static int run_host(ps21_plan* p, const float* h_boxes, long long batch, long lo
             cudaStream_t s;
             PS21_CUDA(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
             p->stage_stream[i] = (void*)s;
-        }
-        if (!p->stage_event[i]) {
-            cudaEvent_t e;
-            PS21_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-            p->stage_event[i] = (void*)e;
         }
     }
     cudaStream_t s_copy = (cudaStream_t)p->stage_stream[0], s_comp = (cudaStream_t)p->stage_stream[1];

@@ -292,8 +292,19 @@ def run_gpu(args):
     evals_per_launch = walkers * args.steps / dom_n
     alg = {"fft_pass1": b_p1, "fft_last_pass_bin": b_last, "fft_pass_mid": 2 * b_last}.get(dom, 0) * evals_per_launch
     achieved = alg / (dom_ms / dom_n * 1e-3) / 1e9 if dom_n else 0.0
+    # DRAM traffic of that kernel from the committed ncu --set full capture (profiles/ncu_traffic.json), scaled
+    # from the profiled launch to this run's spectra per launch
+    traffic = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
+            tr = json.load(f)["kernels"]
+        kname = {"fft_pass1": "k_fused_p1", "fft_last_pass_bin": "k_fused_p2"}.get(dom)
+        if plan.path == "fused" and kname in tr:
+            traffic = tr[kname]["dram_bytes_per_spectrum"] * NCHUNKS * evals_per_launch
+    except Exception:
+        traffic = None
     roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                 "alg_bytes_per_launch": alg, "avg_launch_ms": dom_ms / dom_n,
                 "kernel_ms_per_step": {k: v[0] / args.steps for k, v in kinds.items()},
                 "pipeline": {"alg_bytes_per_eval": b_all,
