@@ -41,6 +41,10 @@ constexpr int SLOTS = 86;              // CTAs per spectrum in pass 2 (12 tiles 
 constexpr int P1_THREADS = 256;
 constexpr int P2_THREADS = 256;
 constexpr int MAX_BINS = 40;
+constexpr int NHK = NZ / 2 + 1;        // 129 k_z values of the half spectrum
+// cylindrical mode: 64 CTAs take the main tiles with tl % 64 == slot (16 tiles each: always the same 8 k_z),
+// 8 CTAs take one Nyquist tile each
+constexpr int CYL_SLOTS = 72;
 static_assert(NTILES % SLOTS == 0, "tiles must divide evenly over the slots");
 static_assert((long long)NTILES * TILE == (long long)NX * NY * (NZ / 2 + 1), "tile order covers the half spectrum exactly");
 
@@ -53,6 +57,8 @@ static float4 c_tw256[256];
 #endif
 
 struct FusedShape {
+    double* cylpart = nullptr;  // cylindrical mode: compact partial sums [item][CYL_SLOTS][nbins][8]
+    long long cylpart_items = 0;
     float4* tw256 = nullptr;   // w = exp(-2 pi i q / 256) stored as (w.x, w.y, -w.y, w.x) for cmul_tw
 };
 
@@ -188,7 +194,7 @@ __device__ __forceinline__ void p2_mode_of(int tile, int task, int r, int& kx, i
 __global__ void k_fused_lut(uint8_t* __restrict__ lut, unsigned long long* __restrict__ counts,
                             const double* __restrict__ k0sq, const double* __restrict__ k1sq,
                             const double* __restrict__ k2sq, const double* __restrict__ edges, int nbins,
-                            int ig_kperp, int ig_kpar, int ig_k0) {
+                            int ig_kperp, int ig_kpar, int ig_k0, int cyl) {
     const long long total = (long long)NTILES * TILE;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
          i += (long long)gridDim.x * blockDim.x) {
@@ -200,11 +206,12 @@ __global__ void k_fused_lut(uint8_t* __restrict__ lut, unsigned long long* __res
         if (ig_kperp && perp0) w = 0;
         if (ig_kpar && kz == 0) w = 0;
         if (ig_k0 && perp0 && kz == 0) w = 0;
-        const int b = digitize_mode(k0sq[kx], k1sq[ky], k2sq[kz], edges, nbins);
+        // spherical: |k| bin.  cylindrical: k_perp bin (the k_par index is implied by the tile position)
+        const int b = digitize_mode(k0sq[kx], k1sq[ky], cyl ? 0.0 : k2sq[kz], edges, nbins);
         uint8_t v = 255;
         if (b >= 0 && w > 0) {
             v = (uint8_t)b;
-            atomicAdd(&counts[b], (unsigned long long)w);
+            atomicAdd(&counts[cyl ? b * NHK + kz : b], (unsigned long long)w);
         }
         lut[i] = v;
     }
@@ -398,6 +405,11 @@ k_fused_p1(const float* __restrict__ boxes, long long batch_stride, int n2_total
 // ------------------------------------------------------------------------------------------------
 // pass 2
 // ------------------------------------------------------------------------------------------------
+// CYL = false: spherical bins, partial sums [box][slot][bins] (slot = blockIdx.x of SLOTS).
+// CYL = true : (k_perp bin, k_z) bins; every thread has one k_z per tile (t = tid & 7), so the lane-private
+//              bins are k_perp bins and the per-tile flush keeps the 8 k_z of the tile apart; partial sums go
+//              to a compact [item][CYL_SLOTS][bins][8] record that k_fused_cyl_reduce expands.
+template <bool CYL>
 __global__ void __launch_bounds__(P2_THREADS, 2)
 k_fused_p2(const float2* __restrict__ scratch, ItemMap im, const ChunkDev* __restrict__ chunks,
            const uint16_t* const* __restrict__ luts, double* __restrict__ partials, long long out_per_box,
@@ -406,8 +418,8 @@ k_fused_p2(const float2* __restrict__ scratch, ItemMap im, const ChunkDev* __res
     uint8_t* lutb = reinterpret_cast<uint8_t*>(tile + TILE);           // [TILE] bin index of every output of the tile
     float4* tw = reinterpret_cast<float4*>(lutb + TILE);               // [256]
     uint64_t* bar = reinterpret_cast<uint64_t*>(tw + 256);
-    double* cbins = reinterpret_cast<double*>(bar + 2);                // [MAX_BINS]
-    float* lbins = reinterpret_cast<float*>(cbins + MAX_BINS);         // [nbins][P2_THREADS]
+    double* cbins = reinterpret_cast<double*>(bar + 2);                // [MAX_BINS] or, CYL, [MAX_BINS][8]
+    float* lbins = reinterpret_cast<float*>(cbins + MAX_BINS * (CYL ? 8 : 1));  // [nbins][P2_THREADS]
     const int tid = threadIdx.x;
     long long box;
     int cid;
@@ -417,13 +429,27 @@ k_fused_p2(const float2* __restrict__ scratch, ItemMap im, const ChunkDev* __res
     const float2* src = scratch + (long long)blockIdx.y * ((long long)NTILES * TILE);
     tw[tid] = tw_g[tid];
     for (int i = tid; i < nbins * P2_THREADS; i += P2_THREADS) lbins[i] = 0.f;
-    if (tid < MAX_BINS) cbins[tid] = 0.0;
+    for (int i = tid; i < MAX_BINS * (CYL ? 8 : 1); i += P2_THREADS) cbins[i] = 0.0;
     if (tid == 0) {
         mbar_init(bar, 1);
         mbar_fence_init();
     }
     __syncthreads();
-    int tl = blockIdx.x;
+    // tile sequence of this CTA: first, first + stride, ... (count tiles)
+    int tl, stride, count;
+    if (!CYL) {
+        tl = blockIdx.x;
+        stride = SLOTS;
+        count = NTILES / SLOTS;
+    } else if (blockIdx.x < 64) {
+        tl = blockIdx.x;
+        stride = 64;
+        count = NT_MAIN / 64;
+    } else {
+        tl = NT_MAIN + (blockIdx.x - 64);
+        stride = 0;
+        count = 1;
+    }
     const uint64_t pol_stream = l2_policy_evict_first(), pol_keep = l2_policy_evict_last();
     auto issue_tile = [&](int t_next) {
         mbar_expect_tx(bar, TILE * 8 + TILE);
@@ -432,7 +458,7 @@ k_fused_p2(const float2* __restrict__ scratch, ItemMap im, const ChunkDev* __res
     };
     if (tid == 0) issue_tile(tl);
     uint32_t phase = 0;
-    for (; tl < NTILES; tl += SLOTS) {
+    for (int it = 0; it < count; ++it, tl += stride) {
         mbar_wait(bar, phase);
         phase ^= 1;
         // ---- S1: 4-point FFT over y_lo (-> ky_b) x radix 8 over x = xa + 32 m (-> m'), twiddle w_256^(xa m');
@@ -502,9 +528,9 @@ k_fused_p2(const float2* __restrict__ scratch, ItemMap im, const ChunkDev* __res
         }
         __syncthreads();
         // tile buffer is free: prefetch the next tile while the bins are flushed
-        if (tid == 0 && tl + SLOTS < NTILES) {
+        if (tid == 0 && it + 1 < count) {
             fence_proxy_async();
-            issue_tile(tl + SLOTS);
+            issue_tile(tl + stride);
         }
         // ---- flush the lane-private fp32 bins into the CTA's fp64 bins, fixed order
         {
@@ -517,21 +543,54 @@ k_fused_p2(const float2* __restrict__ scratch, ItemMap im, const ChunkDev* __res
                     acc += (double)*q;
                     *q = 0.f;
                 }
+                if (!CYL) {
 #pragma unroll
-                for (int s = 16; s > 0; s >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, s);
-                if (lane == 0) cbins[b] += acc;
+                    for (int s = 16; s > 0; s >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, s);
+                    if (lane == 0) cbins[b] += acc;
+                } else {  // lanes with equal (lane & 7) share the k_z of the tile
+                    acc += __shfl_xor_sync(0xffffffffu, acc, 8);
+                    acc += __shfl_xor_sync(0xffffffffu, acc, 16);
+                    if (lane < 8) cbins[b * 8 + lane] += acc;
+                }
             }
         }
         // (the next iteration's barriers order the zeroed lane bins before they are used again)
     }
     __syncthreads();
-    double* out = partials + (box * slots_max + blockIdx.x) * out_per_box + ch.out_off;
-    for (int i = tid; i < nbins; i += P2_THREADS) out[i] = cbins[i];
+    if (!CYL) {
+        double* out = partials + (box * slots_max + blockIdx.x) * out_per_box + ch.out_off;
+        for (int i = tid; i < nbins; i += P2_THREADS) out[i] = cbins[i];
+    } else {
+        double* out = partials + ((long long)blockIdx.y * CYL_SLOTS + blockIdx.x) * nbins * 8;
+        for (int i = tid; i < nbins * 8; i += P2_THREADS) out[i] = cbins[i];
+    }
+}
+
+// cylindrical mode: expand the compact per-CTA records into the standard partial-sum layout (one slot)
+__global__ void k_fused_cyl_reduce(const double* __restrict__ cylpart, ItemMap im, const ChunkDev* __restrict__ chunks,
+                                   double* __restrict__ partials, long long out_per_box, int slots_max, int nbins) {
+    long long box;
+    int cid;
+    item_to_box_chunk(im, blockIdx.x, box, cid);
+    const ChunkDev ch = chunks[cid];
+    const double* rec = cylpart + (long long)blockIdx.x * CYL_SLOTS * nbins * 8;
+    double* out = partials + (box * slots_max) * out_per_box + ch.out_off;
+    for (int i = threadIdx.x; i < nbins * NHK; i += blockDim.x) {
+        const int b = i / NHK, kz = i - b * NHK;
+        double s = 0.0;
+        if (kz < NHC) {
+            for (int q = 0; q < 4; ++q) s += rec[(((kz >> 3) + 16 * q) * nbins + b) * 8 + (kz & 7)];
+        } else {
+            for (int sl = 64; sl < CYL_SLOTS; ++sl)
+                for (int t = 0; t < 8; ++t) s += rec[(sl * nbins + b) * 8 + t];
+        }
+        out[i] = s;
+    }
 }
 
 static size_t p1_smem() { return (size_t)R1 * ROWLD * 8 + 128 * 8 + 66 * 16 + 16; }
-static size_t p2_smem(int nbins) {
-    return (size_t)TILE * 8 + TILE + 256 * 16 + 16 + MAX_BINS * 8 + (size_t)nbins * P2_THREADS * 4;
+static size_t p2_smem(int nbins, bool cyl) {
+    return (size_t)TILE * 8 + TILE + 256 * 16 + 16 + MAX_BINS * 8 * (cyl ? 8 : 1) + (size_t)nbins * P2_THREADS * 4;
 }
 
 }  // namespace fz
@@ -542,8 +601,8 @@ int fused_try_setup(ps21_plan* p, ShapePlan& sp) {
         set_error("fused path supports 256 x 256 x 256 chunks");
         return -1;
     }
-    if (p->mode != PS21_MODE_SPHERICAL || p->nbins > MAX_BINS) {
-        set_error("fused path needs spherical bins and n_psbins <= 40");
+    if (p->nbins > MAX_BINS) {
+        set_error("fused path needs n_psbins <= 40");
         return -1;
     }
     if (p->n2_total % 4 != 0) {
@@ -575,8 +634,10 @@ int fused_try_setup(ps21_plan* p, ShapePlan& sp) {
     if (cudaMalloc((void**)&fs->tw256, sizeof(float4) * 256) != cudaSuccess ||
         cudaMemcpy(fs->tw256, tw.data(), sizeof(float4) * 256, cudaMemcpyHostToDevice) != cudaSuccess ||
         cudaFuncSetAttribute(k_fused_p1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p1_smem()) != cudaSuccess ||
-        cudaFuncSetAttribute(k_fused_p2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p2_smem(MAX_BINS)) !=
-            cudaSuccess) {
+        cudaFuncSetAttribute(k_fused_p2<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)p2_smem(MAX_BINS, false)) != cudaSuccess ||
+        cudaFuncSetAttribute(k_fused_p2<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)p2_smem(MAX_BINS, true)) != cudaSuccess) {
         cudaGetLastError();
         if (fs->tw256) cudaFree(fs->tw256);
         delete fs;
@@ -584,7 +645,7 @@ int fused_try_setup(ps21_plan* p, ShapePlan& sp) {
         return -1;
     }
     sp.fused = fs;
-    for (int c : sp.chunks) p->chunks[c].nslots = SLOTS;
+    for (int c : sp.chunks) p->chunks[c].nslots = (p->mode == PS21_MODE_CYLINDRICAL) ? 1 : SLOTS;
     return 0;
 }
 
@@ -592,6 +653,7 @@ void fused_destroy(ShapePlan& sp) {
     if (!sp.fused) return;
     auto* fs = static_cast<fz::FusedShape*>(sp.fused);
     if (fs->tw256) cudaFree(fs->tw256);
+    if (fs->cylpart) cudaFree(fs->cylpart);
     delete fs;
     sp.fused = nullptr;
 }
@@ -603,7 +665,7 @@ int fused_build_lut(ps21_plan* p, int chunk, const double* d_k0sq, const double*
     const ChunkDev& c = p->chunks[chunk];
     PS21_LAUNCH(fz::k_fused_lut, dim3(PS21_EMU_OR(8, 2048)), dim3(256), 0, st, reinterpret_cast<uint8_t*>(p->d_lut[chunk]),
                 (unsigned long long*)(p->d_counts + c.out_off), d_k0sq, d_k1sq, d_k2sq, d_edges, p->nbins,
-                p->ig_kperp, p->ig_kpar, p->ig_k0);
+                p->ig_kperp, p->ig_kpar, p->ig_k0, p->mode == PS21_MODE_CYLINDRICAL ? 1 : 0);
     PS21_CUDA(cudaGetLastError());
     return PS21_OK;
 }
@@ -625,10 +687,28 @@ int fused_forward(ps21_plan* p, ShapePlan& sp, const float* d_boxes, long long b
     }
     {
         ProfScope ps(p, KK_PASS_BIN, st);
-        PS21_LAUNCH(k_fused_p2, dim3(SLOTS, (unsigned)nitems), dim3(P2_THREADS), p2_smem(p->nbins), st, p->d_scratch,
-                    im, p->d_chunks, (const uint16_t* const*)p->d_lut_table, p->d_partials, p->out_per_box,
-                    p->slots_max, p->d_dc, p->nchunks, fs->tw256, p->nbins);
-        PS21_CUDA(cudaGetLastError());
+        if (p->mode == PS21_MODE_SPHERICAL) {
+            PS21_LAUNCH(k_fused_p2<false>, dim3(SLOTS, (unsigned)nitems), dim3(P2_THREADS), p2_smem(p->nbins, false), st,
+                        p->d_scratch, im, p->d_chunks, (const uint16_t* const*)p->d_lut_table, p->d_partials,
+                        p->out_per_box, p->slots_max, p->d_dc, p->nchunks, fs->tw256, p->nbins);
+            PS21_CUDA(cudaGetLastError());
+        } else {
+            if (fs->cylpart_items < nitems) {
+                if (fs->cylpart) cudaFree(fs->cylpart);
+                fs->cylpart = nullptr;
+                fs->cylpart_items = 0;
+                PS21_CUDA(cudaMalloc((void**)&fs->cylpart, sizeof(double) * nitems * CYL_SLOTS * p->nbins * 8));
+                fs->cylpart_items = nitems;
+            }
+            PS21_LAUNCH(k_fused_p2<true>, dim3(CYL_SLOTS, (unsigned)nitems), dim3(P2_THREADS), p2_smem(p->nbins, true),
+                        st, p->d_scratch, im, p->d_chunks, (const uint16_t* const*)p->d_lut_table, fs->cylpart,
+                        p->out_per_box, p->slots_max, p->d_dc, p->nchunks, fs->tw256, p->nbins);
+            PS21_CUDA(cudaGetLastError());
+            PS21_LAUNCH(k_fused_cyl_reduce, dim3((unsigned)nitems), dim3(256), 0, st, fs->cylpart, im, p->d_chunks,
+                        p->d_partials, p->out_per_box, p->slots_max, p->nbins);
+            PS21_CUDA(cudaGetLastError());
+            p->launches_last += 1;
+        }
     }
     p->launches_last += 2;
     return PS21_OK;

@@ -402,7 +402,7 @@ int ps21_plan_create(const ps21_desc* d, ps21_plan** out) {
         PS21_CUDA(cudaMalloc((void**)&sp.d_chunks, sizeof(int) * sp.chunks.size()));
         PS21_CUDA(cudaMemcpy(sp.d_chunks, sp.chunks.data(), sizeof(int) * sp.chunks.size(), cudaMemcpyHostToDevice));
         sp.path = PS21_PATH_GENERAL;
-        if (d->path != PS21_PATH_GENERAL && d->mode == PS21_MODE_SPHERICAL && fused_try_setup(p, sp) == 0)
+        if (d->path != PS21_PATH_GENERAL && fused_try_setup(p, sp) == 0)
             sp.path = PS21_PATH_FUSED;
         if (d->path == PS21_PATH_FUSED && sp.path != PS21_PATH_FUSED)
             return fail(invalid("fused path requested but this shape/alignment is not supported by it: " + g_err));

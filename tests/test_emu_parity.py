@@ -68,6 +68,15 @@ def test_fused_two_pass_kernels_256(mods):
         mods[0].set_defaults(kernel_path="auto")
 
 
+def test_fused_cylindrical_256(mods):
+    """Cylindrical (k_perp, k_par) binning inside the fused pass 2 (BASELINE config 5 chunk shape)."""
+    mods[0].set_defaults(kernel_path="fused")
+    try:
+        PC.check_cylindrical(mods[0], (256, 256, 256), (384.0, 384.0, 384.0), 12, seed=2)
+    finally:
+        mods[0].set_defaults(kernel_path="auto")
+
+
 def test_too_few_slices_raises_like_reference(mods):
     lk, core, chain = mods
     with pytest.raises(IndexError):

@@ -136,6 +136,32 @@ def test_cylindrical(mods):
     PC.check_cylindrical(mods[0], (20, 20, 9), (30.0, 30.0, 13.5), 4)
 
 
+def test_cylindrical_fused_config5_chunk(mods):
+    """256 x 256 x 256 chunk, cylindrical bins: fused kernels vs the oracle, and vs the general path on a
+    256 x 256 x 512 lightcone with two chunks (config 5 layout)."""
+    import torch
+
+    from py21cmmc_b200.plan import get_plan
+
+    mods[0].set_defaults(kernel_path="fused")
+    try:
+        PC.check_cylindrical(mods[0], (256, 256, 256), (384.0, 384.0, 384.0), 20, seed=4)
+    finally:
+        mods[0].set_defaults(kernel_path="auto")
+    shape, bounds, Ls = (256, 256, 512), [(0, 256), (256, 512)], [(384.0, 384.0, 384.0)] * 2
+    dev = torch.cuda.current_device()
+    pf = get_plan(shape, bounds, Ls, 20, False, True, False, False, "legacy_1.001", "cylindrical", dev, "fused")
+    pg = get_plan(shape, bounds, Ls, 20, False, True, False, False, "legacy_1.001", "cylindrical", dev, "general")
+    assert pf.path == "fused" and pg.path == "general" and pf.out_per_box == 2 * 20 * 129
+    assert np.array_equal(pf.counts, pg.counts)
+    g = torch.Generator(device="cuda").manual_seed(3)
+    boxes = torch.randn((2,) + shape, generator=g, device="cuda", dtype=torch.float32) * 10 + 20
+    a = pf.power_device(boxes).cpu().numpy()
+    b = pg.power_device(boxes).cpu().numpy()
+    assert rel_err(a, b) < 5e-6
+    assert np.array_equal(a, pf.power_device(boxes).cpu().numpy(), equal_nan=True)
+
+
 def test_device_tensor_api_and_determinism(mods, kpath):
     import torch
 
