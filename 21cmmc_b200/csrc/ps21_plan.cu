@@ -194,6 +194,38 @@ __global__ void k_chi2_rows(const double* __restrict__ delta, long long n, long 
     lnl[r] = total;
 }
 
+// one thread per model: nk window-function rows of length nkwf (tens of values each)
+__global__ void k_upper_limit(const double* __restrict__ model, long long nrec, int nk, int nkwf,
+                              const double* __restrict__ wf, const double* __restrict__ limit,
+                              const double* __restrict__ var, const double* __restrict__ model_err, double frac,
+                              double* __restrict__ lnl) {
+    const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= nrec) return;
+    const double* m = model + r * nkwf;
+    double total = 0.0;
+    for (int k = 0; k < nk; ++k) {
+        double after = 0.0, up = 0.0, lo = 0.0;
+        for (int j = 0; j < nkwf; ++j) {
+            const double w = wf[(long long)k * nkwf + j];
+            after += w * m[j];
+            if (model_err) {
+                up += w * (m[j] + model_err[j]);
+                lo += w * (m[j] - model_err[j]);
+            }
+        }
+        double e2 = var[k] + (frac * after) * (frac * after);
+        if (model_err) {
+            const double me = 0.5 * ((up - after) + (after - lo));
+            e2 += me * me;
+        }
+        double like = 0.5 + 0.5 * erf((limit[k] - after) / (sqrt(2.0) * sqrt(e2)));
+        if (like <= 0.0) like = 1e-50;
+        const double l = log(like);
+        if (l == l) total += l;  // nansum
+    }
+    lnl[r] += total;
+}
+
 static void free_dev(void* p) {
     if (p) cudaFree(p);
 }
@@ -742,6 +774,35 @@ int ps21_chi2_host(int32_t device, int64_t nrec, int64_t n, const double* delta,
     if (e == cudaSuccess) e = cudaMemcpy(lnl, dl, sizeof(double) * nrec, cudaMemcpyDeviceToHost);
     free_dev(dd); free_dev(da); free_dev(dn); free_dev(dm); free_dev(ds); free_dev(dl);
     if (e != cudaSuccess) return cuda_fail(e, "ps21_chi2_host");
+    return PS21_OK;
+}
+
+int ps21_upper_limit_host(int32_t device, int64_t nrec, int64_t nk, int64_t nkwf, const double* model,
+                          const double* wf, const double* limit, const double* var, const double* model_err,
+                          double frac, double* lnl) {
+    if (!model || !wf || !limit || !var || !lnl || nrec < 0 || nk < 0 || nkwf < 0) return invalid("null argument");
+    if (nrec == 0 || nk == 0) return PS21_OK;
+    PS21_CUDA(cudaSetDevice(device));
+    double *dm = nullptr, *dw = nullptr, *dl = nullptr, *dv = nullptr, *de = nullptr, *dout = nullptr;
+    cudaError_t e = cudaSuccess;
+    auto up = [&](double** dst, const double* src, size_t n) {
+        if (e == cudaSuccess) e = cudaMalloc((void**)dst, sizeof(double) * (n ? n : 1));
+        if (e == cudaSuccess && n) e = cudaMemcpy(*dst, src, sizeof(double) * n, cudaMemcpyHostToDevice);
+    };
+    up(&dm, model, (size_t)(nrec * nkwf));
+    up(&dw, wf, (size_t)(nk * nkwf));
+    up(&dl, limit, (size_t)nk);
+    up(&dv, var, (size_t)nk);
+    if (model_err) up(&de, model_err, (size_t)nkwf);
+    up(&dout, lnl, (size_t)nrec);
+    if (e == cudaSuccess) {
+        PS21_LAUNCH(k_upper_limit, dim3((unsigned)((nrec + 63) / 64)), dim3(64), 0, (cudaStream_t)0, dm, (long long)nrec,
+                    (int)nk, (int)nkwf, dw, dl, dv, de, frac, dout);
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaMemcpy(lnl, dout, sizeof(double) * nrec, cudaMemcpyDeviceToHost);
+    free_dev(dm); free_dev(dw); free_dev(dl); free_dev(dv); free_dev(de); free_dev(dout);
+    if (e != cudaSuccess) return cuda_fail(e, "ps21_upper_limit_host");
     return PS21_OK;
 }
 

@@ -469,6 +469,88 @@ class Likelihood1DPowerLightcone(Likelihood1DPowerCoeval):
             storage.update({k + "_%s" % i: v for k, v in m.items()})
 
 
+class Likelihood1DPowerLightconeUpper(Likelihood1DPowerLightcone):
+    """Upper-limit (HERA-style) likelihood on the GPU spectra of a lightcone.
+
+    The arithmetic is that of the reference's ``Likelihood1DPowerLightconeUpper.computeLikelihood``
+    (likelihood.py:2249-2335): window-function matrix times the model Delta^2, 20 % model error, one-sided
+    Gaussian (erf) likelihood per (band, field, k).  The reference feeds it from the emulator; here the model
+    comes from the lightcone chunks: chunk ``band_chunks[b]`` is the spectrum of band ``z_bands[b]`` and is
+    interpolated (linear in k, like ``data_spline``) onto that band's window-function k values.
+
+    ``datafile``: ``.npz`` in the reference's layout -- ``z_bands``, ``band{z}`` (nfields, nk, 3) = [k, limit,
+    variance] with NaN-padded k, ``wfband{z}`` (nfields, nk, nkwf), ``kwfband{z}`` (nkwf,).
+    """
+
+    def __init__(self, *args, band_chunks=None, model_error_fraction=0.2, **kwargs):
+        kwargs.setdefault("simulate", False)
+        super().__init__(*args, **kwargs)
+        self.band_chunks = band_chunks
+        self.model_error_fraction = model_error_fraction
+
+    def setup(self):
+        LikelihoodBase.setup(self)
+        self.data = self._read_data()
+        self.redshifts = np.asarray(self.data[0]["z_bands"])
+        self.k = [np.asarray(self.data[0]["kwfband" + str(int(np.round(z)))]) for z in self.redshifts]
+        self.k_len = max(len(i) for i in self.k)
+        if self.band_chunks is None:
+            self.band_chunks = list(range(len(self.redshifts)))
+        if len(self.band_chunks) != len(self.redshifts) or max(self.band_chunks) >= self.nchunks:
+            raise ValueError("band_chunks must name one lightcone chunk per band")
+
+    def _to_bands(self, chunk_models):
+        """Interpolate per-chunk {"k","delta"} onto the window-function k of every band: (nbands, k_len)."""
+        out = np.zeros((len(self.redshifts), self.k_len))
+        for b, c in enumerate(self.band_chunks):
+            m = chunk_models[c]
+            ok = np.isfinite(m["delta"])
+            spl = InterpolatedUnivariateSpline(m["k"][ok], m["delta"][ok], k=1)
+            out[b, : len(self.k[b])] = spl(self.k[b])
+        return out
+
+    def reduce_data(self, ctx):
+        chunk_models = super().reduce_data(ctx)
+        return [{"k": self.k, "delta": self._to_bands(chunk_models)[None], "chunks": chunk_models}]
+
+    def reduce_data_batch(self, ctxs):
+        models = super().likelihood_batch(ctxs, want_lnl=False)[1]
+        return [{"k": self.k, "delta": np.stack([self._to_bands(m) for m in models]), "chunks": models}]
+
+    def computeLikelihood(self, model):
+        """lnL of every model in ``model[0]["delta"]`` (N, nbands, k_len); the matvec + erf run on the device."""
+        import ctypes as C
+
+        lib = _capi.load()
+        delta = np.asarray(model[0]["delta"], dtype=np.float64)
+        N = delta.shape[0]
+        lnl = np.zeros(N)
+        dp = C.POINTER(C.c_double)
+        hd = self.data[0]
+        err_all = model[0].get("delta_err")
+        for band in self.redshifts:
+            key = str(round(float(band)))
+            zbin = int(np.argmin(abs(band - self.redshifts)))
+            nkwf = len(hd["kwfband" + key])
+            m = np.ascontiguousarray(delta[:, zbin, :nkwf])
+            err = None if err_all is None else np.ascontiguousarray(np.asarray(err_all)[zbin, :nkwf], dtype=np.float64)
+            for field in range(hd["band" + key].shape[0]):
+                ks = hd["band" + key][field, :, 0]
+                nk = int(np.sum(~np.isnan(ks)))
+                vals = np.ascontiguousarray(hd["band" + key][field, :nk, 1], dtype=np.float64)
+                var = np.ascontiguousarray(hd["band" + key][field, :nk, 2], dtype=np.float64)
+                wf = np.ascontiguousarray(hd["wfband" + key][field, :nk, :].reshape(nk, nkwf), dtype=np.float64)
+                _capi.check(lib.ps21_upper_limit_host(
+                    _device(self.device), N, nk, nkwf, m.ctypes.data_as(dp), wf.ctypes.data_as(dp),
+                    vals.ctypes.data_as(dp), var.ctypes.data_as(dp),
+                    err.ctypes.data_as(dp) if err is not None else None, float(self.model_error_fraction),
+                    lnl.ctypes.data_as(dp)))
+        return lnl if N > 1 else float(lnl[0])
+
+    def store(self, model, storage):
+        super().store(model[0]["chunks"] if isinstance(model[0]["chunks"][0], dict) else model[0]["chunks"][0], storage)
+
+
 def chi2_device(delta, data, noise, mask, seg, model_uncertainty, error_on_model, device=0):
     """-0.5 * sum_seg sum_k (delta-data)^2 / ((mu*delta|data)^2 + noise^2) for every row of ``delta``."""
     import ctypes as C

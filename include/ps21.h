@@ -139,6 +139,15 @@ int ps21_chi2_host(int32_t device, int64_t nrec, int64_t n, const double* delta,
                    const double* noise, const uint8_t* mask, int64_t nseg, const int64_t* seg_len,
                    double model_uncertainty, int32_t error_on_model, double* lnl);
 
+/* HERA-style consumer of the spectra: one (band, field) block of
+ * Likelihood1DPowerLightconeUpper.computeLikelihood, likelihood.py:2286-2328.  For every one of nrec models:
+ * after = wf[nk][nkwf] . model[nkwf];  err = sqrt(var + (frac*after)^2 + mean_err^2) where mean_err is the
+ * window-weighted model error (model_err may be NULL);  L = 0.5 + 0.5 erf((limit - after)/(sqrt2 err)), values
+ * <= 0 clamped to 1e-50;  lnl[r] += nansum(log L).  HOST arrays; lnl is accumulated into (caller zeroes it). */
+int ps21_upper_limit_host(int32_t device, int64_t nrec, int64_t nk, int64_t nkwf, const double* model,
+                          const double* wf, const double* limit, const double* var, const double* model_err,
+                          double frac, double* lnl);
+
 #ifdef __cplusplus
 }
 #endif

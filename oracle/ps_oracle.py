@@ -254,6 +254,44 @@ def compute_likelihood(model, data, noise=None, min_k=0.1, max_k=1.0, model_unce
     return lnl
 
 
+def upper_limit_likelihood(hera_data, redshifts, delta, delta_err=None):
+    """Likelihood1DPowerLightconeUpper.computeLikelihood, src/py21cmmc/likelihood.py:2249-2335.
+
+    ``hera_data``: dict with ``band{z}`` (nfields, nk, 3) = [k, limit, variance] (NaN-padded k),
+    ``wfband{z}`` (nfields, nk, nkwf), ``kwfband{z}`` (nkwf,).  ``delta``: (N, nbands, nkwf_max) model
+    Delta^2 at the window-function k of every band.  Returns lnL of the N models.
+    """
+    from scipy.special import erf
+
+    redshifts = np.asarray(redshifts)
+    N = delta.shape[0]
+    lnl = np.zeros(N)
+    for i in range(N):
+        for band in redshifts:
+            key = str(round(band))
+            for field in range(hera_data["band" + key].shape[0]):
+                ks = hera_data["band" + key][field, :, 0]
+                nk = len(ks[~np.isnan(ks)])
+                vals = hera_data["band" + key][field, :nk, 1]
+                var = hera_data["band" + key][field, :nk, 2]
+                nkwf = len(hera_data["kwfband" + key])
+                wf = hera_data["wfband" + key][field, :nk, :].reshape([nk, nkwf])
+                zbin = np.argmin(abs(band - redshifts))
+                m = delta[i, zbin, :nkwf]
+                after = np.dot(wf, m)
+                if delta_err is not None:
+                    up = np.dot(wf, m + delta_err[zbin, :nkwf])
+                    lo = np.dot(wf, m - delta_err[zbin, :nkwf])
+                    mean_err = np.mean([up - after, after - lo], axis=0)
+                    err = np.sqrt(var + (0.2 * after) ** 2 + mean_err**2)
+                else:
+                    err = np.sqrt(var + (0.2 * after) ** 2)
+                like = 0.5 + 0.5 * erf((vals - after) / (np.sqrt(2) * err))
+                like[like <= 0.0] = 1e-50
+                lnl[i] += np.nansum(np.log(like))
+    return lnl
+
+
 # --------------------------------------------------------------------------------------
 # Independent cross-checks used by the tests (not reference restatements)
 # --------------------------------------------------------------------------------------

@@ -132,3 +132,63 @@ def check_cylindrical(lk_mod, shape, L, nb, seed=0):
     assert np.array_equal(kperp, O.edges_to_centres(edges, False))
     assert np.allclose(kpar, kpo[0], rtol=1e-15)
     assert rel_err(P2, Po) < POWER_RTOL
+
+
+def synthetic_hera_file(path, kmodel, seed=0):
+    """A small file in the layout of src/py21cmmc/data/HERA_H1C_IDR3.npz (2 bands, 3 fields, NaN-padded k)."""
+    rng = np.random.default_rng(seed)
+    out = {"z_bands": np.array([10.4, 7.9])}
+    for z, nkwf in ((10, 12), (8, 9)):
+        kwf = np.linspace(kmodel.min() * 1.2, kmodel.max() * 0.6, nkwf)
+        nk = 7
+        band = np.full((3, nk, 3), np.nan)
+        wf = np.zeros((3, nk, nkwf))
+        for f in range(3):
+            used = nk - f  # ragged: trailing k entries are NaN
+            band[f, :used, 0] = np.linspace(kwf[1], kwf[-2], used)
+            band[f, :used, 1] = rng.uniform(50.0, 4000.0, used)       # upper limits, mK^2
+            band[f, :used, 2] = rng.uniform(10.0, 900.0, used) ** 2    # variances
+            w = rng.uniform(0.0, 1.0, (used, nkwf))
+            wf[f, :used] = w / w.sum(axis=1, keepdims=True)
+        out[f"band{z}"], out[f"wfband{z}"], out[f"kwfband{z}"] = band, wf, kwf
+    np.savez(path, **out)
+    return out
+
+
+def check_upper_limit_likelihood(lk_mod, core_mod, chain_mod, tmp_path, shape=(16, 16, 48), box_len=24.0):
+    nchunks, nb = 3, 8
+    up = core_mod.UserParams(BOX_LEN=box_len, HII_DIM=shape[0])
+    state = {"box": synth_box(shape, 1)}
+    c = core_mod.CoreLightConeModule(lambda params: state["box"], up)
+    # the k grid of the chunks decides a sensible window-function k range
+    probe = lk_mod.Likelihood1DPowerLightcone(nchunks=nchunks, n_psbins=nb, use_data=False)
+    ch0 = chain_mod.build_computation_chain(c, probe)
+    kmodel = probe.reduce_data(ch0.build_model_data())[0]["k"]
+    hera = synthetic_hera_file(str(tmp_path / "hera.npz"), kmodel)
+    lk = lk_mod.Likelihood1DPowerLightconeUpper(datafile=str(tmp_path / "hera.npz"), nchunks=nchunks, n_psbins=nb,
+                                                band_chunks=[2, 0])
+    chain = chain_mod.build_computation_chain(core_mod.CoreLightConeModule(lambda params: state["box"], up), lk)
+    model = lk.reduce_data(chain.build_model_data())
+    assert model[0]["delta"].shape == (1, 2, 12)
+    lnl = lk.computeLikelihood(model)
+    # oracle: chunk spectra from the oracle, same interpolation, reference arithmetic
+    from scipy.interpolate import InterpolatedUnivariateSpline
+
+    mo = O.reduce_data_lightcone(state["box"], box_len, box_len / shape[0], nchunks, nb)
+    delta_o = np.zeros((1, 2, 12))
+    for b, cidx in enumerate([2, 0]):
+        ok = np.isfinite(mo[cidx]["delta"])
+        kk = hera["kwfband" + ("10" if b == 0 else "8")]
+        delta_o[0, b, :len(kk)] = InterpolatedUnivariateSpline(mo[cidx]["k"][ok], mo[cidx]["delta"][ok], k=1)(kk)
+    lnl_o = O.upper_limit_likelihood(hera, hera["z_bands"], delta_o)[0]
+    assert np.isfinite(lnl_o) and lnl_o < 0
+    assert abs(lnl - lnl_o) <= 1e-6 * abs(lnl_o), (lnl, lnl_o)
+    # the device kernel alone, many models + an error term, against the reference arithmetic
+    rng = np.random.default_rng(5)
+    many = {"k": lk.k, "delta": delta_o * rng.uniform(0.2, 30.0, (9, 1, 1)), "delta_err": np.abs(delta_o[0]) * 0.1}
+    got = lk.computeLikelihood([many])
+    want = O.upper_limit_likelihood(hera, hera["z_bands"], many["delta"], many["delta_err"])
+    assert np.allclose(got, want, rtol=1e-10, atol=1e-12)
+    val, blobs = chain([])
+    assert abs(val - lnl_o) <= 1e-6 * abs(lnl_o) and "delta_0" in blobs
+    return lnl, lnl_o

@@ -77,6 +77,10 @@ def test_fused_cylindrical_256(mods):
         mods[0].set_defaults(kernel_path="auto")
 
 
+def test_upper_limit_likelihood(mods, tmp_path):
+    PC.check_upper_limit_likelihood(*mods, tmp_path)
+
+
 def test_too_few_slices_raises_like_reference(mods):
     lk, core, chain = mods
     with pytest.raises(IndexError):

@@ -162,6 +162,10 @@ def test_cylindrical_fused_config5_chunk(mods):
     assert np.array_equal(a, pf.power_device(boxes).cpu().numpy(), equal_nan=True)
 
 
+def test_upper_limit_likelihood(mods, tmp_path):
+    PC.check_upper_limit_likelihood(*mods, tmp_path, shape=(32, 32, 96), box_len=48.0)
+
+
 def test_device_tensor_api_and_determinism(mods, kpath):
     import torch
 
