@@ -29,12 +29,12 @@
 namespace ps21 {
 namespace fz {
 
-constexpr int NX = 256, NY = 256, NZ = 256;
+constexpr int NX = 256, NY = 256, NZ = 256;   // the headline shape; Geo<128> covers 128 x 128 x 256
 constexpr int NHC = NZ / 2;            // 128 complex per packed row
 constexpr int R1 = 64, R2 = 4;         // NY = R1 * R2: pass 1 transforms R1 rows, pass 2 the remaining R2
 constexpr int T = 8;                   // k_z columns per tile (64-byte runs)
 constexpr int ROWLD = 136;             // complex slots per row in pass-1 shared memory (1088 B: bank offset 64 B)
-constexpr int TILE = NX * R2 * T;      // 8192 complex = 64 KB
+constexpr int TILE = NX * R2 * T;      // 8192 complex = 64 KB (both geometries)
 constexpr int NT_MAIN = R1 * (NHC / T);  // 1024 tiles with k_z < 128
 constexpr int NTILES = NT_MAIN + R1 / T; // + 8 tiles holding the Nyquist plane (k_z = 128): 1032
 constexpr int SLOTS = 86;              // CTAs per spectrum in pass 2 (12 tiles each)
@@ -57,6 +57,7 @@ static float4 c_tw256[256];
 #endif
 
 struct FusedShape {
+    int S = 256;                // sky-plane size: 256 or 128
     double* cylpart = nullptr;  // cylindrical mode: compact partial sums [item][CYL_SLOTS][nbins][8]
     long long cylpart_items = 0;
     float4* tw256 = nullptr;   // w = exp(-2 pi i q / 256) stored as (w.x, w.y, -w.y, w.x) for cmul_tw
@@ -153,54 +154,98 @@ __device__ __forceinline__ void bulk_g2s_hint(void* dst, const void* src, uint32
 #endif
 
 // ------------------------------------------------------------------------------------------------
-// layout of the half-spectrum scratch ("tile order")
+// layout of the half-spectrum scratch ("tile order"), per sky-plane size S (S x S x 256 chunks)
 // ------------------------------------------------------------------------------------------------
-// 64-byte chunk (x, y_lo) inside a tile; the low bit of y_lo is flipped by bit0(x)^bit5(x) so that both
-// x stages of pass 2 (lanes over consecutive x, and over x in steps of 32) touch both halves of every
-// 128-byte bank line (conflict free).
-__device__ __forceinline__ int chunk_of(int x, int yl) { return 4 * x + (yl ^ ((x ^ (x >> 5)) & 1)); }
-__device__ __forceinline__ int tile_idx(int x, int yl, int t) { return chunk_of(x, yl) * T + t; }
-// where pass 1 stores the coefficient (x, y_lo, ky_a, kz)
-__device__ __forceinline__ long long scratch_addr(int x, int yl, int kya, int kz) {
-    int tile, t;
-    if (kz < NHC) {
-        tile = kya * (NHC / T) + (kz >> 3);
-        t = kz & 7;
-    } else {
-        tile = NT_MAIN + (kya >> 3);
-        t = kya & 7;
+template <int S>
+struct Geo;
+
+// S = 256: y = y_lo + 4 j, tile = (ky_a, 8 consecutive k_z), inner [x 256][y_lo 4][k_z 8]
+template <>
+struct Geo<256> {
+    static constexpr int NXS = 256, R2S = 4, TS = 8, NT_MAIN_S = 1024, NTILES_S = 1032, SLOTS_S = 86, TWMUL = 1;
+    // 64-byte chunk (x, y_lo) inside a tile; the low bit of y_lo is flipped by bit0(x)^bit5(x) so that both x
+    // stages of pass 2 (lanes over consecutive x, and over x in steps of 32) touch both halves of every
+    // 128-byte bank line (conflict free).
+    __device__ static __forceinline__ int tile_idx(int x, int yl, int t) {
+        return (4 * x + (yl ^ ((x ^ (x >> 5)) & 1))) * 8 + t;
     }
-    return (long long)tile * TILE + tile_idx(x, yl, t);
-}
-// which Fourier mode the pass-2 output (tile, task, r) is:  r = 0..31 -> kx = m' + 8 r.  The 32 lanes of a
-// warp hold (t, m' & 3): nearly the same |k| for every r, so their bin sequences change at the same r.
-__device__ __forceinline__ void p2_mode_of(int tile, int task, int r, int& kx, int& ky, int& kz) {
-    const int t = task & 7, m1 = ((task >> 3) & 3) | ((task >> 7) << 2), kyb = (task >> 5) & 3;
-    kx = m1 + 8 * r;
-    int kya;
-    if (tile < NT_MAIN) {
-        kya = tile >> 4;
-        kz = 8 * (tile & 15) + t;
-    } else {
-        kya = 8 * (tile - NT_MAIN) + t;
-        kz = NHC;
+    // where pass 1 stores the coefficient (x, y_lo, ky_a, kz)
+    __device__ static __forceinline__ long long scratch_addr(int x, int yl, int kya, int kz) {
+        int tile, t;
+        if (kz < NHC) {
+            tile = kya * 16 + (kz >> 3);
+            t = kz & 7;
+        } else {
+            tile = NT_MAIN_S + (kya >> 3);
+            t = kya & 7;
+        }
+        return (long long)tile * TILE + tile_idx(x, yl, t);
     }
-    ky = kya + R1 * kyb;
-}
+    // which Fourier mode the pass-2 output (tile, task, r) is: r = 0..31 -> kx = m' + 8 r.  The 32 lanes of a
+    // warp hold (t, m' & 3): nearly the same |k| for every r, so their bin sequences change at the same r.
+    __device__ static __forceinline__ void mode_of(int tile, int task, int r, int& kx, int& ky, int& kz) {
+        const int t = task & 7, m1 = ((task >> 3) & 3) | ((task >> 7) << 2), kyb = (task >> 5) & 3;
+        kx = m1 + 8 * r;
+        int kya;
+        if (tile < NT_MAIN_S) {
+            kya = tile >> 4;
+            kz = 8 * (tile & 15) + t;
+        } else {
+            kya = 8 * (tile - NT_MAIN_S) + t;
+            kz = NHC;
+        }
+        ky = kya + R1 * kyb;
+    }
+};
+
+// S = 128: y = y_lo + 2 j, tile = (ky_a, 32 consecutive k_z), inner [x 128][y_lo 2][k_z 32]; every access of
+// pass 2 has its lanes along the 32 k_z of a 256-byte chunk, so no swizzle is needed.
+template <>
+struct Geo<128> {
+    static constexpr int NXS = 128, R2S = 2, TS = 32, NT_MAIN_S = 256, NTILES_S = 258, SLOTS_S = 43, TWMUL = 2;
+    __device__ static __forceinline__ int tile_idx(int x, int yl, int t) { return (2 * x + yl) * 32 + t; }
+    __device__ static __forceinline__ long long scratch_addr(int x, int yl, int kya, int kz) {
+        int tile, t;
+        if (kz < NHC) {
+            tile = kya * 4 + (kz >> 5);
+            t = kz & 31;
+        } else {
+            tile = NT_MAIN_S + (kya >> 5);
+            t = kya & 31;
+        }
+        return (long long)tile * TILE + tile_idx(x, yl, t);
+    }
+    // task = (t, ky_b, m' group), r = 8 i + q: butterfly i of the thread (m' = 4 group + i), output q -> kx = m' + 16 q
+    __device__ static __forceinline__ void mode_of(int tile, int task, int r, int& kx, int& ky, int& kz) {
+        const int t = task & 31, g = task >> 5;
+        const int kyb = g & 1, m1 = 4 * (g >> 1) + (r >> 3);
+        kx = m1 + 16 * (r & 7);
+        int kya;
+        if (tile < NT_MAIN_S) {
+            kya = tile >> 2;
+            kz = 32 * (tile & 3) + t;
+        } else {
+            kya = 32 * (tile - NT_MAIN_S) + t;
+            kz = NHC;
+        }
+        ky = kya + R1 * kyb;
+    }
+};
 
 // ------------------------------------------------------------------------------------------------
 // LUT (one byte per mode, in pass-2 register order) + counts
 // ------------------------------------------------------------------------------------------------
+template <int S>
 __global__ void k_fused_lut(uint8_t* __restrict__ lut, unsigned long long* __restrict__ counts,
                             const double* __restrict__ k0sq, const double* __restrict__ k1sq,
                             const double* __restrict__ k2sq, const double* __restrict__ edges, int nbins,
                             int ig_kperp, int ig_kpar, int ig_k0, int cyl) {
-    const long long total = (long long)NTILES * TILE;
+    const long long total = (long long)Geo<S>::NTILES_S * TILE;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
          i += (long long)gridDim.x * blockDim.x) {
         const int tile = (int)(i / TILE), e = (int)(i % TILE);
         int kx, ky, kz;
-        p2_mode_of(tile, e >> 5, e & 31, kx, ky, kz);
+        Geo<S>::mode_of(tile, e >> 5, e & 31, kx, ky, kz);
         int w = (kz == 0 || kz == NHC) ? 1 : 2;
         const bool perp0 = (kx == 0 && ky == 0);
         if (ig_kperp && perp0) w = 0;
@@ -270,6 +315,7 @@ __device__ __forceinline__ void untangle(float2 ck, float2 cn, float4 wu, float2
 #endif
 }
 
+template <int S>
 __global__ void __launch_bounds__(P1_THREADS, 3)
 k_fused_p1(const float* __restrict__ boxes, long long batch_stride, int n2_total, ItemMap im,
            const ChunkDev* __restrict__ chunks, int nchunks, const float* __restrict__ means,
@@ -285,8 +331,9 @@ k_fused_p1(const float* __restrict__ boxes, long long batch_stride, int n2_total
     const ChunkDev ch = chunks[cid];
     const float mean = means[box * nchunks + cid];
     const int x = blockIdx.x;
-    const float* src = boxes + box * batch_stride + ch.start + (long long)x * NY * n2_total;
-    float2* dst = scratch + (long long)blockIdx.y * ((long long)NTILES * TILE);
+    constexpr int R2S = Geo<S>::R2S;  // units per x slab (y = y_lo + R2S j)
+    const float* src = boxes + box * batch_stride + ch.start + (long long)x * S * n2_total;
+    float2* dst = scratch + (long long)blockIdx.y * ((long long)Geo<S>::NTILES_S * TILE);
     if (tid < 128) {
         const float4 w = tw_g[(2 * (tid & 7) * (tid >> 3)) & 255];
         twz[tid] = make_float2(w.x, w.y);
@@ -310,7 +357,7 @@ k_fused_p1(const float* __restrict__ boxes, long long batch_stride, int n2_total
             if (tid == 0) mbar_expect_tx(bar + half, (R1 / 2) * NZ * 4);
             __syncwarp();
             const int j = half * (R1 / 2) + tid;
-            bulk_g2s_hint(buf + j * ROWLD, src + (long long)(yl + R2 * j) * n2_total, NZ * 4, bar + half, pol);
+            bulk_g2s_hint(buf + j * ROWLD, src + (long long)(yl + R2S * j) * n2_total, NZ * 4, bar + half, pol);
         }
     };
     // second y stage for the butterfly groups m1 in [mlo, mlo+4): rows 8*mlo .. 8*mlo+31
@@ -331,15 +378,16 @@ k_fused_p1(const float* __restrict__ boxes, long long batch_stride, int n2_total
 #pragma unroll
             for (int u = 0; u < 8; ++u) {
                 const int kya = m1 + 8 * u;
-                const float2 o = (yl == 0) ? v[u] : cmul_tw(v[u], c_tw256[(yl * kya) & 255]);  // warp-uniform index
-                dst[scratch_addr(x, yl, kya, kz)] = o;
+                // w_S^(y_lo ky_a), warp-uniform index
+                const float2 o = (yl == 0) ? v[u] : cmul_tw(v[u], c_tw256[(Geo<S>::TWMUL * yl * kya) & 255]);
+                dst[Geo<S>::scratch_addr(x, yl, kya, kz)] = o;
             }
         }
     };
     issue_half(0, 0);
     issue_half(0, 1);
     uint32_t phase = 0;
-    for (int yl = 0; yl < R2; ++yl) {
+    for (int yl = 0; yl < R2S; ++yl) {
         // ---- z: one 128-point FFT per row, 8 threads per row; rows 0..31 as soon as they have landed
         mbar_wait(bar, phase);
         for (int task = tid; task < (R1 / 2) * 8; task += P1_THREADS) zfft_row(buf + (task >> 3) * ROWLD, task & 7, mean, twz);
@@ -389,13 +437,13 @@ k_fused_p1(const float* __restrict__ boxes, long long batch_stride, int n2_total
         //      rows 0..31 are consumed first so that the next unit's first half can start loading early
         ystage2(yl, 0);
         __syncthreads();
-        if (yl + 1 < R2) {
+        if (yl + 1 < R2S) {
             if (tid == 0) fence_proxy_async();
             issue_half(yl + 1, 0);
         }
         ystage2(yl, 4);
         __syncthreads();
-        if (yl + 1 < R2) {
+        if (yl + 1 < R2S) {
             if (tid == 0) fence_proxy_async();
             issue_half(yl + 1, 1);
         }
@@ -469,7 +517,7 @@ k_fused_p2(const float2* __restrict__ scratch, ItemMap im, const ChunkDev* __res
 #pragma unroll
             for (int m = 0; m < 8; ++m)
 #pragma unroll
-                for (int yl = 0; yl < 4; ++yl) v[m][yl] = tile[tile_idx(xa + 32 * m, yl, t)];
+                for (int yl = 0; yl < 4; ++yl) v[m][yl] = tile[Geo<256>::tile_idx(xa + 32 * m, yl, t)];
 #pragma unroll
             for (int m = 0; m < 8; ++m) small_dft<4>(v[m]);
 #pragma unroll
@@ -486,7 +534,7 @@ k_fused_p2(const float2* __restrict__ scratch, ItemMap im, const ChunkDev* __res
                 const float4 f = tw[(xa * m) & 255];
 #pragma unroll
                 for (int yl = 0; yl < 4; ++yl)
-                    tile[tile_idx(xa + 32 * m, yl, t)] = (m == 0) ? v[m][yl] : cmul_tw(v[m][yl], f);
+                    tile[Geo<256>::tile_idx(xa + 32 * m, yl, t)] = (m == 0) ? v[m][yl] : cmul_tw(v[m][yl], f);
             }
         }
         __syncthreads();
@@ -498,7 +546,7 @@ k_fused_p2(const float2* __restrict__ scratch, ItemMap im, const ChunkDev* __res
             const int t = tid & 7, m1 = ((tid >> 3) & 3) | ((tid >> 7) << 2), kyb = (tid >> 5) & 3;
             float2 v[32];
 #pragma unroll
-            for (int xa = 0; xa < 32; ++xa) v[xa] = tile[tile_idx(32 * m1 + xa, kyb, t)];
+            for (int xa = 0; xa < 32; ++xa) v[xa] = tile[Geo<256>::tile_idx(32 * m1 + xa, kyb, t)];
             small_dft<32>(v);
             if (tl == 0 && tid == 0) dc[box * nchunks + cid] = v[0];
             const float mult = (tl >= NT_MAIN || ((tl & 15) == 0 && t == 0)) ? 1.f : 2.f;
@@ -566,6 +614,130 @@ k_fused_p2(const float2* __restrict__ scratch, ItemMap im, const ChunkDev* __res
     }
 }
 
+// pass 2 for the 128 x 128 sky plane (spherical bins): tile = [x 128][y_lo 2][k_z 32].  Lanes run along the 32
+// k_z of a chunk in every access.  S1: 2-point FFT over y_lo x radix 16 over x = xa + 8 m (32 points per
+// thread); S2: four radix-8 butterflies over xa per thread (kx = m' + 16 q), |delta_k|^2 and bins from registers.
+__global__ void __launch_bounds__(P2_THREADS, 2)
+k_fused_p2_s128(const float2* __restrict__ scratch, ItemMap im, const ChunkDev* __restrict__ chunks,
+                const uint16_t* const* __restrict__ luts, double* __restrict__ partials, long long out_per_box,
+                int slots_max, float2* __restrict__ dc, int nchunks, const float4* __restrict__ tw_g, int nbins) {
+    using G = Geo<128>;
+    PS21_DYN_SMEM(float2, tile);                                       // [TILE]
+    uint8_t* lutb = reinterpret_cast<uint8_t*>(tile + TILE);           // [TILE]
+    float4* tw = reinterpret_cast<float4*>(lutb + TILE);               // [256]
+    uint64_t* bar = reinterpret_cast<uint64_t*>(tw + 256);
+    double* cbins = reinterpret_cast<double*>(bar + 2);                // [MAX_BINS]
+    float* lbins = reinterpret_cast<float*>(cbins + MAX_BINS);         // [nbins][P2_THREADS]
+    const int tid = threadIdx.x;
+    long long box;
+    int cid;
+    item_to_box_chunk(im, blockIdx.y, box, cid);
+    const ChunkDev ch = chunks[cid];
+    const uint8_t* __restrict__ lut = reinterpret_cast<const uint8_t*>(luts[cid]);
+    const float2* src = scratch + (long long)blockIdx.y * ((long long)G::NTILES_S * TILE);
+    tw[tid] = tw_g[tid];
+    for (int i = tid; i < nbins * P2_THREADS; i += P2_THREADS) lbins[i] = 0.f;
+    if (tid < MAX_BINS) cbins[tid] = 0.0;
+    if (tid == 0) {
+        mbar_init(bar, 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
+    const uint64_t pol_stream = l2_policy_evict_first(), pol_keep = l2_policy_evict_last();
+    auto issue_tile = [&](int t_next) {
+        mbar_expect_tx(bar, TILE * 8 + TILE);
+        bulk_g2s_hint(tile, src + (long long)t_next * TILE, TILE * 8, bar, pol_stream);
+        bulk_g2s_hint(lutb, lut + (long long)t_next * TILE, TILE, bar, pol_keep);
+    };
+    int tl = blockIdx.x;
+    constexpr int stride = G::SLOTS_S, count = G::NTILES_S / G::SLOTS_S;
+    if (tid == 0) issue_tile(tl);
+    uint32_t phase = 0;
+    for (int it = 0; it < count; ++it, tl += stride) {
+        mbar_wait(bar, phase);
+        phase ^= 1;
+        {   // ---- S1
+            const int t = tid & 31, xa = tid >> 5;
+            float2 v[2][16];  // [yl][m]
+#pragma unroll
+            for (int m = 0; m < 16; ++m)
+#pragma unroll
+                for (int yl = 0; yl < 2; ++yl) v[yl][m] = tile[G::tile_idx(xa + 8 * m, yl, t)];
+#pragma unroll
+            for (int m = 0; m < 16; ++m) {
+                const float2 a = v[0][m], b = v[1][m];
+                v[0][m] = cadd(a, b);
+                v[1][m] = csub(a, b);
+            }
+            small_dft<16>(v[0]);
+            small_dft<16>(v[1]);
+#pragma unroll
+            for (int m = 0; m < 16; ++m) {
+                const float4 f = tw[(2 * xa * m) & 255];  // w_128^(xa m')
+#pragma unroll
+                for (int yl = 0; yl < 2; ++yl)
+                    tile[G::tile_idx(xa + 8 * m, yl, t)] = (m == 0 || xa == 0) ? v[yl][m] : cmul_tw(v[yl][m], f);
+            }
+        }
+        __syncthreads();
+        {   // ---- S2 + bins
+            const int t = tid & 31, g = tid >> 5, kyb = g & 1, mgrp = g >> 1;
+            const float mult = (tl >= G::NT_MAIN_S || ((tl & 3) == 0 && t == 0)) ? 1.f : 2.f;
+            const uint4* lp = reinterpret_cast<const uint4*>(lutb + tid * 32);
+            const uint4 l0 = lp[0], l1 = lp[1];
+            const uint32_t w8[8] = {l0.x, l0.y, l0.z, l0.w, l1.x, l1.y, l1.z, l1.w};
+            uint32_t cur = 255u;
+            float acc = 0.f;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int m1 = 4 * mgrp + i;
+                float2 v[8];
+#pragma unroll
+                for (int xa = 0; xa < 8; ++xa) v[xa] = tile[G::tile_idx(xa + 8 * m1, kyb, t)];
+                small_dft<8>(v);
+                if (i == 0 && tl == 0 && tid == 0) dc[box * nchunks + cid] = v[0];
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    const uint32_t b = (w8[2 * i + (q >> 2)] >> (8 * (q & 3))) & 255u;
+                    const float pw = v[q].x * v[q].x + v[q].y * v[q].y;
+                    if (__any_sync(0xffffffffu, b != cur)) {
+                        if (b != cur) {
+                            if (cur != 255u) lbins[cur * P2_THREADS + tid] += mult * acc;
+                            cur = b;
+                            acc = 0.f;
+                        }
+                    }
+                    acc += pw;
+                }
+            }
+            if (cur != 255u) lbins[cur * P2_THREADS + tid] += mult * acc;
+        }
+        __syncthreads();
+        if (tid == 0 && it + 1 < count) {
+            fence_proxy_async();
+            issue_tile(tl + stride);
+        }
+        {   // ---- flush the lane-private fp32 bins into the CTA's fp64 bins, fixed order
+            const int warp = tid >> 5, lane = tid & 31;
+            for (int b = warp; b < nbins; b += P2_THREADS / 32) {
+                double a = 0.0;
+#pragma unroll
+                for (int i = 0; i < P2_THREADS / 32; ++i) {
+                    float* q = lbins + b * P2_THREADS + lane + 32 * i;
+                    a += (double)*q;
+                    *q = 0.f;
+                }
+#pragma unroll
+                for (int sft = 16; sft > 0; sft >>= 1) a += __shfl_xor_sync(0xffffffffu, a, sft);
+                if (lane == 0) cbins[b] += a;
+            }
+        }
+    }
+    __syncthreads();
+    double* out = partials + (box * slots_max + blockIdx.x) * out_per_box + ch.out_off;
+    for (int i = tid; i < nbins; i += P2_THREADS) out[i] = cbins[i];
+}
+
 // cylindrical mode: expand the compact per-CTA records into the standard partial-sum layout (one slot)
 __global__ void k_fused_cyl_reduce(const double* __restrict__ cylpart, ItemMap im, const ChunkDev* __restrict__ chunks,
                                    double* __restrict__ partials, long long out_per_box, int slots_max, int nbins) {
@@ -597,8 +769,13 @@ static size_t p2_smem(int nbins, bool cyl) {
 
 int fused_try_setup(ps21_plan* p, ShapePlan& sp) {
     using namespace fz;
-    if (p->n0 != NX || p->n1 != NY || sp.nz != NZ) {
-        set_error("fused path supports 256 x 256 x 256 chunks");
+    const int S = p->n0;
+    if (p->n0 != p->n1 || (S != 256 && S != 128) || sp.nz != NZ) {
+        set_error("fused path supports 256 x 256 x 256 and 128 x 128 x 256 chunks");
+        return -1;
+    }
+    if (S == 128 && p->mode != PS21_MODE_SPHERICAL) {
+        set_error("fused cylindrical bins need the 256 x 256 sky plane");
         return -1;
     }
     if (p->nbins > MAX_BINS) {
@@ -615,6 +792,7 @@ int fused_try_setup(ps21_plan* p, ShapePlan& sp) {
             return -1;
         }
     auto* fs = new FusedShape();
+    fs->S = S;
     std::vector<float4> tw(256);
     for (int q = 0; q < 256; ++q) {
         const double a = -2.0 * 3.14159265358979323846 * q / 256.0;
@@ -633,7 +811,10 @@ int fused_try_setup(ps21_plan* p, ShapePlan& sp) {
 #endif
     if (cudaMalloc((void**)&fs->tw256, sizeof(float4) * 256) != cudaSuccess ||
         cudaMemcpy(fs->tw256, tw.data(), sizeof(float4) * 256, cudaMemcpyHostToDevice) != cudaSuccess ||
-        cudaFuncSetAttribute(k_fused_p1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p1_smem()) != cudaSuccess ||
+        cudaFuncSetAttribute(k_fused_p1<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p1_smem()) != cudaSuccess ||
+        cudaFuncSetAttribute(k_fused_p1<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p1_smem()) != cudaSuccess ||
+        cudaFuncSetAttribute(k_fused_p2_s128, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)p2_smem(MAX_BINS, false)) != cudaSuccess ||
         cudaFuncSetAttribute(k_fused_p2<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              (int)p2_smem(MAX_BINS, false)) != cudaSuccess ||
         cudaFuncSetAttribute(k_fused_p2<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -645,7 +826,8 @@ int fused_try_setup(ps21_plan* p, ShapePlan& sp) {
         return -1;
     }
     sp.fused = fs;
-    for (int c : sp.chunks) p->chunks[c].nslots = (p->mode == PS21_MODE_CYLINDRICAL) ? 1 : SLOTS;
+    for (int c : sp.chunks)
+        p->chunks[c].nslots = (p->mode == PS21_MODE_CYLINDRICAL) ? 1 : (S == 256 ? SLOTS : Geo<128>::SLOTS_S);
     return 0;
 }
 
@@ -658,14 +840,20 @@ void fused_destroy(ShapePlan& sp) {
     sp.fused = nullptr;
 }
 
-long long fused_scratch_elems(const ShapePlan&, int, int) { return (long long)fz::NTILES * fz::TILE; }
+long long fused_scratch_elems(const ShapePlan&, int n0, int n1) { return (long long)n0 * n1 * fz::NHK; }
 
 int fused_build_lut(ps21_plan* p, int chunk, const double* d_k0sq, const double* d_k1sq, const double* d_k2sq,
                     const double* d_edges, cudaStream_t st) {
     const ChunkDev& c = p->chunks[chunk];
-    PS21_LAUNCH(fz::k_fused_lut, dim3(PS21_EMU_OR(8, 2048)), dim3(256), 0, st, reinterpret_cast<uint8_t*>(p->d_lut[chunk]),
-                (unsigned long long*)(p->d_counts + c.out_off), d_k0sq, d_k1sq, d_k2sq, d_edges, p->nbins,
-                p->ig_kperp, p->ig_kpar, p->ig_k0, p->mode == PS21_MODE_CYLINDRICAL ? 1 : 0);
+    if (p->n0 == 256)
+        PS21_LAUNCH(fz::k_fused_lut<256>, dim3(PS21_EMU_OR(8, 2048)), dim3(256), 0, st,
+                    reinterpret_cast<uint8_t*>(p->d_lut[chunk]), (unsigned long long*)(p->d_counts + c.out_off), d_k0sq,
+                    d_k1sq, d_k2sq, d_edges, p->nbins, p->ig_kperp, p->ig_kpar, p->ig_k0,
+                    p->mode == PS21_MODE_CYLINDRICAL ? 1 : 0);
+    else
+        PS21_LAUNCH(fz::k_fused_lut<128>, dim3(PS21_EMU_OR(8, 1024)), dim3(256), 0, st,
+                    reinterpret_cast<uint8_t*>(p->d_lut[chunk]), (unsigned long long*)(p->d_counts + c.out_off), d_k0sq,
+                    d_k1sq, d_k2sq, d_edges, p->nbins, p->ig_kperp, p->ig_kpar, p->ig_k0, 0);
     PS21_CUDA(cudaGetLastError());
     return PS21_OK;
 }
@@ -681,13 +869,23 @@ int fused_forward(ps21_plan* p, ShapePlan& sp, const float* d_boxes, long long b
     ItemMap im{sp.d_chunks, (int)sp.chunks.size(), item0};
     {
         ProfScope ps(p, KK_PASS1, st);
-        PS21_LAUNCH(k_fused_p1, dim3(NX, (unsigned)nitems), dim3(P1_THREADS), p1_smem(), st, d_boxes, batch_stride,
-                    p->n2_total, im, p->d_chunks, p->nchunks, p->d_means, p->d_scratch, fs->tw256);
+        if (fs->S == 256)
+            PS21_LAUNCH(k_fused_p1<256>, dim3(256, (unsigned)nitems), dim3(P1_THREADS), p1_smem(), st, d_boxes,
+                        batch_stride, p->n2_total, im, p->d_chunks, p->nchunks, p->d_means, p->d_scratch, fs->tw256);
+        else
+            PS21_LAUNCH(k_fused_p1<128>, dim3(128, (unsigned)nitems), dim3(P1_THREADS), p1_smem(), st, d_boxes,
+                        batch_stride, p->n2_total, im, p->d_chunks, p->nchunks, p->d_means, p->d_scratch, fs->tw256);
         PS21_CUDA(cudaGetLastError());
     }
     {
         ProfScope ps(p, KK_PASS_BIN, st);
-        if (p->mode == PS21_MODE_SPHERICAL) {
+        if (fs->S == 128) {
+            PS21_LAUNCH(k_fused_p2_s128, dim3(Geo<128>::SLOTS_S, (unsigned)nitems), dim3(P2_THREADS),
+                        p2_smem(p->nbins, false), st, p->d_scratch, im, p->d_chunks,
+                        (const uint16_t* const*)p->d_lut_table, p->d_partials, p->out_per_box, p->slots_max, p->d_dc,
+                        p->nchunks, fs->tw256, p->nbins);
+            PS21_CUDA(cudaGetLastError());
+        } else if (p->mode == PS21_MODE_SPHERICAL) {
             PS21_LAUNCH(k_fused_p2<false>, dim3(SLOTS, (unsigned)nitems), dim3(P2_THREADS), p2_smem(p->nbins, false), st,
                         p->d_scratch, im, p->d_chunks, (const uint16_t* const*)p->d_lut_table, p->d_partials,
                         p->out_per_box, p->slots_max, p->d_dc, p->nchunks, fs->tw256, p->nbins);

@@ -68,6 +68,37 @@ def test_fused_path_vs_oracle_256(mods, nb, log, flags):
         mods[0].set_defaults(kernel_path="auto")
 
 
+@pytest.mark.parametrize("nb,log,flags", [(20, True, (True, False, False)), (16, False, (False, False, False))])
+def test_fused_path_vs_oracle_128(mods, nb, log, flags):
+    """128 x 128 x 256 chunk (config 1 chunk shape) through the fused kernels vs the fp64 oracle."""
+    mods[0].set_defaults(kernel_path="fused")
+    try:
+        PC.check_compute_power(mods[0], (128, 128, 256), (192.0, 192.0, 384.0), nb, log, flags, seed=12)
+    finally:
+        mods[0].set_defaults(kernel_path="auto")
+
+
+def test_config1_uses_fused_path_and_is_reproducible(mods):
+    import torch
+
+    from py21cmmc_b200.plan import get_plan
+
+    shape = (128, 128, 1024)
+    bounds = [(i * 256, (i + 1) * 256) for i in range(4)]
+    Ls = [(192.0, 192.0, 384.0)] * 4
+    dev = torch.cuda.current_device()
+    pf = get_plan(shape, bounds, Ls, 20, True, True, False, False, "legacy_1.001", "spherical", dev, "auto")
+    pg = get_plan(shape, bounds, Ls, 20, True, True, False, False, "legacy_1.001", "spherical", dev, "general")
+    assert pf.path == "fused"
+    assert np.array_equal(pf.counts, pg.counts)
+    g = torch.Generator(device="cuda").manual_seed(11)
+    boxes = torch.randn((3,) + shape, generator=g, device="cuda", dtype=torch.float32) * 10 + 20
+    a = pf.power_device(boxes).cpu().numpy()
+    assert rel_err(a, pg.power_device(boxes).cpu().numpy()) < 2e-6
+    assert np.array_equal(a, pf.power_device(boxes).cpu().numpy(), equal_nan=True)
+    assert np.array_equal(a[2], pf.power_device(boxes[2:3].contiguous()).cpu().numpy()[0], equal_nan=True)
+
+
 def test_fused_lightcone_batch_vs_general(mods):
     """Two 256 x 256 x 512 lightcones (2 chunks each): fused == general path to fp32-FFT accuracy, and the
     fused path is bitwise reproducible and batch invariant."""
