@@ -29,6 +29,25 @@ MIN_K, MAX_K, MODEL_UNC = 0.1, 1.0, 0.15
 MU, SIGMA = 20.0, 10.0
 METRIC = "ps_likelihood_evals_per_sec_256x256x1024_lightcone"
 UNIT = "evals/s"
+MODE = "spherical"
+WORKLOAD = "BASELINE config 3: batched emcee step"
+
+# The headline metric is quoted on config 3 (default).  --config 1 / 5 run the other lightcone configurations
+# of BASELINE.json for information (they are parity-test cases, not the bench line).
+CONFIGS = {
+    3: dict(shape=(256, 256, 1024), nchunks=4, mode="spherical", metric=METRIC, workload=WORKLOAD),
+    1: dict(shape=(128, 128, 1024), nchunks=4, mode="spherical",
+            metric="ps_likelihood_evals_per_sec_128x128x1024_lightcone", workload="BASELINE config 1"),
+    5: dict(shape=(256, 256, 2048), nchunks=8, mode="cylindrical",
+            metric="cylindrical_ps_evals_per_sec_256x256x2048_lightcone", workload="BASELINE config 5"),
+}
+
+
+def select_config(n):
+    global SHAPE, NCHUNKS, BOX_LEN, METRIC, MODE, WORKLOAD
+    c = CONFIGS[n]
+    SHAPE, NCHUNKS, MODE, METRIC, WORKLOAD = c["shape"], c["nchunks"], c["mode"], c["metric"], c["workload"]
+    BOX_LEN = SHAPE[0] * CELL
 
 
 def peaks():
@@ -119,8 +138,13 @@ def _cpu_chunk_task(seed):
     nz = SHAPE[2] // NCHUNKS
     box = (rng.standard_normal((SHAPE[0], SHAPE[1], nz), dtype=np.float32) * SIGMA + MU)
     t0 = time.perf_counter()
-    p, k = O.compute_power_lightcone(box, (BOX_LEN, BOX_LEN, nz * CELL), NBINS, log_bins=True,
-                                     fft_dtype=np.float32)
+    L = (BOX_LEN, BOX_LEN, nz * CELL)
+    if MODE == "cylindrical":
+        w2 = np.ones(box.shape[:2])
+        w2[box.shape[0] // 2, box.shape[0] // 2] = 0
+        p = O.get_power(box, L, bins=NBINS, res_ndim=2, k_weights=w2, fft_dtype=np.float32)[0]
+        return time.perf_counter() - t0, float(np.nansum(p))
+    p, k = O.compute_power_lightcone(box, L, NBINS, log_bins=True, fft_dtype=np.float32)
     delta = p * k**3 / (2 * np.pi**2)
     return time.perf_counter() - t0, float(np.nansum(delta))
 
@@ -153,14 +177,15 @@ def run_reference(args):
         total = time.perf_counter() - t0
     evals = args.steps * workers / NCHUNKS
     value = evals / total
-    sample = (f"{workers} chunks of 256x256x256 (= {workers / NCHUNKS:g} evals) per step, one process per core, "
-              "oracle port of powerbox.get_power in float32-FFT mode (NumPy pocketfft)")
+    nzc = SHAPE[2] // NCHUNKS
+    sample = (f"{workers} chunks of {SHAPE[0]}x{SHAPE[1]}x{nzc} (= {workers / NCHUNKS:g} evals) per step, one process "
+              "per core, oracle port of powerbox.get_power in float32-FFT mode (NumPy pocketfft)")
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / max(args.steps, 1),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32 FFT / f64 bins",
         "data": "synthetic",
-        "config": {"workload": "256x256x1024 lightcone, 4 chunks, 20 log-k bins (BASELINE config 3)",
+        "config": {"workload": f"{SHAPE[0]}x{SHAPE[1]}x{SHAPE[2]} lightcone, {NCHUNKS} chunks, 20 bins ({WORKLOAD})",
                    "sample": sample},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": workers, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -190,7 +215,8 @@ def run_gpu(args):
     walkers = args.walkers
     bounds = [(i * SHAPE[2] // NCHUNKS, (i + 1) * SHAPE[2] // NCHUNKS) for i in range(NCHUNKS)]
     lengths = [(BOX_LEN, BOX_LEN, (b - a) * CELL) for a, b in bounds]
-    plan = PowerPlan(SHAPE, bounds, lengths, NBINS, True, True, False, False, "legacy_1.001", "spherical", local,
+    cyl = MODE == "cylindrical"
+    plan = PowerPlan(SHAPE, bounds, lengths, NBINS, not cyl, True, False, False, "legacy_1.001", MODE, local,
                      args.path, workspace_bytes=args.workspace_mb << 20)
 
     # synthetic Gaussian brightness-temperature boxes, generated on the device
@@ -199,23 +225,31 @@ def run_gpu(args):
         g = torch.Generator(device=dev).manual_seed(1234 + 1000 * rank + w)
         boxes[w].normal_(MU, SIGMA, generator=g)
     # "data" = spectrum of walker 0 of rank 0 (the simulate=True convention), broadcast to every rank
-    delta0 = torch.empty((1, plan.out_per_box), dtype=torch.float64, device=dev)
-    power0 = plan.power_device(boxes[:1])
-    kc = torch.from_numpy(np.concatenate(list(plan.kcentres))).to(dev)
-    delta0[0] = power0[0] * kc**3 / (2 * np.pi**2)
-    if world > 1:
-        dist.broadcast(delta0, 0)
-    data = delta0.cpu().numpy().reshape(1, NCHUNKS, NBINS)
-    kmask = ((plan.kcentres >= MIN_K) & (plan.kcentres <= MAX_K)).astype(np.uint8)[None]
-    plan.set_data(np.nan_to_num(data), None, kmask & np.isfinite(data), MODEL_UNC, True)
-
     lnl = torch.empty((walkers,), dtype=torch.float64, device=dev)
     gathered = torch.empty((world * walkers,), dtype=torch.float64, device=dev) if world > 1 else None
-
-    def step():
-        plan.lnl_device(boxes, lnl=lnl)
+    if not cyl:
+        delta0 = torch.empty((1, plan.out_per_box), dtype=torch.float64, device=dev)
+        power0 = plan.power_device(boxes[:1])
+        kc = torch.from_numpy(np.concatenate(list(plan.kcentres))).to(dev)
+        delta0[0] = power0[0] * kc**3 / (2 * np.pi**2)
         if world > 1:
-            dist.all_gather_into_tensor(gathered, lnl)
+            dist.broadcast(delta0, 0)
+        data = delta0.cpu().numpy().reshape(1, NCHUNKS, NBINS)
+        kmask = ((plan.kcentres >= MIN_K) & (plan.kcentres <= MAX_K)).astype(np.uint8)[None]
+        plan.set_data(np.nan_to_num(data), None, kmask & np.isfinite(data), MODEL_UNC, True)
+
+        def step():
+            plan.lnl_device(boxes, lnl=lnl)
+            if world > 1:
+                dist.all_gather_into_tensor(gathered, lnl)
+    else:  # config 5: the 2-D spectra are the product (no chi^2 is defined on them in the reference)
+        p2d = torch.empty((walkers, plan.out_per_box), dtype=torch.float64, device=dev)
+
+        def step():
+            plan.power_device(boxes, out=p2d)
+            if world > 1:
+                lnl.copy_(p2d[:, 0])
+                dist.all_gather_into_tensor(gathered, lnl)
 
     sampler = ClockSampler(local)
     if rank == 0:
@@ -250,11 +284,11 @@ def run_gpu(args):
 
     # parity spot check inside the bench: the timed path's lnL of walker 0 is 0 against its own data
     lnl_host = lnl.cpu().numpy()
-    self_check = float(lnl_host[0]) if rank == 0 else None
+    self_check = float(lnl_host[0]) if (rank == 0 and not cyl) else None
 
     # ------------------------------------------------------------------ end to end (host buffers)
     e2e = None
-    if not args.no_e2e:
+    if not args.no_e2e and not cyl:
         ew = min(walkers, args.e2e_walkers)
         hbuf = torch.empty((ew,) + SHAPE, dtype=torch.float32).pin_memory()
         hbuf.copy_(boxes[:ew])
@@ -299,7 +333,7 @@ def run_gpu(args):
         with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
             tr = json.load(f)["kernels"]
         kname = {"fft_pass1": "k_fused_p1", "fft_last_pass_bin": "k_fused_p2"}.get(dom)
-        if plan.path == "fused" and kname in tr:
+        if plan.path == "fused" and kname in tr and SHAPE[:2] == (256, 256):
             traffic = tr[kname]["dram_bytes_per_spectrum"] * NCHUNKS * evals_per_launch
     except Exception:
         traffic = None
@@ -309,7 +343,7 @@ def run_gpu(args):
                 "kernel_ms_per_step": {k: v[0] / args.steps for k, v in kinds.items()},
                 "pipeline": {"alg_bytes_per_eval": b_all,
                              "achieved": value / world * b_all / 1e9, "frac": value / world * b_all / 1e9 / peak,
-                             "note": "whole likelihood step, per GPU: evals/s x (4N + 16 N_h) x 4 chunks"}}
+                             "note": f"whole step, per GPU: evals/s x (4N + 16 N_h) x {NCHUNKS} chunks"}}
 
     # ------------------------------------------------------------------ CPU baseline (bounded sample)
     cpu = None
@@ -320,16 +354,18 @@ def run_gpu(args):
         with ProcessPoolExecutor(max_workers=workers) as pool:
             v, dt = cpu_step(pool, workers, 0)
         cpu = {"value": v, "unit": UNIT, "cores": workers, "kind": "port",
-               "sample": f"{workers} chunks of 256^3 (= {workers / NCHUNKS:g} evals) in {dt:.1f} s, one process per "
-                         "core, oracle port of powerbox.get_power (float32 FFT)"}
+               "sample": f"{workers} chunks of {SHAPE[0]}x{SHAPE[1]}x{SHAPE[2] // NCHUNKS} (= {workers / NCHUNKS:g} "
+                         f"evals) in {dt:.1f} s, one process per core, oracle port of powerbox.get_power "
+                         "(float32 FFT)"}
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32 FFT / f64 bin accumulation", "data": "synthetic",
-        "config": {"workload": f"{walkers} walkers/GPU x 256x256x1024 float32 lightcone, 4 chunks, 20 log-k bins "
-                               "(BASELINE config 3: batched emcee step)",
-                   "l2": "inputs (16 GiB/GPU at 64 walkers) exceed L2; no flush needed",
+        "config": {"workload": f"{walkers} walkers/GPU x {SHAPE[0]}x{SHAPE[1]}x{SHAPE[2]} float32 lightcone, "
+                               f"{NCHUNKS} chunks, 20 {'k_perp x k_par' if cyl else 'log-k'} bins ({WORKLOAD})",
+                   "l2": f"inputs ({walkers * int(np.prod(SHAPE)) * 4 / 2**30:.1f} GiB/GPU) exceed the 126 MB L2; "
+                         "no flush needed",
                    "kernel_path": plan.path, "walkers_per_gpu": walkers, "parallelism": f"walker-sharded x{world}",
                    "collective": "all_gather of per-walker lnL (fp64) per step" if world > 1 else "none"},
         "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "clocks": clocks,
@@ -350,11 +386,14 @@ def main():
     ap.add_argument("--walkers", type=int, default=64, help="lightcones per GPU per step")
     ap.add_argument("--path", default="auto", choices=["auto", "general", "fused"])
     ap.add_argument("--workspace-mb", type=int, default=0)
+    ap.add_argument("--config", type=int, default=3, choices=[1, 3, 5],
+                    help="BASELINE.json lightcone configuration (3 = the headline metric)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--e2e-walkers", type=int, default=16)
     ap.add_argument("--e2e-steps", type=int, default=3)
     args = ap.parse_args()
+    select_config(args.config)
     if args.warmup < 3 and args.impl == "b200":
         args.warmup = 3  # timing rule: at least 3 warm-up steps
     if args.impl == "reference":
