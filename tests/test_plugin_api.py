@@ -1,0 +1,165 @@
+"""Plugin-API behaviour mirrored from the reference (src/py21cmmc/likelihood.py:136-266, 342-431, 584-607,
+697-732; core.py:92-122): data/noise files, simulate=True, format and length checks, error_on_model, noise
+splines, equality, pickling.  Runs on the emulated kernels (CPU)."""
+import os
+import pickle
+
+import numpy as np
+import pytest
+
+from oracle import ps_oracle as O
+from tests.helpers import LNL_RTOL, synth_box
+
+SHAPE, BOX_LEN, NCHUNKS, NB = (12, 12, 36), 18.0, 3, 6
+
+
+@pytest.fixture(scope="module")
+def mods():
+    from tests.emu.build_emu import build
+
+    lib = build()
+    import py21cmmc_b200  # noqa: F401
+    from py21cmmc_b200 import _capi, chain, core, likelihood, plan
+
+    _capi._testing_set_library(lib)
+    yield likelihood, core, chain
+    plan.clear_plans()
+    _capi._testing_set_library(None)
+
+
+class StateSim:
+    """Picklable stand-in for the simulator: returns whatever box the shared state dict holds."""
+
+    def __init__(self, state):
+        self.state = state
+
+    def __call__(self, params):
+        return self.state["box"]
+
+
+def make(mods, state, **kw):
+    lk_mod, core_mod, chain_mod = mods
+    up = core_mod.UserParams(BOX_LEN=BOX_LEN, HII_DIM=SHAPE[0])
+    c = core_mod.CoreLightConeModule(StateSim(state), up)
+    kw.setdefault("nchunks", NCHUNKS)
+    kw.setdefault("n_psbins", NB)
+    kw.setdefault("min_k", 0.3)
+    kw.setdefault("max_k", 4.0)
+    lk = lk_mod.Likelihood1DPowerLightcone(**kw)
+    return chain_mod.build_computation_chain(c, lk, setup=False), lk
+
+
+def test_simulate_writes_datafiles_and_rereads_them(mods, tmp_path):
+    files = [str(tmp_path / f"data_{i}.npz") for i in range(NCHUNKS)]
+    state = {"box": synth_box(SHAPE, 0)}
+    chain, lk = make(mods, state, datafile=files, simulate=True)
+    chain.setup()
+    assert all(os.path.exists(f) for f in files)
+    d0 = dict(np.load(files[0]))
+    assert set(d0) == {"k", "delta"} and np.array_equal(d0["delta"], lk.data[0]["delta"], equal_nan=True)
+    # a second run moves the old files to .bk (likelihood.py:236-247)
+    chain2, lk2 = make(mods, state, datafile=files, simulate=True)
+    chain2.setup()
+    assert os.path.exists(files[0] + ".bk")
+    # reading the files back instead of simulating gives the same likelihood
+    chain3, lk3 = make(mods, state, datafile=files, simulate=False)
+    chain3.setup()
+    state["box"] = synth_box(SHAPE, 3)
+    a = lk.computeLikelihood(lk.reduce_data(chain.build_model_data()))
+    b = lk3.computeLikelihood(lk3.reduce_data(chain3.build_model_data()))
+    assert a == b and a < 0
+
+
+def test_setup_errors_like_reference(mods, tmp_path):
+    state = {"box": synth_box(SHAPE, 0)}
+    chain, _ = make(mods, state)  # neither datafile nor simulate: datafile="" -> [""] is looked up, as in the reference
+    with pytest.raises(FileNotFoundError):
+        chain.setup()
+    co = mods[0].Likelihood1DPowerCoeval()  # coeval default datafile=None -> the explicit ValueError
+    chc = mods[2].build_computation_chain(
+        mods[1].CoreCoevalModule([7.0], lambda p: [synth_box((8, 8, 8), 0)], mods[1].UserParams(12.0, 8)), co,
+        setup=False)
+    with pytest.raises(ValueError):
+        chc.setup()
+    chain, _ = make(mods, state, datafile=[str(tmp_path / "missing.npz")] * NCHUNKS)
+    with pytest.raises(FileNotFoundError):
+        chain.setup()
+    one = str(tmp_path / "one.npz")
+    np.savez(one, k=np.linspace(0.1, 1, 5), delta=np.ones(5))
+    chain, _ = make(mods, state, datafile=[one])  # 1 file for 3 chunks
+    with pytest.raises(ValueError):
+        chain.setup()
+    bad = str(tmp_path / "bad.npz")
+    np.savez(bad, ks=np.linspace(0.1, 1, 5), delta=np.ones(5))  # wrong key
+    chain, _ = make(mods, state, datafile=[bad] * NCHUNKS)
+    with pytest.raises(ValueError):
+        chain.setup()
+    with pytest.raises(ValueError):
+        mods[0].Likelihood1DPowerCoeval(datafile=["a", "b"], noisefile=["n"])
+    # a likelihood outside a chain has no cores
+    with pytest.raises(AttributeError):
+        mods[0].Likelihood1DPowerLightcone(simulate=True).setup()
+    # required core missing
+    lk = mods[0].Likelihood1DPowerCoeval(simulate=True)
+    ch = mods[2].LikelihoodComputationChain(None)
+    ch.addCoreModule(mods[1].CoreLightConeModule(lambda p: state["box"], mods[1].UserParams(BOX_LEN, SHAPE[0])))
+    ch.addLikelihoodModule(lk)
+    with pytest.raises(ValueError):
+        ch.setup()
+
+
+@pytest.mark.parametrize("error_on_model", [True, False])
+def test_noise_and_error_on_model_match_oracle(mods, tmp_path, error_on_model):
+    state = {"box": synth_box(SHAPE, 0)}
+    data_o = O.reduce_data_lightcone(state["box"], BOX_LEN, BOX_LEN / SHAPE[0], NCHUNKS, NB)
+    dfiles, nfiles, noise = [], [], []
+    rng = np.random.default_rng(1)
+    for i, d in enumerate(data_o):
+        ok = np.isfinite(d["delta"])
+        f = str(tmp_path / f"d{i}.npz")
+        np.savez(f, k=d["k"][ok], delta=d["delta"][ok] * 1.1)  # data on a *different* k grid than the model
+        dfiles.append(f)
+        n = {"k": np.linspace(0.05, 6.0, 9), "errs": rng.uniform(5.0, 50.0, 9)}
+        nf = str(tmp_path / f"n{i}.npz")
+        np.savez(nf, **n)
+        nfiles.append(nf)
+        noise.append(n)
+    chain, lk = make(mods, state, datafile=dfiles, noisefile=nfiles, error_on_model=error_on_model,
+                     model_uncertainty=0.2)
+    chain.setup()
+    state["box"] = synth_box(SHAPE, 5)
+    model = lk.reduce_data(chain.build_model_data())
+    lnl = lk.computeLikelihood(model)
+    model_o = O.reduce_data_lightcone(state["box"], BOX_LEN, BOX_LEN / SHAPE[0], NCHUNKS, NB)
+    data_read = [dict(np.load(f)) for f in dfiles]
+    lnl_o = O.compute_likelihood(model_o, data_read, noise, 0.3, 4.0, 0.2, error_on_model)
+    assert np.isfinite(lnl_o) and abs(lnl - lnl_o) <= LNL_RTOL * abs(lnl_o)
+    # the fused batched path (tables uploaded once) agrees with the per-model call
+    lnls, _ = lk.likelihood_batch([chain.build_model_data()])
+    assert abs(lnls[0] - lnl_o) <= LNL_RTOL * abs(lnl_o)
+
+
+def test_equality_and_pickle(mods):
+    state = {"box": synth_box(SHAPE, 0)}
+    chain, lk = make(mods, state, simulate=True)
+    chain.setup()
+    other = mods[0].Likelihood1DPowerLightcone(nchunks=NCHUNKS, n_psbins=NB, min_k=0.3, max_k=4.0, simulate=False)
+    assert lk == other  # `simulate` is ignored in equality (likelihood.py:134)
+    assert lk != mods[0].Likelihood1DPowerLightcone(nchunks=NCHUNKS, n_psbins=NB + 1, min_k=0.3, max_k=4.0)
+    assert lk != mods[0].Likelihood1DPowerCoeval(n_psbins=NB)
+    lnl = lk.computeLikelihood(lk.reduce_data(chain.build_model_data()))
+    # the chain (cores + likelihood, after a device evaluation) pickles: no device handle lives on the instances
+    lk2 = pickle.loads(pickle.dumps(lk))
+    assert lk2 == lk and lk2.nchunks == NCHUNKS
+    assert [np.array_equal(a["delta"], b["delta"], equal_nan=True) for a, b in zip(lk.data, lk2.data)]
+    assert lnl == 0.0  # own data
+
+
+def test_fiducial_model_and_core_params_exposed(mods):
+    state = {"box": synth_box(SHAPE, 0)}
+    chain, lk = make(mods, state, simulate=True)
+    chain.setup()
+    assert lk.user_params.BOX_LEN == BOX_LEN
+    fid = lk.get_fiducial_model()
+    assert len(fid) == NCHUNKS and set(fid[0]) == {"k", "delta"}
+    assert lk.paired_core is chain.getCoreModules()[0]
