@@ -323,7 +323,7 @@ k_fused_p1(const float* __restrict__ boxes, long long batch_stride, int n2_total
     PS21_DYN_SMEM(float2, buf);                                          // [64][ROWLD]
     float2* twz = buf + R1 * ROWLD;                                      // [16][8] w_128^(t m)
     float4* twu = reinterpret_cast<float4*>(twz + 128);                  // [65]    w_256^p * (-i/2)
-    uint64_t* bar = reinterpret_cast<uint64_t*>(twu + 66);               // [2]: rows 0..31, rows 32..63
+    uint64_t* bar = reinterpret_cast<uint64_t*>(twu + 66);               // [4]: one per quarter of 16 rows
     const int tid = threadIdx.x;
     long long box;
     int cid;
@@ -346,54 +346,44 @@ k_fused_p1(const float* __restrict__ boxes, long long batch_stride, int n2_total
         twu[64] = make_float4(0.f, 0.f, 0.f, 0.f);  // column 64 is handled separately
         const float4 w = tw_g[64];
         twu[64] = make_float4(0.5f * w.y, -0.5f * w.x, 0.5f * w.x, 0.5f * w.y);
-        mbar_init(bar, 1);
-        mbar_init(bar + 1, 1);
+        for (int q = 0; q < 4; ++q) mbar_init(bar + q, 1);
         mbar_fence_init();
     }
     __syncthreads();
     const uint64_t pol = l2_policy_evict_first();
-    auto issue_half = [&](int yl, int half) {  // warp 0: 32 rows of 1 KB each
+    auto issue_quarter = [&](int yl, int q) {  // warp 0: 16 rows of 1 KB each
         if (tid < 32) {
-            if (tid == 0) mbar_expect_tx(bar + half, (R1 / 2) * NZ * 4);
+            if (tid == 0) mbar_expect_tx(bar + q, (R1 / 4) * NZ * 4);
             __syncwarp();
-            const int j = half * (R1 / 2) + tid;
-            bulk_g2s_hint(buf + j * ROWLD, src + (long long)(yl + R2S * j) * n2_total, NZ * 4, bar + half, pol);
-        }
-    };
-    // second y stage for the butterfly groups m1 in [mlo, mlo+4): rows 8*mlo .. 8*mlo+31
-    auto ystage2 = [&](int yl, int mlo) {
-        for (int task = tid; task < 4 * (NHC + 1); task += P1_THREADS) {
-            int kz, m1;
-            if (task < 4 * NHC) {
-                kz = task & (NHC - 1);
-                m1 = mlo + (task >> 7);
-            } else {  // Nyquist column
-                kz = NHC;
-                m1 = mlo + task - 4 * NHC;
-            }
-            float2 v[8];
-#pragma unroll
-            for (int u = 0; u < 8; ++u) v[u] = buf[(8 * m1 + u) * ROWLD + kz];
-            small_dft<8>(v);
-#pragma unroll
-            for (int u = 0; u < 8; ++u) {
-                const int kya = m1 + 8 * u;
-                // w_S^(y_lo ky_a), warp-uniform index
-                const float2 o = (yl == 0) ? v[u] : cmul_tw(v[u], c_tw256[(Geo<S>::TWMUL * yl * kya) & 255]);
-                dst[Geo<S>::scratch_addr(x, yl, kya, kz)] = o;
+            if (tid < R1 / 4) {
+                const int j = q * (R1 / 4) + tid;
+                bulk_g2s_hint(buf + j * ROWLD, src + (long long)(yl + R2S * j) * n2_total, NZ * 4, bar + q, pol);
             }
         }
     };
-    issue_half(0, 0);
-    issue_half(0, 1);
+    // second y stage (radix 8 over rows 8 m1 + u) of one (kz, m1) straight to HBM, times w_S^(y_lo ky_a)
+    auto ystage2 = [&](int yl, int kz, int m1) {
+        float2 v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) v[u] = buf[(8 * m1 + u) * ROWLD + kz];
+        small_dft<8>(v);
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int kya = m1 + 8 * u;
+            // w_S^(y_lo ky_a), warp-uniform index
+            const float2 o = (yl == 0) ? v[u] : cmul_tw(v[u], c_tw256[(Geo<S>::TWMUL * yl * kya) & 255]);
+            dst[Geo<S>::scratch_addr(x, yl, kya, kz)] = o;
+        }
+    };
+    for (int q = 0; q < 4; ++q) issue_quarter(0, q);
     uint32_t phase = 0;
     for (int yl = 0; yl < R2S; ++yl) {
         // ---- z: one 128-point FFT per row, 8 threads per row; rows 0..31 as soon as they have landed
-        mbar_wait(bar, phase);
-        for (int task = tid; task < (R1 / 2) * 8; task += P1_THREADS) zfft_row(buf + (task >> 3) * ROWLD, task & 7, mean, twz);
-        mbar_wait(bar + 1, phase);
-        for (int task = tid; task < (R1 / 2) * 8; task += P1_THREADS)
-            zfft_row(buf + (R1 / 2 + (task >> 3)) * ROWLD, task & 7, mean, twz);
+        // thread tid owns rows tid/8 (quarters 0,1) and 32 + tid/8 (quarters 2,3)
+        mbar_wait(bar + (tid >> 7), phase);
+        zfft_row(buf + (tid >> 3) * ROWLD, tid & 7, mean, twz);
+        mbar_wait(bar + 2 + (tid >> 7), phase);
+        zfft_row(buf + (R1 / 2 + (tid >> 3)) * ROWLD, tid & 7, mean, twz);
         phase ^= 1;
         __syncthreads();
         // ---- untangle + first y stage (radix 8 over rows u + 8m), in place
@@ -433,19 +423,18 @@ k_fused_p1(const float* __restrict__ boxes, long long batch_stride, int n2_total
             }
         }
         __syncthreads();
-        // ---- second y stage (radix 8 over rows 8m' + u) straight to HBM, times w_256^(y_lo ky_a);
-        //      rows 0..31 are consumed first so that the next unit's first half can start loading early
-        ystage2(yl, 0);
-        __syncthreads();
-        if (yl + 1 < R2S) {
-            if (tid == 0) fence_proxy_async();
-            issue_half(yl + 1, 0);
-        }
-        ystage2(yl, 4);
-        __syncthreads();
-        if (yl + 1 < R2S) {
-            if (tid == 0) fence_proxy_async();
-            issue_half(yl + 1, 1);
+        // ---- second y stage straight to HBM.  The Nyquist column (8 tasks) goes first; then four quarters of
+        //      exactly 256 tasks (128 k_z x 2 butterfly groups = rows 16q .. 16q+15): as soon as a quarter of
+        //      the rows has been consumed, the next unit's rows for that quarter start loading.
+        if (tid < 8) ystage2(yl, NHC, tid);
+#pragma unroll 1
+        for (int q = 0; q < 4; ++q) {
+            ystage2(yl, tid & (NHC - 1), 2 * q + (tid >> 7));
+            __syncthreads();
+            if (yl + 1 < R2S) {
+                if (tid == 0) fence_proxy_async();
+                issue_quarter(yl + 1, q);
+            }
         }
     }
 }
@@ -760,7 +749,7 @@ __global__ void k_fused_cyl_reduce(const double* __restrict__ cylpart, ItemMap i
     }
 }
 
-static size_t p1_smem() { return (size_t)R1 * ROWLD * 8 + 128 * 8 + 66 * 16 + 16; }
+static size_t p1_smem() { return (size_t)R1 * ROWLD * 8 + 128 * 8 + 66 * 16 + 32; }
 static size_t p2_smem(int nbins, bool cyl) {
     return (size_t)TILE * 8 + TILE + 256 * 16 + 16 + MAX_BINS * 8 * (cyl ? 8 : 1) + (size_t)nbins * P2_THREADS * 4;
 }
