@@ -386,16 +386,11 @@ k_fused_p1(const float* __restrict__ boxes, long long batch_stride, int n2_total
         zfft_row(buf + (R1 / 2 + (tid >> 3)) * ROWLD, tid & 7, mean, twz);
         phase ^= 1;
         __syncthreads();
-        // ---- untangle + first y stage (radix 8 over rows u + 8m), in place
-        for (int task = tid; task < 65 * 8; task += P1_THREADS) {
-            int p, u;
-            if (task < 512) {
-                p = task & 63;
-                u = task >> 6;
-            } else {
-                p = 64;
-                u = task - 512;
-            }
+        // ---- untangle + first y stage (radix 8 over rows u + 8m), in place: 64 column pairs (p, 128 - p) x 8
+        //      butterfly groups u = exactly two tasks per thread; the thread of the cheap pair (0, 128) also
+        //      takes the unpaired column 64
+        for (int task = tid; task < 64 * 8; task += P1_THREADS) {
+            const int p = task & 63, u = task >> 6;
             float2 c1[8], c2[8];
             const float4 w = twu[p];  // w_256^p * (-i/2)
 #pragma unroll
@@ -405,21 +400,31 @@ k_fused_p1(const float* __restrict__ boxes, long long batch_stride, int n2_total
                 if (p == 0) {
                     c1[m] = make_float2(ck.x + ck.y, 0.f);
                     c2[m] = make_float2(ck.x - ck.y, 0.f);
-                } else if (p == 64) {
-                    c1[m] = make_float2(ck.x, -ck.y);
-                    c2[m] = make_float2(0.f, 0.f);
                 } else {
                     untangle(ck, r[NHC - p], w, c1[m], c2[m]);
                 }
             }
             small_dft<8>(c1);
-            if (p != 64) small_dft<8>(c2);
+            small_dft<8>(c2);
 #pragma unroll
             for (int m = 0; m < 8; ++m) {
                 float2* r = buf + (u + 8 * m) * ROWLD;
                 const float4 f = c_tw256[(4 * u * m) & 255];  // w_64^(u m'), warp-uniform index
                 r[p] = (m == 0) ? c1[m] : cmul_tw(c1[m], f);
-                if (p != 64) r[NHC - p] = (m == 0) ? c2[m] : cmul_tw(c2[m], f);
+                r[NHC - p] = (m == 0) ? c2[m] : cmul_tw(c2[m], f);
+            }
+            if (p == 0) {  // column 64: A_64 = conj(C_64)
+#pragma unroll
+                for (int m = 0; m < 8; ++m) {
+                    const float2 ck = buf[(u + 8 * m) * ROWLD + 64];
+                    c1[m] = make_float2(ck.x, -ck.y);
+                }
+                small_dft<8>(c1);
+#pragma unroll
+                for (int m = 0; m < 8; ++m) {
+                    const float4 f = c_tw256[(4 * u * m) & 255];
+                    buf[(u + 8 * m) * ROWLD + 64] = (m == 0) ? c1[m] : cmul_tw(c1[m], f);
+                }
             }
         }
         __syncthreads();

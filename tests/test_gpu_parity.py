@@ -252,3 +252,32 @@ def test_full_size_properties(mods, kpath):
     # scaling the field by 2 scales every bin by exactly 4 (power-of-two scaling is exact in fp32)
     p2 = plan.power_device((box * 2).contiguous()).cpu().numpy()[0]
     assert np.allclose(p2, 4 * p.ravel(), rtol=1e-12, atol=0, equal_nan=True)
+
+
+def test_config4_512_cube_properties(mods):
+    """512^3 coeval cube (BASELINE config 4 shape, general path): Parseval with every mode weighted, bit-equal
+    counts against the closed form, batch invariance.  (The fp64 oracle would need ~10 GB and a minute here.)"""
+    import torch
+
+    from py21cmmc_b200.plan import get_plan
+
+    n, L = 512, 768.0
+    dev = torch.cuda.current_device()
+    plan = get_plan((n, n, n), [(0, n)], [(L, L, L)], 20, False, False, False, False, "legacy_1.001", "spherical",
+                    dev, "auto")
+    assert plan.path == "general" and int(plan.counts.sum()) == n ** 3
+    g = torch.Generator(device="cuda").manual_seed(5)
+    boxes = torch.randn((2, n, n, n), generator=g, device="cuda", dtype=torch.float32) * 10 + 20
+    p = plan.power_device(boxes).cpu().numpy()
+    for b in range(2):
+        expect = L ** 3 / n ** 3 * float((boxes[b].double() ** 2).sum())
+        got = float(np.nansum(p[b] * plan.counts))
+        assert abs(got / expect - 1) < 2e-6
+    one = plan.power_device(boxes[1:2].contiguous()).cpu().numpy()[0]
+    assert np.allclose(one, p[1], rtol=1e-12, atol=0, equal_nan=True)
+    # log bins with the default masks: white noise gives sigma^2 V / N in every well-populated bin
+    plan2 = get_plan((n, n, n), [(0, n)], [(L, L, L)], 20, True, True, False, False, "legacy_1.001", "spherical",
+                     dev, "auto")
+    q = plan2.power_device(boxes[:1].contiguous()).cpu().numpy()[0]
+    good = plan2.counts > 100000
+    assert good.sum() >= 8 and np.all(np.abs(q[good] / (100.0 * L ** 3 / n ** 3) - 1) < 0.02)
