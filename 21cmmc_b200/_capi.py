@@ -9,7 +9,8 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libps21.so")
+# PS21_LIBRARY selects another build of the same library (A/B comparisons of kernel variants)
+LIB_PATH = os.environ.get("PS21_LIBRARY") or os.path.join(HERE, "libps21.so")
 
 PS21_MODE_SPHERICAL = 0
 PS21_MODE_CYLINDRICAL = 1

@@ -95,6 +95,10 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
                  : "memory");
 }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+// barrier over `nthreads` threads of the CTA (named barrier `id`, 1..15)
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
 // L2 eviction policies: streamed data must not push the (re-used) bin-index table out of L2
 __device__ __forceinline__ uint64_t l2_policy_evict_first() {
     uint64_t pol;
@@ -146,6 +150,7 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
     emu_bar_check(b);
 }
 __device__ __forceinline__ void fence_proxy_async() {}
+__device__ __forceinline__ void named_bar_sync(int, int) { __syncthreads(); }  // stronger, same result
 __device__ __forceinline__ uint64_t l2_policy_evict_first() { return 0; }
 __device__ __forceinline__ uint64_t l2_policy_evict_last() { return 0; }
 __device__ __forceinline__ void bulk_g2s_hint(void* dst, const void* src, uint32_t bytes, uint64_t* bar, uint64_t) {
@@ -323,7 +328,7 @@ k_fused_p1(const float* __restrict__ boxes, long long batch_stride, int n2_total
     PS21_DYN_SMEM(float2, buf);                                          // [64][ROWLD]
     float2* twz = buf + R1 * ROWLD;                                      // [16][8] w_128^(t m)
     float4* twu = reinterpret_cast<float4*>(twz + 128);                  // [65]    w_256^p * (-i/2)
-    uint64_t* bar = reinterpret_cast<uint64_t*>(twu + 66);               // [4]: one per quarter of 16 rows
+    uint64_t* bar = reinterpret_cast<uint64_t*>(twu + 66);               // [8]: one per group of 8 rows
     const int tid = threadIdx.x;
     long long box;
     int cid;
@@ -346,19 +351,22 @@ k_fused_p1(const float* __restrict__ boxes, long long batch_stride, int n2_total
         twu[64] = make_float4(0.f, 0.f, 0.f, 0.f);  // column 64 is handled separately
         const float4 w = tw_g[64];
         twu[64] = make_float4(0.5f * w.y, -0.5f * w.x, 0.5f * w.x, 0.5f * w.y);
-        for (int q = 0; q < 4; ++q) mbar_init(bar + q, 1);
+        for (int g = 0; g < 8; ++g) mbar_init(bar + g, 1);
         mbar_fence_init();
     }
     __syncthreads();
     const uint64_t pol = l2_policy_evict_first();
-    auto issue_quarter = [&](int yl, int q) {  // warp 0: 16 rows of 1 KB each
-        if (tid < 32) {
-            if (tid == 0) mbar_expect_tx(bar + q, (R1 / 4) * NZ * 4);
-            __syncwarp();
-            if (tid < R1 / 4) {
-                const int j = q * (R1 / 4) + tid;
-                bulk_g2s_hint(buf + j * ROWLD, src + (long long)(yl + R2S * j) * n2_total, NZ * 4, bar + q, pol);
-            }
+    // rows 8g .. 8g+7 of unit yl, 1 KB each; called by one whole warp
+    auto issue_group = [&](int yl, int g) {
+        const int lane = tid & 31;
+        if (lane == 0) {
+            fence_proxy_async();
+            mbar_expect_tx(bar + g, 8 * NZ * 4);
+        }
+        __syncwarp();
+        if (lane < 8) {
+            const int j = 8 * g + lane;
+            bulk_g2s_hint(buf + j * ROWLD, src + (long long)(yl + R2S * j) * n2_total, NZ * 4, bar + g, pol);
         }
     };
     // second y stage (radix 8 over rows 8 m1 + u) of one (kz, m1) straight to HBM, times w_S^(y_lo ky_a)
@@ -375,14 +383,15 @@ k_fused_p1(const float* __restrict__ boxes, long long batch_stride, int n2_total
             dst[Geo<S>::scratch_addr(x, yl, kya, kz)] = o;
         }
     };
-    for (int q = 0; q < 4; ++q) issue_quarter(0, q);
+    if (tid < 32)
+        for (int g = 0; g < 8; ++g) issue_group(0, g);
     uint32_t phase = 0;
     for (int yl = 0; yl < R2S; ++yl) {
         // ---- z: one 128-point FFT per row, 8 threads per row; rows 0..31 as soon as they have landed
-        // thread tid owns rows tid/8 (quarters 0,1) and 32 + tid/8 (quarters 2,3)
-        mbar_wait(bar + (tid >> 7), phase);
+        // thread tid owns rows tid/8 (groups 0..3) and 32 + tid/8 (groups 4..7)
+        mbar_wait(bar + (tid >> 6), phase);
         zfft_row(buf + (tid >> 3) * ROWLD, tid & 7, mean, twz);
-        mbar_wait(bar + 2 + (tid >> 7), phase);
+        mbar_wait(bar + 4 + (tid >> 6), phase);
         zfft_row(buf + (R1 / 2 + (tid >> 3)) * ROWLD, tid & 7, mean, twz);
         phase ^= 1;
         __syncthreads();
@@ -428,17 +437,21 @@ k_fused_p1(const float* __restrict__ boxes, long long batch_stride, int n2_total
             }
         }
         __syncthreads();
-        // ---- second y stage straight to HBM.  The Nyquist column (8 tasks) goes first; then four quarters of
-        //      exactly 256 tasks (128 k_z x 2 butterfly groups = rows 16q .. 16q+15): as soon as a quarter of
-        //      the rows has been consumed, the next unit's rows for that quarter start loading.
+        // ---- second y stage straight to HBM.  The Nyquist column (8 tasks) goes first.  Then each half of the
+        //      CTA (128 threads = the 128 k_z of one butterfly group) walks its own groups m1 = half, half + 2,
+        //      ...: a group is 8 rows, and as soon as the half has consumed it (128-thread named barrier) its
+        //      first warp starts the bulk copies of the next unit into those rows.
         if (tid < 8) ystage2(yl, NHC, tid);
+        __syncthreads();  // the Nyquist tasks read rows of every group
+        {
+            const int half = tid >> 7;
 #pragma unroll 1
-        for (int q = 0; q < 4; ++q) {
-            ystage2(yl, tid & (NHC - 1), 2 * q + (tid >> 7));
-            __syncthreads();
-            if (yl + 1 < R2S) {
-                if (tid == 0) fence_proxy_async();
-                issue_quarter(yl + 1, q);
+            for (int q = 0; q < 4; ++q) {
+                const int m1 = 2 * q + half;
+                ystage2(yl, tid & (NHC - 1), m1);
+                if (half == 0) named_bar_sync(1, 128);
+                else named_bar_sync(2, 128);
+                if (yl + 1 < R2S && (tid & 127) < 32) issue_group(yl + 1, m1);
             }
         }
     }
@@ -754,7 +767,7 @@ __global__ void k_fused_cyl_reduce(const double* __restrict__ cylpart, ItemMap i
     }
 }
 
-static size_t p1_smem() { return (size_t)R1 * ROWLD * 8 + 128 * 8 + 66 * 16 + 32; }
+static size_t p1_smem() { return (size_t)R1 * ROWLD * 8 + 128 * 8 + 66 * 16 + 64; }
 static size_t p2_smem(int nbins, bool cyl) {
     return (size_t)TILE * 8 + TILE + 256 * 16 + 16 + MAX_BINS * 8 * (cyl ? 8 : 1) + (size_t)nbins * P2_THREADS * 4;
 }
