@@ -565,18 +565,25 @@ k_fused_p2(const float2* __restrict__ scratch, ItemMap im, const ChunkDev* __res
                 const uint4 lv = lp[h];
                 const uint32_t w4[4] = {lv.x, lv.y, lv.z, lv.w};
 #pragma unroll
-                for (int r = 0; r < 16; ++r) {
-                    const uint32_t b = (w4[r >> 2] >> (8 * (r & 3))) & 255u;
-                    const float2 c = v[16 * h + r];
-                    const float pw = c.x * c.x + c.y * c.y;
-                    if (__any_sync(0xffffffffu, b != cur)) {
-                        if (b != cur) {
-                            if (cur != 255u) lbins[cur * P2_THREADS + tid] += mult * acc;
-                            cur = b;
-                            acc = 0.f;
+                for (int g = 0; g < 4; ++g) {  // four outputs per 32-bit word of bin indices
+                    const int r0 = 16 * h + 4 * g;
+                    float pw[4];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) pw[i] = v[r0 + i].x * v[r0 + i].x + v[r0 + i].y * v[r0 + i].y;
+                    if (__all_sync(0xffffffffu, w4[g] == cur * 0x01010101u)) {
+                        acc += (pw[0] + pw[1]) + (pw[2] + pw[3]);  // whole word stays in the current bin, all lanes
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            const uint32_t b = (w4[g] >> (8 * i)) & 255u;
+                            if (b != cur) {
+                                if (cur != 255u) lbins[cur * P2_THREADS + tid] += mult * acc;
+                                cur = b;
+                                acc = 0.f;
+                            }
+                            acc += pw[i];
                         }
                     }
-                    acc += pw;
                 }
             }
             if (cur != 255u) lbins[cur * P2_THREADS + tid] += mult * acc;

@@ -83,6 +83,7 @@ static inline int __any_sync(unsigned, int pred) {
     ps21emu::syncwarp();
     return any;
 }
+static inline int __all_sync(unsigned m, int pred) { return !__any_sync(m, !pred); }
 enum { cudaFuncAttributeMaxDynamicSharedMemorySize = 8 };
 template <class F>
 static inline int cudaFuncSetAttribute(F, int, int) { return 0; }
