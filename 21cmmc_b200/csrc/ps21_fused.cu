@@ -41,6 +41,7 @@ constexpr int SLOTS = 86;              // CTAs per spectrum in pass 2 (12 tiles 
 constexpr int P1_THREADS = 256;
 constexpr int P2_THREADS = 256;
 constexpr int MAX_BINS = 40;
+constexpr int FLUSH_EVERY = 4;         // pass 2: tiles between two fp32 -> fp64 flushes of the lane-private bins
 constexpr int NHK = NZ / 2 + 1;        // 129 k_z values of the half spectrum
 // cylindrical mode: 64 CTAs take the main tiles with tl % 64 == slot (16 tiles each: always the same 8 k_z),
 // 8 CTAs take one Nyquist tile each
@@ -594,8 +595,9 @@ k_fused_p2(const float2* __restrict__ scratch, ItemMap im, const ChunkDev* __res
             fence_proxy_async();
             issue_tile(tl + stride);
         }
-        // ---- flush the lane-private fp32 bins into the CTA's fp64 bins, fixed order
-        {
+        // ---- every FLUSH_EVERY tiles (and after the last one): flush the lane-private fp32 bins into the CTA's
+        //      fp64 bins in a fixed order; a lane-private bin then holds at most 32 * FLUSH_EVERY fp32 terms
+        if ((it % FLUSH_EVERY) == FLUSH_EVERY - 1 || it + 1 == count) {
             const int warp = tid >> 5, lane = tid & 31;
             for (int b = warp; b < nbins; b += P2_THREADS / 32) {
                 double acc = 0.0;
@@ -731,7 +733,7 @@ k_fused_p2_s128(const float2* __restrict__ scratch, ItemMap im, const ChunkDev* 
             fence_proxy_async();
             issue_tile(tl + stride);
         }
-        {   // ---- flush the lane-private fp32 bins into the CTA's fp64 bins, fixed order
+        if ((it % FLUSH_EVERY) == FLUSH_EVERY - 1 || it + 1 == count) {  // fixed-order fp32 -> fp64 flush
             const int warp = tid >> 5, lane = tid & 31;
             for (int b = warp; b < nbins; b += P2_THREADS / 32) {
                 double a = 0.0;
