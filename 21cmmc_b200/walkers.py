@@ -63,3 +63,68 @@ class BatchedWalkerPool:
                                    self.device)
         blobs = {i: r[1] for i, r in zip(mine, res)}
         return [(float(lnl[i]), blobs.get(i)) for i in range(n)]
+
+
+# ------------------------------------------------------------------------------------------------
+# Blob hand-off: the per-walker ``k_i`` / ``delta_i`` records that ``store`` puts
+# into the context's data dict are persisted by the reference's HDFStorage as ONE structured array per
+# iteration (src/py21cmmc/cosmoHammer.py:227-242 builds the dtype, :281-288 packs a step).
+# ------------------------------------------------------------------------------------------------
+def blob_dtype(blobs: dict):
+    """Structured dtype of a blob dict, exactly as ``HDFStorage.grow`` derives it (cosmoHammer.py:231-236)."""
+    dt = []
+    for k, v in blobs.items():
+        a = np.atleast_1d(v)
+        shape = a.shape
+        if len(shape) == 1:
+            shape = shape[0]
+        dt.append((k, (a.dtype, shape)))
+    return np.dtype(dt)
+
+
+def blobs_to_structured(blob_dicts, dtype=None):
+    """One structured row per walker, as ``HDFStorage.save_step`` packs a step (cosmoHammer.py:281-285).
+
+    ``blob_dicts``: the second element of every ``(lnL, blobs)`` result of ``chain.call_batch`` /
+    ``BatchedWalkerPool.map``; rejected walkers (``[]`` / ``None``) become NaN rows.
+    """
+    first = next((b for b in blob_dicts if b), None)
+    if first is None:
+        return None
+    dtype = dtype or blob_dtype(first)
+    out = np.zeros(len(blob_dicts), dtype=dtype)
+    for name in dtype.names:
+        if np.issubdtype(dtype[name].base, np.floating):
+            out[name] = np.nan
+    for i, b in enumerate(blob_dicts):
+        if b:
+            out[i] = tuple(b[name] for name in dtype.names)
+    return out
+
+
+class BlobChain:
+    """Grow-by-iteration store of structured blob rows: (niter, nwalkers), the layout of the reference's
+    ``blobs`` dataset.  ``save(path)`` writes a ``.npy`` that ``np.load`` returns with named fields, so
+    ``blobs["delta_0"][it, walker]`` reads like the reference's ``samples.get_blobs()``."""
+
+    def __init__(self):
+        self.rows = []
+        self.dtype = None
+
+    def save_step(self, blob_dicts):
+        rec = blobs_to_structured(blob_dicts, self.dtype)
+        if rec is None:
+            if self.rows:
+                raise ValueError("inconsistent use of blobs")  # cosmoHammer.py:297-301
+            return
+        if self.dtype is None:
+            self.dtype = rec.dtype
+        if self.rows and len(rec) != len(self.rows[0]):
+            raise ValueError("number of walkers changed between iterations")
+        self.rows.append(rec)
+
+    def array(self):
+        return np.stack(self.rows) if self.rows else None
+
+    def save(self, path):
+        np.save(path, self.array())

@@ -163,3 +163,35 @@ def test_fiducial_model_and_core_params_exposed(mods):
     fid = lk.get_fiducial_model()
     assert len(fid) == NCHUNKS and set(fid[0]) == {"k", "delta"}
     assert lk.paired_core is chain.getCoreModules()[0]
+
+
+def test_blob_handoff_matches_reference_storage_layout(mods, tmp_path):
+    """call_batch -> structured rows shaped like HDFStorage's `blobs` dataset (cosmoHammer.py:227-242, 281-288)."""
+    from py21cmmc_b200.chain import Params
+    from py21cmmc_b200.walkers import BatchedWalkerPool, BlobChain, blob_dtype
+
+    lk_mod, core_mod, chain_mod = mods
+    up = core_mod.UserParams(BOX_LEN=BOX_LEN, HII_DIM=SHAPE[0])
+
+    class SeedSim:
+        def __call__(self, params):
+            return synth_box(SHAPE, int(round(params.seed)) if len(params) else 0)
+
+    c = core_mod.CoreLightConeModule(SeedSim(), up)
+    lk = lk_mod.Likelihood1DPowerLightcone(nchunks=NCHUNKS, n_psbins=NB, simulate=True, min_k=0.3, max_k=4.0)
+    chain = chain_mod.build_computation_chain(c, lk, params=Params(("seed", [0.0, 0.0, 50.0, 1.0])))
+    pool = BlobChain()
+    mapper = BatchedWalkerPool(chain)
+    for it in range(2):
+        res = mapper.map(None, [[1.0 + it], [2.0 + it], [99.0], [3.0 + it]])  # 99 is outside the prior -> -inf, no blobs
+        assert res[2][0] == -np.inf and not res[2][1]
+        pool.save_step([r[1] for r in res])
+    arr = pool.array()
+    assert arr.shape == (2, 4) and set(arr.dtype.names) == {f"{k}_{i}" for k in ("k", "delta") for i in range(NCHUNKS)}
+    assert arr.dtype == blob_dtype(res[0][1]) and arr["delta_1"].shape == (2, 4, NB)
+    assert np.all(np.isnan(arr["delta_0"][:, 2])) and np.array_equal(arr["k_0"][0, 0], res[0][1]["k_0"])
+    # walker 1 of iteration 0 and walker 0 of iteration 1 saw the same lightcone (seed 2)
+    assert np.array_equal(arr["delta_2"][0, 1], arr["delta_2"][1, 0], equal_nan=True)
+    pool.save(str(tmp_path / "blobs.npy"))
+    back = np.load(str(tmp_path / "blobs.npy"))
+    assert back.dtype == arr.dtype and np.array_equal(back["delta_0"], arr["delta_0"], equal_nan=True)
