@@ -1,6 +1,7 @@
 // Plan management, finalize / likelihood kernels and the extern "C" entry points of include/ps21.h.
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 
@@ -108,7 +109,7 @@ __global__ void k_finalize(const double* __restrict__ partials, int slots_max, l
                            const float2* __restrict__ dc, double* __restrict__ power, double* __restrict__ delta,
                            double* __restrict__ lnl, const double* __restrict__ data,
                            const double* __restrict__ noise2, const uint8_t* __restrict__ mask, int nsets,
-                           double mu, int err_on_model) {
+                           double mu, int err_on_model, long long box0) {
     PS21_DYN_SMEM(double, sdelta);
     const long long box = blockIdx.x;
     for (long long i = threadIdx.x; i < out_per_box; i += blockDim.x) {
@@ -135,7 +136,7 @@ __global__ void k_finalize(const double* __restrict__ partials, int slots_max, l
     if (lnl) {
         __syncthreads();
         if (threadIdx.x == 0) {
-            const long long set = box % nsets;
+            const long long set = (box0 + box) % nsets;  // box0: index of this call's first box in the caller's batch
             double total = 0.0;
             for (int c = 0; c < nchunks; ++c) {
                 const ChunkDev ch = chunks[c];
@@ -263,7 +264,7 @@ static int ensure_scratch(ps21_plan* p, long long want_elems) {
 
 // All kernels of one call, asynchronous on `st`.
 static int run_device(ps21_plan* p, const float* d_boxes, long long batch, long long batch_stride, double* d_power,
-                      double* d_delta, double* d_lnl, cudaStream_t st) {
+                      double* d_delta, double* d_lnl, cudaStream_t st, long long box0 = 0) {
     if (batch <= 0) return PS21_OK;
     if (batch_stride < (long long)p->n0 * p->n1 * p->n2_total)
         return invalid("batch_stride smaller than one box");
@@ -305,7 +306,7 @@ static int run_device(ps21_plan* p, const float* d_boxes, long long batch, long 
     PS21_LAUNCH(k_finalize, dim3((unsigned)batch), dim3(128), smem, st, p->d_partials, p->slots_max, p->out_per_box,
                 p->d_chunks, p->nchunks, p->d_counts, p->mode == PS21_MODE_SPHERICAL ? p->d_kfac : nullptr,
                 p->d_means, p->d_dc, pw, d_delta, d_lnl, p->data.d_data, p->data.d_noise2, p->data.d_mask,
-                p->data.nsets > 0 ? p->data.nsets : 1, p->data.model_uncertainty, p->data.error_on_model);
+                p->data.nsets > 0 ? p->data.nsets : 1, p->data.model_uncertainty, p->data.error_on_model, box0);
     PS21_CUDA(cudaGetLastError());
     p->launches_last++;
     return PS21_OK;
@@ -628,8 +629,13 @@ static int run_host(ps21_plan* p, const float* h_boxes, long long batch, long lo
     if (batch <= 0) return PS21_OK;
     const long long box_elems = (long long)p->n0 * p->n1 * p->n2_total;
     if (batch_stride < box_elems) return invalid("batch_stride smaller than one box");
-    // slice size: at most 1 GiB per staging buffer, at least one box
-    long long per = (1LL << 30) / (box_elems * 4);
+    // slice size: at most 1 GiB per staging buffer (PS21_STAGE_BYTES overrides), at least one box
+    long long stage_bytes = 1LL << 30;
+    if (const char* e = getenv("PS21_STAGE_BYTES")) {
+        const long long v = atoll(e);
+        if (v > 0) stage_bytes = v;
+    }
+    long long per = stage_bytes / (box_elems * 4);
     if (per < 1) per = 1;
     if (per > batch) per = batch;
     if (per > p->stage_boxes) {
@@ -680,7 +686,7 @@ static int run_host(ps21_plan* p, const float* h_boxes, long long batch, long lo
         cudaStreamWaitEvent(s_comp, ev_copy[b], 0);
         rc = run_device(p, p->d_stage[b], n, box_elems, d_res_p + done * p->out_per_box,
                         d_res_d ? d_res_d + done * p->out_per_box : nullptr, d_res_l ? d_res_l + done : nullptr,
-                        s_comp);
+                        s_comp, done);
         cudaEventRecord(ev_comp[b], s_comp);
         done += n;
         ++sl;

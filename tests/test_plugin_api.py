@@ -195,3 +195,31 @@ def test_blob_handoff_matches_reference_storage_layout(mods, tmp_path):
     pool.save(str(tmp_path / "blobs.npy"))
     back = np.load(str(tmp_path / "blobs.npy"))
     assert back.dtype == arr.dtype and np.array_equal(back["delta_0"], arr["delta_0"], equal_nan=True)
+
+
+def test_coeval_data_sets_follow_boxes_across_staging_slices(mods, monkeypatch):
+    """Regression: with several redshifts (data sets) and a host batch staged in several slices, box b must be
+    compared with data set b % nsets whatever slice it travels in."""
+    lk_mod, core_mod, chain_mod = mods
+    n, nz, nwalk = 10, 3, 4
+    up = core_mod.UserParams(BOX_LEN=15.0, HII_DIM=n)
+
+    class Sim:
+        def __init__(self):
+            self.seed = 0
+
+        def __call__(self, params):
+            return [synth_box((n, n, n), 10 * self.seed + z) for z in range(nz)]
+
+    sim = Sim()
+    c = core_mod.CoreCoevalModule([7.0, 8.0, 9.0], sim, up)
+    lk = lk_mod.Likelihood1DPowerCoeval(n_psbins=5, simulate=True, min_k=0.3, max_k=4.0)
+    chain = chain_mod.build_computation_chain(c, lk)
+    ctxs = []
+    for w in range(nwalk):
+        sim.seed = w + 1
+        ctxs.append(chain.build_model_data())
+    single = [lk.computeLikelihood(lk.reduce_data(ctx)) for ctx in ctxs]
+    monkeypatch.setenv("PS21_STAGE_BYTES", str(2 * n * n * n * 4))  # two cubes per slice -> six slices
+    lnls, _ = lk.likelihood_batch(ctxs)
+    assert np.allclose(lnls, single, rtol=1e-9, atol=0) and len(set(np.round(lnls, 6))) == nwalk
