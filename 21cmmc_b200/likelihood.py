@@ -145,6 +145,8 @@ class LikelihoodBaseFile(LikelihoodBase):
     @staticmethod
     def _write(files, records, kind):
         for fl, d in zip(files, records):
+            if not fl:  # the lightcone class defaults to datafile="": nothing to write (the reference would
+                continue  # create a file called ".npz" in the working directory here)
             if path.exists(fl):
                 logger.warning(f"File {fl} already exists. Moving previous version to {fl}.bk")
                 rename(fl, fl + ".bk")
