@@ -63,18 +63,21 @@ int general_build_lut(ps21_plan* p, int chunk, const double* d_k0sq, const doubl
 // Any constant close to the mean works: subtracting it changes only the k = 0 coefficient, which is
 // restored in fp64 by the finalize kernel when that mode is binned at all.
 // ---------------------------------------------------------------------------------------------
-__global__ void k_slab_mean(const float* __restrict__ boxes, long long batch_stride, int n1, int n2_total,
-                            const ChunkDev* __restrict__ chunks, int nchunks, float* __restrict__ means) {
+constexpr int kMeanParts = 8;  // CTAs per chunk in the offset estimate (fixed -> deterministic)
+
+__global__ void k_slab_mean_part(const float* __restrict__ boxes, long long batch_stride, int n1, int n2_total,
+                                 const ChunkDev* __restrict__ chunks, int nchunks, double* __restrict__ parts) {
     __shared__ double red[256];
     const int box = blockIdx.x / nchunks;
     const int c = blockIdx.x % nchunks;
     const ChunkDev ch = chunks[c];
     const float* src = boxes + (long long)box * batch_stride + ch.start;
+    // rows y = part, part + kMeanParts, ... of the x = 0 slab; one warp per row, lanes along z
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
     double acc = 0.0;
-    const int total = n1 * ch.nz;
-    for (int i = threadIdx.x; i < total; i += blockDim.x) {
-        const int y = i / ch.nz, z = i % ch.nz;
-        acc += (double)src[(long long)y * n2_total + z];
+    for (int y = blockIdx.y + kMeanParts * warp; y < n1; y += kMeanParts * nwarps) {
+        const float* r = src + (long long)y * n2_total;
+        for (int z = lane; z < ch.nz; z += 32) acc += (double)r[z];
     }
     red[threadIdx.x] = acc;
     __syncthreads();
@@ -82,14 +85,27 @@ __global__ void k_slab_mean(const float* __restrict__ boxes, long long batch_str
         if ((int)threadIdx.x < s) red[threadIdx.x] += red[threadIdx.x + s];
         __syncthreads();
     }
-    if (threadIdx.x == 0) means[(long long)box * nchunks + c] = (float)(red[0] / (double)total);
+    if (threadIdx.x == 0) parts[((long long)box * nchunks + c) * kMeanParts + blockIdx.y] = red[0];
+}
+
+__global__ void k_slab_mean_finish(const double* __restrict__ parts, int n1, const ChunkDev* __restrict__ chunks,
+                                   int nchunks, long long nitems, float* __restrict__ means) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nitems) return;
+    double s = 0.0;
+    for (int q = 0; q < kMeanParts; ++q) s += parts[i * kMeanParts + q];
+    means[i] = (float)(s / ((double)n1 * (double)chunks[i % nchunks].nz));
 }
 
 int launch_slab_mean(ps21_plan* p, const float* d_boxes, long long batch_stride, long long batch, cudaStream_t st) {
-    PS21_LAUNCH(k_slab_mean, dim3((unsigned)(batch * p->nchunks)), dim3(256), 0, st, d_boxes, batch_stride, p->n1,
-                p->n2_total, p->d_chunks, p->nchunks, p->d_means);
+    const long long nitems = batch * p->nchunks;
+    PS21_LAUNCH(k_slab_mean_part, dim3((unsigned)nitems, kMeanParts), dim3(256), 0, st, d_boxes, batch_stride, p->n1,
+                p->n2_total, p->d_chunks, p->nchunks, p->d_mean_parts);
     PS21_CUDA(cudaGetLastError());
-    p->launches_last++;
+    PS21_LAUNCH(k_slab_mean_finish, dim3((unsigned)((nitems + 127) / 128)), dim3(128), 0, st, p->d_mean_parts, p->n1,
+                p->d_chunks, p->nchunks, nitems, p->d_means);
+    PS21_CUDA(cudaGetLastError());
+    p->launches_last += 2;
     return PS21_OK;
 }
 

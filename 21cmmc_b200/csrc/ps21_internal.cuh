@@ -105,6 +105,7 @@ struct ps21_plan {
     long long spec_max = 0;
     double* d_partials = nullptr;    // [batch][slots_max][out_per_box]
     float* d_means = nullptr;        // [batch][nchunks]
+    double* d_mean_parts = nullptr;  // [batch][nchunks][8] partial sums of the offset estimate
     float2* d_dc = nullptr;          // [batch][nchunks] DC Fourier coefficient of the mean-subtracted chunk
     long long batch_cap = 0;
     ps21::DataTables data;

@@ -235,13 +235,16 @@ static int ensure_batch(ps21_plan* p, long long batch) {
     if (batch <= p->batch_cap) return PS21_OK;
     free_dev(p->d_partials);
     free_dev(p->d_means);
+    free_dev(p->d_mean_parts);
     free_dev(p->d_dc);
     p->d_partials = nullptr;
     p->d_means = nullptr;
+    p->d_mean_parts = nullptr;
     p->d_dc = nullptr;
     p->batch_cap = 0;
     PS21_CUDA(cudaMalloc((void**)&p->d_partials, sizeof(double) * batch * p->slots_max * p->out_per_box));
     PS21_CUDA(cudaMalloc((void**)&p->d_means, sizeof(float) * batch * p->nchunks));
+    PS21_CUDA(cudaMalloc((void**)&p->d_mean_parts, sizeof(double) * batch * p->nchunks * 8));
     PS21_CUDA(cudaMalloc((void**)&p->d_dc, sizeof(float2) * batch * p->nchunks));
     PS21_CUDA(cudaMemset(p->d_dc, 0, sizeof(float2) * batch * p->nchunks));
     p->batch_cap = batch;
@@ -340,6 +343,7 @@ int ps21_plan_destroy(ps21_plan* p) {
     free_dev(p->d_scratch);
     free_dev(p->d_partials);
     free_dev(p->d_means);
+    free_dev(p->d_mean_parts);
     free_dev(p->d_dc);
     free_dev(p->data.d_data);
     free_dev(p->data.d_noise2);
