@@ -157,6 +157,7 @@ __device__ __forceinline__ uint64_t l2_policy_evict_last() { return 0; }
 __device__ __forceinline__ void bulk_g2s_hint(void* dst, const void* src, uint32_t bytes, uint64_t* bar, uint64_t) {
     bulk_g2s(dst, src, bytes, bar);
 }
+
 #endif
 
 // ------------------------------------------------------------------------------------------------

@@ -293,6 +293,10 @@ static int run_device(ps21_plan* p, const float* d_boxes, long long batch, long 
         if (per < 1) per = 1;
         if (per > 32768) per = 32768;
         if (per > total) per = total;
+        {   // equal slices: 256 spectra with room for 121 run as 86 + 85 + 85, not 121 + 121 + 14
+            const long long nslices = (total + per - 1) / per;
+            per = (total + nslices - 1) / nslices;
+        }
         rc = ensure_scratch(p, per * spec);
         if (rc) return rc;
         for (long long i0 = 0; i0 < total; i0 += per) {
@@ -384,7 +388,22 @@ int ps21_plan_create(const ps21_desc* d, ps21_plan** out) {
     p->n0 = d->n0; p->n1 = d->n1; p->n2_total = d->n2_total; p->nchunks = d->nchunks; p->nbins = d->nbins;
     p->mode = d->mode; p->device = d->device; p->path_req = d->path;
     p->ig_kperp = d->ignore_kperp_zero; p->ig_kpar = d->ignore_kpar_zero; p->ig_k0 = d->ignore_k_zero;
-    p->workspace_cap = d->workspace_bytes > 0 ? d->workspace_bytes : (8LL << 30);
+    if (d->workspace_bytes > 0) {
+        p->workspace_cap = d->workspace_bytes;
+    } else {  // default: a sixth of the device memory, at most 24 GiB (a 64-walker config-3 step needs 17.3 GB)
+        p->workspace_cap = 8LL << 30;
+#ifndef PS21_EMU
+        size_t free_b = 0, total_b = 0;
+        if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess && total_b > 0) {
+            long long cap = (long long)(total_b / 6);
+            if (cap > (24LL << 30)) cap = 24LL << 30;
+            if (cap < (1LL << 30)) cap = 1LL << 30;
+            p->workspace_cap = cap;
+        } else {
+            cudaGetLastError();
+        }
+#endif
+    }
     int rc = PS21_OK;
     auto fail = [&](int code) { return code; };  // the guard releases the plan
     // chunks and shapes

@@ -68,7 +68,8 @@ typedef struct ps21_desc {
     int32_t mode;                 /* PS21_MODE_* */
     int32_t device;               /* CUDA device ordinal */
     int32_t path;                 /* PS21_PATH_* */
-    int64_t workspace_bytes;      /* cap for the half-spectrum scratch (0 = default 2 GiB) */
+    int64_t workspace_bytes;      /* cap for the half-spectrum scratch (0 = default: 1/6 of device memory, <= 24 GiB);
+                                     the scratch grows on demand up to the cap */
 } ps21_desc;
 
 typedef struct ps21_info {
