@@ -165,7 +165,19 @@ def cpu_step(pool, workers, step):
 
 
 def cpu_workers():
-    return max(1, min(os.cpu_count() or 1, 16))
+    """All host cores, bounded by memory: one 256^3 chunk needs ~2 GB inside the NumPy port."""
+    n = os.cpu_count() or 1
+    try:
+        n = min(n, len(os.sched_getaffinity(0)))
+    except Exception:
+        pass
+    try:
+        import psutil
+
+        n = min(n, max(1, int(psutil.virtual_memory().available // (3 << 30))))
+    except Exception:
+        n = min(n, 16)
+    return max(1, min(n, 128))
 
 
 def run_reference(args):
