@@ -40,8 +40,13 @@ constexpr int NTILES = NT_MAIN + R1 / T; // + 8 tiles holding the Nyquist plane 
 constexpr int SLOTS = 86;              // CTAs per spectrum in pass 2 (12 tiles each)
 constexpr int P1_THREADS = 256;
 constexpr int P2_THREADS = 256;
-constexpr int MAX_BINS = 40;
-constexpr int FLUSH_EVERY = 4;         // pass 2: tiles between two fp32 -> fp64 flushes of the lane-private bins
+constexpr int MAX_BINS = 40;           // lane-private bin mode (fastest): at most 40 bins (|k|, or k_perp when cylindrical)
+constexpr int MAX_BINS_SPH = 254;      // warp-cooperative bin mode (spherical): byte LUT, 255 = discarded mode
+constexpr int FLUSH_EVERY = 4;         // lane-private mode: tiles between two fp32 -> fp64 flushes of the lane bins
+// pass-2 bin accumulation modes
+constexpr int BM_LANE = 0;             // spherical, nbins <= 40: lane-private fp32 bins (conflict free, no shuffles)
+constexpr int BM_WARP = 1;             // spherical, nbins <= 254: per-warp fp64 bins, warp-cooperative flush
+constexpr int BM_CYL = 2;              // cylindrical, k_perp bins <= 40: lane-private bins, [bins][8 k_z] per CTA
 constexpr int NHK = NZ / 2 + 1;        // 129 k_z values of the half spectrum
 // cylindrical mode: 64 CTAs take the main tiles with tl % 64 == slot (16 tiles each: always the same 8 k_z),
 // 8 CTAs take one Nyquist tile each
@@ -462,11 +467,48 @@ k_fused_p1(const float* __restrict__ boxes, long long batch_stride, int n2_total
 // ------------------------------------------------------------------------------------------------
 // pass 2
 // ------------------------------------------------------------------------------------------------
-// CYL = false: spherical bins, partial sums [box][slot][bins] (slot = blockIdx.x of SLOTS).
-// CYL = true : (k_perp bin, k_z) bins; every thread has one k_z per tile (t = tid & 7), so the lane-private
+// Spherical binning: warp-cooperative flush.  Lanes flagged `chg` leave the run of bin `cur` with the fp32 run sum
+// `val`; lanes that leave the same bin are summed by a shuffle tree and lane 0 adds the total to the warp's
+// private fp64 bin.  Fixed order everywhere -> bitwise reproducible; no atomics, no lane-private arrays.
+__device__ __forceinline__ void warp_flush(double* __restrict__ wb, uint32_t cur, float val, bool chg) {
+    unsigned todo = __ballot_sync(0xffffffffu, chg && cur != 255u);
+    while (todo) {
+        const int leader = __ffs(todo) - 1;
+        const uint32_t b = __shfl_sync(0xffffffffu, cur, leader);
+        const bool mine = chg && cur == b;
+        float v = mine ? val : 0.f;
+#pragma unroll
+        for (int s = 16; s > 0; s >>= 1) v += __shfl_xor_sync(0xffffffffu, v, s);
+        if ((threadIdx.x & 31) == 0) wb[b] += (double)v;
+        todo &= ~__ballot_sync(0xffffffffu, mine);
+    }
+}
+
+// run-length binning of the four outputs of one 32-bit LUT word (spherical mode)
+__device__ __forceinline__ void bin_word(double* __restrict__ wb, uint32_t word, const float (&pw)[4], float mult,
+                                         uint32_t& cur, float& acc) {
+    if (__all_sync(0xffffffffu, word == cur * 0x01010101u)) {
+        acc += (pw[0] + pw[1]) + (pw[2] + pw[3]);  // whole word stays in the current bin, all lanes
+        return;
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const uint32_t b = (word >> (8 * i)) & 255u;
+        const bool chg = b != cur;
+        if (__any_sync(0xffffffffu, chg)) warp_flush(wb, cur, mult * acc, chg);
+        if (chg) {
+            cur = b;
+            acc = 0.f;
+        }
+        acc += pw[i];
+    }
+}
+
+// BM_LANE / BM_WARP: spherical bins, partial sums [box][slot][bins] (slot = blockIdx.x of SLOTS).
+// BM_CYL    : (k_perp bin, k_z) bins; every thread has one k_z per tile (t = tid & 7), so the lane-private
 //              bins are k_perp bins and the per-tile flush keeps the 8 k_z of the tile apart; partial sums go
 //              to a compact [item][CYL_SLOTS][bins][8] record that k_fused_cyl_reduce expands.
-template <bool CYL>
+template <int BM>
 __global__ void __launch_bounds__(P2_THREADS, 2)
 k_fused_p2(const float2* __restrict__ scratch, ItemMap im, const ChunkDev* __restrict__ chunks,
            const uint16_t* const* __restrict__ luts, double* __restrict__ partials, long long out_per_box,
@@ -475,8 +517,12 @@ k_fused_p2(const float2* __restrict__ scratch, ItemMap im, const ChunkDev* __res
     uint8_t* lutb = reinterpret_cast<uint8_t*>(tile + TILE);           // [TILE] bin index of every output of the tile
     float4* tw = reinterpret_cast<float4*>(lutb + TILE);               // [256]
     uint64_t* bar = reinterpret_cast<uint64_t*>(tw + 256);
-    double* cbins = reinterpret_cast<double*>(bar + 2);                // [MAX_BINS] or, CYL, [MAX_BINS][8]
-    float* lbins = reinterpret_cast<float*>(cbins + MAX_BINS * (CYL ? 8 : 1));  // [nbins][P2_THREADS]
+    constexpr bool CYL = BM == BM_CYL, WARPB = BM == BM_WARP;
+    // BM_LANE: CTA fp64 bins [MAX_BINS] + lane fp32 bins [nbins][256];  BM_CYL: [MAX_BINS][8] + lane bins;
+    // BM_WARP: per-warp fp64 bins [8][nbins]
+    double* cbins = reinterpret_cast<double*>(bar + 2);
+    float* lbins = reinterpret_cast<float*>(cbins + MAX_BINS * (CYL ? 8 : 1));
+    double* wb = cbins + (threadIdx.x >> 5) * nbins;
     const int tid = threadIdx.x;
     long long box;
     int cid;
@@ -485,8 +531,12 @@ k_fused_p2(const float2* __restrict__ scratch, ItemMap im, const ChunkDev* __res
     const uint8_t* __restrict__ lut = reinterpret_cast<const uint8_t*>(luts[cid]);
     const float2* src = scratch + (long long)blockIdx.y * ((long long)NTILES * TILE);
     tw[tid] = tw_g[tid];
-    for (int i = tid; i < nbins * P2_THREADS; i += P2_THREADS) lbins[i] = 0.f;
-    for (int i = tid; i < MAX_BINS * (CYL ? 8 : 1); i += P2_THREADS) cbins[i] = 0.0;
+    if (WARPB) {
+        for (int i = tid; i < (P2_THREADS / 32) * nbins; i += P2_THREADS) cbins[i] = 0.0;
+    } else {
+        for (int i = tid; i < nbins * P2_THREADS; i += P2_THREADS) lbins[i] = 0.f;
+        for (int i = tid; i < MAX_BINS * (CYL ? 8 : 1); i += P2_THREADS) cbins[i] = 0.0;
+    }
     if (tid == 0) {
         mbar_init(bar, 1);
         mbar_fence_init();
@@ -572,7 +622,9 @@ k_fused_p2(const float2* __restrict__ scratch, ItemMap im, const ChunkDev* __res
                     float pw[4];
 #pragma unroll
                     for (int i = 0; i < 4; ++i) pw[i] = v[r0 + i].x * v[r0 + i].x + v[r0 + i].y * v[r0 + i].y;
-                    if (__all_sync(0xffffffffu, w4[g] == cur * 0x01010101u)) {
+                    if (WARPB) {
+                        bin_word(wb, w4[g], pw, mult, cur, acc);
+                    } else if (__all_sync(0xffffffffu, w4[g] == cur * 0x01010101u)) {
                         acc += (pw[0] + pw[1]) + (pw[2] + pw[3]);  // whole word stays in the current bin, all lanes
                     } else {
 #pragma unroll
@@ -588,7 +640,8 @@ k_fused_p2(const float2* __restrict__ scratch, ItemMap im, const ChunkDev* __res
                     }
                 }
             }
-            if (cur != 255u) lbins[cur * P2_THREADS + tid] += mult * acc;
+            if (WARPB) warp_flush(wb, cur, mult * acc, true);
+            else if (cur != 255u) lbins[cur * P2_THREADS + tid] += mult * acc;
         }
         __syncthreads();
         // tile buffer is free: prefetch the next tile while the bins are flushed
@@ -598,7 +651,7 @@ k_fused_p2(const float2* __restrict__ scratch, ItemMap im, const ChunkDev* __res
         }
         // ---- every FLUSH_EVERY tiles (and after the last one): flush the lane-private fp32 bins into the CTA's
         //      fp64 bins in a fixed order; a lane-private bin then holds at most 32 * FLUSH_EVERY fp32 terms
-        if ((it % FLUSH_EVERY) == FLUSH_EVERY - 1 || it + 1 == count) {
+        if (!WARPB && ((it % FLUSH_EVERY) == FLUSH_EVERY - 1 || it + 1 == count)) {
             const int warp = tid >> 5, lane = tid & 31;
             for (int b = warp; b < nbins; b += P2_THREADS / 32) {
                 double acc = 0.0;
@@ -622,7 +675,14 @@ k_fused_p2(const float2* __restrict__ scratch, ItemMap im, const ChunkDev* __res
         // (the next iteration's barriers order the zeroed lane bins before they are used again)
     }
     __syncthreads();
-    if (!CYL) {
+    if (WARPB) {
+        double* out = partials + (box * slots_max + blockIdx.x) * out_per_box + ch.out_off;
+        for (int i = tid; i < nbins; i += P2_THREADS) {
+            double a = 0.0;
+            for (int wi = 0; wi < P2_THREADS / 32; ++wi) a += cbins[wi * nbins + i];  // warps in fixed order
+            out[i] = a;
+        }
+    } else if (!CYL) {
         double* out = partials + (box * slots_max + blockIdx.x) * out_per_box + ch.out_off;
         for (int i = tid; i < nbins; i += P2_THREADS) out[i] = cbins[i];
     } else {
@@ -634,6 +694,7 @@ k_fused_p2(const float2* __restrict__ scratch, ItemMap im, const ChunkDev* __res
 // pass 2 for the 128 x 128 sky plane (spherical bins): tile = [x 128][y_lo 2][k_z 32].  Lanes run along the 32
 // k_z of a chunk in every access.  S1: 2-point FFT over y_lo x radix 16 over x = xa + 8 m (32 points per
 // thread); S2: four radix-8 butterflies over xa per thread (kx = m' + 16 q), |delta_k|^2 and bins from registers.
+template <bool WARPB>
 __global__ void __launch_bounds__(P2_THREADS, 2)
 k_fused_p2_s128(const float2* __restrict__ scratch, ItemMap im, const ChunkDev* __restrict__ chunks,
                 const uint16_t* const* __restrict__ luts, double* __restrict__ partials, long long out_per_box,
@@ -643,8 +704,9 @@ k_fused_p2_s128(const float2* __restrict__ scratch, ItemMap im, const ChunkDev* 
     uint8_t* lutb = reinterpret_cast<uint8_t*>(tile + TILE);           // [TILE]
     float4* tw = reinterpret_cast<float4*>(lutb + TILE);               // [256]
     uint64_t* bar = reinterpret_cast<uint64_t*>(tw + 256);
-    double* cbins = reinterpret_cast<double*>(bar + 2);                // [MAX_BINS]
-    float* lbins = reinterpret_cast<float*>(cbins + MAX_BINS);         // [nbins][P2_THREADS]
+    double* cbins = reinterpret_cast<double*>(bar + 2);                // [MAX_BINS], or per-warp [8][nbins] (WARPB)
+    float* lbins = reinterpret_cast<float*>(cbins + MAX_BINS);         // [nbins][P2_THREADS] (lane mode)
+    double* wb = cbins + (threadIdx.x >> 5) * nbins;
     const int tid = threadIdx.x;
     long long box;
     int cid;
@@ -653,8 +715,12 @@ k_fused_p2_s128(const float2* __restrict__ scratch, ItemMap im, const ChunkDev* 
     const uint8_t* __restrict__ lut = reinterpret_cast<const uint8_t*>(luts[cid]);
     const float2* src = scratch + (long long)blockIdx.y * ((long long)G::NTILES_S * TILE);
     tw[tid] = tw_g[tid];
-    for (int i = tid; i < nbins * P2_THREADS; i += P2_THREADS) lbins[i] = 0.f;
-    if (tid < MAX_BINS) cbins[tid] = 0.0;
+    if (WARPB) {
+        for (int i = tid; i < (P2_THREADS / 32) * nbins; i += P2_THREADS) cbins[i] = 0.0;
+    } else {
+        for (int i = tid; i < nbins * P2_THREADS; i += P2_THREADS) lbins[i] = 0.f;
+        if (tid < MAX_BINS) cbins[tid] = 0.0;
+    }
     if (tid == 0) {
         mbar_init(bar, 1);
         mbar_fence_init();
@@ -713,28 +779,40 @@ k_fused_p2_s128(const float2* __restrict__ scratch, ItemMap im, const ChunkDev* 
                 for (int xa = 0; xa < 8; ++xa) v[xa] = tile[G::tile_idx(xa + 8 * m1, kyb, t)];
                 small_dft<8>(v);
                 if (i == 0 && tl == 0 && tid == 0) dc[box * nchunks + cid] = v[0];
+                if (WARPB) {
 #pragma unroll
-                for (int q = 0; q < 8; ++q) {
-                    const uint32_t b = (w8[2 * i + (q >> 2)] >> (8 * (q & 3))) & 255u;
-                    const float pw = v[q].x * v[q].x + v[q].y * v[q].y;
-                    if (__any_sync(0xffffffffu, b != cur)) {
-                        if (b != cur) {
-                            if (cur != 255u) lbins[cur * P2_THREADS + tid] += mult * acc;
-                            cur = b;
-                            acc = 0.f;
-                        }
+                    for (int g = 0; g < 2; ++g) {
+                        float pw[4];
+#pragma unroll
+                        for (int q = 0; q < 4; ++q)
+                            pw[q] = v[4 * g + q].x * v[4 * g + q].x + v[4 * g + q].y * v[4 * g + q].y;
+                        bin_word(wb, w8[2 * i + g], pw, mult, cur, acc);
                     }
-                    acc += pw;
+                } else {
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) {
+                        const uint32_t b = (w8[2 * i + (q >> 2)] >> (8 * (q & 3))) & 255u;
+                        const float pw = v[q].x * v[q].x + v[q].y * v[q].y;
+                        if (__any_sync(0xffffffffu, b != cur)) {
+                            if (b != cur) {
+                                if (cur != 255u) lbins[cur * P2_THREADS + tid] += mult * acc;
+                                cur = b;
+                                acc = 0.f;
+                            }
+                        }
+                        acc += pw;
+                    }
                 }
             }
-            if (cur != 255u) lbins[cur * P2_THREADS + tid] += mult * acc;
+            if (WARPB) warp_flush(wb, cur, mult * acc, true);
+            else if (cur != 255u) lbins[cur * P2_THREADS + tid] += mult * acc;
         }
         __syncthreads();
         if (tid == 0 && it + 1 < count) {
             fence_proxy_async();
             issue_tile(tl + stride);
         }
-        if ((it % FLUSH_EVERY) == FLUSH_EVERY - 1 || it + 1 == count) {  // fixed-order fp32 -> fp64 flush
+        if (!WARPB && ((it % FLUSH_EVERY) == FLUSH_EVERY - 1 || it + 1 == count)) {  // fixed-order fp32 -> fp64 flush
             const int warp = tid >> 5, lane = tid & 31;
             for (int b = warp; b < nbins; b += P2_THREADS / 32) {
                 double a = 0.0;
@@ -752,7 +830,12 @@ k_fused_p2_s128(const float2* __restrict__ scratch, ItemMap im, const ChunkDev* 
     }
     __syncthreads();
     double* out = partials + (box * slots_max + blockIdx.x) * out_per_box + ch.out_off;
-    for (int i = tid; i < nbins; i += P2_THREADS) out[i] = cbins[i];
+    for (int i = tid; i < nbins; i += P2_THREADS) {
+        double a = cbins[i];
+        if (WARPB)
+            for (int wi = 1; wi < P2_THREADS / 32; ++wi) a += cbins[wi * nbins + i];  // warps in fixed order
+        out[i] = a;
+    }
 }
 
 // cylindrical mode: expand the compact per-CTA records into the standard partial-sum layout (one slot)
@@ -778,8 +861,14 @@ __global__ void k_fused_cyl_reduce(const double* __restrict__ cylpart, ItemMap i
 }
 
 static size_t p1_smem() { return (size_t)R1 * ROWLD * 8 + 128 * 8 + 66 * 16 + 64; }
-static size_t p2_smem(int nbins, bool cyl) {
-    return (size_t)TILE * 8 + TILE + 256 * 16 + 16 + MAX_BINS * 8 * (cyl ? 8 : 1) + (size_t)nbins * P2_THREADS * 4;
+static int bin_mode(const ps21_plan* p) {
+    if (p->mode == PS21_MODE_CYLINDRICAL) return BM_CYL;
+    return p->nbins <= MAX_BINS ? BM_LANE : BM_WARP;
+}
+static size_t p2_smem(int nbins, int bm) {
+    const size_t bins = bm == BM_WARP ? (size_t)(P2_THREADS / 32) * nbins * 8
+                                      : (size_t)MAX_BINS * 8 * (bm == BM_CYL ? 8 : 1) + (size_t)nbins * P2_THREADS * 4;
+    return (size_t)TILE * 8 + TILE + 256 * 16 + 16 + bins;
 }
 
 }  // namespace fz
@@ -795,8 +884,8 @@ int fused_try_setup(ps21_plan* p, ShapePlan& sp) {
         set_error("fused cylindrical bins need the 256 x 256 sky plane");
         return -1;
     }
-    if (p->nbins > MAX_BINS) {
-        set_error("fused path needs n_psbins <= 40");
+    if (p->nbins > (p->mode == PS21_MODE_CYLINDRICAL ? MAX_BINS : MAX_BINS_SPH)) {
+        set_error("fused path needs n_psbins <= 254 (spherical) / 40 (cylindrical)");
         return -1;
     }
     if (p->n2_total % 4 != 0) {
@@ -830,12 +919,16 @@ int fused_try_setup(ps21_plan* p, ShapePlan& sp) {
         cudaMemcpy(fs->tw256, tw.data(), sizeof(float4) * 256, cudaMemcpyHostToDevice) != cudaSuccess ||
         cudaFuncSetAttribute(k_fused_p1<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p1_smem()) != cudaSuccess ||
         cudaFuncSetAttribute(k_fused_p1<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p1_smem()) != cudaSuccess ||
-        cudaFuncSetAttribute(k_fused_p2_s128, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             (int)p2_smem(MAX_BINS, false)) != cudaSuccess ||
-        cudaFuncSetAttribute(k_fused_p2<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             (int)p2_smem(MAX_BINS, false)) != cudaSuccess ||
-        cudaFuncSetAttribute(k_fused_p2<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             (int)p2_smem(MAX_BINS, true)) != cudaSuccess) {
+        cudaFuncSetAttribute(k_fused_p2_s128<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)p2_smem(MAX_BINS, BM_LANE)) != cudaSuccess ||
+        cudaFuncSetAttribute(k_fused_p2_s128<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)p2_smem(MAX_BINS_SPH, BM_WARP)) != cudaSuccess ||
+        cudaFuncSetAttribute(k_fused_p2<BM_LANE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)p2_smem(MAX_BINS, BM_LANE)) != cudaSuccess ||
+        cudaFuncSetAttribute(k_fused_p2<BM_WARP>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)p2_smem(MAX_BINS_SPH, BM_WARP)) != cudaSuccess ||
+        cudaFuncSetAttribute(k_fused_p2<BM_CYL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)p2_smem(MAX_BINS, BM_CYL)) != cudaSuccess) {
         cudaGetLastError();
         if (fs->tw256) cudaFree(fs->tw256);
         delete fs;
@@ -896,16 +989,25 @@ int fused_forward(ps21_plan* p, ShapePlan& sp, const float* d_boxes, long long b
     }
     {
         ProfScope ps(p, KK_PASS_BIN, st);
+        const int bm = bin_mode(p);
+#define PS21_P2_ARGS                                                                                                  \
+    p->d_scratch, im, p->d_chunks, (const uint16_t* const*)p->d_lut_table, p->d_partials, p->out_per_box, p->slots_max, \
+        p->d_dc, p->nchunks, fs->tw256, p->nbins
         if (fs->S == 128) {
-            PS21_LAUNCH(k_fused_p2_s128, dim3(Geo<128>::SLOTS_S, (unsigned)nitems), dim3(P2_THREADS),
-                        p2_smem(p->nbins, false), st, p->d_scratch, im, p->d_chunks,
-                        (const uint16_t* const*)p->d_lut_table, p->d_partials, p->out_per_box, p->slots_max, p->d_dc,
-                        p->nchunks, fs->tw256, p->nbins);
+            if (bm == BM_LANE)
+                PS21_LAUNCH(k_fused_p2_s128<false>, dim3(Geo<128>::SLOTS_S, (unsigned)nitems), dim3(P2_THREADS),
+                            p2_smem(p->nbins, bm), st, PS21_P2_ARGS);
+            else
+                PS21_LAUNCH(k_fused_p2_s128<true>, dim3(Geo<128>::SLOTS_S, (unsigned)nitems), dim3(P2_THREADS),
+                            p2_smem(p->nbins, bm), st, PS21_P2_ARGS);
             PS21_CUDA(cudaGetLastError());
-        } else if (p->mode == PS21_MODE_SPHERICAL) {
-            PS21_LAUNCH(k_fused_p2<false>, dim3(SLOTS, (unsigned)nitems), dim3(P2_THREADS), p2_smem(p->nbins, false), st,
-                        p->d_scratch, im, p->d_chunks, (const uint16_t* const*)p->d_lut_table, p->d_partials,
-                        p->out_per_box, p->slots_max, p->d_dc, p->nchunks, fs->tw256, p->nbins);
+        } else if (bm == BM_LANE) {
+            PS21_LAUNCH(k_fused_p2<BM_LANE>, dim3(SLOTS, (unsigned)nitems), dim3(P2_THREADS), p2_smem(p->nbins, bm), st,
+                        PS21_P2_ARGS);
+            PS21_CUDA(cudaGetLastError());
+        } else if (bm == BM_WARP) {
+            PS21_LAUNCH(k_fused_p2<BM_WARP>, dim3(SLOTS, (unsigned)nitems), dim3(P2_THREADS), p2_smem(p->nbins, bm), st,
+                        PS21_P2_ARGS);
             PS21_CUDA(cudaGetLastError());
         } else {
             if (fs->cylpart_items < nitems) {
@@ -915,8 +1017,8 @@ int fused_forward(ps21_plan* p, ShapePlan& sp, const float* d_boxes, long long b
                 PS21_CUDA(cudaMalloc((void**)&fs->cylpart, sizeof(double) * nitems * CYL_SLOTS * p->nbins * 8));
                 fs->cylpart_items = nitems;
             }
-            PS21_LAUNCH(k_fused_p2<true>, dim3(CYL_SLOTS, (unsigned)nitems), dim3(P2_THREADS), p2_smem(p->nbins, true),
-                        st, p->d_scratch, im, p->d_chunks, (const uint16_t* const*)p->d_lut_table, fs->cylpart,
+            PS21_LAUNCH(k_fused_p2<BM_CYL>, dim3(CYL_SLOTS, (unsigned)nitems), dim3(P2_THREADS),
+                        p2_smem(p->nbins, BM_CYL), st, p->d_scratch, im, p->d_chunks, (const uint16_t* const*)p->d_lut_table, fs->cylpart,
                         p->out_per_box, p->slots_max, p->d_dc, p->nchunks, fs->tw256, p->nbins);
             PS21_CUDA(cudaGetLastError());
             PS21_LAUNCH(k_fused_cyl_reduce, dim3((unsigned)nitems), dim3(256), 0, st, fs->cylpart, im, p->d_chunks,

@@ -84,6 +84,30 @@ static inline int __any_sync(unsigned, int pred) {
     return any;
 }
 static inline int __all_sync(unsigned m, int pred) { return !__any_sync(m, !pred); }
+static inline unsigned __ballot_sync(unsigned, int pred) {
+    const int me = ps21emu::linear_tid();
+    *ps21emu::shfl_slot(me) = pred ? 1ull : 0ull;
+    ps21emu::syncwarp();
+    unsigned out = 0;
+    for (int l = 0; l < 32; ++l) out |= (unsigned)(*ps21emu::shfl_slot((me & ~31) | l) & 1ull) << l;
+    ps21emu::syncwarp();
+    return out;
+}
+template <class T>
+static inline T __shfl_sync(unsigned, T v, int src) {
+    static_assert(sizeof(T) <= 8, "shuffle payload");
+    const int me = ps21emu::linear_tid();
+    unsigned long long raw = 0;
+    std::memcpy(&raw, &v, sizeof(T));
+    *ps21emu::shfl_slot(me) = raw;
+    ps21emu::syncwarp();
+    raw = *ps21emu::shfl_slot((me & ~31) | (src & 31));
+    ps21emu::syncwarp();
+    T out;
+    std::memcpy(&out, &raw, sizeof(T));
+    return out;
+}
+static inline int __ffs(unsigned v) { return __builtin_ffs((int)v); }
 enum { cudaFuncAttributeMaxDynamicSharedMemorySize = 8 };
 template <class F>
 static inline int cudaFuncSetAttribute(F, int, int) { return 0; }

@@ -58,6 +58,8 @@ def test_compute_power_lightcone(mods, kpath, shape, L, nb, log, flags, rule):
     (20, True, (True, False, False)),
     (24, False, (False, False, False)),   # DC mode binned: exercises the fp64 offset restoration
     (40, True, (True, True, True)),
+    (None, True, (True, False, False)),   # the reference's default: int(256 / 2.2) = 116 bins
+    (254, False, (True, False, False)),   # the most the byte LUT can address
 ])
 def test_fused_path_vs_oracle_256(mods, nb, log, flags):
     """256 x 256 x 256 chunk (benchmark chunk shape) through the fused kernels vs the fp64 oracle."""
