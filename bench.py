@@ -389,7 +389,7 @@ def run_gpu(args):
         "config": {"workload": f"{walkers} walkers/GPU x "
                                + (f"{NREDSHIFT} coeval cubes " if NREDSHIFT > 1 else "")
                                + f"{SHAPE[0]}x{SHAPE[1]}x{SHAPE[2]} float32, "
-                               f"{NCHUNKS} chunk(s), 20 {'k_perp x k_par' if cyl else 'log-k'} bins ({WORKLOAD})",
+                               f"{NCHUNKS} chunk(s), {NBINS} {'k_perp x k_par' if cyl else 'log-k'} bins ({WORKLOAD})",
                    "l2": f"inputs ({nboxes * int(np.prod(SHAPE)) * 4 / 2**30:.1f} GiB/GPU) exceed the 126 MB L2; "
                          "no flush needed",
                    "kernel_path": plan.path, "walkers_per_gpu": walkers, "parallelism": f"walker-sharded x{world}",
@@ -414,12 +414,15 @@ def main():
     ap.add_argument("--workspace-mb", type=int, default=0)
     ap.add_argument("--config", type=int, default=3, choices=[1, 2, 3, 4, 5],
                     help="BASELINE.json lightcone configuration (3 = the headline metric)")
+    ap.add_argument("--nbins", type=int, default=20,
+                    help="n_psbins (20 = BASELINE; 116 = the reference default for 256^3 chunks)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--e2e-walkers", type=int, default=16)
     ap.add_argument("--e2e-steps", type=int, default=3)
     args = ap.parse_args()
     select_config(args.config)
+    globals()["NBINS"] = args.nbins
     if args.warmup < 3 and args.impl == "b200":
         args.warmup = 3  # timing rule: at least 3 warm-up steps
     if args.impl == "reference":
