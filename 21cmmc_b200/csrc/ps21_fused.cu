@@ -47,6 +47,10 @@ constexpr int FLUSH_EVERY = 4;         // lane-private mode: tiles between two f
 constexpr int BM_LANE = 0;             // spherical, nbins <= 40: lane-private fp32 bins (conflict free, no shuffles)
 constexpr int BM_WARP = 1;             // spherical, nbins <= 254: per-warp fp64 bins, warp-cooperative flush
 constexpr int BM_CYL = 2;              // cylindrical, k_perp bins <= 40: lane-private bins, [bins][8 k_z] per CTA
+constexpr int BM_GROUP = 3;            // spherical, nbins <= 144: one fp32 bin column per group of 4 lanes that share
+                                       // (warp, k_z) and differ only in m' & 3 -> nearly the same |k|; the 4 lanes update
+                                       // the column one after the other (fixed order, no shuffles, no atomics)
+constexpr int MAX_BINS_GROUP = 144;    // 144 bins x 64 groups x 4 B = 36 KB
 constexpr int NHK = NZ / 2 + 1;        // 129 k_z values of the half spectrum
 // cylindrical mode: 64 CTAs take the main tiles with tl % 64 == slot (16 tiles each: always the same 8 k_z),
 // 8 CTAs take one Nyquist tile each
@@ -517,11 +521,13 @@ k_fused_p2(const float2* __restrict__ scratch, ItemMap im, const ChunkDev* __res
     uint8_t* lutb = reinterpret_cast<uint8_t*>(tile + TILE);           // [TILE] bin index of every output of the tile
     float4* tw = reinterpret_cast<float4*>(lutb + TILE);               // [256]
     uint64_t* bar = reinterpret_cast<uint64_t*>(tw + 256);
-    constexpr bool CYL = BM == BM_CYL, WARPB = BM == BM_WARP;
+    constexpr bool CYL = BM == BM_CYL, WARPB = BM == BM_WARP, GROUPB = BM == BM_GROUP;
+    constexpr int NCOL = GROUPB ? P2_THREADS / 4 : P2_THREADS;  // private bin columns per CTA
+    constexpr int CB = GROUPB ? MAX_BINS_GROUP : MAX_BINS;      // CTA fp64 bins
     // BM_LANE: CTA fp64 bins [MAX_BINS] + lane fp32 bins [nbins][256];  BM_CYL: [MAX_BINS][8] + lane bins;
     // BM_WARP: per-warp fp64 bins [8][nbins]
     double* cbins = reinterpret_cast<double*>(bar + 2);
-    float* lbins = reinterpret_cast<float*>(cbins + MAX_BINS * (CYL ? 8 : 1));
+    float* lbins = reinterpret_cast<float*>(cbins + CB * (CYL ? 8 : 1));  // [nbins][NCOL]
     double* wb = cbins + (threadIdx.x >> 5) * nbins;
     const int tid = threadIdx.x;
     long long box;
@@ -534,8 +540,8 @@ k_fused_p2(const float2* __restrict__ scratch, ItemMap im, const ChunkDev* __res
     if (WARPB) {
         for (int i = tid; i < (P2_THREADS / 32) * nbins; i += P2_THREADS) cbins[i] = 0.0;
     } else {
-        for (int i = tid; i < nbins * P2_THREADS; i += P2_THREADS) lbins[i] = 0.f;
-        for (int i = tid; i < MAX_BINS * (CYL ? 8 : 1); i += P2_THREADS) cbins[i] = 0.0;
+        for (int i = tid; i < nbins * NCOL; i += P2_THREADS) lbins[i] = 0.f;
+        for (int i = tid; i < CB * (CYL ? 8 : 1); i += P2_THREADS) cbins[i] = 0.0;
     }
     if (tid == 0) {
         mbar_init(bar, 1);
@@ -612,6 +618,20 @@ k_fused_p2(const float2* __restrict__ scratch, ItemMap im, const ChunkDev* __res
             const uint4* lp = reinterpret_cast<const uint4*>(lutb + tid * 32);
             uint32_t cur = 255u;
             float acc = 0.f;
+            // private bin column of this lane (BM_LANE / BM_CYL) or of its 4-lane group (BM_GROUP: lanes t + 8 j)
+            const int col = GROUPB ? ((tid & 7) | ((tid >> 5) << 3)) : tid;
+            const int member = (tid >> 3) & 3;
+            auto lane_update = [&](uint32_t b, float val, bool on) {
+                if (!GROUPB) {
+                    if (on && b != 255u) lbins[b * NCOL + col] += val;
+                } else {  // the four lanes of a group take turns (warp-uniform call site)
+#pragma unroll
+                    for (int mm = 0; mm < 4; ++mm) {
+                        if (on && b != 255u && member == mm) lbins[b * NCOL + col] += val;
+                        __syncwarp();
+                    }
+                }
+            };
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
                 const uint4 lv = lp[h];
@@ -630,8 +650,9 @@ k_fused_p2(const float2* __restrict__ scratch, ItemMap im, const ChunkDev* __res
 #pragma unroll
                         for (int i = 0; i < 4; ++i) {
                             const uint32_t b = (w4[g] >> (8 * i)) & 255u;
-                            if (b != cur) {
-                                if (cur != 255u) lbins[cur * P2_THREADS + tid] += mult * acc;
+                            const bool chg = b != cur;
+                            if (!GROUPB || __any_sync(0xffffffffu, chg)) lane_update(cur, mult * acc, chg);
+                            if (chg) {
                                 cur = b;
                                 acc = 0.f;
                             }
@@ -641,7 +662,7 @@ k_fused_p2(const float2* __restrict__ scratch, ItemMap im, const ChunkDev* __res
                 }
             }
             if (WARPB) warp_flush(wb, cur, mult * acc, true);
-            else if (cur != 255u) lbins[cur * P2_THREADS + tid] += mult * acc;
+            else lane_update(cur, mult * acc, true);
         }
         __syncthreads();
         // tile buffer is free: prefetch the next tile while the bins are flushed
@@ -656,8 +677,8 @@ k_fused_p2(const float2* __restrict__ scratch, ItemMap im, const ChunkDev* __res
             for (int b = warp; b < nbins; b += P2_THREADS / 32) {
                 double acc = 0.0;
 #pragma unroll
-                for (int i = 0; i < P2_THREADS / 32; ++i) {
-                    float* q = lbins + b * P2_THREADS + lane + 32 * i;
+                for (int i = 0; i < NCOL / 32; ++i) {
+                    float* q = lbins + b * NCOL + lane + 32 * i;
                     acc += (double)*q;
                     *q = 0.f;
                 }
@@ -863,11 +884,13 @@ __global__ void k_fused_cyl_reduce(const double* __restrict__ cylpart, ItemMap i
 static size_t p1_smem() { return (size_t)R1 * ROWLD * 8 + 128 * 8 + 66 * 16 + 64; }
 static int bin_mode(const ps21_plan* p) {
     if (p->mode == PS21_MODE_CYLINDRICAL) return BM_CYL;
-    return p->nbins <= MAX_BINS ? BM_LANE : BM_WARP;
+    if (p->nbins <= MAX_BINS) return BM_LANE;
+    return (p->n0 == 256 && p->nbins <= MAX_BINS_GROUP) ? BM_GROUP : BM_WARP;
 }
 static size_t p2_smem(int nbins, int bm) {
-    const size_t bins = bm == BM_WARP ? (size_t)(P2_THREADS / 32) * nbins * 8
-                                      : (size_t)MAX_BINS * 8 * (bm == BM_CYL ? 8 : 1) + (size_t)nbins * P2_THREADS * 4;
+    const size_t bins = bm == BM_WARP    ? (size_t)(P2_THREADS / 32) * nbins * 8
+                        : bm == BM_GROUP ? (size_t)MAX_BINS_GROUP * 8 + (size_t)nbins * (P2_THREADS / 4) * 4
+                                         : (size_t)MAX_BINS * 8 * (bm == BM_CYL ? 8 : 1) + (size_t)nbins * P2_THREADS * 4;
     return (size_t)TILE * 8 + TILE + 256 * 16 + 16 + bins;
 }
 
@@ -927,6 +950,8 @@ int fused_try_setup(ps21_plan* p, ShapePlan& sp) {
                              (int)p2_smem(MAX_BINS, BM_LANE)) != cudaSuccess ||
         cudaFuncSetAttribute(k_fused_p2<BM_WARP>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              (int)p2_smem(MAX_BINS_SPH, BM_WARP)) != cudaSuccess ||
+        cudaFuncSetAttribute(k_fused_p2<BM_GROUP>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)p2_smem(MAX_BINS_GROUP, BM_GROUP)) != cudaSuccess ||
         cudaFuncSetAttribute(k_fused_p2<BM_CYL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              (int)p2_smem(MAX_BINS, BM_CYL)) != cudaSuccess) {
         cudaGetLastError();
@@ -1003,6 +1028,10 @@ int fused_forward(ps21_plan* p, ShapePlan& sp, const float* d_boxes, long long b
             PS21_CUDA(cudaGetLastError());
         } else if (bm == BM_LANE) {
             PS21_LAUNCH(k_fused_p2<BM_LANE>, dim3(SLOTS, (unsigned)nitems), dim3(P2_THREADS), p2_smem(p->nbins, bm), st,
+                        PS21_P2_ARGS);
+            PS21_CUDA(cudaGetLastError());
+        } else if (bm == BM_GROUP) {
+            PS21_LAUNCH(k_fused_p2<BM_GROUP>, dim3(SLOTS, (unsigned)nitems), dim3(P2_THREADS), p2_smem(p->nbins, bm), st,
                         PS21_P2_ARGS);
             PS21_CUDA(cudaGetLastError());
         } else if (bm == BM_WARP) {
