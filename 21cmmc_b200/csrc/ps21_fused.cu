@@ -448,14 +448,15 @@ k_fused_p1(const float* __restrict__ boxes, long long batch_stride, int n2_total
             }
         }
         __syncthreads();
-        // ---- second y stage straight to HBM.  The Nyquist column (8 tasks) goes first.  Then each half of the
+        // ---- second y stage straight to HBM.  The Nyquist column (8 tasks) goes first.  Each half of the
         //      CTA (128 threads = the 128 k_z of one butterfly group) walks its own groups m1 = half, half + 2,
         //      ...: a group is 8 rows, and as soon as the half has consumed it (128-thread named barrier) its
         //      first warp starts the bulk copies of the next unit into those rows.
-        if (tid < 8) ystage2(yl, NHC, tid);
-        __syncthreads();  // the Nyquist tasks read rows of every group
         {
             const int half = tid >> 7;
+            // the Nyquist column of group m1 = 2q + half is taken by thread q of the half that owns (and later
+            // releases) that group, so the half's own barrier orders it before the reload
+            if ((tid & 127) < 4) ystage2(yl, NHC, 2 * (tid & 127) + half);
 #pragma unroll 1
             for (int q = 0; q < 4; ++q) {
                 const int m1 = 2 * q + half;
