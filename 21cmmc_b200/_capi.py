@@ -22,6 +22,7 @@ EXPORTS = (
     "ps21_last_error", "ps21_version", "ps21_plan_create", "ps21_plan_destroy", "ps21_plan_info",
     "ps21_plan_set_profiling", "ps21_plan_profile", "ps21_plan_layout", "ps21_plan_counts", "ps21_power_batched", "ps21_set_data", "ps21_lnl_batched",
     "ps21_power_host", "ps21_lnl_host", "ps21_lnl_from_delta", "ps21_chi2_host", "ps21_upper_limit_host",
+    "ps21_windowed_gauss_host",
 )
 
 
@@ -76,6 +77,7 @@ def _declare(lib):
     lib.ps21_chi2_host.argtypes = [C.c_int32, i64, i64, dp, dp, dp, C.POINTER(C.c_uint8), i64, C.POINTER(i64),
                                    C.c_double, C.c_int32, dp]
     lib.ps21_upper_limit_host.argtypes = [C.c_int32, i64, i64, i64, dp, dp, dp, dp, dp, C.c_double, dp]
+    lib.ps21_windowed_gauss_host.argtypes = lib.ps21_upper_limit_host.argtypes
     for name in EXPORTS:
         if name not in ("ps21_last_error",):
             getattr(lib, name).restype = C.c_int

@@ -196,10 +196,12 @@ __global__ void k_chi2_rows(const double* __restrict__ delta, long long n, long 
 }
 
 // one thread per model: nk window-function rows of length nkwf (tens of values each)
+// gauss = 0: one-sided erf likelihood of upper limits (likelihood.py:2324-2328);
+// gauss = 1: Gaussian -0.5 (after - value)^2 / err^2 of measured band powers (likelihood.py:569-583)
 __global__ void k_upper_limit(const double* __restrict__ model, long long nrec, int nk, int nkwf,
                               const double* __restrict__ wf, const double* __restrict__ limit,
                               const double* __restrict__ var, const double* __restrict__ model_err, double frac,
-                              double* __restrict__ lnl) {
+                              int gauss, double* __restrict__ lnl) {
     const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= nrec) return;
     const double* m = model + r * nkwf;
@@ -218,6 +220,11 @@ __global__ void k_upper_limit(const double* __restrict__ model, long long nrec, 
         if (model_err) {
             const double me = 0.5 * ((up - after) + (after - lo));
             e2 += me * me;
+        }
+        if (gauss) {
+            const double d = after - limit[k];
+            total += -0.5 * (d * d) / e2;   // np.sum: NaN propagates
+            continue;
         }
         double like = 0.5 + 0.5 * erf((limit[k] - after) / (sqrt(2.0) * sqrt(e2)));
         if (like <= 0.0) like = 1e-50;
@@ -806,9 +813,9 @@ int ps21_chi2_host(int32_t device, int64_t nrec, int64_t n, const double* delta,
     return PS21_OK;
 }
 
-int ps21_upper_limit_host(int32_t device, int64_t nrec, int64_t nk, int64_t nkwf, const double* model,
-                          const double* wf, const double* limit, const double* var, const double* model_err,
-                          double frac, double* lnl) {
+static int windowed_host(int32_t device, int64_t nrec, int64_t nk, int64_t nkwf, const double* model,
+                         const double* wf, const double* limit, const double* var, const double* model_err,
+                         double frac, int gauss, double* lnl) {
     if (!model || !wf || !limit || !var || !lnl || nrec < 0 || nk < 0 || nkwf < 0) return invalid("null argument");
     if (nrec == 0 || nk == 0) return PS21_OK;
     PS21_CUDA(cudaSetDevice(device));
@@ -826,13 +833,25 @@ int ps21_upper_limit_host(int32_t device, int64_t nrec, int64_t nk, int64_t nkwf
     up(&dout, lnl, (size_t)nrec);
     if (e == cudaSuccess) {
         PS21_LAUNCH(k_upper_limit, dim3((unsigned)((nrec + 63) / 64)), dim3(64), 0, (cudaStream_t)0, dm, (long long)nrec,
-                    (int)nk, (int)nkwf, dw, dl, dv, de, frac, dout);
+                    (int)nk, (int)nkwf, dw, dl, dv, de, frac, gauss, dout);
         e = cudaGetLastError();
     }
     if (e == cudaSuccess) e = cudaMemcpy(lnl, dout, sizeof(double) * nrec, cudaMemcpyDeviceToHost);
     free_dev(dm); free_dev(dw); free_dev(dl); free_dev(dv); free_dev(de); free_dev(dout);
-    if (e != cudaSuccess) return cuda_fail(e, "ps21_upper_limit_host");
+    if (e != cudaSuccess) return cuda_fail(e, gauss ? "ps21_windowed_gauss_host" : "ps21_upper_limit_host");
     return PS21_OK;
+}
+
+int ps21_upper_limit_host(int32_t device, int64_t nrec, int64_t nk, int64_t nkwf, const double* model,
+                          const double* wf, const double* limit, const double* var, const double* model_err,
+                          double frac, double* lnl) {
+    return windowed_host(device, nrec, nk, nkwf, model, wf, limit, var, model_err, frac, 0, lnl);
+}
+
+int ps21_windowed_gauss_host(int32_t device, int64_t nrec, int64_t nk, int64_t nkwf, const double* model,
+                             const double* wf, const double* value, const double* var, const double* model_err,
+                             double frac, double* lnl) {
+    return windowed_host(device, nrec, nk, nkwf, model, wf, value, var, model_err, frac, 1, lnl);
 }
 
 }  // extern "C"

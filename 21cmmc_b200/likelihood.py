@@ -484,6 +484,8 @@ class Likelihood1DPowerLightconeUpper(Likelihood1DPowerLightcone):
     variance] with NaN-padded k, ``wfband{z}`` (nfields, nk, nkwf), ``kwfband{z}`` (nkwf,).
     """
 
+    _entry = "ps21_upper_limit_host"
+
     def __init__(self, *args, band_chunks=None, model_error_fraction=0.2, **kwargs):
         kwargs.setdefault("simulate", False)
         super().__init__(*args, **kwargs)
@@ -542,7 +544,7 @@ class Likelihood1DPowerLightconeUpper(Likelihood1DPowerLightcone):
                 vals = np.ascontiguousarray(hd["band" + key][field, :nk, 1], dtype=np.float64)
                 var = np.ascontiguousarray(hd["band" + key][field, :nk, 2], dtype=np.float64)
                 wf = np.ascontiguousarray(hd["wfband" + key][field, :nk, :].reshape(nk, nkwf), dtype=np.float64)
-                _capi.check(lib.ps21_upper_limit_host(
+                _capi.check(getattr(lib, self._entry)(
                     _device(self.device), N, nk, nkwf, m.ctypes.data_as(dp), wf.ctypes.data_as(dp),
                     vals.ctypes.data_as(dp), var.ctypes.data_as(dp),
                     err.ctypes.data_as(dp) if err is not None else None, float(self.model_error_fraction),
@@ -551,6 +553,15 @@ class Likelihood1DPowerLightconeUpper(Likelihood1DPowerLightcone):
 
     def store(self, model, storage):
         super().store(model[0]["chunks"] if isinstance(model[0]["chunks"][0], dict) else model[0]["chunks"][0], storage)
+
+
+class Likelihood1DPowerLightconeWindowed(Likelihood1DPowerLightconeUpper):
+    """Measured (not upper-limit) band powers seen through window functions: the Gaussian branch of the
+    reference's ``Likelihood1DPowerCoeval.computeLikelihood`` (likelihood.py:517-583) -- same data layout, window
+    matvec, 20 % model error and optional emulator-style ``delta_err`` term as the upper-limit class, with
+    ``-0.5 (W.model - value)^2 / err^2`` instead of the one-sided erf."""
+
+    _entry = "ps21_windowed_gauss_host"
 
 
 def chi2_device(delta, data, noise, mask, seg, model_uncertainty, error_on_model, device=0):

@@ -149,6 +149,13 @@ int ps21_upper_limit_host(int32_t device, int64_t nrec, int64_t nk, int64_t nkwf
                           const double* wf, const double* limit, const double* var, const double* model_err,
                           double frac, double* lnl);
 
+/* Same window-function matvec and error model, but for measured band powers instead of limits: the Gaussian
+ * branch of Likelihood1DPowerCoeval.computeLikelihood, likelihood.py:517-583:
+ * lnl[r] += -0.5 * sum_k (after - value)^2 / (var + (frac*after)^2 + mean_err^2)   (NaN propagates, np.sum). */
+int ps21_windowed_gauss_host(int32_t device, int64_t nrec, int64_t nk, int64_t nkwf, const double* model,
+                             const double* wf, const double* value, const double* var, const double* model_err,
+                             double frac, double* lnl);
+
 #ifdef __cplusplus
 }
 #endif

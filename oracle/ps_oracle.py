@@ -254,8 +254,10 @@ def compute_likelihood(model, data, noise=None, min_k=0.1, max_k=1.0, model_unce
     return lnl
 
 
-def upper_limit_likelihood(hera_data, redshifts, delta, delta_err=None):
-    """Likelihood1DPowerLightconeUpper.computeLikelihood, src/py21cmmc/likelihood.py:2249-2335.
+def upper_limit_likelihood(hera_data, redshifts, delta, delta_err=None, gaussian=False):
+    """Likelihood1DPowerLightconeUpper.computeLikelihood, src/py21cmmc/likelihood.py:2249-2335; with
+    ``gaussian=True`` the measured-band-power branch of Likelihood1DPowerCoeval.computeLikelihood, :517-583
+    (identical window matvec and error model, Gaussian chi^2 with np.sum instead of erf with nansum).
 
     ``hera_data``: dict with ``band{z}`` (nfields, nk, 3) = [k, limit, variance] (NaN-padded k),
     ``wfband{z}`` (nfields, nk, nkwf), ``kwfband{z}`` (nkwf,).  ``delta``: (N, nbands, nkwf_max) model
@@ -286,6 +288,9 @@ def upper_limit_likelihood(hera_data, redshifts, delta, delta_err=None):
                     err = np.sqrt(var + (0.2 * after) ** 2 + mean_err**2)
                 else:
                     err = np.sqrt(var + (0.2 * after) ** 2)
+                if gaussian:
+                    lnl[i] += -0.5 * np.sum((after - vals) ** 2 / (err**2))
+                    continue
                 like = 0.5 + 0.5 * erf((vals - after) / (np.sqrt(2) * err))
                 like[like <= 0.0] = 1e-50
                 lnl[i] += np.nansum(np.log(like))

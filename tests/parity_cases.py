@@ -191,4 +191,11 @@ def check_upper_limit_likelihood(lk_mod, core_mod, chain_mod, tmp_path, shape=(1
     assert np.allclose(got, want, rtol=1e-10, atol=1e-12)
     val, blobs = chain([])
     assert abs(val - lnl_o) <= 1e-6 * abs(lnl_o) and "delta_0" in blobs
+    # measured band powers (Gaussian branch, likelihood.py:517-583) through the same window functions
+    lkg = lk_mod.Likelihood1DPowerLightconeWindowed(datafile=str(tmp_path / "hera.npz"), nchunks=nchunks,
+                                                    n_psbins=nb, band_chunks=[2, 0])
+    chain_mod.build_computation_chain(core_mod.CoreLightConeModule(lambda params: state["box"], up), lkg)
+    gotg = lkg.computeLikelihood([many])
+    wantg = O.upper_limit_likelihood(hera, hera["z_bands"], many["delta"], many["delta_err"], gaussian=True)
+    assert np.all(wantg < 0) and np.allclose(gotg, wantg, rtol=1e-10, atol=1e-12)
     return lnl, lnl_o
