@@ -70,6 +70,28 @@ def bin_edges(ksq_axes, nbins: int, log_bins: bool, edge_rule: str = "legacy_1.0
     return np.logspace(np.log10(mn), np.log10(top), nbins + 1)
 
 
+def detect_edge_rule():
+    """Edge rule of the powerbox installed next to this package, or None when powerbox is not importable.
+
+    SURVEY.md section 8c: the top-edge rule changed between powerbox generations, so it is probed rather than
+    assumed: a small anisotropic white-noise box is run through ``powerbox.get_power`` and the returned edges are
+    compared with both rules.
+    """
+    try:
+        from powerbox.tools import get_power
+    except Exception:
+        return None
+    shape, length = (8, 8, 12), (8.0, 8.0, 6.0)
+    box = np.random.default_rng(0).normal(size=shape).astype(np.float32)
+    edges = np.asarray(get_power(box, boxlength=list(length), bins=5, bin_ave=False, get_variance=False,
+                                 log_bins=False)[1])
+    k2 = [axis_wavenumbers(n, l) ** 2 for n, l in zip(shape, length)]
+    for rule in EDGE_RULES:
+        if np.allclose(edges, bin_edges(k2, 5, False, rule), rtol=1e-12, atol=0.0):
+            return rule
+    raise RuntimeError("installed powerbox matches neither known bin-edge rule; pass explicit edges")
+
+
 def bin_centres(edges: np.ndarray, log_bins: bool) -> np.ndarray:
     """likelihood.py:792-797."""
     k = np.asarray(edges)

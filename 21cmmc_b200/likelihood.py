@@ -37,6 +37,8 @@ def set_defaults(device=None, edge_rule=None, kernel_path=None):
     """Defaults used by the ``compute_power`` staticmethods (which have no instance to ask)."""
     if device is not None:
         _DEFAULTS["device"] = int(device)
+    if edge_rule == "auto":
+        edge_rule = binning.detect_edge_rule() or "legacy_1.001"
     if edge_rule is not None:
         if edge_rule not in binning.EDGE_RULES:
             raise ValueError(f"edge_rule must be one of {binning.EDGE_RULES}")
