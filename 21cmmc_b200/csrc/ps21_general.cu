@@ -9,13 +9,23 @@
 
 namespace ps21 {
 
+static int ilog2(int v) {
+    int l = 0;
+    while ((1 << l) < v) ++l;
+    return l;
+}
+
 // ---------------------------------------------------------------------------------------------
-// LUT: bin index of every half-spectrum mode, natural layout [x][y][kz]
+// LUT: bin index of every half-spectrum mode in the order the x pass consumes it: the (k_y,k_z) plane is cut
+// into tiles of `tile` consecutive columns m = y*nh + kz; tile tl holds [x][t] (m = tl*tile + t) in a block of
+// lut_blk entries (n0*tile rounded up to 16 bytes) -> one contiguous asynchronous copy per tile.  The table is
+// preset to kDiscard, which also covers the padding.
 // ---------------------------------------------------------------------------------------------
 __global__ void k_general_lut(uint16_t* __restrict__ lut, unsigned long long* __restrict__ counts, int n0, int n1,
                               int nz, int nh, const double* __restrict__ k0sq, const double* __restrict__ k1sq,
                               const double* __restrict__ k2sq, const double* __restrict__ edges, int nbins,
-                              int mode, int ig_kperp, int ig_kpar, int ig_k0, int y_zero) {
+                              int mode, int ig_kperp, int ig_kpar, int ig_k0, int y_zero, int lc,
+                              long long lut_blk) {
     const long long total = (long long)n0 * n1 * nh;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
          i += (long long)gridDim.x * blockDim.x) {
@@ -39,8 +49,16 @@ __global__ void k_general_lut(uint16_t* __restrict__ lut, unsigned long long* __
             v = (uint16_t)b;
             atomicAdd(&counts[b], (unsigned long long)w);
         }
-        lut[i] = v;
+        const long long m = (long long)y * nh + kz;
+        lut[(m >> lc) * lut_blk + ((long long)x << lc) + (m & ((1 << lc) - 1))] = v;
     }
+}
+
+long long general_lut_block(int n0, int tile) { return (((long long)n0 * tile + 7) / 8) * 8; }
+
+long long general_lut_elems(int n0, int n1, int nh, int tile) {
+    const long long plane = (long long)n1 * nh;
+    return ((plane + tile - 1) / tile) * general_lut_block(n0, tile);
 }
 
 int general_build_lut(ps21_plan* p, int chunk, const double* d_k0sq, const double* d_k1sq, const double* d_k2sq,
@@ -51,9 +69,13 @@ int general_build_lut(ps21_plan* p, int chunk, const double* d_k0sq, const doubl
     if (grid > 4096) grid = 4096;
     // y index of the "k_perp = 0" line exactly as the reference writes it: shifted [n0//2, n0//2, :]
     int y_zero = ((p->n0 / 2 - p->n1 / 2) % p->n1 + p->n1) % p->n1;
+    const ShapePlan& sp = p->shapes[c.shape];
+    PS21_CUDA(cudaMemsetAsync(p->d_lut[chunk], 0xFF,
+                              sizeof(uint16_t) * general_lut_elems(p->n0, p->n1, c.nh, sp.g3_tile), st));
     PS21_LAUNCH(k_general_lut, dim3(grid), dim3(256), 0, st, p->d_lut[chunk],
                 (unsigned long long*)(p->d_counts + c.out_off), p->n0, p->n1, c.nz, c.nh, d_k0sq, d_k1sq, d_k2sq,
-                d_edges, p->nbins, p->mode, p->ig_kperp, p->ig_kpar, p->ig_k0, y_zero);
+                d_edges, p->nbins, p->mode, p->ig_kperp, p->ig_kpar, p->ig_k0, y_zero, ilog2(sp.g3_tile),
+                general_lut_block(p->n0, sp.g3_tile));
     PS21_CUDA(cudaGetLastError());
     return PS21_OK;
 }
@@ -165,27 +187,52 @@ __global__ void k_general_zpass(const float* __restrict__ boxes, long long batch
 // ---------------------------------------------------------------------------------------------
 // g2: y pass, in place.  CTA = fixed x, `tile` consecutive k_z.
 // ---------------------------------------------------------------------------------------------
-__global__ void k_general_ypass(float2* __restrict__ scratch, long long spec_elems, int n1, int nh, FftFactors fy,
-                                const float2* __restrict__ tw, int lc) {
+// A CTA owns kYPassItems consecutive (x, k_z tile) work items and pipelines them through three rotating buffers:
+// the rows of item i+1 stream in with cp.async while item i is transformed and stored.
+constexpr int kYPassItems = 8;
+
+__global__ void k_general_ypass(float2* __restrict__ scratch, long long spec_elems, int n0, int n1, int nh,
+                                FftFactors fy, const float2* __restrict__ tw, int lc) {
     PS21_DYN_SMEM(float2, smem);
     const int tile = 1 << lc;
     const int ntile = (nh + tile - 1) >> lc;
-    const int x = blockIdx.x / ntile;
-    const int k0 = (blockIdx.x - x * ntile) << lc;
-    const int cols = min(tile, nh - k0);
     const int ld = tile | 1;
-    float2* A = smem;
-    float2* B = smem + (size_t)n1 * ld;
-    float2* base = scratch + (long long)blockIdx.y * spec_elems + (long long)x * n1 * nh + k0;
-    for (int i = threadIdx.x; i < (n1 << lc); i += blockDim.x) {
-        const int y = i >> lc, t = i & (tile - 1);
-        A[y * ld + t] = (t < cols) ? base[(long long)y * nh + t] : make_float2(0.f, 0.f);
-    }
-    __syncthreads();
-    const float2* R = column_fft(A, B, fy, ld, lc, tw);
-    for (int i = threadIdx.x; i < (n1 << lc); i += blockDim.x) {
-        const int y = i >> lc, t = i & (tile - 1);
-        if (t < cols) base[(long long)y * nh + t] = R[y * ld + t];
+    const size_t bufsz = (size_t)n1 * ld;
+    const int nwork = n0 * ntile;
+    const int w0 = blockIdx.x * kYPassItems;
+    const int w1 = min(nwork, w0 + kYPassItems);
+    float2* spec = scratch + (long long)blockIdx.y * spec_elems;
+    auto fetch = [&](int w, float2* X) {
+        const int x = w / ntile;
+        const int k0 = (w - x * ntile) << lc;
+        const int cols = min(tile, nh - k0);
+        const float2* base = spec + (long long)x * n1 * nh + k0;
+        for (int i = threadIdx.x; i < (n1 << lc); i += blockDim.x) {
+            const int y = i >> lc, t = i & (tile - 1);
+            if (t < cols) cp_async8(&X[y * ld + t], &base[(long long)y * nh + t]);
+            else X[y * ld + t] = make_float2(0.f, 0.f);
+        }
+        cp_async_commit();
+    };
+    int c = 0;
+    if (w0 < w1) fetch(w0, smem);
+    for (int w = w0; w < w1; ++w) {
+        float2* X0 = smem + c * bufsz;
+        float2* X1 = smem + ((c + 1) % 3) * bufsz;
+        float2* X2 = smem + ((c + 2) % 3) * bufsz;
+        cp_async_wait<0>();
+        __syncthreads();   // item w has landed in X0; the previous item's result has been stored by everybody
+        if (w + 1 < w1) fetch(w + 1, X2);
+        const float2* R = column_fft(X0, X1, fy, ld, lc, tw);
+        const int x = w / ntile;
+        const int k0 = (w - x * ntile) << lc;
+        const int cols = min(tile, nh - k0);
+        float2* base = spec + (long long)x * n1 * nh + k0;
+        for (int i = threadIdx.x; i < (n1 << lc); i += blockDim.x) {
+            const int y = i >> lc, t = i & (tile - 1);
+            if (t < cols) base[(long long)y * nh + t] = R[y * ld + t];
+        }
+        c = (c + 2) % 3;
     }
 }
 
@@ -194,12 +241,22 @@ __global__ void k_general_ypass(float2* __restrict__ scratch, long long spec_ele
 // consecutive (k_y,k_z) columns; fp64 bins privatised in shared memory; one flush per CTA into its
 // own partial-sum slot (no global atomics -> the cross-CTA reduction order is fixed).
 // ---------------------------------------------------------------------------------------------
+// Binning walk of the x pass: each thread walks a contiguous k_x segment of one column.  The bin index changes
+// rarely along k_x, so powers are summed in a register (at most 32 fp32 terms) and the CTA's fp64 bins in shared
+// memory are updated once per run with an atomic add.  (Two warp-cooperative variants without atomics -- a shuffle
+// flush per run and lanes-along-k_x warp sums -- were measured 20-130 % slower: the dependent shuffle chains cost
+// more than the few contended atomics.)
+//
+// Software pipeline: three FFT buffers rotate.  While tile i is transformed (ping-pong between two of them) and
+// binned, the strided rows of tile i+1 stream into the third with cp.async; the bin indices of tile i arrive in
+// their own commit group during the FFT.  The CTA therefore always has a tile of loads in flight.
 __global__ void k_general_xpass_bin(const float2* __restrict__ scratch, long long spec_elems, int n0, int n1,
                                     int nh, int nz, FftFactors fx, const float2* __restrict__ tw, int lc,
                                     ItemMap im, const ChunkDev* __restrict__ chunks,
-                                    const uint16_t* const* __restrict__ luts, double* __restrict__ partials,
-                                    long long out_per_box, int slots_max, float2* __restrict__ dc, int nchunks) {
-    PS21_DYN_SMEM(float2, smem);
+                                    const uint16_t* const* __restrict__ luts, long long lut_blk,
+                                    double* __restrict__ partials, long long out_per_box, int slots_max,
+                                    float2* __restrict__ dc, int nchunks) {
+    PS21_DYN_SMEM(float2, smem_raw);
     long long box;
     int cid;
     item_to_box_chunk(im, blockIdx.y, box, cid);
@@ -207,42 +264,61 @@ __global__ void k_general_xpass_bin(const float2* __restrict__ scratch, long lon
     const uint16_t* __restrict__ lut = luts[cid];
     const int tile = 1 << lc;
     const int ld = tile | 1;
-    float2* A = smem;
-    float2* B = smem + (size_t)n0 * ld;
-    double* bins = reinterpret_cast<double*>(smem + 2 * (size_t)n0 * ld);
-    for (int i = threadIdx.x; i < ch.nbins_out; i += blockDim.x) bins[i] = 0.0;
+    const size_t bufsz = (size_t)n0 * ld;
+    // layout: bin indices first (16-byte aligned for the 16-byte async copies; lut_blk*2 is a multiple of 16),
+    // then the three FFT buffers, then the fp64 bins
+    uint16_t* lutS = reinterpret_cast<uint16_t*>(smem_raw);            // [n0][tile] bin index of the tile's modes
+    float2* smem = reinterpret_cast<float2*>(lutS + lut_blk);
+    double* bins = reinterpret_cast<double*>(smem + 3 * bufsz);
+    const int nbin_store = ch.nbins_out;
+    for (int i = threadIdx.x; i < nbin_store; i += blockDim.x) bins[i] = 0.0;
     const long long plane = (long long)n1 * nh;
     const long long ntiles = (plane + tile - 1) / tile;
     const float2* base = scratch + (long long)blockIdx.y * spec_elems;
+    auto fetch_tile = [&](long long tl, float2* X) {
+        const long long m0 = tl * tile;
+        const int cols = (int)min((long long)tile, plane - m0);
+        for (int i = threadIdx.x; i < (n0 << lc); i += blockDim.x) {
+            const int x = i >> lc, t = i & (tile - 1);
+            if (t < cols) cp_async8(&X[x * ld + t], &base[(long long)x * plane + m0 + t]);
+            else X[x * ld + t] = make_float2(0.f, 0.f);
+        }
+        cp_async_commit();
+    };
+    int c = 0;
+    if ((long long)blockIdx.x < ntiles) fetch_tile(blockIdx.x, smem);
     for (long long tl = blockIdx.x; tl < ntiles; tl += gridDim.x) {
         const long long m0 = tl * tile;
         const int cols = (int)min((long long)tile, plane - m0);
-        __syncthreads();
-        for (int i = threadIdx.x; i < (n0 << lc); i += blockDim.x) {
-            const int x = i >> lc, t = i & (tile - 1);
-            A[x * ld + t] = (t < cols) ? base[(long long)x * plane + m0 + t] : make_float2(0.f, 0.f);
+        float2* X0 = smem + c * bufsz;
+        float2* X1 = smem + ((c + 1) % 3) * bufsz;
+        float2* X2 = smem + ((c + 2) % 3) * bufsz;
+        cp_async_wait<0>();
+        __syncthreads();   // tile tl has landed in X0; everybody is done with the previous tile's buffers and lutS
+        {
+            const uint16_t* lsrc = lut + tl * lut_blk;
+            for (int i = threadIdx.x; i < (int)(lut_blk >> 3); i += blockDim.x) cp_async16(lutS + 8 * i, lsrc + 8 * i);
+            cp_async_commit();
         }
+        if (tl + gridDim.x < ntiles) fetch_tile(tl + gridDim.x, X2);
+        else cp_async_commit();   // keep the group count uniform
+        const float2* R = column_fft(X0, X1, fx, ld, lc, tw);
+        cp_async_wait<1>();        // bin indices of this tile (the next tile's rows may still be in flight)
         __syncthreads();
-        const float2* R = column_fft(A, B, fx, ld, lc, tw);
-        // Each thread walks a contiguous k_x segment of one column: the bin index changes rarely along
-        // k_x, so powers are summed in a register and the shared fp64 bin is touched once per run.
         {
             const int nseg = blockDim.x >> lc;                   // segments per column
             const int t = threadIdx.x & (tile - 1), seg = threadIdx.x >> lc;
+            const int xlen = (n0 + nseg - 1) / nseg;
+            const int x0 = seg * xlen, x1 = min(n0, x0 + xlen);
+            const long long m = m0 + t;
+            const int kz = (int)(m % nh);
+            const float w = (kz == 0 || 2 * kz == nz) ? 1.f : 2.f;
             if (t < cols) {
-                const int xlen = (n0 + nseg - 1) / nseg;
-                const int x0 = seg * xlen, x1 = min(n0, x0 + xlen);
-                const long long m = m0 + t;
-                const int kz = (int)(m % nh);
-                const float w = (kz == 0 || 2 * kz == nz) ? 1.f : 2.f;
                 unsigned cur = kDiscard;
                 float acc = 0.f;
                 int run = 0;
-                for (int x = x0; x < x1; ++x) {
-                    const float2 v = R[x * ld + t];
-                    if (x == 0 && m == 0) dc[box * nchunks + cid] = v;
-                    const unsigned b = lut[(long long)x * plane + m];
-                    if (b != cur || run == 32) {  // bounded fp32 run length: at most 32 terms before fp64
+                auto step = [&](float2 v, unsigned b) {
+                    if (b != cur || run == 32) {
                         if (cur != kDiscard) atomicAdd(&bins[cur], (double)(w * acc));
                         cur = b;
                         acc = 0.f;
@@ -250,14 +326,38 @@ __global__ void k_general_xpass_bin(const float2* __restrict__ scratch, long lon
                     }
                     acc += v.x * v.x + v.y * v.y;
                     ++run;
+                };
+                if (x0 == 0 && m == 0 && x1 > 0) dc[box * nchunks + cid] = R[t];
+                int x = x0;
+                for (; x + 4 <= x1; x += 4) {   // four independent shared-memory loads in flight per step
+                    float2 v[4];
+                    unsigned b[4];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        v[j] = R[(x + j) * ld + t];
+                        b[j] = lutS[((x + j) << lc) + t];
+                    }
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) step(v[j], b[j]);
                 }
+                for (; x < x1; ++x) step(R[x * ld + t], lutS[(x << lc) + t]);
                 if (cur != kDiscard) atomicAdd(&bins[cur], (double)(w * acc));
             }
         }
+        c = (c + 2) % 3;
     }
+    cp_async_wait<0>();
     __syncthreads();
     double* out = partials + (box * slots_max + blockIdx.x) * out_per_box + ch.out_off;
-    for (int i = threadIdx.x; i < ch.nbins_out; i += blockDim.x) out[i] = bins[i];
+    for (int i = threadIdx.x; i < ch.nbins_out; i += blockDim.x) {
+        out[i] = bins[i];
+    }
+}
+
+// shared memory of the x pass besides the two ping-pong FFT buffers
+size_t general_xpass_extra(int nb_out, int n0, int tile) {
+    return (size_t)n0 * (tile | 1) * sizeof(float2)   // third FFT buffer (prefetch target)
+           + (size_t)nb_out * sizeof(double) + (size_t)general_lut_block(n0, tile) * sizeof(uint16_t);
 }
 
 int general_init() {
@@ -270,11 +370,6 @@ int general_init() {
     return PS21_OK;
 }
 
-static int ilog2(int v) {
-    int l = 0;
-    while ((1 << l) < v) ++l;
-    return l;
-}
 static size_t fft_smem_bytes(int n, int tile) { return 2 * (size_t)n * (tile | 1) * sizeof(float2); }
 
 int general_forward(ps21_plan* p, ShapePlan& sp, const float* d_boxes, long long batch_stride, long long item0,
@@ -294,19 +389,20 @@ int general_forward(ps21_plan* p, ShapePlan& sp, const float* d_boxes, long long
     {
         ProfScope ps(p, KK_PASS_MID, st);
         const int ntile = (sp.nh + sp.g2_tile - 1) / sp.g2_tile;
-        dim3 grid(n0 * ntile, (unsigned)nitems);
-        PS21_LAUNCH(k_general_ypass, grid, dim3(256), fft_smem_bytes(n1, sp.g2_tile), st, p->d_scratch, spec_elems,
-                    n1, sp.nh, sp.fy, sp.tw_y, ilog2(sp.g2_tile));
+        dim3 grid((n0 * ntile + kYPassItems - 1) / kYPassItems, (unsigned)nitems);
+        PS21_LAUNCH(k_general_ypass, grid, dim3(256), fft_smem_bytes(n1, sp.g2_tile) * 3 / 2, st, p->d_scratch,
+                    spec_elems, n0, n1, sp.nh, sp.fy, sp.tw_y, ilog2(sp.g2_tile));
         PS21_CUDA(cudaGetLastError());
     }
     {
         ProfScope ps(p, KK_PASS_BIN, st);
         const int nb_out = p->chunks[sp.chunks[0]].nbins_out;
         dim3 grid(sp.g3_slots, (unsigned)nitems);
-        size_t smem = fft_smem_bytes(n0, sp.g3_tile) + (size_t)nb_out * sizeof(double);
+        size_t smem = fft_smem_bytes(n0, sp.g3_tile) + general_xpass_extra(nb_out, n0, sp.g3_tile);
         PS21_LAUNCH(k_general_xpass_bin, grid, dim3(256), smem, st, p->d_scratch, spec_elems, n0, n1, sp.nh, sp.nz,
                     sp.fx, sp.tw_x, ilog2(sp.g3_tile), im, p->d_chunks, (const uint16_t* const*)p->d_lut_table,
-                    p->d_partials, p->out_per_box, p->slots_max, p->d_dc, p->nchunks);
+                    general_lut_block(n0, sp.g3_tile), p->d_partials, p->out_per_box, p->slots_max, p->d_dc,
+                    p->nchunks);
         PS21_CUDA(cudaGetLastError());
     }
     p->launches_last += 3;

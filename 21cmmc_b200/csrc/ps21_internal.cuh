@@ -139,7 +139,41 @@ int cuda_fail(cudaError_t e, const char* what);
 // general path (ps21_general.cu)
 int general_build_lut(ps21_plan* p, int chunk, const double* d_k0sq, const double* d_k1sq, const double* d_k2sq,
                       const double* d_edges, cudaStream_t st);
+// cp.async (LDGSTS): 8- and 16-byte asynchronous global -> shared copies, commit groups
+__device__ __forceinline__ void cp_async8(void* smem_dst, const void* gsrc) {
+#ifdef PS21_EMU
+    *reinterpret_cast<float2*>(smem_dst) = *reinterpret_cast<const float2*>(gsrc);
+#else
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)),
+                 "l"(gsrc)
+                 : "memory");
+#endif
+}
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+#ifdef PS21_EMU
+    *reinterpret_cast<float4*>(smem_dst) = *reinterpret_cast<const float4*>(gsrc);
+#else
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)),
+                 "l"(gsrc)
+                 : "memory");
+#endif
+}
+__device__ __forceinline__ void cp_async_commit() {
+#ifndef PS21_EMU
+    asm volatile("cp.async.commit_group;" ::: "memory");
+#endif
+}
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+#ifndef PS21_EMU
+    asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+#endif
+}
+
 int general_init();
+size_t general_xpass_extra(int nb_out, int n0, int tile);
+long long general_lut_block(int n0, int tile);
+long long general_lut_elems(int n0, int n1, int nh, int tile);
 int launch_slab_mean(ps21_plan* p, const float* d_boxes, long long batch_stride, long long batch, cudaStream_t st);
 int general_forward(ps21_plan* p, ShapePlan& sp, const float* d_boxes, long long batch_stride, long long item0,
                     long long nitems, cudaStream_t st);

@@ -57,10 +57,17 @@ static FftFactors factorize(int n) {
             m /= r;
         }
     };
-    take(16);
-    take(8);
-    take(4);
-    take(2);
+    // powers of two: as few stages as radix 16 allows, bits spread evenly (512 = 8*8*8, not 16*16*2: the same
+    // number of stages and barriers, but every stage keeps all threads of a small tile busy)
+    int k = 0;
+    while (m % 2 == 0) {
+        m /= 2;
+        ++k;
+    }
+    if (k > 0) {
+        const int st = (k + 3) / 4, base = k / st, extra = k % st;
+        for (int i = 0; i < st && ns < 14; ++i) f.radix[ns++] = 1 << (base + (i < extra ? 1 : 0));
+    }
     take(3);
     take(5);
     for (int pr = 7; m > 1 && ns < 14; pr += 2) take(pr);
@@ -86,11 +93,12 @@ static int upload_twiddles(int n, float2** out) {
     return PS21_OK;
 }
 
-static int pick_tile(int n, size_t extra) {
+template <class Extra>
+static int pick_tile(int n, Extra extra) {
     const int cand[5] = {16, 8, 4, 2, 1};
-    for (size_t budget : {(size_t)100 * 1024, (size_t)220 * 1024})
+    for (size_t budget : {(size_t)112 * 1024, (size_t)220 * 1024})
         for (int t : cand)
-            if (2 * (size_t)n * (t | 1) * sizeof(float2) + extra <= budget) return t;
+            if (2 * (size_t)n * (t | 1) * sizeof(float2) + extra(t) <= budget) return t;
     return 0;
 }
 
@@ -470,9 +478,12 @@ int ps21_plan_create(const ps21_desc* d, ps21_plan** out) {
         if (d->path == PS21_PATH_FUSED && sp.path != PS21_PATH_FUSED)
             return fail(invalid("fused path requested but this shape/alignment is not supported by it: " + g_err));
         const int nb_out = p->chunks[sp.chunks[0]].nbins_out;
-        sp.g1_cols = pick_tile(sp.nz, 0);
-        sp.g2_tile = pick_tile(d->n1, 0);
-        sp.g3_tile = pick_tile(d->n0, sizeof(double) * nb_out);
+        auto none = [](int) { return (size_t)0; };
+        sp.g1_cols = pick_tile(sp.nz, none);
+        sp.g2_tile = pick_tile(d->n1, [&](int t) { return (size_t)d->n1 * (t | 1) * sizeof(float2); });  // third buffer
+        sp.g3_tile = pick_tile(d->n0, [&](int t) { return general_xpass_extra(nb_out, d->n0, t); });
+        if (const char* e = std::getenv("PS21_G2_TILE")) sp.g2_tile = std::atoi(e);  // tuning experiments only
+        if (const char* e = std::getenv("PS21_G3_TILE")) sp.g3_tile = std::atoi(e);
         if (!sp.g1_cols || !sp.g2_tile || !sp.g3_tile) return fail(invalid("axis too long for the shared-memory FFT"));
         const long long ntiles = ((long long)d->n1 * sp.nh + sp.g3_tile - 1) / sp.g3_tile;
         const long long cap = d->mode == PS21_MODE_SPHERICAL ? 64 : 16;
@@ -533,7 +544,7 @@ int ps21_plan_create(const ps21_desc* d, ps21_plan** out) {
             }
             p->lut_owned[c] = 1;
             const long long spec = (sp.path == PS21_PATH_FUSED) ? fused_scratch_elems(sp, d->n0, d->n1)
-                                                                 : (long long)d->n0 * d->n1 * sp.nh;
+                                                                 : general_lut_elems(d->n0, d->n1, sp.nh, sp.g3_tile);
             if (cudaMalloc((void**)&p->d_lut[c], sizeof(uint16_t) * spec) != cudaSuccess) {
                 cudaGetLastError();
                 set_error("cannot allocate bin-index table");

@@ -409,7 +409,8 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--walkers", type=int, default=64, help="lightcones per GPU per step")
+    ap.add_argument("--walkers", type=int, default=None,
+                    help="walkers per GPU per step (default 64; config 4: 2, its inputs are 8 GiB per walker)")
     ap.add_argument("--path", default="auto", choices=["auto", "general", "fused"])
     ap.add_argument("--workspace-mb", type=int, default=0)
     ap.add_argument("--config", type=int, default=3, choices=[1, 2, 3, 4, 5],
@@ -422,6 +423,8 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=3)
     args = ap.parse_args()
     select_config(args.config)
+    if args.walkers is None:
+        args.walkers = 2 if args.config == 4 else 64
     globals()["NBINS"] = args.nbins
     if args.warmup < 3 and args.impl == "b200":
         args.warmup = 3  # timing rule: at least 3 warm-up steps

@@ -157,6 +157,10 @@ static inline cudaError_t cudaMemset(void* d, int v, size_t n) {
     std::memset(d, v, n);
     return 0;
 }
+static inline cudaError_t cudaMemsetAsync(void* d, int v, size_t n, cudaStream_t) {
+    std::memset(d, v, n);
+    return 0;
+}
 static inline cudaError_t cudaStreamCreateWithFlags(cudaStream_t* s, int) {
     *s = (void*)1;
     return 0;
