@@ -255,7 +255,7 @@ __global__ void k_general_xpass_bin(const float2* __restrict__ scratch, long lon
                                     ItemMap im, const ChunkDev* __restrict__ chunks,
                                     const uint16_t* const* __restrict__ luts, long long lut_blk,
                                     double* __restrict__ partials, long long out_per_box, int slots_max,
-                                    float2* __restrict__ dc, int nchunks) {
+                                    float2* __restrict__ dc, int nchunks, int ncopy) {
     PS21_DYN_SMEM(float2, smem_raw);
     long long box;
     int cid;
@@ -270,8 +270,11 @@ __global__ void k_general_xpass_bin(const float2* __restrict__ scratch, long lon
     uint16_t* lutS = reinterpret_cast<uint16_t*>(smem_raw);            // [n0][tile] bin index of the tile's modes
     float2* smem = reinterpret_cast<float2*>(lutS + lut_blk);
     double* bins = reinterpret_cast<double*>(smem + 3 * bufsz);
-    const int nbin_store = ch.nbins_out;
+    // `ncopy` (power of two) copies of the fp64 bins, chosen by the low thread-index bits (= the k_z column of the
+    // tile): threads that flush at the same step mostly hit different copies -> short CAS loops in the atomics
+    const int nbin_store = ncopy * ch.nbins_out;
     for (int i = threadIdx.x; i < nbin_store; i += blockDim.x) bins[i] = 0.0;
+    double* mybins = bins + (threadIdx.x & (ncopy - 1)) * ch.nbins_out;
     const long long plane = (long long)n1 * nh;
     const long long ntiles = (plane + tile - 1) / tile;
     const float2* base = scratch + (long long)blockIdx.y * spec_elems;
@@ -319,7 +322,7 @@ __global__ void k_general_xpass_bin(const float2* __restrict__ scratch, long lon
                 int run = 0;
                 auto step = [&](float2 v, unsigned b) {
                     if (b != cur || run == 32) {
-                        if (cur != kDiscard) atomicAdd(&bins[cur], (double)(w * acc));
+                        if (cur != kDiscard) atomicAdd(&mybins[cur], (double)(w * acc));
                         cur = b;
                         acc = 0.f;
                         run = 0;
@@ -341,7 +344,7 @@ __global__ void k_general_xpass_bin(const float2* __restrict__ scratch, long lon
                     for (int j = 0; j < 4; ++j) step(v[j], b[j]);
                 }
                 for (; x < x1; ++x) step(R[x * ld + t], lutS[(x << lc) + t]);
-                if (cur != kDiscard) atomicAdd(&bins[cur], (double)(w * acc));
+                if (cur != kDiscard) atomicAdd(&mybins[cur], (double)(w * acc));
             }
         }
         c = (c + 2) % 3;
@@ -350,14 +353,22 @@ __global__ void k_general_xpass_bin(const float2* __restrict__ scratch, long lon
     __syncthreads();
     double* out = partials + (box * slots_max + blockIdx.x) * out_per_box + ch.out_off;
     for (int i = threadIdx.x; i < ch.nbins_out; i += blockDim.x) {
-        out[i] = bins[i];
+        double a = 0.0;
+        for (int q = 0; q < ncopy; ++q) a += bins[q * ch.nbins_out + i];
+        out[i] = a;
     }
 }
 
 // shared memory of the x pass besides the two ping-pong FFT buffers
+int general_bin_copies(int nb_out) {
+    int c = 16;
+    while (c > 1 && (size_t)c * nb_out * sizeof(double) > 16 * 1024) c >>= 1;
+    return c;
+}
+
 size_t general_xpass_extra(int nb_out, int n0, int tile) {
     return (size_t)n0 * (tile | 1) * sizeof(float2)   // third FFT buffer (prefetch target)
-           + (size_t)nb_out * sizeof(double) + (size_t)general_lut_block(n0, tile) * sizeof(uint16_t);
+           + (size_t)general_bin_copies(nb_out) * nb_out * sizeof(double) + (size_t)general_lut_block(n0, tile) * sizeof(uint16_t);
 }
 
 int general_init() {
@@ -402,7 +413,7 @@ int general_forward(ps21_plan* p, ShapePlan& sp, const float* d_boxes, long long
         PS21_LAUNCH(k_general_xpass_bin, grid, dim3(256), smem, st, p->d_scratch, spec_elems, n0, n1, sp.nh, sp.nz,
                     sp.fx, sp.tw_x, ilog2(sp.g3_tile), im, p->d_chunks, (const uint16_t* const*)p->d_lut_table,
                     general_lut_block(n0, sp.g3_tile), p->d_partials, p->out_per_box, p->slots_max, p->d_dc,
-                    p->nchunks);
+                    p->nchunks, general_bin_copies(nb_out));
         PS21_CUDA(cudaGetLastError());
     }
     p->launches_last += 3;
