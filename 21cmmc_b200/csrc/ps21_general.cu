@@ -187,29 +187,36 @@ __global__ void k_general_zpass(const float* __restrict__ boxes, long long batch
 // ---------------------------------------------------------------------------------------------
 // g2: y pass, in place.  CTA = fixed x, `tile` consecutive k_z.
 // ---------------------------------------------------------------------------------------------
-// A CTA owns kYPassItems consecutive (x, k_z tile) work items and pipelines them through three rotating buffers:
-// the rows of item i+1 stream in with cp.async while item i is transformed and stored.
+// Columns of the y transform are the (x, k_z) pairs, flattened to q = x*nh + k_z and cut into tiles of `tile`
+// consecutive q (no ragged last tile per x: nh = nz/2+1 is odd for even nz).  A CTA owns kYPassItems consecutive
+// tiles and pipelines them through three rotating buffers: the rows of tile i+1 stream in with cp.async while tile i
+// is transformed and stored.  blockDim is a multiple of the tile width, so a thread always serves the same column.
 constexpr int kYPassItems = 8;
 
 __global__ void k_general_ypass(float2* __restrict__ scratch, long long spec_elems, int n0, int n1, int nh,
                                 FftFactors fy, const float2* __restrict__ tw, int lc) {
     PS21_DYN_SMEM(float2, smem);
     const int tile = 1 << lc;
-    const int ntile = (nh + tile - 1) >> lc;
     const int ld = tile | 1;
     const size_t bufsz = (size_t)n1 * ld;
-    const int nwork = n0 * ntile;
+    const long long ncol = (long long)n0 * nh;
+    const int nwork = (int)((ncol + tile - 1) >> lc);
     const int w0 = blockIdx.x * kYPassItems;
     const int w1 = min(nwork, w0 + kYPassItems);
     float2* spec = scratch + (long long)blockIdx.y * spec_elems;
+    const int t = threadIdx.x & (tile - 1);
+    const int ystep = blockDim.x >> lc, yfirst = threadIdx.x >> lc;
+    // address of (y = 0) of this thread's column in tile w, or nullptr past the last column
+    auto column = [&](int w) -> float2* {
+        const long long q = ((long long)w << lc) + t;
+        if (q >= ncol) return nullptr;
+        const int x = (int)(q / nh);
+        return spec + (long long)x * n1 * nh + (q - (long long)x * nh);
+    };
     auto fetch = [&](int w, float2* X) {
-        const int x = w / ntile;
-        const int k0 = (w - x * ntile) << lc;
-        const int cols = min(tile, nh - k0);
-        const float2* base = spec + (long long)x * n1 * nh + k0;
-        for (int i = threadIdx.x; i < (n1 << lc); i += blockDim.x) {
-            const int y = i >> lc, t = i & (tile - 1);
-            if (t < cols) cp_async8(&X[y * ld + t], &base[(long long)y * nh + t]);
+        const float2* col = column(w);
+        for (int y = yfirst; y < n1; y += ystep) {
+            if (col) cp_async8(&X[y * ld + t], col + (long long)y * nh);
             else X[y * ld + t] = make_float2(0.f, 0.f);
         }
         cp_async_commit();
@@ -221,17 +228,12 @@ __global__ void k_general_ypass(float2* __restrict__ scratch, long long spec_ele
         float2* X1 = smem + ((c + 1) % 3) * bufsz;
         float2* X2 = smem + ((c + 2) % 3) * bufsz;
         cp_async_wait<0>();
-        __syncthreads();   // item w has landed in X0; the previous item's result has been stored by everybody
+        __syncthreads();   // tile w has landed in X0; the previous tile's result has been stored by everybody
         if (w + 1 < w1) fetch(w + 1, X2);
         const float2* R = column_fft(X0, X1, fy, ld, lc, tw);
-        const int x = w / ntile;
-        const int k0 = (w - x * ntile) << lc;
-        const int cols = min(tile, nh - k0);
-        float2* base = spec + (long long)x * n1 * nh + k0;
-        for (int i = threadIdx.x; i < (n1 << lc); i += blockDim.x) {
-            const int y = i >> lc, t = i & (tile - 1);
-            if (t < cols) base[(long long)y * nh + t] = R[y * ld + t];
-        }
+        float2* col = column(w);
+        if (col)
+            for (int y = yfirst; y < n1; y += ystep) col[(long long)y * nh] = R[y * ld + t];
         c = (c + 2) % 3;
     }
 }
@@ -399,8 +401,8 @@ int general_forward(ps21_plan* p, ShapePlan& sp, const float* d_boxes, long long
     }
     {
         ProfScope ps(p, KK_PASS_MID, st);
-        const int ntile = (sp.nh + sp.g2_tile - 1) / sp.g2_tile;
-        dim3 grid((n0 * ntile + kYPassItems - 1) / kYPassItems, (unsigned)nitems);
+        const long long ntile = ((long long)n0 * sp.nh + sp.g2_tile - 1) / sp.g2_tile;
+        dim3 grid((unsigned)((ntile + kYPassItems - 1) / kYPassItems), (unsigned)nitems);
         PS21_LAUNCH(k_general_ypass, grid, dim3(256), fft_smem_bytes(n1, sp.g2_tile) * 3 / 2, st, p->d_scratch,
                     spec_elems, n0, n1, sp.nh, sp.fy, sp.tw_y, ilog2(sp.g2_tile));
         PS21_CUDA(cudaGetLastError());
