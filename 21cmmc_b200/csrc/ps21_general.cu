@@ -152,34 +152,34 @@ __global__ void k_general_zpass(const float* __restrict__ boxes, long long batch
     const float mean = means[box * nchunks + cid];
     const int row0 = blockIdx.x * 2 * cols;
     const float* src = boxes + box * batch_stride + ch.start;
-    float* Af = reinterpret_cast<float*>(A);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
-    for (int rr = warp; rr < 2 * cols; rr += nwarps) {  // one real row per warp iteration, lanes along z
-        const int row = row0 + rr;
-        const float* r = src + (long long)row * n2_total;
-        const int base = 2 * (rr >> 1) + (rr & 1);
-        for (int z = lane; z < nz; z += 32) Af[2 * z * ld + base] = (row < nrows) ? r[z] - mean : 0.f;
+    // one pair of real rows (= one complex column) per warp iteration, lanes along z: two coalesced loads and one
+    // 8-byte shared-memory store per element (row stride ld is odd -> conflict free)
+    for (int pr = warp; pr < cols; pr += nwarps) {
+        const int ra = row0 + 2 * pr, rb = ra + 1;
+        const float* pa = src + (long long)ra * n2_total;
+        const float* pb = src + (long long)rb * n2_total;
+        for (int z = lane; z < nz; z += 32) {
+            float2 v = make_float2(0.f, 0.f);
+            if (ra < nrows) v.x = pa[z] - mean;
+            if (rb < nrows) v.y = pb[z] - mean;
+            A[z * ld + pr] = v;
+        }
     }
     __syncthreads();
     const float2* R = column_fft(A, B, fz, ld, lc, tw);
     float2* dst = scratch + (long long)blockIdx.y * spec_elems;
-    for (int rr = warp; rr < 2 * cols; rr += nwarps) {
-        const int row = row0 + rr;
-        if (row >= nrows) continue;
-        const int col = rr >> 1;
-        float2* o = dst + (long long)row * nh;
+    for (int pr = warp; pr < cols; pr += nwarps) {
+        const int ra = row0 + 2 * pr, rb = ra + 1;
+        if (ra >= nrows) continue;
+        float2* oa = dst + (long long)ra * nh;
+        float2* ob = dst + (long long)rb * nh;
         for (int k = lane; k < nh; k += 32) {
-            const float2 Z = R[k * ld + col];
-            const float2 Zc = R[((k == 0) ? 0 : nz - k) * ld + col];
-            float2 v;
-            if ((rr & 1) == 0) {  // even row: (Z + conj(Z*))/2
-                v.x = 0.5f * (Z.x + Zc.x);
-                v.y = 0.5f * (Z.y - Zc.y);
-            } else {  // odd row: (Z - conj(Z*)) / (2i)
-                v.x = 0.5f * (Z.y + Zc.y);
-                v.y = -0.5f * (Z.x - Zc.x);
-            }
-            o[k] = v;
+            const float2 Z = R[k * ld + pr];
+            const float2 Zc = R[((k == 0) ? 0 : nz - k) * ld + pr];
+            // even row: (Z + conj(Z*))/2, odd row: (Z - conj(Z*)) / (2i)
+            oa[k] = make_float2(0.5f * (Z.x + Zc.x), 0.5f * (Z.y - Zc.y));
+            if (rb < nrows) ob[k] = make_float2(0.5f * (Z.y + Zc.y), -0.5f * (Z.x - Zc.x));
         }
     }
 }
