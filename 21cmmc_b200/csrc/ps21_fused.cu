@@ -109,6 +109,10 @@ __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
+// non-blocking arrival at named barrier `id` (the warps that call named_bar_sync on it wait for `nthreads` arrivals)
+__device__ __forceinline__ void named_bar_arrive(int id, int nthreads) {
+    asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
 // L2 eviction policies: streamed data must not push the (re-used) bin-index table out of L2
 __device__ __forceinline__ uint64_t l2_policy_evict_first() {
     uint64_t pol;
@@ -161,6 +165,7 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
 }
 __device__ __forceinline__ void fence_proxy_async() {}
 __device__ __forceinline__ void named_bar_sync(int, int) { __syncthreads(); }  // stronger, same result
+__device__ __forceinline__ void named_bar_arrive(int, int) { __syncthreads(); }
 __device__ __forceinline__ uint64_t l2_policy_evict_first() { return 0; }
 __device__ __forceinline__ uint64_t l2_policy_evict_last() { return 0; }
 __device__ __forceinline__ void bulk_g2s_hint(void* dst, const void* src, uint32_t bytes, uint64_t* bar, uint64_t) {
@@ -513,11 +518,14 @@ __device__ __forceinline__ void bin_word(double* __restrict__ wb, uint32_t word,
 // BM_CYL    : (k_perp bin, k_z) bins; every thread has one k_z per tile (t = tid & 7), so the lane-private
 //              bins are k_perp bins and the per-tile flush keeps the 8 k_z of the tile apart; partial sums go
 //              to a compact [item][CYL_SLOTS][bins][8] record that k_fused_cyl_reduce expands.
-template <int BM>
+template <int BM, bool EARLY>
 __global__ void __launch_bounds__(P2_THREADS, 2)
 k_fused_p2(const float2* __restrict__ scratch, ItemMap im, const ChunkDev* __restrict__ chunks,
            const uint16_t* const* __restrict__ luts, double* __restrict__ partials, long long out_per_box,
            int slots_max, float2* __restrict__ dc, int nchunks, const float4* __restrict__ tw_g, int nbins) {
+    // EARLY: the next tile is requested as soon as the tile and bin-index buffers are dead (inside S2, below);
+    // otherwise after the binning (a compile-time switch: the barrier branch costs the vote-heavy BM_WARP code)
+    constexpr int early = EARLY ? 1 : 0;
     PS21_DYN_SMEM(float2, tile);               // [TILE]
     uint8_t* lutb = reinterpret_cast<uint8_t*>(tile + TILE);           // [TILE] bin index of every output of the tile
     float4* tw = reinterpret_cast<float4*>(lutb + TILE);               // [256]
@@ -614,9 +622,25 @@ k_fused_p2(const float2* __restrict__ scratch, ItemMap im, const ChunkDev* __res
 #pragma unroll
             for (int xa = 0; xa < 32; ++xa) v[xa] = tile[Geo<256>::tile_idx(32 * m1 + xa, kyb, t)];
             small_dft<32>(v);
+            // Every thread has its 32 inputs and its 32 bin indices in registers: tile and table buffers are dead.
+            // Warps 1..7 signal that without waiting (bar.arrive); warp 0 waits for them (bar.sync) and starts the
+            // copy of the next tile, which then overlaps the binning and the flush of this tile.  (Issuing before the
+            // 32-point transforms, or from the last warp to finish via a counter, measured no better.)
+            const uint4 lv2[2] = {reinterpret_cast<const uint4*>(lutb + tid * 32)[0],
+                                  reinterpret_cast<const uint4*>(lutb + tid * 32)[1]};
+            if (early && it + 1 < count) {
+                if (tid >= 32) {
+                    named_bar_arrive(3, P2_THREADS);
+                } else {
+                    named_bar_sync(3, P2_THREADS);
+                    if (tid == 0) {
+                        fence_proxy_async();
+                        issue_tile(tl + stride);
+                    }
+                }
+            }
             if (tl == 0 && tid == 0) dc[box * nchunks + cid] = v[0];
             const float mult = (tl >= NT_MAIN || ((tl & 15) == 0 && t == 0)) ? 1.f : 2.f;
-            const uint4* lp = reinterpret_cast<const uint4*>(lutb + tid * 32);
             uint32_t cur = 255u;
             float acc = 0.f;
             // private bin column of this lane (BM_LANE / BM_CYL) or of its 4-lane group (BM_GROUP: lanes t + 8 j)
@@ -635,7 +659,7 @@ k_fused_p2(const float2* __restrict__ scratch, ItemMap im, const ChunkDev* __res
             };
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
-                const uint4 lv = lp[h];
+                const uint4 lv = lv2[h];
                 const uint32_t w4[4] = {lv.x, lv.y, lv.z, lv.w};
 #pragma unroll
                 for (int g = 0; g < 4; ++g) {  // four outputs per 32-bit word of bin indices
@@ -665,15 +689,19 @@ k_fused_p2(const float2* __restrict__ scratch, ItemMap im, const ChunkDev* __res
             if (WARPB) warp_flush(wb, cur, mult * acc, true);
             else lane_update(cur, mult * acc, true);
         }
-        __syncthreads();
-        // tile buffer is free: prefetch the next tile while the bins are flushed
-        if (tid == 0 && it + 1 < count) {
-            fence_proxy_async();
-            issue_tile(tl + stride);
-        }
         // ---- every FLUSH_EVERY tiles (and after the last one): flush the lane-private fp32 bins into the CTA's
-        //      fp64 bins in a fixed order; a lane-private bin then holds at most 32 * FLUSH_EVERY fp32 terms
+        //      fp64 bins in a fixed order; a lane-private bin then holds at most 32 * FLUSH_EVERY fp32 terms.
+        //      (Between flushes no barrier is needed here: a thread only touches its own bin column, the tile
+        //      buffer was handed over above, and the table buffers alternate.)
+        if (!early) {
+            __syncthreads();
+            if (tid == 0 && it + 1 < count) {
+                fence_proxy_async();
+                issue_tile(tl + stride);
+            }
+        }
         if (!WARPB && ((it % FLUSH_EVERY) == FLUSH_EVERY - 1 || it + 1 == count)) {
+            if (early) __syncthreads();
             const int warp = tid >> 5, lane = tid & 31;
             for (int b = warp; b < nbins; b += P2_THREADS / 32) {
                 double acc = 0.0;
@@ -716,7 +744,7 @@ k_fused_p2(const float2* __restrict__ scratch, ItemMap im, const ChunkDev* __res
 // pass 2 for the 128 x 128 sky plane (spherical bins): tile = [x 128][y_lo 2][k_z 32].  Lanes run along the 32
 // k_z of a chunk in every access.  S1: 2-point FFT over y_lo x radix 16 over x = xa + 8 m (32 points per
 // thread); S2: four radix-8 butterflies over xa per thread (kx = m' + 16 q), |delta_k|^2 and bins from registers.
-template <bool WARPB>
+template <bool WARPB, bool EARLY>
 __global__ void __launch_bounds__(P2_THREADS, 2)
 k_fused_p2_s128(const float2* __restrict__ scratch, ItemMap im, const ChunkDev* __restrict__ chunks,
                 const uint16_t* const* __restrict__ luts, double* __restrict__ partials, long long out_per_box,
@@ -793,12 +821,26 @@ k_fused_p2_s128(const float2* __restrict__ scratch, ItemMap im, const ChunkDev* 
             const uint32_t w8[8] = {l0.x, l0.y, l0.z, l0.w, l1.x, l1.y, l1.z, l1.w};
             uint32_t cur = 255u;
             float acc = 0.f;
+            float2 vv[4][8];
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int xa = 0; xa < 8; ++xa) vv[i][xa] = tile[G::tile_idx(xa + 8 * (4 * mgrp + i), kyb, t)];
+            // inputs and bin indices are in registers: tile and table buffers are dead (see k_fused_p2)
+            if (EARLY && it + 1 < count) {
+                if (tid >= 32) {
+                    named_bar_arrive(3, P2_THREADS);
+                } else {
+                    named_bar_sync(3, P2_THREADS);
+                    if (tid == 0) {
+                        fence_proxy_async();
+                        issue_tile(tl + stride);
+                    }
+                }
+            }
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-                const int m1 = 4 * mgrp + i;
-                float2 v[8];
-#pragma unroll
-                for (int xa = 0; xa < 8; ++xa) v[xa] = tile[G::tile_idx(xa + 8 * m1, kyb, t)];
+                float2(&v)[8] = vv[i];
                 small_dft<8>(v);
                 if (i == 0 && tl == 0 && tid == 0) dc[box * nchunks + cid] = v[0];
                 if (WARPB) {
@@ -829,12 +871,15 @@ k_fused_p2_s128(const float2* __restrict__ scratch, ItemMap im, const ChunkDev* 
             if (WARPB) warp_flush(wb, cur, mult * acc, true);
             else if (cur != 255u) lbins[cur * P2_THREADS + tid] += mult * acc;
         }
-        __syncthreads();
-        if (tid == 0 && it + 1 < count) {
-            fence_proxy_async();
-            issue_tile(tl + stride);
+        if (!EARLY) {
+            __syncthreads();
+            if (tid == 0 && it + 1 < count) {
+                fence_proxy_async();
+                issue_tile(tl + stride);
+            }
         }
         if (!WARPB && ((it % FLUSH_EVERY) == FLUSH_EVERY - 1 || it + 1 == count)) {  // fixed-order fp32 -> fp64 flush
+            if (EARLY) __syncthreads();
             const int warp = tid >> 5, lane = tid & 31;
             for (int b = warp; b < nbins; b += P2_THREADS / 32) {
                 double a = 0.0;
@@ -943,17 +988,25 @@ int fused_try_setup(ps21_plan* p, ShapePlan& sp) {
         cudaMemcpy(fs->tw256, tw.data(), sizeof(float4) * 256, cudaMemcpyHostToDevice) != cudaSuccess ||
         cudaFuncSetAttribute(k_fused_p1<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p1_smem()) != cudaSuccess ||
         cudaFuncSetAttribute(k_fused_p1<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p1_smem()) != cudaSuccess ||
-        cudaFuncSetAttribute(k_fused_p2_s128<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        cudaFuncSetAttribute(k_fused_p2_s128<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              (int)p2_smem(MAX_BINS, BM_LANE)) != cudaSuccess ||
-        cudaFuncSetAttribute(k_fused_p2_s128<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        cudaFuncSetAttribute(k_fused_p2_s128<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              (int)p2_smem(MAX_BINS_SPH, BM_WARP)) != cudaSuccess ||
-        cudaFuncSetAttribute(k_fused_p2<BM_LANE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        cudaFuncSetAttribute(k_fused_p2<BM_LANE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              (int)p2_smem(MAX_BINS, BM_LANE)) != cudaSuccess ||
-        cudaFuncSetAttribute(k_fused_p2<BM_WARP>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        cudaFuncSetAttribute(k_fused_p2<BM_LANE, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)p2_smem(MAX_BINS, BM_LANE)) != cudaSuccess ||
+        cudaFuncSetAttribute(k_fused_p2<BM_WARP, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              (int)p2_smem(MAX_BINS_SPH, BM_WARP)) != cudaSuccess ||
-        cudaFuncSetAttribute(k_fused_p2<BM_GROUP>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        cudaFuncSetAttribute(k_fused_p2<BM_WARP, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)p2_smem(MAX_BINS_SPH, BM_WARP)) != cudaSuccess ||
+        cudaFuncSetAttribute(k_fused_p2<BM_GROUP, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              (int)p2_smem(MAX_BINS_GROUP, BM_GROUP)) != cudaSuccess ||
-        cudaFuncSetAttribute(k_fused_p2<BM_CYL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        cudaFuncSetAttribute(k_fused_p2<BM_GROUP, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)p2_smem(MAX_BINS_GROUP, BM_GROUP)) != cudaSuccess ||
+        cudaFuncSetAttribute(k_fused_p2<BM_CYL, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)p2_smem(MAX_BINS, BM_CYL)) != cudaSuccess ||
+        cudaFuncSetAttribute(k_fused_p2<BM_CYL, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              (int)p2_smem(MAX_BINS, BM_CYL)) != cudaSuccess) {
         cudaGetLastError();
         if (fs->tw256) cudaFree(fs->tw256);
@@ -1016,28 +1069,37 @@ int fused_forward(ps21_plan* p, ShapePlan& sp, const float* d_boxes, long long b
     {
         ProfScope ps(p, KK_PASS_BIN, st);
         const int bm = bin_mode(p);
+        // request the next tile inside S2: -8 % in the lane and cylindrical modes, +1.5 % in the vote-heavy group and
+        // warp modes (measured), which therefore keep the request after the binning
+        const int early = bm == BM_LANE || bm == BM_CYL;
+#define PS21_P2_LAUNCH(BM, NSLOTS, ...)                                                                           \
+    do {                                                                                                          \
+        if (early)                                                                                                \
+            PS21_LAUNCH((k_fused_p2<BM, true>), dim3(NSLOTS, (unsigned)nitems), dim3(P2_THREADS),                 \
+                        p2_smem(p->nbins, BM), st, __VA_ARGS__);                                                  \
+        else                                                                                                      \
+            PS21_LAUNCH((k_fused_p2<BM, false>), dim3(NSLOTS, (unsigned)nitems), dim3(P2_THREADS),                \
+                        p2_smem(p->nbins, BM), st, __VA_ARGS__);                                                  \
+    } while (0)
 #define PS21_P2_ARGS                                                                                                  \
     p->d_scratch, im, p->d_chunks, (const uint16_t* const*)p->d_lut_table, p->d_partials, p->out_per_box, p->slots_max, \
         p->d_dc, p->nchunks, fs->tw256, p->nbins
         if (fs->S == 128) {
             if (bm == BM_LANE)
-                PS21_LAUNCH(k_fused_p2_s128<false>, dim3(Geo<128>::SLOTS_S, (unsigned)nitems), dim3(P2_THREADS),
+                PS21_LAUNCH((k_fused_p2_s128<false, true>), dim3(Geo<128>::SLOTS_S, (unsigned)nitems), dim3(P2_THREADS),
                             p2_smem(p->nbins, bm), st, PS21_P2_ARGS);
             else
-                PS21_LAUNCH(k_fused_p2_s128<true>, dim3(Geo<128>::SLOTS_S, (unsigned)nitems), dim3(P2_THREADS),
+                PS21_LAUNCH((k_fused_p2_s128<true, false>), dim3(Geo<128>::SLOTS_S, (unsigned)nitems), dim3(P2_THREADS),
                             p2_smem(p->nbins, bm), st, PS21_P2_ARGS);
             PS21_CUDA(cudaGetLastError());
         } else if (bm == BM_LANE) {
-            PS21_LAUNCH(k_fused_p2<BM_LANE>, dim3(SLOTS, (unsigned)nitems), dim3(P2_THREADS), p2_smem(p->nbins, bm), st,
-                        PS21_P2_ARGS);
+            PS21_P2_LAUNCH(BM_LANE, SLOTS, PS21_P2_ARGS);
             PS21_CUDA(cudaGetLastError());
         } else if (bm == BM_GROUP) {
-            PS21_LAUNCH(k_fused_p2<BM_GROUP>, dim3(SLOTS, (unsigned)nitems), dim3(P2_THREADS), p2_smem(p->nbins, bm), st,
-                        PS21_P2_ARGS);
+            PS21_P2_LAUNCH(BM_GROUP, SLOTS, PS21_P2_ARGS);
             PS21_CUDA(cudaGetLastError());
         } else if (bm == BM_WARP) {
-            PS21_LAUNCH(k_fused_p2<BM_WARP>, dim3(SLOTS, (unsigned)nitems), dim3(P2_THREADS), p2_smem(p->nbins, bm), st,
-                        PS21_P2_ARGS);
+            PS21_P2_LAUNCH(BM_WARP, SLOTS, PS21_P2_ARGS);
             PS21_CUDA(cudaGetLastError());
         } else {
             if (fs->cylpart_items < nitems) {
@@ -1047,9 +1109,8 @@ int fused_forward(ps21_plan* p, ShapePlan& sp, const float* d_boxes, long long b
                 PS21_CUDA(cudaMalloc((void**)&fs->cylpart, sizeof(double) * nitems * CYL_SLOTS * p->nbins * 8));
                 fs->cylpart_items = nitems;
             }
-            PS21_LAUNCH(k_fused_p2<BM_CYL>, dim3(CYL_SLOTS, (unsigned)nitems), dim3(P2_THREADS),
-                        p2_smem(p->nbins, BM_CYL), st, p->d_scratch, im, p->d_chunks, (const uint16_t* const*)p->d_lut_table, fs->cylpart,
-                        p->out_per_box, p->slots_max, p->d_dc, p->nchunks, fs->tw256, p->nbins);
+            PS21_P2_LAUNCH(BM_CYL, CYL_SLOTS, p->d_scratch, im, p->d_chunks, (const uint16_t* const*)p->d_lut_table,
+                           fs->cylpart, p->out_per_box, p->slots_max, p->d_dc, p->nchunks, fs->tw256, p->nbins);
             PS21_CUDA(cudaGetLastError());
             PS21_LAUNCH(k_fused_cyl_reduce, dim3((unsigned)nitems), dim3(256), 0, st, fs->cylpart, im, p->d_chunks,
                         p->d_partials, p->out_per_box, p->slots_max, p->nbins);

@@ -123,6 +123,8 @@ static inline T atomicAdd(T* p, T v) {
     *p = old + v;
     return old;
 }
+static inline void __threadfence_block() {}
+static inline void __threadfence() {}
 using std::max;
 using std::min;
 

@@ -57,6 +57,7 @@ def test_compute_power_lightcone(mods, kpath, shape, L, nb, log, flags, rule):
 @pytest.mark.parametrize("nb,log,flags", [
     (20, True, (True, False, False)),
     (24, False, (False, False, False)),   # DC mode binned: exercises the fp64 offset restoration
+    (32, True, (True, False, False)),     # lane bins without the second bin-index buffer (keeps 2 CTAs/SM)
     (40, True, (True, True, True)),
     (None, True, (True, False, False)),   # the reference's default: int(256 / 2.2) = 116 bins
     (254, False, (True, False, False)),   # the most the byte LUT can address
