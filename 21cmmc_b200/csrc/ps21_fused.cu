@@ -744,7 +744,7 @@ k_fused_p2(const float2* __restrict__ scratch, ItemMap im, const ChunkDev* __res
 // pass 2 for the 128 x 128 sky plane (spherical bins): tile = [x 128][y_lo 2][k_z 32].  Lanes run along the 32
 // k_z of a chunk in every access.  S1: 2-point FFT over y_lo x radix 16 over x = xa + 8 m (32 points per
 // thread); S2: four radix-8 butterflies over xa per thread (kx = m' + 16 q), |delta_k|^2 and bins from registers.
-template <bool WARPB, bool EARLY>
+template <int BM, bool EARLY>
 __global__ void __launch_bounds__(P2_THREADS, 2)
 k_fused_p2_s128(const float2* __restrict__ scratch, ItemMap im, const ChunkDev* __restrict__ chunks,
                 const uint16_t* const* __restrict__ luts, double* __restrict__ partials, long long out_per_box,
@@ -754,8 +754,12 @@ k_fused_p2_s128(const float2* __restrict__ scratch, ItemMap im, const ChunkDev* 
     uint8_t* lutb = reinterpret_cast<uint8_t*>(tile + TILE);           // [TILE]
     float4* tw = reinterpret_cast<float4*>(lutb + TILE);               // [256]
     uint64_t* bar = reinterpret_cast<uint64_t*>(tw + 256);
-    double* cbins = reinterpret_cast<double*>(bar + 2);                // [MAX_BINS], or per-warp [8][nbins] (WARPB)
-    float* lbins = reinterpret_cast<float*>(cbins + MAX_BINS);         // [nbins][P2_THREADS] (lane mode)
+    constexpr bool WARPB = BM == BM_WARP, GROUPB = BM == BM_GROUP;
+    // BM_GROUP: the four lanes 4c .. 4c+3 (adjacent k_z, nearly the same |k|) share one fp32 bin column
+    constexpr int NCOL = GROUPB ? P2_THREADS / 4 : P2_THREADS;
+    constexpr int CB = GROUPB ? MAX_BINS_GROUP : MAX_BINS;
+    double* cbins = reinterpret_cast<double*>(bar + 2);                // [CB], or per-warp [8][nbins] (WARPB)
+    float* lbins = reinterpret_cast<float*>(cbins + CB);               // [nbins][NCOL] (lane / group mode)
     double* wb = cbins + (threadIdx.x >> 5) * nbins;
     const int tid = threadIdx.x;
     long long box;
@@ -768,8 +772,8 @@ k_fused_p2_s128(const float2* __restrict__ scratch, ItemMap im, const ChunkDev* 
     if (WARPB) {
         for (int i = tid; i < (P2_THREADS / 32) * nbins; i += P2_THREADS) cbins[i] = 0.0;
     } else {
-        for (int i = tid; i < nbins * P2_THREADS; i += P2_THREADS) lbins[i] = 0.f;
-        if (tid < MAX_BINS) cbins[tid] = 0.0;
+        for (int i = tid; i < nbins * NCOL; i += P2_THREADS) lbins[i] = 0.f;
+        if (tid < CB) cbins[tid] = 0.0;
     }
     if (tid == 0) {
         mbar_init(bar, 1);
@@ -821,6 +825,18 @@ k_fused_p2_s128(const float2* __restrict__ scratch, ItemMap im, const ChunkDev* 
             const uint32_t w8[8] = {l0.x, l0.y, l0.z, l0.w, l1.x, l1.y, l1.z, l1.w};
             uint32_t cur = 255u;
             float acc = 0.f;
+            const int col = GROUPB ? (tid >> 2) : tid;
+            auto lane_update = [&](uint32_t b, float val, bool on) {
+                if (!GROUPB) {
+                    if (on && b != 255u) lbins[b * NCOL + col] += val;
+                } else {  // the four lanes of a group take turns (warp-uniform call site)
+#pragma unroll
+                    for (int mm = 0; mm < 4; ++mm) {
+                        if (on && b != 255u && (tid & 3) == mm) lbins[b * NCOL + col] += val;
+                        __syncwarp();
+                    }
+                }
+            };
             float2 vv[4][8];
 #pragma unroll
             for (int i = 0; i < 4; ++i)
@@ -858,8 +874,9 @@ k_fused_p2_s128(const float2* __restrict__ scratch, ItemMap im, const ChunkDev* 
                         const uint32_t b = (w8[2 * i + (q >> 2)] >> (8 * (q & 3))) & 255u;
                         const float pw = v[q].x * v[q].x + v[q].y * v[q].y;
                         if (__any_sync(0xffffffffu, b != cur)) {
-                            if (b != cur) {
-                                if (cur != 255u) lbins[cur * P2_THREADS + tid] += mult * acc;
+                            const bool chg = b != cur;
+                            lane_update(cur, mult * acc, chg);
+                            if (chg) {
                                 cur = b;
                                 acc = 0.f;
                             }
@@ -869,7 +886,7 @@ k_fused_p2_s128(const float2* __restrict__ scratch, ItemMap im, const ChunkDev* 
                 }
             }
             if (WARPB) warp_flush(wb, cur, mult * acc, true);
-            else if (cur != 255u) lbins[cur * P2_THREADS + tid] += mult * acc;
+            else lane_update(cur, mult * acc, true);
         }
         if (!EARLY) {
             __syncthreads();
@@ -884,8 +901,8 @@ k_fused_p2_s128(const float2* __restrict__ scratch, ItemMap im, const ChunkDev* 
             for (int b = warp; b < nbins; b += P2_THREADS / 32) {
                 double a = 0.0;
 #pragma unroll
-                for (int i = 0; i < P2_THREADS / 32; ++i) {
-                    float* q = lbins + b * P2_THREADS + lane + 32 * i;
+                for (int i = 0; i < NCOL / 32; ++i) {
+                    float* q = lbins + b * NCOL + lane + 32 * i;
                     a += (double)*q;
                     *q = 0.f;
                 }
@@ -931,7 +948,7 @@ static size_t p1_smem() { return (size_t)R1 * ROWLD * 8 + 128 * 8 + 66 * 16 + 64
 static int bin_mode(const ps21_plan* p) {
     if (p->mode == PS21_MODE_CYLINDRICAL) return BM_CYL;
     if (p->nbins <= MAX_BINS) return BM_LANE;
-    return (p->n0 == 256 && p->nbins <= MAX_BINS_GROUP) ? BM_GROUP : BM_WARP;
+    return p->nbins <= MAX_BINS_GROUP ? BM_GROUP : BM_WARP;
 }
 static size_t p2_smem(int nbins, int bm) {
     const size_t bins = bm == BM_WARP    ? (size_t)(P2_THREADS / 32) * nbins * 8
@@ -988,9 +1005,11 @@ int fused_try_setup(ps21_plan* p, ShapePlan& sp) {
         cudaMemcpy(fs->tw256, tw.data(), sizeof(float4) * 256, cudaMemcpyHostToDevice) != cudaSuccess ||
         cudaFuncSetAttribute(k_fused_p1<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p1_smem()) != cudaSuccess ||
         cudaFuncSetAttribute(k_fused_p1<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p1_smem()) != cudaSuccess ||
-        cudaFuncSetAttribute(k_fused_p2_s128<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        cudaFuncSetAttribute(k_fused_p2_s128<BM_LANE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              (int)p2_smem(MAX_BINS, BM_LANE)) != cudaSuccess ||
-        cudaFuncSetAttribute(k_fused_p2_s128<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        cudaFuncSetAttribute(k_fused_p2_s128<BM_GROUP, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)p2_smem(MAX_BINS_GROUP, BM_GROUP)) != cudaSuccess ||
+        cudaFuncSetAttribute(k_fused_p2_s128<BM_WARP, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              (int)p2_smem(MAX_BINS_SPH, BM_WARP)) != cudaSuccess ||
         cudaFuncSetAttribute(k_fused_p2<BM_LANE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              (int)p2_smem(MAX_BINS, BM_LANE)) != cudaSuccess ||
@@ -1086,11 +1105,14 @@ int fused_forward(ps21_plan* p, ShapePlan& sp, const float* d_boxes, long long b
         p->d_dc, p->nchunks, fs->tw256, p->nbins
         if (fs->S == 128) {
             if (bm == BM_LANE)
-                PS21_LAUNCH((k_fused_p2_s128<false, true>), dim3(Geo<128>::SLOTS_S, (unsigned)nitems), dim3(P2_THREADS),
-                            p2_smem(p->nbins, bm), st, PS21_P2_ARGS);
+                PS21_LAUNCH((k_fused_p2_s128<BM_LANE, true>), dim3(Geo<128>::SLOTS_S, (unsigned)nitems),
+                            dim3(P2_THREADS), p2_smem(p->nbins, bm), st, PS21_P2_ARGS);
+            else if (bm == BM_GROUP)
+                PS21_LAUNCH((k_fused_p2_s128<BM_GROUP, false>), dim3(Geo<128>::SLOTS_S, (unsigned)nitems),
+                            dim3(P2_THREADS), p2_smem(p->nbins, bm), st, PS21_P2_ARGS);
             else
-                PS21_LAUNCH((k_fused_p2_s128<true, false>), dim3(Geo<128>::SLOTS_S, (unsigned)nitems), dim3(P2_THREADS),
-                            p2_smem(p->nbins, bm), st, PS21_P2_ARGS);
+                PS21_LAUNCH((k_fused_p2_s128<BM_WARP, false>), dim3(Geo<128>::SLOTS_S, (unsigned)nitems),
+                            dim3(P2_THREADS), p2_smem(p->nbins, bm), st, PS21_P2_ARGS);
             PS21_CUDA(cudaGetLastError());
         } else if (bm == BM_LANE) {
             PS21_P2_LAUNCH(BM_LANE, SLOTS, PS21_P2_ARGS);

@@ -68,11 +68,12 @@ def test_fused_two_pass_kernels_256(mods):
         mods[0].set_defaults(kernel_path="auto")
 
 
-def test_fused_two_pass_kernels_128(mods):
+@pytest.mark.parametrize("nb", [20, None])   # None: the reference default, 73 bins -> 4-lane group bin mode
+def test_fused_two_pass_kernels_128(mods, nb):
     """128 x 128 x 256 chunk (BASELINE config 1 chunk shape) through the fused kernels."""
     mods[0].set_defaults(kernel_path="fused")
     try:
-        PC.check_compute_power(mods[0], (128, 128, 256), (192.0, 192.0, 384.0), 20, True, seed=3)
+        PC.check_compute_power(mods[0], (128, 128, 256), (192.0, 192.0, 384.0), nb, True, seed=3)
     finally:
         mods[0].set_defaults(kernel_path="auto")
 

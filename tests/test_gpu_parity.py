@@ -71,7 +71,9 @@ def test_fused_path_vs_oracle_256(mods, nb, log, flags):
         mods[0].set_defaults(kernel_path="auto")
 
 
-@pytest.mark.parametrize("nb,log,flags", [(20, True, (True, False, False)), (16, False, (False, False, False))])
+@pytest.mark.parametrize("nb,log,flags", [(20, True, (True, False, False)), (16, False, (False, False, False)),
+                                          (None, True, (True, False, False)),    # default 73 bins: group bin mode
+                                          (200, False, (True, False, False))])   # warp bin mode
 def test_fused_path_vs_oracle_128(mods, nb, log, flags):
     """128 x 128 x 256 chunk (config 1 chunk shape) through the fused kernels vs the fp64 oracle."""
     mods[0].set_defaults(kernel_path="fused")
