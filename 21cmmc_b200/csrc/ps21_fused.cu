@@ -945,16 +945,18 @@ __global__ void k_fused_cyl_reduce(const double* __restrict__ cylpart, ItemMap i
 }
 
 static size_t p1_smem() { return (size_t)R1 * ROWLD * 8 + 128 * 8 + 66 * 16 + 64; }
-static int bin_mode(const ps21_plan* p) {
-    if (p->mode == PS21_MODE_CYLINDRICAL) return BM_CYL;
-    if (p->nbins <= MAX_BINS) return BM_LANE;
-    return p->nbins <= MAX_BINS_GROUP ? BM_GROUP : BM_WARP;
-}
 static size_t p2_smem(int nbins, int bm) {
     const size_t bins = bm == BM_WARP    ? (size_t)(P2_THREADS / 32) * nbins * 8
                         : bm == BM_GROUP ? (size_t)MAX_BINS_GROUP * 8 + (size_t)nbins * (P2_THREADS / 4) * 4
                                          : (size_t)MAX_BINS * 8 * (bm == BM_CYL ? 8 : 1) + (size_t)nbins * P2_THREADS * 4;
     return (size_t)TILE * 8 + TILE + 256 * 16 + 16 + bins;
+}
+static int bin_mode(const ps21_plan* p) {
+    if (p->mode == PS21_MODE_CYLINDRICAL) return BM_CYL;
+    // lane-private columns up to 40 bins; on the 128^2 plane only while two CTAs still fit an SM (<= 36 bins; above,
+    // the group mode measured 7 % faster there, 4 % slower on the 256^2 plane)
+    if (p->nbins <= MAX_BINS && (p->n0 == 256 || p2_smem(p->nbins, BM_LANE) <= (228 * 1024) / 2 - 1024)) return BM_LANE;
+    return p->nbins <= MAX_BINS_GROUP ? BM_GROUP : BM_WARP;
 }
 
 }  // namespace fz
