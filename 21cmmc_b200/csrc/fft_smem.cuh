@@ -245,22 +245,35 @@ __device__ __forceinline__ void stage_radix(const float2* __restrict__ in, float
     const int nb = n / R;
     const int tws = n / (Ns * R);
     const int cmask = (1 << lc) - 1;
+    // byte strides between the R inputs / outputs of a butterfly: addresses advance by one add per element
+    const int sin = nb * ld * (int)sizeof(float2), sout = Ns * ld * (int)sizeof(float2);
     for (int task = threadIdx.x; task < (nb << lc); task += blockDim.x) {
         const int c = task & cmask;
         const int j = task >> lc;
         const int k = j - fast_div(j, dns) * Ns;
         float2 v[R];
+        const char* pi = reinterpret_cast<const char*>(in + (j * ld + c));
 #pragma unroll
-        for (int m = 0; m < R; ++m) v[m] = in[(j + m * nb) * ld + c];
+        for (int m = 0; m < R; ++m) {
+            v[m] = *reinterpret_cast<const float2*>(pi);
+            pi += sin;
+        }
         if (Ns > 1) {
+            const float2* pt = tw + k * tws;
             const int step = k * tws;
 #pragma unroll
-            for (int m = 1; m < R; ++m) v[m] = cmul_w2(v[m], __ldg(&tw[m * step]));
+            for (int m = 1; m < R; ++m) {
+                v[m] = cmul_w2(v[m], __ldg(pt));
+                pt += step;
+            }
         }
         small_dft<R>(v);
-        const int j0 = (j - k) * R + k;
+        char* po = reinterpret_cast<char*>(out + (((j - k) * R + k) * ld + c));
 #pragma unroll
-        for (int m = 0; m < R; ++m) out[(j0 + m * Ns) * ld + c] = v[m];
+        for (int m = 0; m < R; ++m) {
+            *reinterpret_cast<float2*>(po) = v[m];
+            po += sout;
+        }
     }
 }
 

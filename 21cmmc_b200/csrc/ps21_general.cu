@@ -215,9 +215,15 @@ __global__ void k_general_ypass(float2* __restrict__ scratch, long long spec_ele
     };
     auto fetch = [&](int w, float2* X) {
         const float2* col = column(w);
+        const float2* g = col + (long long)yfirst * nh;
+        const long long gs = (long long)ystep * nh;
+        float2* sp = X + yfirst * ld + t;
+        const int ss = ystep * ld;
         for (int y = yfirst; y < n1; y += ystep) {
-            if (col) cp_async8(&X[y * ld + t], col + (long long)y * nh);
-            else X[y * ld + t] = make_float2(0.f, 0.f);
+            if (col) cp_async8(sp, g);
+            else *sp = make_float2(0.f, 0.f);
+            g += gs;
+            sp += ss;
         }
         cp_async_commit();
     };
@@ -232,8 +238,17 @@ __global__ void k_general_ypass(float2* __restrict__ scratch, long long spec_ele
         if (w + 1 < w1) fetch(w + 1, X2);
         const float2* R = column_fft(X0, X1, fy, ld, lc, tw);
         float2* col = column(w);
-        if (col)
-            for (int y = yfirst; y < n1; y += ystep) col[(long long)y * nh] = R[y * ld + t];
+        if (col) {
+            float2* g = col + (long long)yfirst * nh;
+            const long long gs = (long long)ystep * nh;
+            const float2* sp = R + yfirst * ld + t;
+            const int ss = ystep * ld;
+            for (int y = yfirst; y < n1; y += ystep) {
+                *g = *sp;
+                g += gs;
+                sp += ss;
+            }
+        }
         c = (c + 2) % 3;
     }
 }
@@ -280,13 +295,20 @@ __global__ void k_general_xpass_bin(const float2* __restrict__ scratch, long lon
     const long long plane = (long long)n1 * nh;
     const long long ntiles = (plane + tile - 1) / tile;
     const float2* base = scratch + (long long)blockIdx.y * spec_elems;
+    // blockDim is a multiple of the tile width: a thread always serves column t and walks x in steps of xs
+    const int tcol = threadIdx.x & (tile - 1), xfirst = threadIdx.x >> lc, xs = blockDim.x >> lc;
     auto fetch_tile = [&](long long tl, float2* X) {
         const long long m0 = tl * tile;
-        const int cols = (int)min((long long)tile, plane - m0);
-        for (int i = threadIdx.x; i < (n0 << lc); i += blockDim.x) {
-            const int x = i >> lc, t = i & (tile - 1);
-            if (t < cols) cp_async8(&X[x * ld + t], &base[(long long)x * plane + m0 + t]);
-            else X[x * ld + t] = make_float2(0.f, 0.f);
+        const bool in = m0 + tcol < plane;
+        const float2* g = base + (long long)xfirst * plane + m0 + tcol;
+        const long long gs = (long long)xs * plane;
+        float2* sp = X + xfirst * ld + tcol;
+        const int ss = xs * ld;
+        for (int x = xfirst; x < n0; x += xs) {
+            if (in) cp_async8(sp, g);
+            else *sp = make_float2(0.f, 0.f);
+            g += gs;
+            sp += ss;
         }
         cp_async_commit();
     };
