@@ -286,3 +286,15 @@ def test_config4_512_cube_properties(mods):
     q = plan2.power_device(boxes[:1].contiguous()).cpu().numpy()[0]
     good = plan2.counts > 100000
     assert good.sum() >= 8 and np.all(np.abs(q[good] / (100.0 * L ** 3 / n ** 3) - 1) < 0.02)
+
+
+def test_random_shape_sweep(mods):
+    """120 seeded random cases (odd and prime lengths, coeval cubes, cylindrical, both edge rules, all flags)."""
+    import importlib.util
+
+    spec = importlib.util.spec_from_file_location(
+        "gpu_random_sweep", os.path.join(os.path.dirname(os.path.dirname(__file__)), "scripts", "gpu_random_sweep.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    fails, worst = mod.sweep(120, 31, mods[0])
+    assert fails == 0 and worst < POWER_RTOL
