@@ -246,6 +246,14 @@ static void free_dev(void* p) {
     if (p) cudaFree(p);
 }
 
+// temporary device buffer of an entry point: released on every return path
+template <class T>
+struct DevTmp {
+    T* p = nullptr;
+    ~DevTmp() { free_dev(p); }
+    cudaError_t alloc(size_t n) { return cudaMalloc((void**)&p, sizeof(T) * (n ? n : 1)); }
+};
+
 static int ensure_batch(ps21_plan* p, long long batch) {
     if (batch <= p->batch_cap) return PS21_OK;
     free_dev(p->d_partials);
@@ -705,10 +713,11 @@ static int run_host(ps21_plan* p, const float* h_boxes, long long batch, long lo
     cudaStream_t s_copy = (cudaStream_t)p->stage_stream[0], s_comp = (cudaStream_t)p->stage_stream[1];
     int rc = ensure_batch(p, per);
     if (rc) return rc;
-    double *d_res_p = nullptr, *d_res_d = nullptr, *d_res_l = nullptr;
-    PS21_CUDA(cudaMalloc((void**)&d_res_p, sizeof(double) * batch * p->out_per_box));
-    if (h_delta) PS21_CUDA(cudaMalloc((void**)&d_res_d, sizeof(double) * batch * p->out_per_box));
-    if (h_lnl) PS21_CUDA(cudaMalloc((void**)&d_res_l, sizeof(double) * batch));
+    DevTmp<double> res_p, res_d, res_l;
+    PS21_CUDA(res_p.alloc((size_t)batch * p->out_per_box));
+    if (h_delta) PS21_CUDA(res_d.alloc((size_t)batch * p->out_per_box));
+    if (h_lnl) PS21_CUDA(res_l.alloc((size_t)batch));
+    double *d_res_p = res_p.p, *d_res_d = res_d.p, *d_res_l = res_l.p;
     // events: [0] = "copy into buffer b done" is recorded per slice on s_copy; compute waits on it.
     // buffer reuse: copy of slice i+2 waits for the compute of slice i (event recorded on s_comp).
     cudaEvent_t ev_copy[2], ev_comp[2];
@@ -752,7 +761,6 @@ static int run_host(ps21_plan* p, const float* h_boxes, long long batch, long lo
         cudaEventDestroy(ev_copy[i]);
         cudaEventDestroy(ev_comp[i]);
     }
-    free_dev(d_res_p); free_dev(d_res_d); free_dev(d_res_l);
     if (rc) return rc;
     if (e1 != cudaSuccess) return cuda_fail(e1, "host staging copy stream");
     if (e2 != cudaSuccess) return cuda_fail(e2, "host staging compute stream");
@@ -782,16 +790,16 @@ int ps21_lnl_from_delta(ps21_plan* p, const double* h_delta, int64_t batch, doub
     }
     PS21_CUDA(cudaSetDevice(p->device));
     if (batch <= 0) return PS21_OK;
-    double *dd = nullptr, *dl = nullptr;
-    PS21_CUDA(cudaMalloc((void**)&dd, sizeof(double) * batch * p->out_per_box));
-    PS21_CUDA(cudaMalloc((void**)&dl, sizeof(double) * batch));
+    DevTmp<double> tdd, tdl;
+    PS21_CUDA(tdd.alloc((size_t)batch * p->out_per_box));
+    PS21_CUDA(tdl.alloc((size_t)batch));
+    double *dd = tdd.p, *dl = tdl.p;
     PS21_CUDA(cudaMemcpy(dd, h_delta, sizeof(double) * batch * p->out_per_box, cudaMemcpyHostToDevice));
     PS21_LAUNCH(k_lnl_from_delta, dim3((unsigned)((batch + 63) / 64)), dim3(64), 0, (cudaStream_t)0, dd,
                 p->out_per_box, p->d_chunks, p->nchunks, dl, p->data.d_data, p->data.d_noise2, p->data.d_mask,
                 p->data.nsets, p->data.model_uncertainty, p->data.error_on_model, (long long)batch);
     cudaError_t e = cudaGetLastError();
     if (e == cudaSuccess) e = cudaMemcpy(h_lnl, dl, sizeof(double) * batch, cudaMemcpyDeviceToHost);
-    free_dev(dd); free_dev(dl);
     if (e != cudaSuccess) return cuda_fail(e, "lnl_from_delta");
     p->launches_last = 1;
     return PS21_OK;
