@@ -1,5 +1,5 @@
 # A/B of the general path on one box: config-3 workload (16 walkers), config 2 (200^3), config 4 (512^3), 116 bins
-for args in "--path general --walkers 16" "--config 2" "--config 4 --e2e-walkers 1" "--path general --walkers 16 --nbins 116" "--config 5 --path general --walkers 8"; do
+for args in "--path general --walkers 16" "--config 1 --path general" "--config 2" "--config 4 --e2e-walkers 1" "--path general --walkers 16 --nbins 116" "--config 5 --path general --walkers 8"; do
 for v in A B; do
   PS21_LIBRARY=$PWD/ab/libps21_$v.so python bench.py --steps 5 --warmup 3 --no-cpu --no-e2e $args > gpurun_out/abg.log 2>&1
   python - "$v" "$args" <<'PY'
