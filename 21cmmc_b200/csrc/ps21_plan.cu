@@ -491,15 +491,19 @@ int ps21_plan_create(const ps21_desc* d, ps21_plan** out) {
         sp.g1_cols = pick_tile(sp.nz, none);
         sp.g2_tile = pick_tile(d->n1, [&](int t) { return (size_t)d->n1 * (t | 1) * sizeof(float2); });  // third buffer
         sp.g3_tile = pick_tile(d->n0, [&](int t) { return general_xpass_extra(nb_out, d->n0, t); });
-        // tuning experiments only: a smaller power-of-two tile than the automatic choice
-        auto tile_override = [](const char* name, int& tile) {
+        // tuning experiments only: another power-of-two tile (<= 16) than the automatic choice, if it fits
+        auto tile_override = [](const char* name, int& tile, int n, auto extra) {
             const char* e = std::getenv(name);
             if (!e) return;
             const int t = std::atoi(e);
-            if (t >= 1 && t <= tile && (t & (t - 1)) == 0) tile = t;
+            if (t >= 1 && t <= 16 && (t & (t - 1)) == 0 &&
+                2 * (size_t)n * (t | 1) * sizeof(float2) + extra(t) <= (size_t)220 * 1024)
+                tile = t;
         };
-        tile_override("PS21_G2_TILE", sp.g2_tile);
-        tile_override("PS21_G3_TILE", sp.g3_tile);
+        tile_override("PS21_G1_TILE", sp.g1_cols, sp.nz, none);
+        tile_override("PS21_G2_TILE", sp.g2_tile, d->n1,
+                      [&](int t) { return (size_t)d->n1 * (t | 1) * sizeof(float2); });
+        tile_override("PS21_G3_TILE", sp.g3_tile, d->n0, [&](int t) { return general_xpass_extra(nb_out, d->n0, t); });
         if (!sp.g1_cols || !sp.g2_tile || !sp.g3_tile) return fail(invalid("axis too long for the shared-memory FFT"));
         const long long ntiles = ((long long)d->n1 * sp.nh + sp.g3_tile - 1) / sp.g3_tile;
         const long long cap = d->mode == PS21_MODE_SPHERICAL ? 64 : 16;
