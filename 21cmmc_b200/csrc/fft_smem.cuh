@@ -305,6 +305,9 @@ __device__ __forceinline__ void stage_generic(const float2* __restrict__ in, flo
 }
 
 // Full column FFT over 2^lc columns.  Returns the buffer that holds the result (a or b).  Ends with a barrier.
+// R32: also instantiate the radix-32 stage (512 = 32*16, 1024 = 32*32).  It needs ~100 registers, so the kernels
+// that may meet it are compiled separately and the common ones keep their occupancy.
+template <bool R32 = false>
 __device__ __forceinline__ float2* column_fft(float2* a, float2* b, const FftFactors& f, int ld, int lc,
                                               const float2* __restrict__ tw) {
     float2* in = a;
@@ -319,6 +322,9 @@ __device__ __forceinline__ float2* column_fft(float2* a, float2* b, const FftFac
             case 5: stage_radix<5>(in, out, f.n, Ns, f.div_ns[s], ld, lc, tw); break;
             case 8: stage_radix<8>(in, out, f.n, Ns, f.div_ns[s], ld, lc, tw); break;
             case 16: stage_radix<16>(in, out, f.n, Ns, f.div_ns[s], ld, lc, tw); break;
+            case 32:
+                if (R32) stage_radix<32>(in, out, f.n, Ns, f.div_ns[s], ld, lc, tw);
+                break;
             default: stage_generic(in, out, f.n, Ns, f.div_ns[s], f.div_nb[s], r, ld, lc, tw); break;
         }
         __syncthreads();

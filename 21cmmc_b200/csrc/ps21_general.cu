@@ -134,6 +134,7 @@ int launch_slab_mean(ps21_plan* p, const float* d_boxes, long long batch_stride,
 // ---------------------------------------------------------------------------------------------
 // g1: z pass.  CTA = `cols` complex columns = 2*cols consecutive (x,y) rows of one spectrum.
 // ---------------------------------------------------------------------------------------------
+template <bool R32>
 __global__ void k_general_zpass(const float* __restrict__ boxes, long long batch_stride, int n2_total, int nrows,
                                 ItemMap im, const ChunkDev* __restrict__ chunks, int nchunks,
                                 const float* __restrict__ means, float2* __restrict__ scratch,
@@ -167,7 +168,7 @@ __global__ void k_general_zpass(const float* __restrict__ boxes, long long batch
         }
     }
     __syncthreads();
-    const float2* R = column_fft(A, B, fz, ld, lc, tw);
+    const float2* R = column_fft<R32>(A, B, fz, ld, lc, tw);
     float2* dst = scratch + (long long)blockIdx.y * spec_elems;
     for (int pr = warp; pr < cols; pr += nwarps) {
         const int ra = row0 + 2 * pr, rb = ra + 1;
@@ -193,6 +194,7 @@ __global__ void k_general_zpass(const float* __restrict__ boxes, long long batch
 // is transformed and stored.  blockDim is a multiple of the tile width, so a thread always serves the same column.
 constexpr int kYPassItems = 8;
 
+template <bool R32>
 __global__ void k_general_ypass(float2* __restrict__ scratch, long long spec_elems, int n0, int n1, int nh,
                                 FftFactors fy, const float2* __restrict__ tw, int lc) {
     PS21_DYN_SMEM(float2, smem);
@@ -236,7 +238,7 @@ __global__ void k_general_ypass(float2* __restrict__ scratch, long long spec_ele
         cp_async_wait<0>();
         __syncthreads();   // tile w has landed in X0; the previous tile's result has been stored by everybody
         if (w + 1 < w1) fetch(w + 1, X2);
-        const float2* R = column_fft(X0, X1, fy, ld, lc, tw);
+        const float2* R = column_fft<R32>(X0, X1, fy, ld, lc, tw);
         float2* col = column(w);
         if (col) {
             float2* g = col + (long long)yfirst * nh;
@@ -267,6 +269,7 @@ __global__ void k_general_ypass(float2* __restrict__ scratch, long long spec_ele
 // Software pipeline: three FFT buffers rotate.  While tile i is transformed (ping-pong between two of them) and
 // binned, the strided rows of tile i+1 stream into the third with cp.async; the bin indices of tile i arrive in
 // their own commit group during the FFT.  The CTA therefore always has a tile of loads in flight.
+template <bool R32>
 __global__ void k_general_xpass_bin(const float2* __restrict__ scratch, long long spec_elems, int n0, int n1,
                                     int nh, int nz, FftFactors fx, const float2* __restrict__ tw, int lc,
                                     ItemMap im, const ChunkDev* __restrict__ chunks,
@@ -329,7 +332,7 @@ __global__ void k_general_xpass_bin(const float2* __restrict__ scratch, long lon
         }
         if (tl + gridDim.x < ntiles) fetch_tile(tl + gridDim.x, X2);
         else cp_async_commit();   // keep the group count uniform
-        const float2* R = column_fft(X0, X1, fx, ld, lc, tw);
+        const float2* R = column_fft<R32>(X0, X1, fx, ld, lc, tw);
         cp_async_wait<1>();        // bin indices of this tile (the next tile's rows may still be in flight)
         __syncthreads();
         {
@@ -398,14 +401,23 @@ size_t general_xpass_extra(int nb_out, int n0, int tile) {
 int general_init() {
 #ifndef PS21_EMU
     const int big = 220 * 1024;
-    PS21_CUDA(cudaFuncSetAttribute(k_general_zpass, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
-    PS21_CUDA(cudaFuncSetAttribute(k_general_ypass, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
-    PS21_CUDA(cudaFuncSetAttribute(k_general_xpass_bin, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+    PS21_CUDA(cudaFuncSetAttribute(k_general_zpass<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+    PS21_CUDA(cudaFuncSetAttribute(k_general_ypass<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+    PS21_CUDA(cudaFuncSetAttribute(k_general_xpass_bin<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+    PS21_CUDA(cudaFuncSetAttribute(k_general_zpass<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+    PS21_CUDA(cudaFuncSetAttribute(k_general_ypass<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+    PS21_CUDA(cudaFuncSetAttribute(k_general_xpass_bin<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
 #endif
     return PS21_OK;
 }
 
 static size_t fft_smem_bytes(int n, int tile) { return 2 * (size_t)n * (tile | 1) * sizeof(float2); }
+
+static bool has_radix32(const FftFactors& f) {
+    for (int s = 0; s < f.nstages; ++s)
+        if (f.radix[s] == 32) return true;
+    return false;
+}
 
 int general_forward(ps21_plan* p, ShapePlan& sp, const float* d_boxes, long long batch_stride, long long item0,
                     long long nitems, cudaStream_t st) {
@@ -416,17 +428,26 @@ int general_forward(ps21_plan* p, ShapePlan& sp, const float* d_boxes, long long
     {
         ProfScope ps(p, KK_PASS1, st);
         dim3 grid((nrows + 2 * sp.g1_cols - 1) / (2 * sp.g1_cols), (unsigned)nitems);
-        PS21_LAUNCH(k_general_zpass, grid, dim3(256), fft_smem_bytes(sp.nz, sp.g1_cols), st, d_boxes, batch_stride,
-                    p->n2_total, nrows, im, p->d_chunks, p->nchunks, p->d_means, p->d_scratch, spec_elems, sp.fz,
-                    sp.tw_z, ilog2(sp.g1_cols));
+#define PS21_ZPASS_ARGS                                                                                            \
+    d_boxes, batch_stride, p->n2_total, nrows, im, p->d_chunks, p->nchunks, p->d_means, p->d_scratch, spec_elems,  \
+        sp.fz, sp.tw_z, ilog2(sp.g1_cols)
+        if (has_radix32(sp.fz))
+            PS21_LAUNCH(k_general_zpass<true>, grid, dim3(256), fft_smem_bytes(sp.nz, sp.g1_cols), st, PS21_ZPASS_ARGS);
+        else
+            PS21_LAUNCH(k_general_zpass<false>, grid, dim3(256), fft_smem_bytes(sp.nz, sp.g1_cols), st, PS21_ZPASS_ARGS);
         PS21_CUDA(cudaGetLastError());
     }
     {
         ProfScope ps(p, KK_PASS_MID, st);
         const long long ntile = ((long long)n0 * sp.nh + sp.g2_tile - 1) / sp.g2_tile;
         dim3 grid((unsigned)((ntile + kYPassItems - 1) / kYPassItems), (unsigned)nitems);
-        PS21_LAUNCH(k_general_ypass, grid, dim3(256), fft_smem_bytes(n1, sp.g2_tile) * 3 / 2, st, p->d_scratch,
-                    spec_elems, n0, n1, sp.nh, sp.fy, sp.tw_y, ilog2(sp.g2_tile));
+#define PS21_YPASS_ARGS p->d_scratch, spec_elems, n0, n1, sp.nh, sp.fy, sp.tw_y, ilog2(sp.g2_tile)
+        if (has_radix32(sp.fy))
+            PS21_LAUNCH(k_general_ypass<true>, grid, dim3(256), fft_smem_bytes(n1, sp.g2_tile) * 3 / 2, st,
+                        PS21_YPASS_ARGS);
+        else
+            PS21_LAUNCH(k_general_ypass<false>, grid, dim3(256), fft_smem_bytes(n1, sp.g2_tile) * 3 / 2, st,
+                        PS21_YPASS_ARGS);
         PS21_CUDA(cudaGetLastError());
     }
     {
@@ -434,10 +455,14 @@ int general_forward(ps21_plan* p, ShapePlan& sp, const float* d_boxes, long long
         const int nb_out = p->chunks[sp.chunks[0]].nbins_out;
         dim3 grid(sp.g3_slots, (unsigned)nitems);
         size_t smem = fft_smem_bytes(n0, sp.g3_tile) + general_xpass_extra(nb_out, n0, sp.g3_tile);
-        PS21_LAUNCH(k_general_xpass_bin, grid, dim3(256), smem, st, p->d_scratch, spec_elems, n0, n1, sp.nh, sp.nz,
-                    sp.fx, sp.tw_x, ilog2(sp.g3_tile), im, p->d_chunks, (const uint16_t* const*)p->d_lut_table,
-                    general_lut_block(n0, sp.g3_tile), p->d_partials, p->out_per_box, p->slots_max, p->d_dc,
-                    p->nchunks, general_bin_copies(nb_out));
+#define PS21_XPASS_ARGS                                                                                          \
+    p->d_scratch, spec_elems, n0, n1, sp.nh, sp.nz, sp.fx, sp.tw_x, ilog2(sp.g3_tile), im, p->d_chunks,           \
+        (const uint16_t* const*)p->d_lut_table, general_lut_block(n0, sp.g3_tile), p->d_partials, p->out_per_box, \
+        p->slots_max, p->d_dc, p->nchunks, general_bin_copies(nb_out)
+        if (has_radix32(sp.fx))
+            PS21_LAUNCH(k_general_xpass_bin<true>, grid, dim3(256), smem, st, PS21_XPASS_ARGS);
+        else
+            PS21_LAUNCH(k_general_xpass_bin<false>, grid, dim3(256), smem, st, PS21_XPASS_ARGS);
         PS21_CUDA(cudaGetLastError());
     }
     p->launches_last += 3;

@@ -47,7 +47,7 @@ static FastDiv make_fastdiv(int d) {
     return f;
 }
 
-static FftFactors factorize(int n) {
+static FftFactors factorize(int n, bool allow32) {
     FftFactors f{};
     f.n = n;
     int m = n, ns = 0;
@@ -64,7 +64,12 @@ static FftFactors factorize(int n) {
         m /= 2;
         ++k;
     }
-    if (k > 0) {
+    // 512 = 32*16, 1024 = 32*32: two stages instead of three.  Measured on 512^3: y pass 17.0 -> 14.9 ms, x pass
+    // 19.0 -> 16.2 ms, but the z pass 11.7 -> 13.9 ms (its untangle epilogue pays for the registers) -> y and x only
+    if (allow32 && (k == 9 || k == 10)) {
+        f.radix[ns++] = 32;
+        f.radix[ns++] = 1 << (k - 5);
+    } else if (k > 0) {
         const int st = (k + 3) / 4, base = k / st, extra = k % st;
         for (int i = 0; i < st && ns < 14; ++i) f.radix[ns++] = 1 << (base + (i < extra ? 1 : 0));
     }
@@ -473,7 +478,9 @@ int ps21_plan_create(const ps21_desc* d, ps21_plan** out) {
     long long spec_max = 0;
     p->slots_max = 1;
     for (auto& sp : p->shapes) {
-        sp.fz = factorize(sp.nz); sp.fy = factorize(d->n1); sp.fx = factorize(d->n0);
+        sp.fz = factorize(sp.nz, false);
+        sp.fy = factorize(d->n1, true);
+        sp.fx = factorize(d->n0, true);
         if (sp.fz.nstages < 0 || sp.fy.nstages < 0 || sp.fx.nstages < 0)
             return fail(invalid("axis length has too many prime factors"));
         if ((rc = upload_twiddles(sp.nz, &sp.tw_z))) return fail(rc);

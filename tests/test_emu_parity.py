@@ -29,6 +29,7 @@ def mods():
     ((15, 15, 17), (22.5, 22.5, 25.5), 7, True, (True, True, False), "legacy_1.001"),    # odd sizes
     ((24, 24, 18), (36.0, 36.0, 27.0), 10, False, (True, False, True), "inscribed"),
     ((10, 10, 14), (15.0, 15.0, 21.0), None, True, (True, False, False), "legacy_1.001"),  # default bins
+    ((512, 512, 4), (768.0, 768.0, 6.0), 10, True, (True, False, False), "legacy_1.001"),  # radix-32 stages (y, x)
 ])
 def test_compute_power_lightcone(mods, shape, L, nb, log, flags, rule):
     PC.check_compute_power(mods[0], shape, L, nb, log, flags, rule)
