@@ -187,6 +187,49 @@ __device__ __forceinline__ void small_dft<16>(float2 (&v)[16]) {
     }
 }
 
+// 25-point DFT as 5x5: i = j + 5 i2, k = q + 5 p;  w25^(ik) = w25^(jq) w5^(jp) w5^(i2 q).
+// (200 = 25*8, 100 = 25*4, 50 = 25*2: box sizes in multiples of 50 are common, and a 25-point butterfly saves a stage.)
+template <>
+__device__ __forceinline__ void small_dft<25>(float2 (&v)[25]) {
+    // cos / sin of 2 pi m / 25, m = 0..16
+    constexpr float W[17][2] = {
+        {1.00000000000000000000f, 0.00000000000000000000f},
+        {0.96858316112863107605f, 0.24868988716485479484f},
+        {0.87630668004386358394f, 0.48175367410171532345f},
+        {0.72896862742141155245f, 0.68454710592868861507f},
+        {0.53582679497899654564f, 0.84432792550201507531f},
+        {0.30901699437494745126f, 0.95105651629515353118f},
+        {0.06279051952931352654f, 0.99802672842827155897f},
+        {-0.18738131458572460097f, 0.98228725072868872115f},
+        {-0.42577929156507271502f, 0.90482705246601946580f},
+        {-0.63742398974868974548f, 0.77051324277578925326f},
+        {-0.80901699437494734024f, 0.58778525229247324813f},
+        {-0.92977648588825134723f, 0.36812455268467814129f},
+        {-0.99211470131447776488f, 0.12533323356430453588f},
+        {-0.99211470131447787590f, -0.12533323356430428608f},
+        {-0.92977648588825145826f, -0.36812455268467791925f},
+        {-0.80901699437494778433f, -0.58778525229247269301f},
+        {-0.63742398974868952344f, -0.77051324277578936428f},
+    };
+    float2 a[5][5];
+#pragma unroll
+    for (int j = 0; j < 5; ++j) {
+        float2 t[5];
+#pragma unroll
+        for (int i2 = 0; i2 < 5; ++i2) t[i2] = v[j + 5 * i2];
+        small_dft<5>(t);
+#pragma unroll
+        for (int q = 0; q < 5; ++q) a[j][q] = (j * q == 0) ? t[q] : crot(t[q], W[j * q][0], W[j * q][1]);
+    }
+#pragma unroll
+    for (int q = 0; q < 5; ++q) {
+        float2 t[5] = {a[0][q], a[1][q], a[2][q], a[3][q], a[4][q]};
+        small_dft<5>(t);
+#pragma unroll
+        for (int p = 0; p < 5; ++p) v[q + 5 * p] = t[p];
+    }
+}
+
 // 32-point DFT as 8x4: i = j + 4 i2, k = q + 8 p;  w32^(ik) = w32^(jq) w4^(jp) w8^(i2 q).
 template <>
 __device__ __forceinline__ void small_dft<32>(float2 (&v)[32]) {
@@ -305,7 +348,7 @@ __device__ __forceinline__ void stage_generic(const float2* __restrict__ in, flo
 }
 
 // Full column FFT over 2^lc columns.  Returns the buffer that holds the result (a or b).  Ends with a barrier.
-// R32: also instantiate the radix-32 stage (512 = 32*16, 1024 = 32*32).  It needs ~100 registers, so the kernels
+// R32: also instantiate the radix-32 and radix-25 stages (512 = 32*16, 200 = 25*8).  They need ~100 registers, so the kernels
 // that may meet it are compiled separately and the common ones keep their occupancy.
 template <bool R32 = false>
 __device__ __forceinline__ float2* column_fft(float2* a, float2* b, const FftFactors& f, int ld, int lc,
@@ -315,17 +358,20 @@ __device__ __forceinline__ float2* column_fft(float2* a, float2* b, const FftFac
     int Ns = 1;
     for (int s = 0; s < f.nstages; ++s) {
         const int r = f.radix[s];
-        switch (r) {
-            case 2: stage_radix<2>(in, out, f.n, Ns, f.div_ns[s], ld, lc, tw); break;
-            case 3: stage_radix<3>(in, out, f.n, Ns, f.div_ns[s], ld, lc, tw); break;
-            case 4: stage_radix<4>(in, out, f.n, Ns, f.div_ns[s], ld, lc, tw); break;
-            case 5: stage_radix<5>(in, out, f.n, Ns, f.div_ns[s], ld, lc, tw); break;
-            case 8: stage_radix<8>(in, out, f.n, Ns, f.div_ns[s], ld, lc, tw); break;
-            case 16: stage_radix<16>(in, out, f.n, Ns, f.div_ns[s], ld, lc, tw); break;
-            case 32:
-                if (R32) stage_radix<32>(in, out, f.n, Ns, f.div_ns[s], ld, lc, tw);
-                break;
-            default: stage_generic(in, out, f.n, Ns, f.div_ns[s], f.div_nb[s], r, ld, lc, tw); break;
+        if (R32 && r == 32) {   // compile-time dead in the common kernels: their code does not change
+            stage_radix<32>(in, out, f.n, Ns, f.div_ns[s], ld, lc, tw);
+        } else if (R32 && r == 25) {
+            stage_radix<25>(in, out, f.n, Ns, f.div_ns[s], ld, lc, tw);
+        } else {
+            switch (r) {
+                case 2: stage_radix<2>(in, out, f.n, Ns, f.div_ns[s], ld, lc, tw); break;
+                case 3: stage_radix<3>(in, out, f.n, Ns, f.div_ns[s], ld, lc, tw); break;
+                case 4: stage_radix<4>(in, out, f.n, Ns, f.div_ns[s], ld, lc, tw); break;
+                case 5: stage_radix<5>(in, out, f.n, Ns, f.div_ns[s], ld, lc, tw); break;
+                case 8: stage_radix<8>(in, out, f.n, Ns, f.div_ns[s], ld, lc, tw); break;
+                case 16: stage_radix<16>(in, out, f.n, Ns, f.div_ns[s], ld, lc, tw); break;
+                default: stage_generic(in, out, f.n, Ns, f.div_ns[s], f.div_nb[s], r, ld, lc, tw); break;
+            }
         }
         __syncthreads();
         float2* t = in;

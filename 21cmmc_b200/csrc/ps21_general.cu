@@ -415,7 +415,7 @@ static size_t fft_smem_bytes(int n, int tile) { return 2 * (size_t)n * (tile | 1
 
 static bool has_radix32(const FftFactors& f) {
     for (int s = 0; s < f.nstages; ++s)
-        if (f.radix[s] == 32) return true;
+        if (f.radix[s] == 32 || f.radix[s] == 25) return true;
     return false;
 }
 

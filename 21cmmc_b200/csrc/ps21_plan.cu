@@ -73,6 +73,10 @@ static FftFactors factorize(int n, bool allow32) {
         const int st = (k + 3) / 4, base = k / st, extra = k % st;
         for (int i = 0; i < st && ns < 14; ++i) f.radix[ns++] = 1 << (base + (i < extra ? 1 : 0));
     }
+    if (allow32 && m % 25 == 0 && ns < 14) {   // 200 = 8*25, 100 = 4*25, 250 = 2*25*5: one 25-point stage (y, x)
+        f.radix[ns++] = 25;
+        m /= 25;
+    }
     take(3);
     take(5);
     for (int pr = 7; m > 1 && ns < 14; pr += 2) take(pr);

@@ -30,6 +30,8 @@ def mods():
     ((24, 24, 18), (36.0, 36.0, 27.0), 10, False, (True, False, True), "inscribed"),
     ((10, 10, 14), (15.0, 15.0, 21.0), None, True, (True, False, False), "legacy_1.001"),  # default bins
     ((512, 512, 4), (768.0, 768.0, 6.0), 10, True, (True, False, False), "legacy_1.001"),  # radix-32 stages (y, x)
+    ((100, 100, 6), (150.0, 150.0, 9.0), 12, False, (True, False, False), "legacy_1.001"),  # radix-25 stages (y, x)
+    ((75, 75, 10), (110.0, 110.0, 15.0), 9, True, (True, False, False), "inscribed"),      # 75 = 25 * 3
 ])
 def test_compute_power_lightcone(mods, shape, L, nb, log, flags, rule):
     PC.check_compute_power(mods[0], shape, L, nb, log, flags, rule)
