@@ -12,6 +12,11 @@ from py21cmmc_b200 import likelihood as lk  # noqa: E402
 from tests import parity_cases as PC  # noqa: E402
 
 
+# bins below 1 % of the median power are compared against that floor (see tests/helpers.rel_err): single-mode bins of
+# tiny planes can hold 1/1000 of the typical power, where every fp32 FFT, the reference's included, loses digits
+FLOOR = 0.01
+
+
 def sweep(n, seed, lk_mod=lk):
     """Returns (number of failing cases, worst relative power error of the passing ones)."""
     rng = np.random.default_rng(seed)
@@ -29,10 +34,10 @@ def sweep(n, seed, lk_mod=lk):
         rule = "legacy_1.001" if rng.random() < 0.6 else "inscribed"
         try:
             if rng.random() < 0.2 and not coeval:
-                PC.check_cylindrical(lk_mod, shape, L, int(rng.integers(2, 12)), seed=i)
-                err = 0.0
+                err = PC.check_cylindrical(lk_mod, shape, L, int(rng.integers(2, 12)), seed=i, floor_frac=FLOOR)
             else:
-                err = PC.check_compute_power(lk_mod, shape, L, nb, log, flags, rule, seed=i, coeval=coeval)
+                err = PC.check_compute_power(lk_mod, shape, L, nb, log, flags, rule, seed=i, coeval=coeval,
+                                             floor_frac=FLOOR)
             worst = max(worst, err)
         except Exception as e:  # noqa: BLE001
             fails += 1

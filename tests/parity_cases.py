@@ -11,7 +11,7 @@ from tests.helpers import LNL_RTOL, POWER_RTOL, rel_err, synth_box
 
 
 def check_compute_power(lk_mod, shape, L, nb, log, flags=(True, False, False), rule="legacy_1.001", seed=0,
-                        coeval=False):
+                        coeval=False, floor_frac=0.0):
     from py21cmmc_b200.plan import get_plan
 
     box = synth_box(shape, seed)
@@ -31,7 +31,7 @@ def check_compute_power(lk_mod, shape, L, nb, log, flags=(True, False, False), r
         lk_mod.set_defaults(edge_rule="legacy_1.001")
     assert np.array_equal(k, ko), "bin centres must be bit-identical (same NumPy expressions)"
     assert np.array_equal(plan.counts, sw.astype(np.int64)), "mode counts must be bit-exact"
-    err = rel_err(p, po)
+    err = rel_err(p, po, floor_frac)
     assert err < POWER_RTOL, f"power rel err {err}"
     return err
 
@@ -122,7 +122,7 @@ def check_coeval_likelihood(lk_mod, core_mod, chain_mod, n, box_len, nb, redshif
     return lnl, lnl_o
 
 
-def check_cylindrical(lk_mod, shape, L, nb, seed=0):
+def check_cylindrical(lk_mod, shape, L, nb, seed=0, floor_frac=0.0):
     box = synth_box(shape, seed)
     P2, kperp, kpar = lk_mod.Likelihood1DPowerLightcone.compute_power_2d(box, L, nb)
     w2 = np.ones(shape[:2])
@@ -131,7 +131,9 @@ def check_cylindrical(lk_mod, shape, L, nb, seed=0):
     assert P2.shape == Po.shape
     assert np.array_equal(kperp, O.edges_to_centres(edges, False))
     assert np.allclose(kpar, kpo[0], rtol=1e-15)
-    assert rel_err(P2, Po) < POWER_RTOL
+    err = rel_err(P2, Po, floor_frac)
+    assert err < POWER_RTOL, f"cylindrical power rel err {err}"
+    return err
 
 
 def synthetic_hera_file(path, kmodel, seed=0):
