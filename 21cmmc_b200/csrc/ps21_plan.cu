@@ -130,7 +130,9 @@ __global__ void k_finalize(const double* __restrict__ partials, int slots_max, l
                            double mu, int err_on_model, long long box0) {
     PS21_DYN_SMEM(double, sdelta);
     const long long box = blockIdx.x;
-    for (long long i = threadIdx.x; i < out_per_box; i += blockDim.x) {
+    // gridDim.y > 1 only without lnL (cylindrical spectra have tens of thousands of outputs per box)
+    for (long long i = (long long)blockIdx.y * blockDim.x + threadIdx.x; i < out_per_box;
+         i += (long long)gridDim.y * blockDim.x) {
         int c = 0;
         while (c + 1 < nchunks && chunks[c + 1].out_off <= i) ++c;
         const ChunkDev ch = chunks[c];
@@ -343,7 +345,9 @@ static int run_device(ps21_plan* p, const float* d_boxes, long long batch, long 
     const bool want_lnl = d_lnl != nullptr;
     const size_t smem = want_lnl ? sizeof(double) * p->out_per_box : 0;
     ProfScope psf(p, KK_FINALIZE, st);
-    PS21_LAUNCH(k_finalize, dim3((unsigned)batch), dim3(128), smem, st, p->d_partials, p->slots_max, p->out_per_box,
+    unsigned fparts = want_lnl ? 1u : (unsigned)((p->out_per_box + 1023) / 1024);
+    if (fparts > 64u) fparts = 64u;
+    PS21_LAUNCH(k_finalize, dim3((unsigned)batch, fparts), dim3(128), smem, st, p->d_partials, p->slots_max, p->out_per_box,
                 p->d_chunks, p->nchunks, p->d_counts, p->mode == PS21_MODE_SPHERICAL ? p->d_kfac : nullptr,
                 p->d_means, p->d_dc, pw, d_delta, d_lnl, p->data.d_data, p->data.d_noise2, p->data.d_mask,
                 p->data.nsets > 0 ? p->data.nsets : 1, p->data.model_uncertainty, p->data.error_on_model, box0);
