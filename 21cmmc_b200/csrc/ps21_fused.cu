@@ -41,16 +41,15 @@ constexpr int SLOTS = 86;              // CTAs per spectrum in pass 2 (12 tiles 
 constexpr int P1_THREADS = 256;
 constexpr int P2_THREADS = 256;
 constexpr int MAX_BINS = 40;           // lane-private bin mode (fastest): at most 40 bins (|k|, or k_perp when cylindrical)
-constexpr int MAX_BINS_SPH = 254;      // warp-cooperative bin mode (spherical): byte LUT, 255 = discarded mode
+constexpr int MAX_BINS_SPH = 254;      // most spherical bins the byte LUT can address (255 = discarded mode)
 constexpr int FLUSH_EVERY = 4;         // lane-private mode: tiles between two fp32 -> fp64 flushes of the lane bins
 // pass-2 bin accumulation modes
 constexpr int BM_LANE = 0;             // spherical, nbins <= 40: lane-private fp32 bins (conflict free, no shuffles)
-constexpr int BM_WARP = 1;             // spherical, nbins <= 254: per-warp fp64 bins, warp-cooperative flush
 constexpr int BM_CYL = 2;              // cylindrical, k_perp bins <= 40: lane-private bins, [bins][8 k_z] per CTA
-constexpr int BM_GROUP = 3;            // spherical, nbins <= 144: one fp32 bin column per group of 4 lanes that share
+constexpr int BM_GROUP = 3;            // spherical, 41..254 bins: one fp32 bin column per group of 4 lanes that share
                                        // (warp, k_z) and differ only in m' & 3 -> nearly the same |k|; the 4 lanes update
                                        // the column one after the other (fixed order, no shuffles, no atomics)
-constexpr int MAX_BINS_GROUP = 144;    // 144 bins x 64 groups x 4 B = 36 KB
+constexpr int MAX_BINS_GROUP = 254;    // 254 bins x 64 groups x 4 B = 65 KB (one CTA per SM above 144 bins)
 constexpr int NHK = NZ / 2 + 1;        // 129 k_z values of the half spectrum
 // cylindrical mode: 64 CTAs take the main tiles with tl % 64 == slot (16 tiles each: always the same 8 k_z),
 // 8 CTAs take one Nyquist tile each
@@ -477,44 +476,7 @@ k_fused_p1(const float* __restrict__ boxes, long long batch_stride, int n2_total
 // ------------------------------------------------------------------------------------------------
 // pass 2
 // ------------------------------------------------------------------------------------------------
-// Spherical binning: warp-cooperative flush.  Lanes flagged `chg` leave the run of bin `cur` with the fp32 run sum
-// `val`; lanes that leave the same bin are summed by a shuffle tree and lane 0 adds the total to the warp's
-// private fp64 bin.  Fixed order everywhere -> bitwise reproducible; no atomics, no lane-private arrays.
-__device__ __forceinline__ void warp_flush(double* __restrict__ wb, uint32_t cur, float val, bool chg) {
-    unsigned todo = __ballot_sync(0xffffffffu, chg && cur != 255u);
-    while (todo) {
-        const int leader = __ffs(todo) - 1;
-        const uint32_t b = __shfl_sync(0xffffffffu, cur, leader);
-        const bool mine = chg && cur == b;
-        float v = mine ? val : 0.f;
-#pragma unroll
-        for (int s = 16; s > 0; s >>= 1) v += __shfl_xor_sync(0xffffffffu, v, s);
-        if ((threadIdx.x & 31) == 0) wb[b] += (double)v;
-        todo &= ~__ballot_sync(0xffffffffu, mine);
-    }
-}
-
-// run-length binning of the four outputs of one 32-bit LUT word (spherical mode)
-__device__ __forceinline__ void bin_word(double* __restrict__ wb, uint32_t word, const float (&pw)[4], float mult,
-                                         uint32_t& cur, float& acc) {
-    if (__all_sync(0xffffffffu, word == cur * 0x01010101u)) {
-        acc += (pw[0] + pw[1]) + (pw[2] + pw[3]);  // whole word stays in the current bin, all lanes
-        return;
-    }
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const uint32_t b = (word >> (8 * i)) & 255u;
-        const bool chg = b != cur;
-        if (__any_sync(0xffffffffu, chg)) warp_flush(wb, cur, mult * acc, chg);
-        if (chg) {
-            cur = b;
-            acc = 0.f;
-        }
-        acc += pw[i];
-    }
-}
-
-// BM_LANE / BM_WARP: spherical bins, partial sums [box][slot][bins] (slot = blockIdx.x of SLOTS).
+// BM_LANE / BM_GROUP: spherical bins, partial sums [box][slot][bins] (slot = blockIdx.x of SLOTS).
 // BM_CYL    : (k_perp bin, k_z) bins; every thread has one k_z per tile (t = tid & 7), so the lane-private
 //              bins are k_perp bins and the per-tile flush keeps the 8 k_z of the tile apart; partial sums go
 //              to a compact [item][CYL_SLOTS][bins][8] record that k_fused_cyl_reduce expands.
@@ -524,20 +486,18 @@ k_fused_p2(const float2* __restrict__ scratch, ItemMap im, const ChunkDev* __res
            const uint16_t* const* __restrict__ luts, double* __restrict__ partials, long long out_per_box,
            int slots_max, float2* __restrict__ dc, int nchunks, const float4* __restrict__ tw_g, int nbins) {
     // EARLY: the next tile is requested as soon as the tile and bin-index buffers are dead (inside S2, below);
-    // otherwise after the binning (a compile-time switch: the barrier branch costs the vote-heavy BM_WARP code)
+    // otherwise after the binning (a compile-time switch: the barrier branch costs the vote-heavy group mode)
     constexpr int early = EARLY ? 1 : 0;
     PS21_DYN_SMEM(float2, tile);               // [TILE]
     uint8_t* lutb = reinterpret_cast<uint8_t*>(tile + TILE);           // [TILE] bin index of every output of the tile
     float4* tw = reinterpret_cast<float4*>(lutb + TILE);               // [256]
     uint64_t* bar = reinterpret_cast<uint64_t*>(tw + 256);
-    constexpr bool CYL = BM == BM_CYL, WARPB = BM == BM_WARP, GROUPB = BM == BM_GROUP;
+    constexpr bool CYL = BM == BM_CYL, GROUPB = BM == BM_GROUP;
     constexpr int NCOL = GROUPB ? P2_THREADS / 4 : P2_THREADS;  // private bin columns per CTA
     constexpr int CB = GROUPB ? MAX_BINS_GROUP : MAX_BINS;      // CTA fp64 bins
     // BM_LANE: CTA fp64 bins [MAX_BINS] + lane fp32 bins [nbins][256];  BM_CYL: [MAX_BINS][8] + lane bins;
-    // BM_WARP: per-warp fp64 bins [8][nbins]
     double* cbins = reinterpret_cast<double*>(bar + 2);
     float* lbins = reinterpret_cast<float*>(cbins + CB * (CYL ? 8 : 1));  // [nbins][NCOL]
-    double* wb = cbins + (threadIdx.x >> 5) * nbins;
     const int tid = threadIdx.x;
     long long box;
     int cid;
@@ -546,12 +506,8 @@ k_fused_p2(const float2* __restrict__ scratch, ItemMap im, const ChunkDev* __res
     const uint8_t* __restrict__ lut = reinterpret_cast<const uint8_t*>(luts[cid]);
     const float2* src = scratch + (long long)blockIdx.y * ((long long)NTILES * TILE);
     tw[tid] = tw_g[tid];
-    if (WARPB) {
-        for (int i = tid; i < (P2_THREADS / 32) * nbins; i += P2_THREADS) cbins[i] = 0.0;
-    } else {
-        for (int i = tid; i < nbins * NCOL; i += P2_THREADS) lbins[i] = 0.f;
-        for (int i = tid; i < CB * (CYL ? 8 : 1); i += P2_THREADS) cbins[i] = 0.0;
-    }
+    for (int i = tid; i < nbins * NCOL; i += P2_THREADS) lbins[i] = 0.f;
+    for (int i = tid; i < CB * (CYL ? 8 : 1); i += P2_THREADS) cbins[i] = 0.0;
     if (tid == 0) {
         mbar_init(bar, 1);
         mbar_fence_init();
@@ -667,9 +623,7 @@ k_fused_p2(const float2* __restrict__ scratch, ItemMap im, const ChunkDev* __res
                     float pw[4];
 #pragma unroll
                     for (int i = 0; i < 4; ++i) pw[i] = v[r0 + i].x * v[r0 + i].x + v[r0 + i].y * v[r0 + i].y;
-                    if (WARPB) {
-                        bin_word(wb, w4[g], pw, mult, cur, acc);
-                    } else if (__all_sync(0xffffffffu, w4[g] == cur * 0x01010101u)) {
+                    if (__all_sync(0xffffffffu, w4[g] == cur * 0x01010101u)) {
                         acc += (pw[0] + pw[1]) + (pw[2] + pw[3]);  // whole word stays in the current bin, all lanes
                     } else {
 #pragma unroll
@@ -686,8 +640,7 @@ k_fused_p2(const float2* __restrict__ scratch, ItemMap im, const ChunkDev* __res
                     }
                 }
             }
-            if (WARPB) warp_flush(wb, cur, mult * acc, true);
-            else lane_update(cur, mult * acc, true);
+            lane_update(cur, mult * acc, true);
         }
         // ---- every FLUSH_EVERY tiles (and after the last one): flush the lane-private fp32 bins into the CTA's
         //      fp64 bins in a fixed order; a lane-private bin then holds at most 32 * FLUSH_EVERY fp32 terms.
@@ -700,7 +653,7 @@ k_fused_p2(const float2* __restrict__ scratch, ItemMap im, const ChunkDev* __res
                 issue_tile(tl + stride);
             }
         }
-        if (!WARPB && ((it % FLUSH_EVERY) == FLUSH_EVERY - 1 || it + 1 == count)) {
+        if ((it % FLUSH_EVERY) == FLUSH_EVERY - 1 || it + 1 == count) {
             if (early) __syncthreads();
             const int warp = tid >> 5, lane = tid & 31;
             for (int b = warp; b < nbins; b += P2_THREADS / 32) {
@@ -725,14 +678,7 @@ k_fused_p2(const float2* __restrict__ scratch, ItemMap im, const ChunkDev* __res
         // (the next iteration's barriers order the zeroed lane bins before they are used again)
     }
     __syncthreads();
-    if (WARPB) {
-        double* out = partials + (box * slots_max + blockIdx.x) * out_per_box + ch.out_off;
-        for (int i = tid; i < nbins; i += P2_THREADS) {
-            double a = 0.0;
-            for (int wi = 0; wi < P2_THREADS / 32; ++wi) a += cbins[wi * nbins + i];  // warps in fixed order
-            out[i] = a;
-        }
-    } else if (!CYL) {
+    if (!CYL) {
         double* out = partials + (box * slots_max + blockIdx.x) * out_per_box + ch.out_off;
         for (int i = tid; i < nbins; i += P2_THREADS) out[i] = cbins[i];
     } else {
@@ -754,13 +700,12 @@ k_fused_p2_s128(const float2* __restrict__ scratch, ItemMap im, const ChunkDev* 
     uint8_t* lutb = reinterpret_cast<uint8_t*>(tile + TILE);           // [TILE]
     float4* tw = reinterpret_cast<float4*>(lutb + TILE);               // [256]
     uint64_t* bar = reinterpret_cast<uint64_t*>(tw + 256);
-    constexpr bool WARPB = BM == BM_WARP, GROUPB = BM == BM_GROUP;
+    constexpr bool GROUPB = BM == BM_GROUP;
     // BM_GROUP: the four lanes 4c .. 4c+3 (adjacent k_z, nearly the same |k|) share one fp32 bin column
     constexpr int NCOL = GROUPB ? P2_THREADS / 4 : P2_THREADS;
     constexpr int CB = GROUPB ? MAX_BINS_GROUP : MAX_BINS;
-    double* cbins = reinterpret_cast<double*>(bar + 2);                // [CB], or per-warp [8][nbins] (WARPB)
+    double* cbins = reinterpret_cast<double*>(bar + 2);                // [CB]
     float* lbins = reinterpret_cast<float*>(cbins + CB);               // [nbins][NCOL] (lane / group mode)
-    double* wb = cbins + (threadIdx.x >> 5) * nbins;
     const int tid = threadIdx.x;
     long long box;
     int cid;
@@ -769,12 +714,8 @@ k_fused_p2_s128(const float2* __restrict__ scratch, ItemMap im, const ChunkDev* 
     const uint8_t* __restrict__ lut = reinterpret_cast<const uint8_t*>(luts[cid]);
     const float2* src = scratch + (long long)blockIdx.y * ((long long)G::NTILES_S * TILE);
     tw[tid] = tw_g[tid];
-    if (WARPB) {
-        for (int i = tid; i < (P2_THREADS / 32) * nbins; i += P2_THREADS) cbins[i] = 0.0;
-    } else {
-        for (int i = tid; i < nbins * NCOL; i += P2_THREADS) lbins[i] = 0.f;
-        if (tid < CB) cbins[tid] = 0.0;
-    }
+    for (int i = tid; i < nbins * NCOL; i += P2_THREADS) lbins[i] = 0.f;
+    if (tid < CB) cbins[tid] = 0.0;
     if (tid == 0) {
         mbar_init(bar, 1);
         mbar_fence_init();
@@ -859,34 +800,22 @@ k_fused_p2_s128(const float2* __restrict__ scratch, ItemMap im, const ChunkDev* 
                 float2(&v)[8] = vv[i];
                 small_dft<8>(v);
                 if (i == 0 && tl == 0 && tid == 0) dc[box * nchunks + cid] = v[0];
-                if (WARPB) {
 #pragma unroll
-                    for (int g = 0; g < 2; ++g) {
-                        float pw[4];
-#pragma unroll
-                        for (int q = 0; q < 4; ++q)
-                            pw[q] = v[4 * g + q].x * v[4 * g + q].x + v[4 * g + q].y * v[4 * g + q].y;
-                        bin_word(wb, w8[2 * i + g], pw, mult, cur, acc);
-                    }
-                } else {
-#pragma unroll
-                    for (int q = 0; q < 8; ++q) {
-                        const uint32_t b = (w8[2 * i + (q >> 2)] >> (8 * (q & 3))) & 255u;
-                        const float pw = v[q].x * v[q].x + v[q].y * v[q].y;
-                        if (__any_sync(0xffffffffu, b != cur)) {
-                            const bool chg = b != cur;
-                            lane_update(cur, mult * acc, chg);
-                            if (chg) {
-                                cur = b;
-                                acc = 0.f;
-                            }
+                for (int q = 0; q < 8; ++q) {
+                    const uint32_t b = (w8[2 * i + (q >> 2)] >> (8 * (q & 3))) & 255u;
+                    const float pw = v[q].x * v[q].x + v[q].y * v[q].y;
+                    if (__any_sync(0xffffffffu, b != cur)) {
+                        const bool chg = b != cur;
+                        lane_update(cur, mult * acc, chg);
+                        if (chg) {
+                            cur = b;
+                            acc = 0.f;
                         }
-                        acc += pw;
                     }
+                    acc += pw;
                 }
             }
-            if (WARPB) warp_flush(wb, cur, mult * acc, true);
-            else lane_update(cur, mult * acc, true);
+            lane_update(cur, mult * acc, true);
         }
         if (!EARLY) {
             __syncthreads();
@@ -895,7 +824,7 @@ k_fused_p2_s128(const float2* __restrict__ scratch, ItemMap im, const ChunkDev* 
                 issue_tile(tl + stride);
             }
         }
-        if (!WARPB && ((it % FLUSH_EVERY) == FLUSH_EVERY - 1 || it + 1 == count)) {  // fixed-order fp32 -> fp64 flush
+        if ((it % FLUSH_EVERY) == FLUSH_EVERY - 1 || it + 1 == count) {  // fixed-order fp32 -> fp64 flush
             if (EARLY) __syncthreads();
             const int warp = tid >> 5, lane = tid & 31;
             for (int b = warp; b < nbins; b += P2_THREADS / 32) {
@@ -914,12 +843,7 @@ k_fused_p2_s128(const float2* __restrict__ scratch, ItemMap im, const ChunkDev* 
     }
     __syncthreads();
     double* out = partials + (box * slots_max + blockIdx.x) * out_per_box + ch.out_off;
-    for (int i = tid; i < nbins; i += P2_THREADS) {
-        double a = cbins[i];
-        if (WARPB)
-            for (int wi = 1; wi < P2_THREADS / 32; ++wi) a += cbins[wi * nbins + i];  // warps in fixed order
-        out[i] = a;
-    }
+    for (int i = tid; i < nbins; i += P2_THREADS) out[i] = cbins[i];
 }
 
 // cylindrical mode: expand the compact per-CTA records into the standard partial-sum layout (one slot)
@@ -946,9 +870,8 @@ __global__ void k_fused_cyl_reduce(const double* __restrict__ cylpart, ItemMap i
 
 static size_t p1_smem() { return (size_t)R1 * ROWLD * 8 + 128 * 8 + 66 * 16 + 64; }
 static size_t p2_smem(int nbins, int bm) {
-    const size_t bins = bm == BM_WARP    ? (size_t)(P2_THREADS / 32) * nbins * 8
-                        : bm == BM_GROUP ? (size_t)MAX_BINS_GROUP * 8 + (size_t)nbins * (P2_THREADS / 4) * 4
-                                         : (size_t)MAX_BINS * 8 * (bm == BM_CYL ? 8 : 1) + (size_t)nbins * P2_THREADS * 4;
+    const size_t bins = bm == BM_GROUP ? (size_t)MAX_BINS_GROUP * 8 + (size_t)nbins * (P2_THREADS / 4) * 4
+                                       : (size_t)MAX_BINS * 8 * (bm == BM_CYL ? 8 : 1) + (size_t)nbins * P2_THREADS * 4;
     return (size_t)TILE * 8 + TILE + 256 * 16 + 16 + bins;
 }
 static int bin_mode(const ps21_plan* p) {
@@ -956,7 +879,7 @@ static int bin_mode(const ps21_plan* p) {
     // lane-private columns up to 40 bins; on the 128^2 plane only while two CTAs still fit an SM (<= 36 bins; above,
     // the group mode measured 7 % faster there, 4 % slower on the 256^2 plane)
     if (p->nbins <= MAX_BINS && (p->n0 == 256 || p2_smem(p->nbins, BM_LANE) <= (228 * 1024) / 2 - 1024)) return BM_LANE;
-    return p->nbins <= MAX_BINS_GROUP ? BM_GROUP : BM_WARP;
+    return BM_GROUP;   // up to MAX_BINS_GROUP = 254 bins (the byte LUT's range); one CTA per SM above 144 bins
 }
 
 }  // namespace fz
@@ -1011,16 +934,10 @@ int fused_try_setup(ps21_plan* p, ShapePlan& sp) {
                              (int)p2_smem(MAX_BINS, BM_LANE)) != cudaSuccess ||
         cudaFuncSetAttribute(k_fused_p2_s128<BM_GROUP, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              (int)p2_smem(MAX_BINS_GROUP, BM_GROUP)) != cudaSuccess ||
-        cudaFuncSetAttribute(k_fused_p2_s128<BM_WARP, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             (int)p2_smem(MAX_BINS_SPH, BM_WARP)) != cudaSuccess ||
         cudaFuncSetAttribute(k_fused_p2<BM_LANE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              (int)p2_smem(MAX_BINS, BM_LANE)) != cudaSuccess ||
         cudaFuncSetAttribute(k_fused_p2<BM_LANE, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              (int)p2_smem(MAX_BINS, BM_LANE)) != cudaSuccess ||
-        cudaFuncSetAttribute(k_fused_p2<BM_WARP, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             (int)p2_smem(MAX_BINS_SPH, BM_WARP)) != cudaSuccess ||
-        cudaFuncSetAttribute(k_fused_p2<BM_WARP, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             (int)p2_smem(MAX_BINS_SPH, BM_WARP)) != cudaSuccess ||
         cudaFuncSetAttribute(k_fused_p2<BM_GROUP, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              (int)p2_smem(MAX_BINS_GROUP, BM_GROUP)) != cudaSuccess ||
         cudaFuncSetAttribute(k_fused_p2<BM_GROUP, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -1109,11 +1026,8 @@ int fused_forward(ps21_plan* p, ShapePlan& sp, const float* d_boxes, long long b
             if (bm == BM_LANE)
                 PS21_LAUNCH((k_fused_p2_s128<BM_LANE, true>), dim3(Geo<128>::SLOTS_S, (unsigned)nitems),
                             dim3(P2_THREADS), p2_smem(p->nbins, bm), st, PS21_P2_ARGS);
-            else if (bm == BM_GROUP)
-                PS21_LAUNCH((k_fused_p2_s128<BM_GROUP, false>), dim3(Geo<128>::SLOTS_S, (unsigned)nitems),
-                            dim3(P2_THREADS), p2_smem(p->nbins, bm), st, PS21_P2_ARGS);
             else
-                PS21_LAUNCH((k_fused_p2_s128<BM_WARP, false>), dim3(Geo<128>::SLOTS_S, (unsigned)nitems),
+                PS21_LAUNCH((k_fused_p2_s128<BM_GROUP, false>), dim3(Geo<128>::SLOTS_S, (unsigned)nitems),
                             dim3(P2_THREADS), p2_smem(p->nbins, bm), st, PS21_P2_ARGS);
             PS21_CUDA(cudaGetLastError());
         } else if (bm == BM_LANE) {
@@ -1121,9 +1035,6 @@ int fused_forward(ps21_plan* p, ShapePlan& sp, const float* d_boxes, long long b
             PS21_CUDA(cudaGetLastError());
         } else if (bm == BM_GROUP) {
             PS21_P2_LAUNCH(BM_GROUP, SLOTS, PS21_P2_ARGS);
-            PS21_CUDA(cudaGetLastError());
-        } else if (bm == BM_WARP) {
-            PS21_P2_LAUNCH(BM_WARP, SLOTS, PS21_P2_ARGS);
             PS21_CUDA(cudaGetLastError());
         } else {
             if (fs->cylpart_items < nitems) {
