@@ -62,11 +62,12 @@ def test_cylindrical(mods):
     PC.check_cylindrical(mods[0], (10, 10, 9), (15.0, 15.0, 13.5), 4)
 
 
-def test_fused_two_pass_kernels_256(mods):
+@pytest.mark.parametrize("nb", [20, None])   # None: the reference default, 116 bins -> 4-lane group bin mode
+def test_fused_two_pass_kernels_256(mods, nb):
     """The fused sm_100a kernels (bulk copies modelled as memcpy) on one 256^3 chunk vs the oracle."""
     mods[0].set_defaults(kernel_path="fused")
     try:
-        PC.check_compute_power(mods[0], (256, 256, 256), (384.0, 384.0, 384.0), 20, True, seed=5)
+        PC.check_compute_power(mods[0], (256, 256, 256), (384.0, 384.0, 384.0), nb, True, seed=5)
     finally:
         mods[0].set_defaults(kernel_path="auto")
 
