@@ -1,6 +1,6 @@
 """Seeded random sweep of the real library against the oracle (run on a GPU box):
 general-path shapes incl. primes and odd sizes, spherical and cylindrical, both edge rules, all ignore flags.
-usage: python scripts/gpu_random_sweep.py [ncases] [seed]"""
+usage: python scripts/gpu_random_sweep.py [ncases] [seed] [smax] [nzmax]"""
 import os
 import sys
 
@@ -17,13 +17,13 @@ from tests import parity_cases as PC  # noqa: E402
 FLOOR = 0.01
 
 
-def sweep(n, seed, lk_mod=lk):
+def sweep(n, seed, lk_mod=lk, smax=72, nzmax=150):
     """Returns (number of failing cases, worst relative power error of the passing ones)."""
     rng = np.random.default_rng(seed)
     worst, fails = 0.0, 0
     for i in range(n):
-        s = int(rng.integers(4, 72))
-        nz = int(rng.integers(4, 150))
+        s = int(rng.integers(4, smax))
+        nz = int(rng.integers(4, nzmax))
         coeval = rng.random() < 0.25
         shape = (s, s, s) if coeval else (s, s, nz)
         cell = float(rng.uniform(0.5, 3.0))
@@ -47,6 +47,8 @@ def sweep(n, seed, lk_mod=lk):
 
 if __name__ == "__main__":
     n = int(sys.argv[1]) if len(sys.argv) > 1 else 150
-    fails, worst = sweep(n, int(sys.argv[2]) if len(sys.argv) > 2 else 2024)
+    fails, worst = sweep(n, int(sys.argv[2]) if len(sys.argv) > 2 else 2024,
+                         smax=int(sys.argv[3]) if len(sys.argv) > 3 else 72,
+                         nzmax=int(sys.argv[4]) if len(sys.argv) > 4 else 150)
     print(f"random sweep: {n} cases, {fails} failures, worst power rel err {worst:.3e}")
     sys.exit(1 if fails else 0)
