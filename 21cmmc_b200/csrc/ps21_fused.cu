@@ -179,6 +179,12 @@ __device__ __forceinline__ void bulk_g2s_hint(void* dst, const void* src, uint32
 template <int S>
 struct Geo;
 
+// Pass 2 (S = 256) bins the 32 outputs r of a thread (k_x = m' + 8 r) in the order 0, 31, 1, 30, ...: |k_x| then
+// rises monotonically (m', 8 - m', m' + 8, 16 - m', ...), so a thread meets every bin in one run instead of two (one on
+// the way up through the positive, one on the way down through the negative frequencies).  The LUT is stored in that
+// visiting order.
+__host__ __device__ constexpr int visit256(int i) { return (i & 1) ? 31 - (i >> 1) : (i >> 1); }
+
 // S = 256: y = y_lo + 4 j, tile = (ky_a, 8 consecutive k_z), inner [x 256][y_lo 4][k_z 8]
 template <>
 struct Geo<256> {
@@ -205,7 +211,7 @@ struct Geo<256> {
     // warp hold (t, m' & 3): nearly the same |k| for every r, so their bin sequences change at the same r.
     __device__ static __forceinline__ void mode_of(int tile, int task, int r, int& kx, int& ky, int& kz) {
         const int t = task & 7, m1 = ((task >> 3) & 3) | ((task >> 7) << 2), kyb = (task >> 5) & 3;
-        kx = m1 + 8 * r;
+        kx = m1 + 8 * visit256(r);   // r = position in the visiting order
         int kya;
         if (tile < NT_MAIN_S) {
             kya = tile >> 4;
@@ -622,7 +628,10 @@ k_fused_p2(const float2* __restrict__ scratch, ItemMap im, const ChunkDev* __res
                     const int r0 = 16 * h + 4 * g;
                     float pw[4];
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) pw[i] = v[r0 + i].x * v[r0 + i].x + v[r0 + i].y * v[r0 + i].y;
+                    for (int i = 0; i < 4; ++i) {
+                        const float2 o = v[visit256(r0 + i)];
+                        pw[i] = o.x * o.x + o.y * o.y;
+                    }
                     if (__all_sync(0xffffffffu, w4[g] == cur * 0x01010101u)) {
                         acc += (pw[0] + pw[1]) + (pw[2] + pw[3]);  // whole word stays in the current bin, all lanes
                     } else {
