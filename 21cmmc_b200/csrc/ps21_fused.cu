@@ -184,6 +184,7 @@ struct Geo;
 // the way up through the positive, one on the way down through the negative frequencies).  The LUT is stored in that
 // visiting order.
 __host__ __device__ constexpr int visit256(int i) { return (i & 1) ? 31 - (i >> 1) : (i >> 1); }
+__host__ __device__ constexpr int visit8(int j) { return (j & 1) ? 7 - (j >> 1) : (j >> 1); }   // S = 128, see there
 
 // S = 256: y = y_lo + 4 j, tile = (ky_a, 8 consecutive k_z), inner [x 256][y_lo 4][k_z 8]
 template <>
@@ -244,8 +245,8 @@ struct Geo<128> {
     // task = (t, ky_b, m' group), r = 8 i + q: butterfly i of the thread (m' = 4 group + i), output q -> kx = m' + 16 q
     __device__ static __forceinline__ void mode_of(int tile, int task, int r, int& kx, int& ky, int& kz) {
         const int t = task & 31, g = task >> 5;
-        const int kyb = g & 1, m1 = 4 * (g >> 1) + (r >> 3);
-        kx = m1 + 16 * (r & 7);
+        const int kyb = g & 1, m1 = 4 * (g >> 1) + (r & 3);   // r = position in the visiting order of pass 2
+        kx = m1 + 16 * visit8(r >> 2);
         int kya;
         if (tile < NT_MAIN_S) {
             kya = tile >> 2;
@@ -805,24 +806,24 @@ k_fused_p2_s128(const float2* __restrict__ scratch, ItemMap im, const ChunkDev* 
                 }
             }
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                float2(&v)[8] = vv[i];
-                small_dft<8>(v);
-                if (i == 0 && tl == 0 && tid == 0) dc[box * nchunks + cid] = v[0];
+            for (int i = 0; i < 4; ++i) small_dft<8>(vv[i]);
+            if (tl == 0 && tid == 0) dc[box * nchunks + cid] = vv[0][0];
+            // the 32 outputs (k_x = 4 mgrp + i + 16 q) are binned in rising |k_x| order: position p = 4 j + i with
+            // q = visit8(j) = 0, 7, 1, 6, ... -> every bin is met in one run; the LUT is stored in that order
 #pragma unroll
-                for (int q = 0; q < 8; ++q) {
-                    const uint32_t b = (w8[2 * i + (q >> 2)] >> (8 * (q & 3))) & 255u;
-                    const float pw = v[q].x * v[q].x + v[q].y * v[q].y;
-                    if (__any_sync(0xffffffffu, b != cur)) {
-                        const bool chg = b != cur;
-                        lane_update(cur, mult * acc, chg);
-                        if (chg) {
-                            cur = b;
-                            acc = 0.f;
-                        }
+            for (int p = 0; p < 32; ++p) {
+                const float2 o = vv[p & 3][visit8(p >> 2)];
+                const uint32_t b = (w8[p >> 2] >> (8 * (p & 3))) & 255u;
+                const float pw = o.x * o.x + o.y * o.y;
+                if (__any_sync(0xffffffffu, b != cur)) {
+                    const bool chg = b != cur;
+                    lane_update(cur, mult * acc, chg);
+                    if (chg) {
+                        cur = b;
+                        acc = 0.f;
                     }
-                    acc += pw;
                 }
+                acc += pw;
             }
             lane_update(cur, mult * acc, true);
         }
