@@ -190,6 +190,7 @@ __host__ __device__ constexpr int visit8(int j) { return (j & 1) ? 7 - (j >> 1) 
 template <>
 struct Geo<256> {
     static constexpr int NXS = 256, R2S = 4, TS = 8, NT_MAIN_S = 1024, NTILES_S = 1032, SLOTS_S = 86, TWMUL = 1;
+    static constexpr int P1_SLABS = 1;   // x slabs per pass-1 CTA (two measured 1.4 % slower here)
     // 64-byte chunk (x, y_lo) inside a tile; the low bit of y_lo is flipped by bit0(x)^bit5(x) so that both x
     // stages of pass 2 (lanes over consecutive x, and over x in steps of 32) touch both halves of every
     // 128-byte bank line (conflict free).
@@ -230,6 +231,7 @@ struct Geo<256> {
 template <>
 struct Geo<128> {
     static constexpr int NXS = 128, R2S = 2, TS = 32, NT_MAIN_S = 256, NTILES_S = 258, SLOTS_S = 43, TWMUL = 2;
+    static constexpr int P1_SLABS = 2;   // x slabs per pass-1 CTA: a slab has only two units, half of them cold starts
     __device__ static __forceinline__ int tile_idx(int x, int yl, int t) { return (2 * x + yl) * 32 + t; }
     __device__ static __forceinline__ long long scratch_addr(int x, int yl, int kya, int kz) {
         int tile, t;
@@ -357,9 +359,15 @@ k_fused_p1(const float* __restrict__ boxes, long long batch_stride, int n2_total
     item_to_box_chunk(im, blockIdx.y, box, cid);
     const ChunkDev ch = chunks[cid];
     const float mean = means[box * nchunks + cid];
-    const int x = blockIdx.x;
     constexpr int R2S = Geo<S>::R2S;  // units per x slab (y = y_lo + R2S j)
-    const float* src = boxes + box * batch_stride + ch.start + (long long)x * S * n2_total;
+    constexpr int P1_SLABS = Geo<S>::P1_SLABS;
+    // A CTA takes P1_SLABS consecutive x slabs of one spectrum; the row prefetch runs across them, so only the first
+    // unit of the first slab waits for its loads with nothing to overlap.  (Fully persistent CTAs, 3 per SM looping
+    // over everything, were measured 29 % slower: started together they march in phase.)
+    int x = blockIdx.x * P1_SLABS;
+    const int x_end = x + P1_SLABS;
+    const float* spec_src = boxes + box * batch_stride + ch.start;
+    const float* src = spec_src + (long long)x * S * n2_total;
     float2* dst = scratch + (long long)blockIdx.y * ((long long)Geo<S>::NTILES_S * TILE);
     if (tid < 128) {
         const float4 w = tw_g[(2 * (tid & 7) * (tid >> 3)) & 255];
@@ -379,7 +387,7 @@ k_fused_p1(const float* __restrict__ boxes, long long batch_stride, int n2_total
     __syncthreads();
     const uint64_t pol = l2_policy_evict_first();
     // rows 8g .. 8g+7 of unit yl, 1 KB each; called by one whole warp
-    auto issue_group = [&](int yl, int g) {
+    auto issue_group = [&](const float* src, int yl, int g) {
         const int lane = tid & 31;
         if (lane == 0) {
             fence_proxy_async();
@@ -406,8 +414,9 @@ k_fused_p1(const float* __restrict__ boxes, long long batch_stride, int n2_total
         }
     };
     if (tid < 32)
-        for (int g = 0; g < 8; ++g) issue_group(0, g);
+        for (int g = 0; g < 8; ++g) issue_group(src, 0, g);
     uint32_t phase = 0;
+    for (; x < x_end; ++x, src += (long long)S * n2_total)
     for (int yl = 0; yl < R2S; ++yl) {
         // ---- z: one 128-point FFT per row, 8 threads per row; rows 0..31 as soon as they have landed
         // thread tid owns rows tid/8 (groups 0..3) and 32 + tid/8 (groups 4..7)
@@ -476,9 +485,14 @@ k_fused_p1(const float* __restrict__ boxes, long long batch_stride, int n2_total
                 ystage2(yl, tid & (NHC - 1), m2);
                 if (half == 0) named_bar_sync(1, 128);
                 else named_bar_sync(2, 128);
-                if (yl + 1 < R2S && (tid & 127) < 32) {
-                    issue_group(yl + 1, m1);
-                    issue_group(yl + 1, m2);
+                if ((tid & 127) < 32) {
+                    if (yl + 1 < R2S) {
+                        issue_group(src, yl + 1, m1);
+                        issue_group(src, yl + 1, m2);
+                    } else if (x + 1 < x_end) {   // first unit of the next slab
+                        issue_group(src + (long long)S * n2_total, 0, m1);
+                        issue_group(src + (long long)S * n2_total, 0, m2);
+                    }
                 }
             }
         }
@@ -1012,10 +1026,10 @@ int fused_forward(ps21_plan* p, ShapePlan& sp, const float* d_boxes, long long b
     {
         ProfScope ps(p, KK_PASS1, st);
         if (fs->S == 256)
-            PS21_LAUNCH(k_fused_p1<256>, dim3(256, (unsigned)nitems), dim3(P1_THREADS), p1_smem(), st, d_boxes,
+            PS21_LAUNCH(k_fused_p1<256>, dim3(256 / Geo<256>::P1_SLABS, (unsigned)nitems), dim3(P1_THREADS), p1_smem(), st, d_boxes,
                         batch_stride, p->n2_total, im, p->d_chunks, p->nchunks, p->d_means, p->d_scratch, fs->tw256);
         else
-            PS21_LAUNCH(k_fused_p1<128>, dim3(128, (unsigned)nitems), dim3(P1_THREADS), p1_smem(), st, d_boxes,
+            PS21_LAUNCH(k_fused_p1<128>, dim3(128 / Geo<128>::P1_SLABS, (unsigned)nitems), dim3(P1_THREADS), p1_smem(), st, d_boxes,
                         batch_stride, p->n2_total, im, p->d_chunks, p->nchunks, p->d_means, p->d_scratch, fs->tw256);
         PS21_CUDA(cudaGetLastError());
     }
