@@ -1,9 +1,9 @@
 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?" >> gpurun_out/pytest_gpu.log
-python bench.py --steps 10 --warmup 3 --no-cpu > gpurun_out/bench_v20.log 2>&1
+python bench.py --steps 10 --warmup 3 --no-cpu > gpurun_out/bench_v21.log 2>&1
 tail -4 gpurun_out/pytest_gpu.log
 python - <<'PY'
 import json
-for f in ["bench_v20"]:
+for f in ["bench_v21"]:
     l=[x for x in open(f"gpurun_out/{f}.log") if x.startswith("{")]
     if not l:
         print(f, "no json"); print(open(f"gpurun_out/{f}.log").read()[-2000:]); continue
