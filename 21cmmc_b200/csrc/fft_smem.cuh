@@ -333,15 +333,19 @@ __device__ __forceinline__ void stage_generic(const float2* __restrict__ in, flo
         const int mo = fast_div(q, dnb);
         const int j = q - mo * nb;
         const int k = j - fast_div(j, dns) * Ns;
-        const int step = k * tws;
+        // twiddle of term mi: w_n^(mi*k*tws) * w_p^(mi*mo) = w_n^(mi * inc) with inc = k*tws + mo*nb (n = p*nb):
+        // one running index, reduced mod n by a compare and subtract
+        int inc = k * tws + mo * nb;
+        if (inc >= n) inc -= n;
         float2 acc = make_float2(0.f, 0.f);
-        int rot = 0;  // (mi*mo) % p
+        int idx = 0;
+        const char* pi = reinterpret_cast<const char*>(in + (j * ld + c));
+        const int sin = nb * ld * (int)sizeof(float2);
         for (int mi = 0; mi < p; ++mi) {
-            int idx = mi * step + rot * nb;
+            acc = cadd(acc, cmul_w2(*reinterpret_cast<const float2*>(pi), __ldg(&tw[idx])));
+            pi += sin;
+            idx += inc;
             if (idx >= n) idx -= n;
-            acc = cadd(acc, cmul_w2(in[(j + mi * nb) * ld + c], __ldg(&tw[idx])));
-            rot += mo;
-            if (rot >= p) rot -= p;
         }
         out[((j - k) * p + k + mo * Ns) * ld + c] = acc;
     }
