@@ -14,10 +14,12 @@
 //                        4-point FFT over y_lo and 256-point FFT over x in TWO stages of 32 points per
 //                        thread (4x8, then 32; in place, XOR-swizzled 64-byte chunks so both stages are
 //                        bank-conflict free) -- the kernel is bound by shared-memory bandwidth, so every
-//                        stage saved counts; |delta_k|^2 straight from registers, bin index from the
-//                        byte LUT staged next to the tile, lane-private fp32 bins in shared memory,
-//                        flushed per tile into fp64 bins in a fixed order (bitwise reproducible), one
-//                        partial-sum record per CTA (no global atomics).
+//                        stage saved counts; |delta_k|^2 straight from registers in rising |k_x| order, bin
+//                        index from the byte LUT staged next to the tile, lane-private (<= 40 bins) or
+//                        4-lane-group (<= 254 bins) fp32 bins in shared memory, flushed every 4 tiles into
+//                        fp64 bins in a fixed order (bitwise reproducible), one partial-sum record per CTA
+//                        (no global atomics).  The copy of the next tile is requested inside S2, as soon as
+//                        every thread holds its inputs and bin indices in registers (bar.arrive/bar.sync).
 //
 // All transforms are decimation-in-frequency and in place: a thread writes exactly the locations it
 // read, so no ping-pong buffer and no barrier between the read and the write of a stage.

@@ -1,7 +1,10 @@
-// General three-pass path: any box size (mixed radix 2/3/4/5/8 + generic prime radix).
-//   g1: z pencils, real-to-complex (two real rows per complex transform), mean subtracted on load
-//   g2: y transform in place on the half spectrum, tiles of contiguous k_z
-//   g3: x transform fused with |delta_k|^2 and the bin histogram (spectrum is never written back)
+// General three-pass path: any box size (radices 2/3/4/5/8/16, 25- and 32-point stages for the y and x axes,
+// generic prime radix for everything else).
+//   g1: z pencils, real-to-complex (two real rows per complex transform), offset subtracted on load
+//   g2: y transform in place on the half spectrum; columns = flattened (x, k_z) pairs; a CTA pipelines 8 tiles
+//       through three rotating shared-memory buffers (cp.async prefetch of tile i+1 while tile i is transformed)
+//   g3: x transform fused with |delta_k|^2 and the bin histogram (spectrum is never written back); same pipeline,
+//       bin indices from a table kept in this pass's tile order
 // HBM traffic 4N + 32 N_h bytes per spectrum.  The fused two-pass kernels (ps21_fused.cu) replace it
 // for the power-of-two shapes of the benchmark configurations.
 #include "ps21_internal.cuh"
