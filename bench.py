@@ -189,7 +189,7 @@ def run_reference(args):
     workers = cpu_workers()
     with ProcessPoolExecutor(max_workers=workers) as pool:
         for w in range(args.warmup):
-            cpu_step(pool, workers, -1 - w)
+            cpu_step(pool, workers, 100000 + w)   # seeds must be non-negative
         t0 = time.perf_counter()
         for s in range(args.steps):
             cpu_step(pool, workers, s)
