@@ -22,7 +22,9 @@ EXPORTS = (
     "ps21_last_error", "ps21_version", "ps21_plan_create", "ps21_plan_destroy", "ps21_plan_info",
     "ps21_plan_set_profiling", "ps21_plan_profile", "ps21_plan_layout", "ps21_plan_counts", "ps21_power_batched", "ps21_set_data", "ps21_lnl_batched",
     "ps21_power_host", "ps21_lnl_host", "ps21_lnl_from_delta", "ps21_chi2_host", "ps21_upper_limit_host",
-    "ps21_windowed_gauss_host",
+    "ps21_windowed_gauss_host", "ps21_power_host_ptrs", "ps21_lnl_host_ptrs", "ps21_host_alloc", "ps21_host_free",
+    "ps21_host_register", "ps21_host_unregister", "ps21_plan_set_graphs", "ps21_plan_graph_stats",
+    "ps21_plan_release_workspace",
 )
 
 
@@ -78,6 +80,15 @@ def _declare(lib):
                                    C.c_double, C.c_int32, dp]
     lib.ps21_upper_limit_host.argtypes = [C.c_int32, i64, i64, i64, dp, dp, dp, dp, dp, C.c_double, dp]
     lib.ps21_windowed_gauss_host.argtypes = lib.ps21_upper_limit_host.argtypes
+    lib.ps21_power_host_ptrs.argtypes = [vp, C.POINTER(vp), i64, vp]
+    lib.ps21_lnl_host_ptrs.argtypes = [vp, C.POINTER(vp), i64, vp, vp, vp]
+    lib.ps21_host_alloc.argtypes = [C.POINTER(vp), i64]
+    lib.ps21_host_free.argtypes = [vp]
+    lib.ps21_host_register.argtypes = [vp, i64]
+    lib.ps21_host_unregister.argtypes = [vp]
+    lib.ps21_plan_set_graphs.argtypes = [vp, C.c_int32]
+    lib.ps21_plan_graph_stats.argtypes = [vp, C.POINTER(i64), C.POINTER(i64)]
+    lib.ps21_plan_release_workspace.argtypes = [vp]
     for name in EXPORTS:
         if name not in ("ps21_last_error",):
             getattr(lib, name).restype = C.c_int

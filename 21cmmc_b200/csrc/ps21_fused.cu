@@ -349,7 +349,7 @@ __device__ __forceinline__ void untangle(float2 ck, float2 cn, float4 wu, float2
 template <int S>
 __global__ void __launch_bounds__(P1_THREADS, 3)
 k_fused_p1(const float* __restrict__ boxes, long long batch_stride, int n2_total, ItemMap im,
-           const ChunkDev* __restrict__ chunks, int nchunks, const float* __restrict__ means,
+           const ChunkDev* __restrict__ chunks, int nchunks, const double* __restrict__ mean_parts,
            float2* __restrict__ scratch, const float4* __restrict__ tw_g) {
     PS21_DYN_SMEM(float2, buf);                                          // [64][ROWLD]
     float2* twz = buf + R1 * ROWLD;                                      // [16][8] w_128^(t m)
@@ -360,7 +360,7 @@ k_fused_p1(const float* __restrict__ boxes, long long batch_stride, int n2_total
     int cid;
     item_to_box_chunk(im, blockIdx.y, box, cid);
     const ChunkDev ch = chunks[cid];
-    const float mean = means[box * nchunks + cid];
+    const float mean = chunk_offset(mean_parts, box * nchunks + cid, S, ch.nz);
     constexpr int R2S = Geo<S>::R2S;  // units per x slab (y = y_lo + R2S j)
     constexpr int P1_SLABS = Geo<S>::P1_SLABS;
     // A CTA takes P1_SLABS consecutive x slabs of one spectrum; the row prefetch runs across them, so only the first
@@ -1016,6 +1016,19 @@ int fused_build_lut(ps21_plan* p, int chunk, const double* d_k0sq, const double*
     return PS21_OK;
 }
 
+int fused_reserve(ps21_plan* p, ShapePlan& sp, long long nitems) {
+    using namespace fz;
+    auto* fs = static_cast<FusedShape*>(sp.fused);
+    if (p->mode != PS21_MODE_CYLINDRICAL || fs->cylpart_items >= nitems) return PS21_OK;
+    drop_graphs(p);
+    if (fs->cylpart) cudaFree(fs->cylpart);
+    fs->cylpart = nullptr;
+    fs->cylpart_items = 0;
+    PS21_CUDA(cudaMalloc((void**)&fs->cylpart, sizeof(double) * nitems * CYL_SLOTS * p->nbins * 8));
+    fs->cylpart_items = nitems;
+    return PS21_OK;
+}
+
 int fused_forward(ps21_plan* p, ShapePlan& sp, const float* d_boxes, long long batch_stride, long long item0,
                   long long nitems, cudaStream_t st) {
     using namespace fz;
@@ -1029,10 +1042,10 @@ int fused_forward(ps21_plan* p, ShapePlan& sp, const float* d_boxes, long long b
         ProfScope ps(p, KK_PASS1, st);
         if (fs->S == 256)
             PS21_LAUNCH(k_fused_p1<256>, dim3(256 / Geo<256>::P1_SLABS, (unsigned)nitems), dim3(P1_THREADS), p1_smem(), st, d_boxes,
-                        batch_stride, p->n2_total, im, p->d_chunks, p->nchunks, p->d_means, p->d_scratch, fs->tw256);
+                        batch_stride, p->n2_total, im, p->d_chunks, p->nchunks, p->d_mean_parts, p->d_scratch, fs->tw256);
         else
             PS21_LAUNCH(k_fused_p1<128>, dim3(128 / Geo<128>::P1_SLABS, (unsigned)nitems), dim3(P1_THREADS), p1_smem(), st, d_boxes,
-                        batch_stride, p->n2_total, im, p->d_chunks, p->nchunks, p->d_means, p->d_scratch, fs->tw256);
+                        batch_stride, p->n2_total, im, p->d_chunks, p->nchunks, p->d_mean_parts, p->d_scratch, fs->tw256);
         PS21_CUDA(cudaGetLastError());
     }
     {
@@ -1068,12 +1081,9 @@ int fused_forward(ps21_plan* p, ShapePlan& sp, const float* d_boxes, long long b
             PS21_P2_LAUNCH(BM_GROUP, SLOTS, PS21_P2_ARGS);
             PS21_CUDA(cudaGetLastError());
         } else {
-            if (fs->cylpart_items < nitems) {
-                if (fs->cylpart) cudaFree(fs->cylpart);
-                fs->cylpart = nullptr;
-                fs->cylpart_items = 0;
-                PS21_CUDA(cudaMalloc((void**)&fs->cylpart, sizeof(double) * nitems * CYL_SLOTS * p->nbins * 8));
-                fs->cylpart_items = nitems;
+            {
+                const int rrc = fused_reserve(p, sp, nitems);
+                if (rrc) return rrc;
             }
             PS21_P2_LAUNCH(BM_CYL, CYL_SLOTS, p->d_scratch, im, p->d_chunks, (const uint16_t* const*)p->d_lut_table,
                            fs->cylpart, p->out_per_box, p->slots_max, p->d_dc, p->nchunks, fs->tw256, p->nbins);

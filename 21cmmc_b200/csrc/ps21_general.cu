@@ -88,7 +88,6 @@ int general_build_lut(ps21_plan* p, int chunk, const double* d_k0sq, const doubl
 // Any constant close to the mean works: subtracting it changes only the k = 0 coefficient, which is
 // restored in fp64 by the finalize kernel when that mode is binned at all.
 // ---------------------------------------------------------------------------------------------
-constexpr int kMeanParts = 8;  // CTAs per chunk in the offset estimate (fixed -> deterministic)
 
 __global__ void k_slab_mean_part(const float* __restrict__ boxes, long long batch_stride, int n1, int n2_total,
                                  const ChunkDev* __restrict__ chunks, int nchunks, double* __restrict__ parts) {
@@ -113,24 +112,14 @@ __global__ void k_slab_mean_part(const float* __restrict__ boxes, long long batc
     if (threadIdx.x == 0) parts[((long long)box * nchunks + c) * kMeanParts + blockIdx.y] = red[0];
 }
 
-__global__ void k_slab_mean_finish(const double* __restrict__ parts, int n1, const ChunkDev* __restrict__ chunks,
-                                   int nchunks, long long nitems, float* __restrict__ means) {
-    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= nitems) return;
-    double s = 0.0;
-    for (int q = 0; q < kMeanParts; ++q) s += parts[i * kMeanParts + q];
-    means[i] = (float)(s / ((double)n1 * (double)chunks[i % nchunks].nz));
-}
-
 int launch_slab_mean(ps21_plan* p, const float* d_boxes, long long batch_stride, long long batch, cudaStream_t st) {
     const long long nitems = batch * p->nchunks;
+    // the consumers (first FFT pass, finalize) add the kMeanParts partial sums themselves in a fixed order
+    // (chunk_offset), so no second launch is needed
     PS21_LAUNCH(k_slab_mean_part, dim3((unsigned)nitems, kMeanParts), dim3(256), 0, st, d_boxes, batch_stride, p->n1,
                 p->n2_total, p->d_chunks, p->nchunks, p->d_mean_parts);
     PS21_CUDA(cudaGetLastError());
-    PS21_LAUNCH(k_slab_mean_finish, dim3((unsigned)((nitems + 127) / 128)), dim3(128), 0, st, p->d_mean_parts, p->n1,
-                p->d_chunks, p->nchunks, nitems, p->d_means);
-    PS21_CUDA(cudaGetLastError());
-    p->launches_last += 2;
+    p->launches_last += 1;
     return PS21_OK;
 }
 
@@ -142,7 +131,7 @@ int launch_slab_mean(ps21_plan* p, const float* d_boxes, long long batch_stride,
 template <bool R32>
 __global__ void __launch_bounds__(256, R32 ? 2 : 4) k_general_zpass(const float* __restrict__ boxes, long long batch_stride, int n2_total, int nrows,
                                 ItemMap im, const ChunkDev* __restrict__ chunks, int nchunks,
-                                const float* __restrict__ means, float2* __restrict__ scratch,
+                                const double* __restrict__ mean_parts, int n1, float2* __restrict__ scratch,
                                 long long spec_elems, FftFactors fz, const float2* __restrict__ tw, int lc) {
     PS21_DYN_SMEM(float2, smem);
     const int nz = fz.n;
@@ -155,7 +144,7 @@ __global__ void __launch_bounds__(256, R32 ? 2 : 4) k_general_zpass(const float*
     int cid;
     item_to_box_chunk(im, blockIdx.y, box, cid);
     const ChunkDev ch = chunks[cid];
-    const float mean = means[box * nchunks + cid];
+    const float mean = chunk_offset(mean_parts, box * nchunks + cid, n1, ch.nz);
     const int row0 = blockIdx.x * 2 * cols;
     const float* src = boxes + box * batch_stride + ch.start;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
@@ -434,7 +423,7 @@ int general_forward(ps21_plan* p, ShapePlan& sp, const float* d_boxes, long long
         ProfScope ps(p, KK_PASS1, st);
         dim3 grid((nrows + 2 * sp.g1_cols - 1) / (2 * sp.g1_cols), (unsigned)nitems);
 #define PS21_ZPASS_ARGS                                                                                            \
-    d_boxes, batch_stride, p->n2_total, nrows, im, p->d_chunks, p->nchunks, p->d_means, p->d_scratch, spec_elems,  \
+    d_boxes, batch_stride, p->n2_total, nrows, im, p->d_chunks, p->nchunks, p->d_mean_parts, p->n1, p->d_scratch, spec_elems,  \
         sp.fz, sp.tw_z, ilog2(sp.g1_cols)
         if (has_radix32(sp.fz))
             PS21_LAUNCH(k_general_zpass<true>, grid, dim3(256), fft_smem_bytes(sp.nz, sp.g1_cols), st, PS21_ZPASS_ARGS);

@@ -73,6 +73,8 @@ struct ShapePlan {
 
 struct DataTables {
     int nsets = 0;
+    long long cap = 0;           // doubles allocated per table
+    long long gen = 0;           // bumped by every ps21_set_data (captured graphs hold the old values)
     double* d_data = nullptr;    // [nsets][out_per_box]
     double* d_noise2 = nullptr;  // [nsets][out_per_box] noise^2
     uint8_t* d_mask = nullptr;   // [nsets][out_per_box]
@@ -104,8 +106,7 @@ struct ps21_plan {
     long long scratch_elems = 0;
     long long spec_max = 0;
     double* d_partials = nullptr;    // [batch][slots_max][out_per_box]
-    float* d_means = nullptr;        // [batch][nchunks]
-    double* d_mean_parts = nullptr;  // [batch][nchunks][8] partial sums of the offset estimate
+    double* d_mean_parts = nullptr;  // [batch][nchunks][kMeanParts] partial sums of the offset estimate
     float2* d_dc = nullptr;          // [batch][nchunks] DC Fourier coefficient of the mean-subtracted chunk
     long long batch_cap = 0;
     ps21::DataTables data;
@@ -118,6 +119,21 @@ struct ps21_plan {
     float* d_stage[2] = {nullptr, nullptr};
     long long stage_boxes = 0;
     void* stage_stream[2] = {nullptr, nullptr};
+    void* stage_ev[4] = {nullptr, nullptr, nullptr, nullptr};   // copy done [2], compute done [2]
+    double* d_res[3] = {nullptr, nullptr, nullptr};             // power, Delta^2, lnL of a *_host call
+    long long res_boxes = 0;
+    // CUDA graphs of whole calls (ps21_plan_set_graphs)
+    struct GraphKey {
+        const float* boxes; long long batch, stride; double *power, *delta, *lnl; long long box0, data_gen;
+    };
+    struct GraphEntry { GraphKey key; void* exec; long long launches; unsigned long long last_use; };
+    std::vector<GraphEntry> graphs;
+    int graph_mode = 0;
+    int graph_miss_streak = 0;
+    unsigned long long graph_clock = 0;
+    long long graph_captures = 0, graph_replays = 0;
+    void* graph_stream = nullptr;
+    void* graph_ev[2] = {nullptr, nullptr};
 };
 
 namespace ps21 {
@@ -129,6 +145,7 @@ struct ProfScope {
     ~ProfScope();
 };
 void set_error(const std::string& msg);
+void drop_graphs(ps21_plan* p);   // captured launches hold raw pointers: dropped whenever a buffer they name is reallocated
 int cuda_fail(cudaError_t e, const char* what);
 #define PS21_CUDA(call)                                        \
     do {                                                       \
@@ -186,6 +203,8 @@ int fused_build_lut(ps21_plan* p, int chunk, const double* d_k0sq, const double*
 int fused_forward(ps21_plan* p, ShapePlan& sp, const float* d_boxes, long long batch_stride, long long item0,
                   long long nitems, cudaStream_t st);
 long long fused_scratch_elems(const ShapePlan& sp, int n0, int n1);
+// allocations fused_forward would need for `nitems` spectra per launch (none may happen while a graph is captured)
+int fused_reserve(ps21_plan* p, ShapePlan& sp, long long nitems);
 
 // item -> (box, chunk) for a shape whose chunk-id list is `ids[0..nper)`
 struct ItemMap {
@@ -197,6 +216,16 @@ __device__ __forceinline__ void item_to_box_chunk(const ItemMap& m, long long lo
     const long long it = m.item0 + local;
     box = it / m.nper;
     chunk = m.ids[it % m.nper];
+}
+
+// Offset estimate of a chunk (mean of its x = 0 slab): k_slab_mean_part leaves kMeanParts partial sums per chunk;
+// every consumer adds them in the same fixed order, so all CTAs of a spectrum subtract the same constant.
+constexpr int kMeanParts = 8;
+__device__ __forceinline__ float chunk_offset(const double* __restrict__ parts, long long item, int n1, int nz) {
+    double s = 0.0;
+#pragma unroll
+    for (int q = 0; q < kMeanParts; ++q) s += parts[item * kMeanParts + q];
+    return (float)(s / ((double)n1 * (double)nz));
 }
 
 // exact fp64 digitisation shared by both LUT builders: np.digitize(sqrt((a+b)+c), edges) - 1, or -1

@@ -123,15 +123,17 @@ __device__ __forceinline__ double chi2_term(double delta, double data, double no
     return d * d / (mod * mod + noise2);
 }
 
-__global__ void k_finalize(const double* __restrict__ partials, int slots_max, long long out_per_box,
-                           const ChunkDev* __restrict__ chunks, int nchunks, const long long* __restrict__ counts,
-                           const double* __restrict__ kfac, const float* __restrict__ means,
-                           const float2* __restrict__ dc, double* __restrict__ power, double* __restrict__ delta,
-                           double* __restrict__ lnl, const double* __restrict__ data,
-                           const double* __restrict__ noise2, const uint8_t* __restrict__ mask, int nsets,
-                           double mu, int err_on_model, long long box0) {
-    PS21_DYN_SMEM(double, sdelta);
+__global__ void __launch_bounds__(128)
+k_finalize(const double* __restrict__ partials, int slots_max, long long out_per_box,
+           const ChunkDev* __restrict__ chunks, int nchunks, const long long* __restrict__ counts,
+           const double* __restrict__ kfac, const double* __restrict__ mean_parts, int n1,
+           const float2* __restrict__ dc, double* __restrict__ power, double* __restrict__ delta,
+           double* __restrict__ lnl, const double* __restrict__ data, const double* __restrict__ noise2,
+           const uint8_t* __restrict__ mask, int nsets, double mu, int err_on_model, long long box0) {
+    __shared__ double red[128];
     const long long box = blockIdx.x;
+    const long long set = (box0 + box) % nsets;  // box0: index of this call's first box in the caller's batch
+    double chi = 0.0;
     // gridDim.y > 1 only without lnL (cylindrical spectra have tens of thousands of outputs per box)
     for (long long i = (long long)blockIdx.y * blockDim.x + threadIdx.x; i < out_per_box;
          i += (long long)gridDim.y * blockDim.x) {
@@ -143,7 +145,7 @@ __global__ void k_finalize(const double* __restrict__ partials, int slots_max, l
         if (ch.dc_bin >= 0 && ch.out_off + ch.dc_bin == i) {
             // restore the k=0 power removed by the offset subtraction: |F'(0) + N c|^2 - |F'(0)|^2
             const float2 f0 = dc[box * nchunks + c];
-            const double shift = ch.ncells * (double)means[box * nchunks + c];
+            const double shift = ch.ncells * (double)chunk_offset(mean_parts, box * nchunks + c, n1, ch.nz);
             const double full = (double)f0.x + shift;
             s += full * full - (double)f0.x * (double)f0.x;
         }
@@ -152,26 +154,20 @@ __global__ void k_finalize(const double* __restrict__ partials, int slots_max, l
         if (kfac) {
             const double d = pw * kfac[i];
             if (delta) delta[box * out_per_box + i] = d;
-            if (lnl) sdelta[i] = d;
+            if (lnl) {   // likelihood.py:601-604; a NaN bin inside the k mask propagates, as in the reference
+                const long long j = set * out_per_box + i;
+                if (mask[j]) chi += chi2_term(d, data[j], noise2[j], mu, err_on_model);
+            }
         }
     }
-    if (lnl) {
+    if (lnl) {   // fixed-order tree sum over the 128 threads (gridDim.y == 1): bitwise reproducible
+        red[threadIdx.x] = chi;
         __syncthreads();
-        if (threadIdx.x == 0) {
-            const long long set = (box0 + box) % nsets;  // box0: index of this call's first box in the caller's batch
-            double total = 0.0;
-            for (int c = 0; c < nchunks; ++c) {
-                const ChunkDev ch = chunks[c];
-                double cs = 0.0;
-                for (int b = 0; b < ch.nbins_out; ++b) {
-                    const long long i = ch.out_off + b;
-                    const long long j = set * out_per_box + i;
-                    if (mask[j]) cs += chi2_term(sdelta[i], data[j], noise2[j], mu, err_on_model);
-                }
-                total += -0.5 * cs;
-            }
-            lnl[box] = total;
+        for (int s = 64; s > 0; s >>= 1) {
+            if ((int)threadIdx.x < s) red[threadIdx.x] += red[threadIdx.x + s];
+            __syncthreads();
         }
+        if (threadIdx.x == 0) lnl[box] = -0.5 * red[0];
     }
 }
 
@@ -268,20 +264,26 @@ struct DevTmp {
     cudaError_t alloc(size_t n) { return cudaMalloc((void**)&p, sizeof(T) * (n ? n : 1)); }
 };
 
+void drop_graphs(ps21_plan* p) {
+#ifndef PS21_EMU
+    for (auto& g : p->graphs)
+        if (g.exec) cudaGraphExecDestroy((cudaGraphExec_t)g.exec);
+#endif
+    p->graphs.clear();
+}
+
 static int ensure_batch(ps21_plan* p, long long batch) {
     if (batch <= p->batch_cap) return PS21_OK;
+    drop_graphs(p);   // captured launches hold the old pointers
     free_dev(p->d_partials);
-    free_dev(p->d_means);
     free_dev(p->d_mean_parts);
     free_dev(p->d_dc);
     p->d_partials = nullptr;
-    p->d_means = nullptr;
     p->d_mean_parts = nullptr;
     p->d_dc = nullptr;
     p->batch_cap = 0;
     PS21_CUDA(cudaMalloc((void**)&p->d_partials, sizeof(double) * batch * p->slots_max * p->out_per_box));
-    PS21_CUDA(cudaMalloc((void**)&p->d_means, sizeof(float) * batch * p->nchunks));
-    PS21_CUDA(cudaMalloc((void**)&p->d_mean_parts, sizeof(double) * batch * p->nchunks * 8));
+    PS21_CUDA(cudaMalloc((void**)&p->d_mean_parts, sizeof(double) * batch * p->nchunks * kMeanParts));
     PS21_CUDA(cudaMalloc((void**)&p->d_dc, sizeof(float2) * batch * p->nchunks));
     PS21_CUDA(cudaMemset(p->d_dc, 0, sizeof(float2) * batch * p->nchunks));
     p->batch_cap = batch;
@@ -290,6 +292,7 @@ static int ensure_batch(ps21_plan* p, long long batch) {
 
 static int ensure_scratch(ps21_plan* p, long long want_elems) {
     if (p->scratch_elems >= want_elems) return PS21_OK;
+    drop_graphs(p);
     free_dev(p->d_scratch);
     p->d_scratch = nullptr;
     p->scratch_elems = 0;
@@ -302,9 +305,61 @@ static int ensure_scratch(ps21_plan* p, long long want_elems) {
     return PS21_OK;
 }
 
-// All kernels of one call, asynchronous on `st`.
+// spectra of shape `sp` per scratch slice for a batch of `batch` boxes (equal slices: 256 spectra with room for
+// 121 run as 86 + 85 + 85, not 121 + 121 + 14)
+static long long slice_items(const ps21_plan* p, const ShapePlan& sp, long long batch, long long* spec_out) {
+    const long long total = batch * (long long)sp.chunks.size();
+    const long long spec = (sp.path == PS21_PATH_FUSED) ? fused_scratch_elems(sp, p->n0, p->n1)
+                                                         : (long long)p->n0 * p->n1 * sp.nh;
+    long long per = p->workspace_cap / (spec * (long long)sizeof(float2));
+    if (per < 1) per = 1;
+    if (per > 32768) per = 32768;
+    if (per > total) per = total;
+    const long long nslices = (total + per - 1) / per;
+    per = (total + nslices - 1) / nslices;
+    if (spec_out) *spec_out = spec;
+    return per;
+}
+
+// Every kernel of one call, in order, on `st` (directly, or while `st` is being captured into a CUDA graph).
+static int issue_launches(ps21_plan* p, const float* d_boxes, long long batch, long long batch_stride,
+                          double* d_power, double* d_delta, double* d_lnl, cudaStream_t st, long long box0) {
+    int rc;
+    {
+        ProfScope ps(p, KK_MEAN, st);
+        rc = launch_slab_mean(p, d_boxes, batch_stride, batch, st);
+    }
+    if (rc) return rc;
+    for (auto& sp : p->shapes) {
+        const long long total = batch * (long long)sp.chunks.size();
+        const long long per = slice_items(p, sp, batch, nullptr);
+        for (long long i0 = 0; i0 < total; i0 += per) {
+            const long long n = (total - i0 < per) ? (total - i0) : per;
+            rc = (sp.path == PS21_PATH_FUSED) ? fused_forward(p, sp, d_boxes, batch_stride, i0, n, st)
+                                              : general_forward(p, sp, d_boxes, batch_stride, i0, n, st);
+            if (rc) return rc;
+        }
+    }
+    const bool want_lnl = d_lnl != nullptr;
+    ProfScope psf(p, KK_FINALIZE, st);
+    unsigned fparts = want_lnl ? 1u : (unsigned)((p->out_per_box + 1023) / 1024);
+    if (fparts > 64u) fparts = 64u;
+    PS21_LAUNCH(k_finalize, dim3((unsigned)batch, fparts), dim3(128), 0, st, p->d_partials, p->slots_max,
+                p->out_per_box, p->d_chunks, p->nchunks, p->d_counts,
+                p->mode == PS21_MODE_SPHERICAL ? p->d_kfac : nullptr, p->d_mean_parts, p->n1, p->d_dc, d_power,
+                d_delta, d_lnl, p->data.d_data, p->data.d_noise2, p->data.d_mask,
+                p->data.nsets > 0 ? p->data.nsets : 1, p->data.model_uncertainty, p->data.error_on_model, box0);
+    PS21_CUDA(cudaGetLastError());
+    p->launches_last++;
+    return PS21_OK;
+}
+
+// All kernels of one call, asynchronous on `st`.  With graphs enabled (ps21_plan_set_graphs) the launch sequence
+// of a call is captured once per distinct argument set and replayed with one cudaGraphLaunch afterwards: an MCMC
+// step calls with the same device buffers every iteration, and at 8 walkers per GPU (config 3 on 8 GPUs) the whole
+// step is ~1.4 ms, where launch gaps count.
 static int run_device(ps21_plan* p, const float* d_boxes, long long batch, long long batch_stride, double* d_power,
-                      double* d_delta, double* d_lnl, cudaStream_t st, long long box0 = 0) {
+                      double* d_delta, double* d_lnl, cudaStream_t st, long long box0 = 0, bool allow_graph = true) {
     if (batch <= 0) return PS21_OK;
     if (batch_stride < (long long)p->n0 * p->n1 * p->n2_total)
         return invalid("batch_stride smaller than one box");
@@ -316,46 +371,106 @@ static int run_device(ps21_plan* p, const float* d_boxes, long long batch, long 
         return invalid("Delta^2 / lnL are defined for the spherical mode only");
     int rc = ensure_batch(p, batch);
     if (rc) return rc;
-    {
-        ProfScope ps(p, KK_MEAN, st);
-        rc = launch_slab_mean(p, d_boxes, batch_stride, batch, st);
-    }
-    if (rc) return rc;
-    for (auto& sp : p->shapes) {
-        const long long nper = (long long)sp.chunks.size();
-        const long long total = batch * nper;
-        const long long spec = (sp.path == PS21_PATH_FUSED) ? fused_scratch_elems(sp, p->n0, p->n1)
-                                                             : (long long)p->n0 * p->n1 * sp.nh;
-        long long per = p->workspace_cap / (spec * (long long)sizeof(float2));
-        if (per < 1) per = 1;
-        if (per > 32768) per = 32768;
-        if (per > total) per = total;
-        {   // equal slices: 256 spectra with room for 121 run as 86 + 85 + 85, not 121 + 121 + 14
-            const long long nslices = (total + per - 1) / per;
-            per = (total + nslices - 1) / nslices;
+    {   // the scratch serves the shapes one after the other: size it for the largest slice up front
+        long long want = 0;
+        for (auto& sp : p->shapes) {
+            long long spec = 0;
+            const long long per = slice_items(p, sp, batch, &spec);
+            if (per * spec > want) want = per * spec;
+            if (sp.path == PS21_PATH_FUSED && (rc = fused_reserve(p, sp, per))) return rc;
         }
-        rc = ensure_scratch(p, per * spec);
+        rc = ensure_scratch(p, want);
         if (rc) return rc;
-        for (long long i0 = 0; i0 < total; i0 += per) {
-            const long long n = (total - i0 < per) ? (total - i0) : per;
-            rc = (sp.path == PS21_PATH_FUSED) ? fused_forward(p, sp, d_boxes, batch_stride, i0, n, st)
-                                              : general_forward(p, sp, d_boxes, batch_stride, i0, n, st);
-            if (rc) return rc;
-        }
     }
-    double* pw = d_power;
-    const bool want_lnl = d_lnl != nullptr;
-    const size_t smem = want_lnl ? sizeof(double) * p->out_per_box : 0;
-    ProfScope psf(p, KK_FINALIZE, st);
-    unsigned fparts = want_lnl ? 1u : (unsigned)((p->out_per_box + 1023) / 1024);
-    if (fparts > 64u) fparts = 64u;
-    PS21_LAUNCH(k_finalize, dim3((unsigned)batch, fparts), dim3(128), smem, st, p->d_partials, p->slots_max, p->out_per_box,
-                p->d_chunks, p->nchunks, p->d_counts, p->mode == PS21_MODE_SPHERICAL ? p->d_kfac : nullptr,
-                p->d_means, p->d_dc, pw, d_delta, d_lnl, p->data.d_data, p->data.d_noise2, p->data.d_mask,
-                p->data.nsets > 0 ? p->data.nsets : 1, p->data.model_uncertainty, p->data.error_on_model, box0);
-    PS21_CUDA(cudaGetLastError());
-    p->launches_last++;
-    return PS21_OK;
+#ifndef PS21_EMU
+    if (allow_graph && p->graph_mode && !p->profiling) {
+        const ps21_plan::GraphKey key{d_boxes, batch, batch_stride, d_power, d_delta, d_lnl, box0, p->data.gen};
+        ps21_plan::GraphEntry* hit = nullptr;
+        for (auto& g : p->graphs)
+            if (std::memcmp(&g.key, &key, sizeof(key)) == 0) hit = &g;
+        if (!p->graph_stream) {
+            cudaStream_t s;
+            PS21_CUDA(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+            p->graph_stream = (void*)s;
+            cudaEvent_t e0, e1;
+            PS21_CUDA(cudaEventCreateWithFlags(&e0, cudaEventDisableTiming));
+            PS21_CUDA(cudaEventCreateWithFlags(&e1, cudaEventDisableTiming));
+            p->graph_ev[0] = (void*)e0;
+            p->graph_ev[1] = (void*)e1;
+        }
+        cudaStream_t gs = (cudaStream_t)p->graph_stream;
+        if (!hit && p->graph_miss_streak < 16) {
+            // capture on the plan's own stream (the caller's may be the legacy default stream, which cannot be captured)
+            if (p->graphs.size() >= 16) {   // evict the least recently used entry
+                size_t lru = 0;
+                for (size_t i = 1; i < p->graphs.size(); ++i)
+                    if (p->graphs[i].last_use < p->graphs[lru].last_use) lru = i;
+                if (p->graphs[lru].exec) cudaGraphExecDestroy((cudaGraphExec_t)p->graphs[lru].exec);
+                p->graphs.erase(p->graphs.begin() + lru);
+            }
+            p->launches_last = 0;
+            PS21_CUDA(cudaStreamBeginCapture(gs, cudaStreamCaptureModeThreadLocal));
+            rc = issue_launches(p, d_boxes, batch, batch_stride, d_power, d_delta, d_lnl, gs, box0);
+            cudaGraph_t graph = nullptr;
+            cudaError_t ce = cudaStreamEndCapture(gs, &graph);
+            if (rc) {
+                if (graph) cudaGraphDestroy(graph);
+                return rc;
+            }
+            if (ce != cudaSuccess) return cuda_fail(ce, "cudaStreamEndCapture");
+            cudaGraphExec_t exec = nullptr;
+            ce = cudaGraphInstantiate(&exec, graph, 0);
+            cudaGraphDestroy(graph);
+            if (ce != cudaSuccess) return cuda_fail(ce, "cudaGraphInstantiate");
+            p->graphs.push_back({key, (void*)exec, p->launches_last, 0});
+            hit = &p->graphs.back();
+            p->graph_captures++;
+            p->graph_miss_streak++;
+        } else if (hit) {
+            p->graph_miss_streak = 0;
+        }
+        if (hit) {
+            hit->last_use = ++p->graph_clock;
+            p->launches_last = hit->launches;
+            // fork from / join into the caller's stream
+            PS21_CUDA(cudaEventRecord((cudaEvent_t)p->graph_ev[0], st));
+            PS21_CUDA(cudaStreamWaitEvent(gs, (cudaEvent_t)p->graph_ev[0], 0));
+            PS21_CUDA(cudaGraphLaunch((cudaGraphExec_t)hit->exec, gs));
+            PS21_CUDA(cudaEventRecord((cudaEvent_t)p->graph_ev[1], gs));
+            PS21_CUDA(cudaStreamWaitEvent(st, (cudaEvent_t)p->graph_ev[1], 0));
+            p->graph_replays++;
+            return PS21_OK;
+        }
+        // the caller changes buffers on every call: graphs would be re-captured each time -> direct launches
+    }
+#endif
+    p->launches_last = 0;
+    return issue_launches(p, d_boxes, batch, batch_stride, d_power, d_delta, d_lnl, st, box0);
+}
+
+// everything that regrows on demand: half-spectrum scratch, partial sums, staging and result buffers, graphs
+static void release_workspace(ps21_plan* p) {
+    drop_graphs(p);
+    free_dev(p->d_scratch);
+    p->d_scratch = nullptr;
+    p->scratch_elems = 0;
+    free_dev(p->d_partials);
+    free_dev(p->d_mean_parts);
+    free_dev(p->d_dc);
+    p->d_partials = nullptr;
+    p->d_mean_parts = nullptr;
+    p->d_dc = nullptr;
+    p->batch_cap = 0;
+    for (int i = 0; i < 2; ++i) {
+        free_dev(p->d_stage[i]);
+        p->d_stage[i] = nullptr;
+    }
+    p->stage_boxes = 0;
+    for (int i = 0; i < 3; ++i) {
+        free_dev(p->d_res[i]);
+        p->d_res[i] = nullptr;
+    }
+    p->res_boxes = 0;
 }
 
 }  // namespace ps21
@@ -383,19 +498,78 @@ int ps21_plan_destroy(ps21_plan* p) {
     free_dev(p->d_chunks);
     free_dev(p->d_counts);
     free_dev(p->d_kfac);
-    free_dev(p->d_scratch);
-    free_dev(p->d_partials);
-    free_dev(p->d_means);
-    free_dev(p->d_mean_parts);
-    free_dev(p->d_dc);
+    release_workspace(p);
     free_dev(p->data.d_data);
     free_dev(p->data.d_noise2);
     free_dev(p->data.d_mask);
-    for (int i = 0; i < 2; ++i) {
-        free_dev(p->d_stage[i]);
+    for (int i = 0; i < 2; ++i)
         if (p->stage_stream[i]) cudaStreamDestroy((cudaStream_t)p->stage_stream[i]);
-    }
+    for (int i = 0; i < 4; ++i)
+        if (p->stage_ev[i]) cudaEventDestroy((cudaEvent_t)p->stage_ev[i]);
+#ifndef PS21_EMU
+    if (p->graph_stream) cudaStreamDestroy((cudaStream_t)p->graph_stream);
+    for (int i = 0; i < 2; ++i)
+        if (p->graph_ev[i]) cudaEventDestroy((cudaEvent_t)p->graph_ev[i]);
+#endif
     delete p;
+    return PS21_OK;
+}
+
+int ps21_plan_release_workspace(ps21_plan* p) {
+    if (!p) return invalid("null argument");
+    PS21_CUDA(cudaSetDevice(p->device));
+    PS21_CUDA(cudaDeviceSynchronize());
+    release_workspace(p);
+    return PS21_OK;
+}
+
+int ps21_plan_set_graphs(ps21_plan* p, int32_t on) {
+    if (!p) return invalid("null argument");
+    p->graph_mode = on ? 1 : 0;
+    p->graph_miss_streak = 0;
+    if (!on) drop_graphs(p);
+    return PS21_OK;
+}
+
+int ps21_plan_graph_stats(const ps21_plan* p, int64_t* captures, int64_t* replays) {
+    if (!p || !captures || !replays) return invalid("null argument");
+    *captures = p->graph_captures;
+    *replays = p->graph_replays;
+    return PS21_OK;
+}
+
+int ps21_host_alloc(void** ptr, int64_t bytes) {
+    if (!ptr || bytes <= 0) return invalid("null argument / bytes <= 0");
+#ifdef PS21_EMU
+    *ptr = std::malloc((size_t)bytes);
+    return *ptr ? PS21_OK : PS21_ERR_NOMEM;
+#else
+    PS21_CUDA(cudaHostAlloc(ptr, (size_t)bytes, cudaHostAllocPortable));
+    return PS21_OK;
+#endif
+}
+
+int ps21_host_free(void* ptr) {
+#ifdef PS21_EMU
+    std::free(ptr);
+#else
+    if (ptr) PS21_CUDA(cudaFreeHost(ptr));
+#endif
+    return PS21_OK;
+}
+
+int ps21_host_register(void* ptr, int64_t bytes) {
+    if (!ptr || bytes <= 0) return invalid("null argument / bytes <= 0");
+#ifndef PS21_EMU
+    PS21_CUDA(cudaHostRegister(ptr, (size_t)bytes, cudaHostRegisterPortable));
+#endif
+    return PS21_OK;
+}
+
+int ps21_host_unregister(void* ptr) {
+#ifndef PS21_EMU
+    if (ptr) PS21_CUDA(cudaHostUnregister(ptr));
+#endif
     return PS21_OK;
 }
 
@@ -665,20 +839,28 @@ int ps21_set_data(ps21_plan* p, int32_t nsets, const double* data, const double*
     if (!p || !data || !kmask || nsets < 1) return invalid("null argument / nsets < 1");
     if (p->mode != PS21_MODE_SPHERICAL) return invalid("likelihood data need the spherical mode");
     PS21_CUDA(cudaSetDevice(p->device));
-    free_dev(p->data.d_data); free_dev(p->data.d_noise2); free_dev(p->data.d_mask);
-    p->data = DataTables{};
     const long long n = (long long)nsets * p->out_per_box;
+    if (n > p->data.cap) {   // tables are reused while they are large enough
+        drop_graphs(p);
+        free_dev(p->data.d_data); free_dev(p->data.d_noise2); free_dev(p->data.d_mask);
+        p->data.d_data = p->data.d_noise2 = nullptr;
+        p->data.d_mask = nullptr;
+        p->data.cap = 0;
+        p->data.nsets = 0;
+        PS21_CUDA(cudaMalloc((void**)&p->data.d_data, sizeof(double) * n));
+        PS21_CUDA(cudaMalloc((void**)&p->data.d_noise2, sizeof(double) * n));
+        PS21_CUDA(cudaMalloc((void**)&p->data.d_mask, n));
+        p->data.cap = n;
+    }
     std::vector<double> n2(n, 0.0);
     if (noise) for (long long i = 0; i < n; ++i) n2[i] = noise[i] * noise[i];
-    PS21_CUDA(cudaMalloc((void**)&p->data.d_data, sizeof(double) * n));
-    PS21_CUDA(cudaMalloc((void**)&p->data.d_noise2, sizeof(double) * n));
-    PS21_CUDA(cudaMalloc((void**)&p->data.d_mask, n));
     PS21_CUDA(cudaMemcpy(p->data.d_data, data, sizeof(double) * n, cudaMemcpyHostToDevice));
     PS21_CUDA(cudaMemcpy(p->data.d_noise2, n2.data(), sizeof(double) * n, cudaMemcpyHostToDevice));
     PS21_CUDA(cudaMemcpy(p->data.d_mask, kmask, n, cudaMemcpyHostToDevice));
     p->data.nsets = nsets;
     p->data.model_uncertainty = model_uncertainty;
     p->data.error_on_model = error_on_model ? 1 : 0;
+    p->data.gen++;   // nsets / model_uncertainty / error_on_model are baked into captured launches
     return PS21_OK;
 }
 
@@ -698,15 +880,20 @@ int ps21_lnl_batched(ps21_plan* p, const float* d_boxes, int64_t batch, int64_t 
     return run_device(p, d_boxes, batch, batch_stride, d_power, d_delta, d_lnl, (cudaStream_t)stream);
 }
 
-// Host-buffer variants: boxes are staged through two device buffers; the copy of slice i+1 overlaps
-// the kernels of slice i.
-static int run_host(ps21_plan* p, const float* h_boxes, long long batch, long long batch_stride, double* h_lnl,
-                    double* h_delta, double* h_power) {
+// Host-buffer variants: boxes are staged through two device buffers; the copy of slice i+1 overlaps the kernels
+// of slice i.  Box b is read from h_ptrs[b] when a pointer array is given (walker-owned buffers, no gather on the
+// host), else from h_boxes + b * batch_stride.  Staging buffers, result buffers, streams and events belong to
+// the plan and are reused from call to call.
+static int run_host(ps21_plan* p, const float* const* h_ptrs, const float* h_boxes, long long batch,
+                    long long batch_stride, double* h_lnl, double* h_delta, double* h_power) {
     PS21_CUDA(cudaSetDevice(p->device));
     p->launches_last = 0;
     if (batch <= 0) return PS21_OK;
     const long long box_elems = (long long)p->n0 * p->n1 * p->n2_total;
-    if (batch_stride < box_elems) return invalid("batch_stride smaller than one box");
+    if (!h_ptrs && batch_stride < box_elems) return invalid("batch_stride smaller than one box");
+    if (h_ptrs)
+        for (long long i = 0; i < batch; ++i)
+            if (!h_ptrs[i]) return invalid("null box pointer");
     // slice size: at most 1 GiB per staging buffer (PS21_STAGE_BYTES overrides), at least one box
     long long stage_bytes = 1LL << 30;
     if (const char* e = getenv("PS21_STAGE_BYTES")) {
@@ -732,44 +919,58 @@ static int run_host(ps21_plan* p, const float* h_boxes, long long batch, long lo
             p->stage_stream[i] = (void*)s;
         }
     }
+    for (int i = 0; i < 4; ++i) {
+        if (!p->stage_ev[i]) {
+            cudaEvent_t e;
+            PS21_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+            p->stage_ev[i] = (void*)e;
+        }
+    }
+    if (batch > p->res_boxes) {
+        for (int i = 0; i < 3; ++i) {
+            free_dev(p->d_res[i]);
+            p->d_res[i] = nullptr;
+        }
+        p->res_boxes = 0;
+        PS21_CUDA(cudaMalloc((void**)&p->d_res[0], sizeof(double) * batch * p->out_per_box));
+        PS21_CUDA(cudaMalloc((void**)&p->d_res[1], sizeof(double) * batch * p->out_per_box));
+        PS21_CUDA(cudaMalloc((void**)&p->d_res[2], sizeof(double) * batch));
+        p->res_boxes = batch;
+    }
     cudaStream_t s_copy = (cudaStream_t)p->stage_stream[0], s_comp = (cudaStream_t)p->stage_stream[1];
     int rc = ensure_batch(p, per);
     if (rc) return rc;
-    DevTmp<double> res_p, res_d, res_l;
-    PS21_CUDA(res_p.alloc((size_t)batch * p->out_per_box));
-    if (h_delta) PS21_CUDA(res_d.alloc((size_t)batch * p->out_per_box));
-    if (h_lnl) PS21_CUDA(res_l.alloc((size_t)batch));
-    double *d_res_p = res_p.p, *d_res_d = res_d.p, *d_res_l = res_l.p;
-    // events: [0] = "copy into buffer b done" is recorded per slice on s_copy; compute waits on it.
-    // buffer reuse: copy of slice i+2 waits for the compute of slice i (event recorded on s_comp).
-    cudaEvent_t ev_copy[2], ev_comp[2];
-    for (int i = 0; i < 2; ++i) {
-        cudaEventCreateWithFlags(&ev_copy[i], cudaEventDisableTiming);
-        cudaEventCreateWithFlags(&ev_comp[i], cudaEventDisableTiming);
-    }
-    long long done = 0;
+    double *d_res_p = p->d_res[0], *d_res_d = h_delta ? p->d_res[1] : nullptr, *d_res_l = h_lnl ? p->d_res[2] : nullptr;
+    // "copy into buffer b done" is recorded per slice on s_copy and compute waits on it; the copy of slice i+2
+    // waits for the compute of slice i (recorded on s_comp) before it overwrites the buffer
+    cudaEvent_t ev_copy[2] = {(cudaEvent_t)p->stage_ev[0], (cudaEvent_t)p->stage_ev[1]};
+    cudaEvent_t ev_comp[2] = {(cudaEvent_t)p->stage_ev[2], (cudaEvent_t)p->stage_ev[3]};
+    long long done = 0, launches = 0;
     int sl = 0;
     while (done < batch && rc == PS21_OK) {
         const long long n = (batch - done < per) ? (batch - done) : per;
         const int b = sl & 1;
         if (sl >= 2) cudaStreamWaitEvent(s_copy, ev_comp[b], 0);
-        if (batch_stride == box_elems) {
+        if (!h_ptrs && batch_stride == box_elems) {
             cudaMemcpyAsync(p->d_stage[b], h_boxes + done * batch_stride, sizeof(float) * n * box_elems,
                             cudaMemcpyHostToDevice, s_copy);
         } else {
             for (long long i = 0; i < n; ++i)
-                cudaMemcpyAsync(p->d_stage[b] + i * box_elems, h_boxes + (done + i) * batch_stride,
+                cudaMemcpyAsync(p->d_stage[b] + i * box_elems,
+                                h_ptrs ? h_ptrs[done + i] : h_boxes + (done + i) * batch_stride,
                                 sizeof(float) * box_elems, cudaMemcpyHostToDevice, s_copy);
         }
         cudaEventRecord(ev_copy[b], s_copy);
         cudaStreamWaitEvent(s_comp, ev_copy[b], 0);
         rc = run_device(p, p->d_stage[b], n, box_elems, d_res_p + done * p->out_per_box,
                         d_res_d ? d_res_d + done * p->out_per_box : nullptr, d_res_l ? d_res_l + done : nullptr,
-                        s_comp, done);
+                        s_comp, done, /*allow_graph=*/false);
+        launches += p->launches_last;
         cudaEventRecord(ev_comp[b], s_comp);
         done += n;
         ++sl;
     }
+    p->launches_last = launches;
     if (rc == PS21_OK) {
         if (h_power)
             cudaMemcpyAsync(h_power, d_res_p, sizeof(double) * batch * p->out_per_box, cudaMemcpyDeviceToHost, s_comp);
@@ -779,10 +980,6 @@ static int run_host(ps21_plan* p, const float* h_boxes, long long batch, long lo
     }
     cudaError_t e1 = cudaStreamSynchronize(s_copy);
     cudaError_t e2 = cudaStreamSynchronize(s_comp);
-    for (int i = 0; i < 2; ++i) {
-        cudaEventDestroy(ev_copy[i]);
-        cudaEventDestroy(ev_comp[i]);
-    }
     if (rc) return rc;
     if (e1 != cudaSuccess) return cuda_fail(e1, "host staging copy stream");
     if (e2 != cudaSuccess) return cuda_fail(e2, "host staging compute stream");
@@ -791,7 +988,7 @@ static int run_host(ps21_plan* p, const float* h_boxes, long long batch, long lo
 
 int ps21_power_host(ps21_plan* p, const float* h_boxes, int64_t batch, int64_t batch_stride, double* h_power) {
     if (!p || !h_boxes || !h_power) return invalid("null argument");
-    return run_host(p, h_boxes, batch, batch_stride, nullptr, nullptr, h_power);
+    return run_host(p, nullptr, h_boxes, batch, batch_stride, nullptr, nullptr, h_power);
 }
 
 int ps21_lnl_host(ps21_plan* p, const float* h_boxes, int64_t batch, int64_t batch_stride, double* h_lnl,
@@ -801,7 +998,22 @@ int ps21_lnl_host(ps21_plan* p, const float* h_boxes, int64_t batch, int64_t bat
         set_error("ps21_set_data must be called before a likelihood evaluation");
         return PS21_ERR_STATE;
     }
-    return run_host(p, h_boxes, batch, batch_stride, h_lnl, h_delta, h_power);
+    return run_host(p, nullptr, h_boxes, batch, batch_stride, h_lnl, h_delta, h_power);
+}
+
+int ps21_power_host_ptrs(ps21_plan* p, const float* const* h_box_ptrs, int64_t batch, double* h_power) {
+    if (!p || !h_box_ptrs || !h_power) return invalid("null argument");
+    return run_host(p, h_box_ptrs, nullptr, batch, 0, nullptr, nullptr, h_power);
+}
+
+int ps21_lnl_host_ptrs(ps21_plan* p, const float* const* h_box_ptrs, int64_t batch, double* h_lnl, double* h_delta,
+                       double* h_power) {
+    if (!p || !h_box_ptrs || !h_lnl) return invalid("null argument");
+    if (p->data.nsets == 0) {
+        set_error("ps21_set_data must be called before a likelihood evaluation");
+        return PS21_ERR_STATE;
+    }
+    return run_host(p, h_box_ptrs, nullptr, batch, 0, h_lnl, h_delta, h_power);
 }
 
 int ps21_lnl_from_delta(ps21_plan* p, const double* h_delta, int64_t batch, double* h_lnl) {

@@ -30,18 +30,40 @@ from .plan import get_plan
 logger = logging.getLogger("21cmFAST")
 np.seterr(invalid="ignore", divide="ignore")  # likelihood.py:22: empty bins are NaN, silently
 
-_DEFAULTS = {"device": None, "edge_rule": "legacy_1.001", "kernel_path": "auto"}
+_DEFAULTS = {"device": None, "edge_rule": "auto", "kernel_path": "auto"}
+_AUTO_RULE = []   # the probed rule, once per process
+
+
+def resolve_edge_rule(rule=None):
+    """``"auto"`` / ``None`` -> the top-edge rule of the powerbox installed next to this package.
+
+    The rule changed between powerbox generations and the reference pins only
+    ``powerbox>=0.5.7``, so the installed package is probed once per process
+    (``binning.detect_edge_rule``).  Without powerbox the legacy rule is used and a warning is logged: datafiles
+    written by a reference install with a newer powerbox then sit on a different k grid."""
+    if rule is None or rule == "auto":
+        rule = _DEFAULTS["edge_rule"]   # an explicit process default (set_defaults) wins over probing
+    if rule != "auto":
+        if rule not in binning.EDGE_RULES:
+            raise ValueError(f"edge_rule must be 'auto' or one of {binning.EDGE_RULES}")
+        return rule
+    if not _AUTO_RULE:
+        found = binning.detect_edge_rule()
+        if found is None:
+            logger.warning("powerbox is not importable: cannot probe its bin-edge rule, using 'legacy_1.001' "
+                           "(pass edge_rule='inscribed' to match powerbox >= 0.7)")
+            found = "legacy_1.001"
+        _AUTO_RULE.append(found)
+    return _AUTO_RULE[0]
 
 
 def set_defaults(device=None, edge_rule=None, kernel_path=None):
     """Defaults used by the ``compute_power`` staticmethods (which have no instance to ask)."""
     if device is not None:
         _DEFAULTS["device"] = int(device)
-    if edge_rule == "auto":
-        edge_rule = binning.detect_edge_rule() or "legacy_1.001"
     if edge_rule is not None:
-        if edge_rule not in binning.EDGE_RULES:
-            raise ValueError(f"edge_rule must be one of {binning.EDGE_RULES}")
+        if edge_rule != "auto" and edge_rule not in binning.EDGE_RULES:
+            raise ValueError(f"edge_rule must be 'auto' or one of {binning.EDGE_RULES}")
         _DEFAULTS["edge_rule"] = edge_rule
     if kernel_path is not None:
         _DEFAULTS["kernel_path"] = kernel_path
@@ -67,9 +89,14 @@ def _is_cuda_tensor(x):
 
 
 def _power_records(plan, boxes):
-    """(batch, out_per_box) float64 power for host arrays or CUDA tensors."""
+    """(batch, out_per_box) float64 power for a host array, a CUDA tensor, or a list of per-walker boxes of either
+    kind (host boxes go to the library by pointer: no gather on the host)."""
+    if isinstance(boxes, (list, tuple)) and boxes and _is_cuda_tensor(boxes[0]):
+        import torch
+
+        boxes = torch.stack([b.contiguous() for b in boxes])
     if _is_cuda_tensor(boxes):
-        return plan.power_device(boxes).cpu().numpy()
+        return plan.power_device(boxes.contiguous()).cpu().numpy()
     return plan.power_host(boxes)
 
 
@@ -144,15 +171,18 @@ class LikelihoodBaseFile(LikelihoodBase):
     def _read_noise(self):
         return self._load_all(self.noisefile, "noise") if self.noisefile else None
 
-    @staticmethod
-    def _write(files, records, kind):
+    def _file_meta(self):
+        """Extra keys written next to the reference's ones (ignored by the reference's reader)."""
+        return {}
+
+    def _write(self, files, records, kind):
         for fl, d in zip(files, records):
             if not fl:  # the lightcone class defaults to datafile="": nothing to write (the reference would
                 continue  # create a file called ".npz" in the working directory here)
             if path.exists(fl):
                 logger.warning(f"File {fl} already exists. Moving previous version to {fl}.bk")
                 rename(fl, fl + ".bk")
-            np.savez(fl, **d)
+            np.savez(fl, **d, **self._file_meta())
             logger.info(f"Saved {kind} file: {fl}")
 
     def _write_data(self):
@@ -170,13 +200,13 @@ class Likelihood1DPowerCoeval(LikelihoodBaseFile):
 
     def __init__(self, n_psbins=None, min_k=0.1, max_k=1.0, logk=True, model_uncertainty=0.15,
                  error_on_model=True, ignore_kperp_zero=True, ignore_kpar_zero=False, ignore_k_zero=False,
-                 name="", device=None, edge_rule="legacy_1.001", kernel_path="auto", *args, **kwargs):
+                 name="", device=None, edge_rule="auto", kernel_path="auto", *args, **kwargs):
         super().__init__(*args, **kwargs)
         if self.noisefile and self.datafile and len(self.datafile) != len(self.noisefile):
             raise ValueError("If noisefile or datafile are provided, they should have the same number "
                              "of files (one for each coeval box)")
-        if edge_rule not in binning.EDGE_RULES:
-            raise ValueError(f"edge_rule must be one of {binning.EDGE_RULES}")
+        if edge_rule != "auto" and edge_rule not in binning.EDGE_RULES:
+            raise ValueError(f"edge_rule must be 'auto' or one of {binning.EDGE_RULES}")
         self.n_psbins = n_psbins
         self.min_k = min_k
         self.max_k = max_k
@@ -205,6 +235,18 @@ class Likelihood1DPowerCoeval(LikelihoodBaseFile):
     def _n_expected(self):
         return len(self.redshift)
 
+    def _file_meta(self):
+        return {"edge_rule": np.array(resolve_edge_rule(self.edge_rule))}
+
+    def _check_edge_rule(self):
+        """A datafile simulated under another bin-edge rule sits on a different k grid: say so."""
+        mine = resolve_edge_rule(self.edge_rule)
+        for i, d in enumerate(self.data or []):
+            theirs = d.get("edge_rule") if hasattr(d, "get") else None
+            if theirs is not None and str(theirs) != mine:
+                logger.warning(f"datafile #{i + 1} was written with bin-edge rule {theirs}, this likelihood uses "
+                               f"{mine}: the model and the data are binned on different k grids")
+
     def setup(self):
         super().setup()
         if not self._use_data:
@@ -215,6 +257,7 @@ class Likelihood1DPowerCoeval(LikelihoodBaseFile):
         if self.noise and len(self.noise) != self._n_expected():
             raise ValueError(f"There needs to be one dataset (noisefile) for each {what}!")
         self._check_data_format()
+        self._check_edge_rule()
         if self.noise:
             self._check_noise_format()
 
@@ -251,7 +294,7 @@ class Likelihood1DPowerCoeval(LikelihoodBaseFile):
                                           "different length; pass n_psbins explicitly")
             n_psbins = nbs.pop()
         return get_plan(shape, bounds, lengths, int(n_psbins), log_bins, ikperp, ikpar, ik0,
-                        edge_rule or _DEFAULTS["edge_rule"], mode, _device(device),
+                        resolve_edge_rule(edge_rule), mode, _device(device),
                         kernel_path or _DEFAULTS["kernel_path"])
 
     @staticmethod
@@ -278,13 +321,6 @@ class Likelihood1DPowerCoeval(LikelihoodBaseFile):
         plan = self._own_plan(shape, [(0, shape[2])], [(L, L, L)])
         return cubes, plan
 
-    def _stack(self, cubes):
-        if _is_cuda_tensor(cubes[0]):
-            import torch
-
-            return torch.stack(list(cubes)).contiguous()
-        return np.stack([np.asarray(c, dtype=np.float32) for c in cubes])
-
     def _models_from_power(self, plan, rec):
         """rec: (nrec, out_per_box) power -> list over records of {"k","delta"} per chunk (likelihood.py:863)."""
         out = []
@@ -300,7 +336,7 @@ class Likelihood1DPowerCoeval(LikelihoodBaseFile):
     def reduce_data(self, ctx):
         """One ``{"k", "delta"}`` dict per redshift (likelihood.py:639-654), all cubes in one device call."""
         cubes, plan = self._geometry(ctx)
-        rec = _power_records(plan, self._stack(cubes))
+        rec = _power_records(plan, list(cubes))
         return [m[0] for m in self._models_from_power(plan, rec)]
 
     def _tables(self, ks):
@@ -330,43 +366,60 @@ class Likelihood1DPowerCoeval(LikelihoodBaseFile):
             storage.update({k + "_z%s" % self.redshift[i]: v for k, v in m.items()})
 
     # ------------------------------------------------------------------ batched walkers
+    def __getstate__(self):
+        st = self.__dict__.copy()
+        st.pop("_plan_tables", None)   # per-process cache (holds plan handles): not pickled into pool workers
+        return st
+
     def _prepare_plan_data(self, plan):
-        ks = [plan.kcentres[0]] * self._n_expected() if self._variant == "coeval" else list(plan.kcentres)
-        data, noise, mask = self._tables(ks)
-        nsets = self._n_expected() if self._variant == "coeval" else 1
-        shape = (nsets, plan.nchunks, plan.nbins)
-        plan.set_data(np.array(data).reshape(shape), np.array(noise).reshape(shape),
-                      np.array(mask, dtype=np.uint8).reshape(shape), self.model_uncertainty, self.error_on_model)
+        """Upload this likelihood's data / noise / k-mask tables at the plan's bin centres (walker independent).
+
+        The spline evaluations are cached per plan, and the plan skips the upload when the tables already on the
+        device are the same (``PowerPlan.set_data``); callers hold ``plan._lock`` across this and the evaluation."""
+        cache = self.__dict__.setdefault("_plan_tables", {})
+        hit = cache.get(id(plan))
+        if hit is None or hit[0] is not plan:
+            ks = [plan.kcentres[0]] * self._n_expected() if self._variant == "coeval" else list(plan.kcentres)
+            data, noise, mask = self._tables(ks)
+            nsets = self._n_expected() if self._variant == "coeval" else 1
+            shape = (nsets, plan.nchunks, plan.nbins)
+            hit = (plan, np.array(data).reshape(shape), np.array(noise).reshape(shape),
+                   np.array(mask, dtype=np.uint8).reshape(shape))
+            cache.clear()   # one geometry at a time is the rule; do not pin old plans
+            cache[id(plan)] = hit
+        plan.set_data(hit[1], hit[2], hit[3], self.model_uncertainty, self.error_on_model)
 
     def reduce_data_batch(self, ctxs):
         """``[reduce_data(ctx) for ctx in ctxs]`` with a single device call."""
         return self.likelihood_batch(ctxs, want_lnl=False)[1]
 
     def likelihood_batch(self, ctxs, want_lnl=True):
-        """(lnL array, list of models) for many contexts: one batched FFT + binning + chi^2 call."""
+        """(lnL array, list of models) for many contexts: one batched FFT + binning + chi^2 call.
+
+        Host lightcones / cubes are handed to the library by pointer (``ps21_lnl_host_ptrs``): nothing is stacked
+        or concatenated on the host, and page-locked arrays (``plan.pinned_empty``) copy at the PCIe line rate."""
         if not ctxs:
             return np.zeros(0), []
-        stacks, plan = [], None
+        boxes, plan, per = [], None, 1
         for ctx in ctxs:
-            cubes, plan = self._geometry(ctx)
-            stacks.append(self._stack(cubes))
-        per = stacks[0].shape[0]
-        if _is_cuda_tensor(stacks[0]):
-            import torch
-
-            boxes = torch.cat(stacks)
-        else:
-            boxes = np.concatenate(stacks)
+            cubes, pl = self._geometry(ctx)
+            if plan is not None and pl is not plan:
+                raise ValueError("all contexts of a batch must share one box geometry")
+            plan, per = pl, len(cubes)
+            boxes.extend(cubes)
+        on_device = _is_cuda_tensor(boxes[0])
         if want_lnl:
-            self._prepare_plan_data(plan)
-            if _is_cuda_tensor(boxes):
-                import torch
+            with plan._lock:   # data tables and evaluation belong together (plans are shared between likelihoods)
+                self._prepare_plan_data(plan)
+                if on_device:
+                    import torch
 
-                delta = torch.empty((boxes.shape[0], plan.out_per_box), dtype=torch.float64, device=boxes.device)
-                lnl = plan.lnl_device(boxes, delta=delta).cpu().numpy()
-                delta = delta.cpu().numpy()
-            else:
-                lnl, delta, _ = plan.lnl_host(boxes, want_delta=True)
+                    t = torch.stack([b.contiguous() for b in boxes])
+                    delta = torch.empty((t.shape[0], plan.out_per_box), dtype=torch.float64, device=t.device)
+                    lnl = plan.lnl_device(t, delta=delta).cpu().numpy()
+                    delta = delta.cpu().numpy()
+                else:
+                    lnl, delta, _ = plan.lnl_host(boxes, want_delta=True)
             lnl = lnl.reshape(len(ctxs), per).sum(axis=1)
             recs = [[{"k": plan.kcentres[c].copy(), "delta": plan._chunk_view(r, c).copy()}
                      for c in range(plan.nchunks)] for r in delta]
@@ -403,6 +456,7 @@ class Likelihood1DPowerLightcone(Likelihood1DPowerCoeval):
         if self.noise and len(self.noise) != self.nchunks:
             raise ValueError("There needs to be one dataset (noisefile) for each chunk!")
         self._check_data_format()
+        self._check_edge_rule()
         if self.noise:
             self._check_noise_format()
 
@@ -464,7 +518,7 @@ class Likelihood1DPowerLightcone(Likelihood1DPowerCoeval):
     def reduce_data(self, ctx):
         """One ``{"k", "delta"}`` dict per chunk (likelihood.py:833-865), all chunks in one device call."""
         boxes, plan = self._geometry(ctx)
-        rec = _power_records(plan, self._stack(boxes))
+        rec = _power_records(plan, list(boxes))
         return self._models_from_power(plan, rec)[0]
 
     def store(self, model, storage):
@@ -520,8 +574,24 @@ class Likelihood1DPowerLightconeUpper(Likelihood1DPowerLightcone):
         return [{"k": self.k, "delta": self._to_bands(chunk_models)[None], "chunks": chunk_models}]
 
     def reduce_data_batch(self, ctxs):
-        models = super().likelihood_batch(ctxs, want_lnl=False)[1]
-        return [{"k": self.k, "delta": np.stack([self._to_bands(m) for m in models]), "chunks": models}]
+        """``[reduce_data(ctx) for ctx in ctxs]``: the chunk spectra of all walkers come from one device call."""
+        return self.likelihood_batch(ctxs, want_lnl=False)[1]
+
+    def likelihood_batch(self, ctxs, want_lnl=True):
+        """(lnL array, per-walker models) -- the batched route of ``chain.call_batch`` / ``BatchedWalkerPool``.
+
+        The Gaussian chi^2 of the parent class does not apply here (the data file holds limits and window
+        functions, no ``k`` / ``delta``): chunk spectra come from the parent's batched reduction, the likelihood
+        from this class's own ``computeLikelihood`` on all walkers at once."""
+        if not ctxs:
+            return np.zeros(0), []
+        chunk_models = Likelihood1DPowerLightcone.likelihood_batch(self, ctxs, want_lnl=False)[1]
+        delta = np.stack([self._to_bands(m) for m in chunk_models])          # (N, nbands, k_len)
+        models = [[{"k": self.k, "delta": delta[i][None], "chunks": chunk_models[i]}] for i in range(len(ctxs))]
+        lnl = None
+        if want_lnl:
+            lnl = np.atleast_1d(np.asarray(self.computeLikelihood([{"k": self.k, "delta": delta}]), dtype=float))
+        return lnl, models
 
     def computeLikelihood(self, model):
         """lnL of every model in ``model[0]["delta"]`` (N, nbands, k_len); the matvec + erf run on the device."""

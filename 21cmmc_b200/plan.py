@@ -6,7 +6,9 @@ src/py21cmmc/mcmc.py:580-583).
 """
 from __future__ import annotations
 
+import collections
 import ctypes as C
+import os
 import threading
 
 import numpy as np
@@ -108,7 +110,10 @@ class PowerPlan:
         _capi.check(self._lib.ps21_plan_counts(self._h, cnt.ctypes.data_as(C.POINTER(C.c_int64))))
         self.counts = cnt
         self._has_data = False
-        self._lock = threading.Lock()
+        self._data_key = None
+        # re-entrant: a likelihood holds it across set_data + lnl so that two likelihoods sharing this (cached)
+        # plan cannot evaluate against each other's data tables
+        self._lock = threading.RLock()
 
     # ------------------------------------------------------------------ bookkeeping
     def close(self):
@@ -131,6 +136,21 @@ class PowerPlan:
 
     def set_profiling(self, on=True):
         _capi.check(self._lib.ps21_plan_set_profiling(self._h, int(bool(on))))
+
+    def set_graphs(self, on=True):
+        """Replay the kernel sequence of repeated ``*_device`` calls as one CUDA graph (ps21_plan_set_graphs)."""
+        _capi.check(self._lib.ps21_plan_set_graphs(self._h, int(bool(on))))
+
+    def graph_stats(self):
+        cap, rep = C.c_int64(), C.c_int64()
+        _capi.check(self._lib.ps21_plan_graph_stats(self._h, C.byref(cap), C.byref(rep)))
+        return {"captures": cap.value, "replays": rep.value}
+
+    def release_workspace(self):
+        """Free scratch / staging / result buffers (they regrow on demand); the plan stays usable."""
+        with self._lock:
+            if getattr(self, "_h", None):
+                _capi.check(self._lib.ps21_plan_release_workspace(self._h))
 
     def profile(self):
         """{kind: (total ms, launches)} since the last query (CUDA events on the launching stream)."""
@@ -168,8 +188,32 @@ class PowerPlan:
             raise ValueError(f"boxes of shape {a.shape[1:]} do not match the plan {self.shape}")
         return np.ascontiguousarray(a)
 
+    def _box_pointers(self, boxes):
+        """(pointer array, keep-alive list) for a sequence of per-walker host boxes; no gather into one buffer.
+
+        A box that already is a C-contiguous float32 (n0, n1, n2_total) array is passed as it is (zero copy); anything
+        else (another dtype, a strided view) is converted first, which is the only copy made on the host."""
+        keep = []
+        for b in boxes:
+            a = np.asarray(b)
+            if a.shape != self.shape:
+                raise ValueError(f"box of shape {a.shape} does not match the plan {self.shape}")
+            if a.dtype != np.float32 or not a.flags.c_contiguous:
+                a = np.ascontiguousarray(a, dtype=np.float32)
+            keep.append(a)
+        ptrs = (C.c_void_p * len(keep))(*[a.ctypes.data for a in keep])
+        return ptrs, keep
+
     def power_host(self, boxes):
-        """Power of every chunk of every box.  boxes: (batch, n0, n1, n2_total) or one box. -> (batch, out_per_box)."""
+        """Power of every chunk of every box -> (batch, out_per_box).
+
+        boxes: (batch, n0, n1, n2_total) array, one box, or a list / tuple of per-walker boxes (passed by pointer)."""
+        if isinstance(boxes, (list, tuple)):
+            ptrs, keep = self._box_pointers(boxes)
+            out = np.empty((len(keep), self.out_per_box), dtype=np.float64)
+            with self._lock:
+                _capi.check(self._lib.ps21_power_host_ptrs(self._h, ptrs, len(keep), out.ctypes.data))
+            return out
         a = self._as_host_batch(boxes)
         out = np.empty((a.shape[0], self.out_per_box), dtype=np.float64)
         with self._lock:
@@ -188,22 +232,38 @@ class PowerPlan:
         if kmask is None:
             kmask = np.ones_like(data, dtype=np.uint8)
         kmask = np.ascontiguousarray(kmask, dtype=np.uint8).reshape(nsets, self.out_per_box)
+        # the tables are walker independent: skip the upload when they are the ones already on the device
+        key = (nsets, data.tobytes(), None if noise is None else noise.tobytes(), kmask.tobytes(),
+               float(model_uncertainty), bool(error_on_model))
         with self._lock:
+            if key == self._data_key:
+                return
             _capi.check(self._lib.ps21_set_data(self._h, nsets, _dptr(data), noise_p,
                                                 kmask.ctypes.data_as(C.POINTER(C.c_uint8)),
                                                 float(model_uncertainty), int(bool(error_on_model))))
-        self._has_data = True
+            self._data_key = key
+            self._has_data = True
 
     def lnl_host(self, boxes, want_delta=False, want_power=False):
-        a = self._as_host_batch(boxes)
-        n = a.shape[0]
+        """(lnL[batch], Delta^2 or None, power or None) for host boxes (array, or list of per-walker arrays)."""
+        by_ptr = isinstance(boxes, (list, tuple))
+        if by_ptr:
+            ptrs, keep = self._box_pointers(boxes)
+            n = len(keep)
+        else:
+            a = self._as_host_batch(boxes)
+            n = a.shape[0]
         lnl = np.empty(n, dtype=np.float64)
         delta = np.empty((n, self.out_per_box), dtype=np.float64) if want_delta else None
         power = np.empty((n, self.out_per_box), dtype=np.float64) if want_power else None
+        dp = delta.ctypes.data if want_delta else None
+        pp = power.ctypes.data if want_power else None
         with self._lock:
-            _capi.check(self._lib.ps21_lnl_host(
-                self._h, a.ctypes.data, n, self.box_elems(), lnl.ctypes.data,
-                delta.ctypes.data if want_delta else None, power.ctypes.data if want_power else None))
+            if by_ptr:
+                _capi.check(self._lib.ps21_lnl_host_ptrs(self._h, ptrs, n, lnl.ctypes.data, dp, pp))
+            else:
+                _capi.check(self._lib.ps21_lnl_host(self._h, a.ctypes.data, n, self.box_elems(), lnl.ctypes.data,
+                                                    dp, pp))
         return lnl, delta, power
 
     def lnl_from_delta(self, delta):
@@ -254,8 +314,12 @@ class PowerPlan:
         return lnl
 
 
-_PLANS = {}
+# Per-process plan cache, least recently used first.  A plan keeps its bin-index tables and a half-spectrum scratch
+# that grows up to 1/6 of the device memory, so the cache is bounded (PS21_PLAN_CACHE, default 8 plans): an evicted
+# plan gives its workspace back at once and is destroyed when the last likelihood using it lets go of it.
+_PLANS = collections.OrderedDict()
 _PLANS_LOCK = threading.Lock()
+_PLAN_CACHE_MAX = max(1, int(os.environ.get("PS21_PLAN_CACHE", "8")))
 
 
 def get_plan(shape, chunk_bounds, lengths, nbins=None, log_bins=True, ignore_kperp_zero=True,
@@ -268,10 +332,18 @@ def get_plan(shape, chunk_bounds, lengths, nbins=None, log_bins=True, ignore_kpe
            path, library)
     with _PLANS_LOCK:
         pl = _PLANS.get(key)
-        if pl is None:
-            pl = PowerPlan(shape, chunk_bounds, lengths, nbins, log_bins, ignore_kperp_zero, ignore_kpar_zero,
-                           ignore_k_zero, edge_rule, mode, device, path, library=library)
-            _PLANS[key] = pl
+        if pl is not None:
+            _PLANS.move_to_end(key)
+            return pl
+        pl = PowerPlan(shape, chunk_bounds, lengths, nbins, log_bins, ignore_kperp_zero, ignore_kpar_zero,
+                       ignore_k_zero, edge_rule, mode, device, path, library=library)
+        _PLANS[key] = pl
+        while len(_PLANS) > _PLAN_CACHE_MAX:
+            _, old = _PLANS.popitem(last=False)
+            try:
+                old.release_workspace()
+            except Exception:
+                pass
     return pl
 
 
@@ -280,3 +352,40 @@ def clear_plans():
         for pl in _PLANS.values():
             pl.close()
         _PLANS.clear()
+
+
+# ---------------------------------------------------------------------------------------------------------
+# page-locked host buffers for walker lightcones (copies from them run at the PCIe line rate)
+# ---------------------------------------------------------------------------------------------------------
+class _PinnedOwner:
+    def __init__(self, lib, ptr):
+        self.lib, self.ptr = lib, ptr
+
+    def __del__(self):
+        try:
+            self.lib.ps21_host_free(self.ptr)
+        except Exception:
+            pass
+
+
+def pinned_empty(shape, dtype=np.float32, library=None):
+    """Uninitialised NumPy array in page-locked memory (cudaHostAlloc through the C ABI); freed with the array."""
+    lib = _capi.load(library)
+    dtype = np.dtype(dtype)
+    nbytes = int(np.prod(shape)) * dtype.itemsize
+    ptr = C.c_void_p()
+    _capi.check(lib.ps21_host_alloc(C.byref(ptr), max(nbytes, 1)))
+    owner = _PinnedOwner(lib, ptr)
+    buf = (C.c_char * max(nbytes, 1)).from_address(ptr.value)
+    buf._owner = owner   # the ctypes buffer keeps the allocation alive, the array keeps the buffer alive
+    return np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
+
+
+def pin_array(a, library=None):
+    """Page-lock an existing C-contiguous array in place (cudaHostRegister); returns an unpin callable."""
+    lib = _capi.load(library)
+    a = np.asarray(a)
+    if not a.flags.c_contiguous:
+        raise ValueError("only C-contiguous arrays can be pinned")
+    _capi.check(lib.ps21_host_register(a.ctypes.data, a.nbytes))
+    return lambda: _capi.check(lib.ps21_host_unregister(a.ctypes.data))

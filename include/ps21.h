@@ -96,6 +96,17 @@ int ps21_plan_info(const ps21_plan* plan, ps21_info* info);
 int ps21_plan_set_profiling(ps21_plan* plan, int32_t on);
 int ps21_plan_profile(ps21_plan* plan, double* ms_by_kind, int64_t* launches_by_kind);
 
+/* CUDA graphs: with on != 0 the kernel sequence of a ps21_power_batched / ps21_lnl_batched call is captured once per
+ * distinct argument set (buffers, batch) and replayed with a single cudaGraphLaunch afterwards (the launches run on a
+ * stream owned by the plan, ordered after / before the caller's stream by events).  Callers that pass new buffers on
+ * every call fall back to direct launches after 16 captures without a replay.  Off by default. */
+int ps21_plan_set_graphs(ps21_plan* plan, int32_t on);
+int ps21_plan_graph_stats(const ps21_plan* plan, int64_t* captures, int64_t* replays);
+
+/* Frees everything that regrows on demand (half-spectrum scratch, partial sums, staging and result buffers, graphs);
+ * the plan stays usable.  Synchronises the device. */
+int ps21_plan_release_workspace(ps21_plan* plan);
+
 /* offsets[c] = first double of chunk c inside one box's power record; offsets[nchunks] = out_per_box.
  * Spherical: nbins per chunk.  Cylindrical: nbins * (nz_c/2+1), row-major [bin][k_par index 0..nz_c/2]. */
 int ps21_plan_layout(const ps21_plan* plan, int64_t* offsets);
@@ -129,6 +140,20 @@ int ps21_power_host(ps21_plan* plan, const float* h_boxes, int64_t batch, int64_
                     double* h_power);
 int ps21_lnl_host(ps21_plan* plan, const float* h_boxes, int64_t batch, int64_t batch_stride,
                   double* h_lnl, double* h_delta, double* h_power);
+
+/* The same with one HOST pointer per box (each a C-contiguous (n0, n1, n2_total) float32 array owned by its walker,
+ * e.g. the LightCone.brightness_temp arrays of the contexts of one emcee step, likelihood.py:834-856): no gather into
+ * one buffer on the host.  Pinned (ps21_host_alloc / ps21_host_register) buffers copy at the PCIe line rate. */
+int ps21_power_host_ptrs(ps21_plan* plan, const float* const* h_box_ptrs, int64_t batch, double* h_power);
+int ps21_lnl_host_ptrs(ps21_plan* plan, const float* const* h_box_ptrs, int64_t batch, double* h_lnl,
+                       double* h_delta, double* h_power);
+
+/* Page-locked host memory for walker buffers (thin wrappers over cudaHostAlloc / cudaHostRegister, so that the
+ * Python host layer needs no CUDA binding of its own). */
+int ps21_host_alloc(void** ptr, int64_t bytes);
+int ps21_host_free(void* ptr);
+int ps21_host_register(void* ptr, int64_t bytes);
+int ps21_host_unregister(void* ptr);
 
 /* computeLikelihood on already reduced models: h_delta [batch][nchunks][nbins] (host) -> h_lnl [batch]. */
 int ps21_lnl_from_delta(ps21_plan* plan, const double* h_delta, int64_t batch, double* h_lnl);

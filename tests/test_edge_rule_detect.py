@@ -28,10 +28,17 @@ def test_detects_generation(monkeypatch, rule):
     assert binning.detect_edge_rule() == rule
     old = dict(likelihood._DEFAULTS)
     try:
+        likelihood._AUTO_RULE.clear()
         likelihood.set_defaults(edge_rule="auto")
-        assert likelihood._DEFAULTS["edge_rule"] == rule
+        assert likelihood.resolve_edge_rule() == rule            # probed once per process ...
+        assert likelihood.resolve_edge_rule("auto") == rule      # ... also for instances built with the default
+        assert likelihood._AUTO_RULE == [rule]
+        likelihood.set_defaults(edge_rule="inscribed")           # an explicit process default wins over probing
+        assert likelihood.resolve_edge_rule("auto") == "inscribed"
+        assert likelihood.resolve_edge_rule("legacy_1.001") == "legacy_1.001"
     finally:
         likelihood._DEFAULTS.update(old)
+        likelihood._AUTO_RULE.clear()
 
 
 def test_unknown_generation_is_loud(monkeypatch):
@@ -47,3 +54,22 @@ def test_absent_powerbox_means_none(monkeypatch):
     monkeypatch.setitem(sys.modules, "powerbox", None)
     monkeypatch.setitem(sys.modules, "powerbox.tools", None)
     assert binning.detect_edge_rule() is None
+
+
+def test_auto_without_powerbox_falls_back_to_legacy_with_a_warning(monkeypatch, caplog):
+    monkeypatch.setitem(sys.modules, "powerbox", None)
+    monkeypatch.setitem(sys.modules, "powerbox.tools", None)
+    old = dict(likelihood._DEFAULTS)
+    try:
+        likelihood._AUTO_RULE.clear()
+        likelihood.set_defaults(edge_rule="auto")
+        with caplog.at_level("WARNING", logger="21cmFAST"):
+            assert likelihood.resolve_edge_rule() == "legacy_1.001"
+        assert any("powerbox is not importable" in r.message for r in caplog.records)
+        lk = likelihood.Likelihood1DPowerLightcone(nchunks=2, use_data=False)   # the constructor default is "auto"
+        assert lk.edge_rule == "auto"
+        with pytest.raises(ValueError):
+            likelihood.Likelihood1DPowerLightcone(nchunks=2, edge_rule="newest")
+    finally:
+        likelihood._DEFAULTS.update(old)
+        likelihood._AUTO_RULE.clear()

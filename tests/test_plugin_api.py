@@ -56,7 +56,9 @@ def test_simulate_writes_datafiles_and_rereads_them(mods, tmp_path):
     chain.setup()
     assert all(os.path.exists(f) for f in files)
     d0 = dict(np.load(files[0]))
-    assert set(d0) == {"k", "delta"} and np.array_equal(d0["delta"], lk.data[0]["delta"], equal_nan=True)
+    # the reference's keys plus the bin-edge rule the file was simulated under (ignored by the reference's reader)
+    assert set(d0) == {"k", "delta", "edge_rule"} and str(d0["edge_rule"]) == "legacy_1.001"
+    assert np.array_equal(d0["delta"], lk.data[0]["delta"], equal_nan=True)
     # a second run moves the old files to .bk (likelihood.py:236-247)
     chain2, lk2 = make(mods, state, datafile=files, simulate=True)
     chain2.setup()
@@ -68,6 +70,17 @@ def test_simulate_writes_datafiles_and_rereads_them(mods, tmp_path):
     a = lk.computeLikelihood(lk.reduce_data(chain.build_model_data()))
     b = lk3.computeLikelihood(lk3.reduce_data(chain3.build_model_data()))
     assert a == b and a < 0
+
+
+def test_datafile_written_under_another_edge_rule_is_reported(mods, tmp_path, caplog):
+    files = [str(tmp_path / f"data_{i}.npz") for i in range(NCHUNKS)]
+    state = {"box": synth_box(SHAPE, 0)}
+    chain, _ = make(mods, state, datafile=files, simulate=True, edge_rule="inscribed")
+    chain.setup()
+    chain2, _ = make(mods, state, datafile=files, simulate=False, edge_rule="legacy_1.001")
+    with caplog.at_level("WARNING", logger="21cmFAST"):
+        chain2.setup()
+    assert any("different k grids" in r.message for r in caplog.records)
 
 
 def test_setup_errors_like_reference(mods, tmp_path):
@@ -223,3 +236,116 @@ def test_coeval_data_sets_follow_boxes_across_staging_slices(mods, monkeypatch):
     monkeypatch.setenv("PS21_STAGE_BYTES", str(2 * n * n * n * 4))  # two cubes per slice -> six slices
     lnls, _ = lk.likelihood_batch(ctxs)
     assert np.allclose(lnls, single, rtol=1e-9, atol=0) and len(set(np.round(lnls, 6))) == nwalk
+
+
+def test_call_batch_composes_with_upper_limit_and_windowed_likelihoods(mods, tmp_path):
+    """f-1 (walker batches) and f-2 (HERA-style consumers) must compose: chain.call_batch on the
+    Upper / Windowed classes takes their own likelihood, not the Gaussian chi^2 of the parent class."""
+    from tests import parity_cases as PC
+
+    lk_mod, core_mod, chain_mod = mods
+    shape, box_len, nchunks, nb = (16, 16, 48), 24.0, 3, 8
+    up = core_mod.UserParams(BOX_LEN=box_len, HII_DIM=shape[0])
+
+    class SeedSim:
+        def __call__(self, params):
+            return synth_box(shape, int(round(params.seed)))
+
+    from py21cmmc_b200.chain import Params
+
+    probe = lk_mod.Likelihood1DPowerLightcone(nchunks=nchunks, n_psbins=nb, use_data=False)
+    ch0 = chain_mod.build_computation_chain(core_mod.CoreLightConeModule(lambda p: synth_box(shape, 1), up), probe)
+    kmodel = probe.reduce_data(ch0.build_model_data())[0]["k"]
+    PC.synthetic_hera_file(str(tmp_path / "hera.npz"), kmodel)
+    for cls in (lk_mod.Likelihood1DPowerLightconeUpper, lk_mod.Likelihood1DPowerLightconeWindowed):
+        lk = cls(datafile=str(tmp_path / "hera.npz"), nchunks=nchunks, n_psbins=nb, band_chunks=[2, 0])
+        chain = chain_mod.build_computation_chain(core_mod.CoreLightConeModule(SeedSim(), up), lk,
+                                                  params=Params(("seed", [0.0, 0.0, 50.0, 1.0])))
+        plist = [[1.0], [2.0], [77.0], [3.0]]   # 77 is outside the prior
+        batch = chain.call_batch(plist)
+        assert batch[2][0] == -np.inf and not batch[2][1]
+        for p, (lnl, blobs) in zip(plist, batch):
+            if p[0] > 50:
+                continue
+            one, blobs1 = chain(p)
+            assert np.isfinite(one) and abs(lnl - one) <= 1e-12 * abs(one)
+            assert set(blobs) == set(blobs1) and np.array_equal(blobs["delta_1"], blobs1["delta_1"], equal_nan=True)
+        # reduce_data_batch == [reduce_data(ctx)]
+        ctxs = [chain.build_model_data(p) for p in ([1.0], [3.0])]
+        many = lk.reduce_data_batch(ctxs)
+        for ctx, m in zip(ctxs, many):
+            assert np.array_equal(m[0]["delta"], lk.reduce_data(ctx)[0]["delta"])
+
+
+def test_host_pointer_path_equals_array_path_and_accepts_pinned_buffers(mods):
+    """ps21_lnl_host_ptrs / ps21_power_host_ptrs: per-walker buffers by pointer (no gather on the host) give the very
+    results of the contiguous-array entry points; page-locked helpers round-trip."""
+    from py21cmmc_b200 import _capi
+    from py21cmmc_b200.plan import PowerPlan, pin_array, pinned_empty
+
+    shape = (10, 10, 24)
+    pl = PowerPlan(shape, [(0, 12), (12, 24)], [(15.0, 15.0, 18.0)] * 2, 5, library=_capi.LIB_PATH)
+    boxes = [synth_box(shape, s) for s in range(5)]
+    pinned = pinned_empty(shape)
+    pinned[...] = boxes[1]
+    boxes[1] = pinned
+    unpin = pin_array(boxes[2])
+    strided = np.asfortranarray(boxes[3])          # not C-contiguous: converted, the others go zero copy
+    f64 = boxes[4].astype(np.float64)              # another dtype: converted
+    as_list = [boxes[0], boxes[1], boxes[2], strided, f64]
+    stack = np.stack([np.asarray(b, dtype=np.float32) for b in boxes])
+    a = pl.power_host(stack)
+    b = pl.power_host(as_list)
+    assert np.array_equal(a, b, equal_nan=True)
+    data = a[0].reshape(1, 2, 5) * 1.3
+    pl.set_data(np.nan_to_num(data), None, np.isfinite(data), 0.15, True)
+    la, da, _ = pl.lnl_host(stack, want_delta=True)
+    lb, db, pb = pl.lnl_host(as_list, want_delta=True, want_power=True)
+    assert np.array_equal(la, lb) and np.array_equal(da, db, equal_nan=True) and np.array_equal(pb, a, equal_nan=True)
+    with pytest.raises(ValueError):
+        pl.power_host([np.zeros((10, 10, 23), np.float32)])
+    unpin()
+    # giving the workspace back keeps the plan usable
+    pl.release_workspace()
+    assert pl.info()["workspace_bytes"] == 0
+    assert np.array_equal(pl.power_host(as_list), a, equal_nan=True)
+    pl.close()
+
+
+def test_two_likelihoods_sharing_a_cached_plan_keep_their_own_data(mods):
+    """plans are cached per geometry and shared; the data tables are bound to the call."""
+    lk_mod, core_mod, chain_mod = mods
+    state = {"box": synth_box(SHAPE, 0)}
+    chain_a, lk_a = make(mods, state, simulate=True, min_k=0.3, max_k=4.0)
+    chain_a.setup()
+    chain_b, lk_b = make(mods, state, simulate=True, min_k=0.8, max_k=3.0, model_uncertainty=0.3)
+    chain_b.setup()
+    state["box"] = synth_box(SHAPE, 4)
+    ctx = chain_a.build_model_data()
+    assert lk_a._geometry(ctx)[1] is lk_b._geometry(ctx)[1]      # one plan, two likelihoods
+    want_a = lk_a.computeLikelihood(lk_a.reduce_data(ctx))
+    want_b = lk_b.computeLikelihood(lk_b.reduce_data(ctx))
+    assert want_a != want_b
+    plan = lk_a._geometry(ctx)[1]
+    for _ in range(3):   # interleaved: every call re-binds its own tables; repeated calls skip the upload
+        assert abs(lk_a.likelihood_batch([ctx])[0][0] - want_a) <= LNL_RTOL * abs(want_a)
+        key_a = plan._data_key
+        assert abs(lk_a.likelihood_batch([ctx, ctx])[0][1] - want_a) <= LNL_RTOL * abs(want_a)
+        assert plan._data_key is key_a
+        assert abs(lk_b.likelihood_batch([ctx])[0][0] - want_b) <= LNL_RTOL * abs(want_b)
+    pickle.loads(pickle.dumps(lk_a))   # the per-process table cache is not pickled
+
+
+def test_plan_cache_is_bounded(mods, monkeypatch):
+    from py21cmmc_b200 import plan as plan_mod
+
+    monkeypatch.setattr(plan_mod, "_PLAN_CACHE_MAX", 2)
+    plan_mod.clear_plans()
+    plans = [plan_mod.get_plan((8, 8, 8 + 2 * i), [(0, 8 + 2 * i)], [(12.0, 12.0, 12.0 + 3 * i)], 4) for i in range(4)]
+    assert len(plan_mod._PLANS) == 2
+    first = plans[0]
+    box = synth_box(first.shape, 0)
+    want = first.power_host(box)            # an evicted plan still works for whoever holds it
+    assert np.isfinite(want).any()
+    assert plan_mod.get_plan((8, 8, 14), [(0, 14)], [(12.0, 12.0, 21.0)], 4) is plans[3]
+    plan_mod.clear_plans()
