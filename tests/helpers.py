@@ -31,3 +31,19 @@ def rel_err(a, b, floor_frac=0.0):
 # tolerances stated by BASELINE.json north_star
 POWER_RTOL = 1e-5
 LNL_RTOL = 1e-6
+
+
+def power_law_box(shape, index=-3.0, seed=0, mean=20.0, sigma=10.0):
+    """float32 Gaussian random field with P(k) ~ |k|^index (a realistic, steep 21-cm-like spectrum instead of
+    white noise): one bin then mixes modes of very different power."""
+    rng = np.random.default_rng(seed)
+    white = rng.standard_normal(shape)
+    F = np.fft.rfftn(white)
+    k = [np.fft.fftfreq(n) for n in shape[:2]] + [np.fft.rfftfreq(shape[2])]
+    kk = np.sqrt(k[0][:, None, None] ** 2 + k[1][None, :, None] ** 2 + k[2][None, None, :] ** 2)
+    kk[0, 0, 0] = 1.0
+    F *= kk ** (index / 2.0)
+    F[0, 0, 0] = 0.0
+    x = np.fft.irfftn(F, s=shape, axes=(0, 1, 2))
+    x *= sigma / x.std()
+    return (x + mean).astype(np.float32)

@@ -201,3 +201,67 @@ def check_upper_limit_likelihood(lk_mod, core_mod, chain_mod, tmp_path, shape=(1
     wantg = O.upper_limit_likelihood(hera, hera["z_bands"], many["delta"], many["delta_err"], gaussian=True)
     assert np.all(wantg < 0) and np.allclose(gotg, wantg, rtol=1e-10, atol=1e-12)
     return lnl, lnl_o
+
+
+def check_noise_and_error_on_model(mods, tmp_path, error_on_model, shape, box_len, nchunks, nb, min_k=0.3, max_k=4.0):
+    """Noise spline, error_on_model on / off and data on another k grid than the model (likelihood.py:584-604):
+    per-model chi^2 entry and the fused finalize kernel against the oracle."""
+    lk_mod, core_mod, chain_mod = mods
+    state = {"box": synth_box(shape, 0)}
+    cell = box_len / shape[0]
+    data_o = O.reduce_data_lightcone(state["box"], box_len, cell, nchunks, nb)
+    dfiles, nfiles, noise = [], [], []
+    rng = np.random.default_rng(1)
+    for i, d in enumerate(data_o):
+        ok = np.isfinite(d["delta"])
+        f = str(tmp_path / f"d{i}.npz")
+        np.savez(f, k=d["k"][ok], delta=d["delta"][ok] * 1.1)  # data on a *different* k grid than the model
+        dfiles.append(f)
+        n = {"k": np.linspace(0.05, 6.0, 9), "errs": rng.uniform(5.0, 50.0, 9)}
+        nf = str(tmp_path / f"n{i}.npz")
+        np.savez(nf, **n)
+        nfiles.append(nf)
+        noise.append(n)
+    up = core_mod.UserParams(BOX_LEN=box_len, HII_DIM=shape[0])
+    c = core_mod.CoreLightConeModule(lambda params: state["box"], up)
+    lk = lk_mod.Likelihood1DPowerLightcone(nchunks=nchunks, n_psbins=nb, min_k=min_k, max_k=max_k, datafile=dfiles,
+                                           noisefile=nfiles, error_on_model=error_on_model, model_uncertainty=0.2)
+    chain = chain_mod.build_computation_chain(c, lk, setup=True)
+    state["box"] = synth_box(shape, 5)
+    model = lk.reduce_data(chain.build_model_data())
+    lnl = lk.computeLikelihood(model)
+    model_o = O.reduce_data_lightcone(state["box"], box_len, cell, nchunks, nb)
+    data_read = [dict(np.load(f)) for f in dfiles]
+    lnl_o = O.compute_likelihood(model_o, data_read, noise, min_k, max_k, 0.2, error_on_model)
+    assert np.isfinite(lnl_o) and lnl_o < 0 and abs(lnl - lnl_o) <= LNL_RTOL * abs(lnl_o)
+    # the fused batched path (k_finalize with the noise^2 / error_on_model branches) agrees with the oracle too
+    lnls, _ = lk.likelihood_batch([chain.build_model_data(), chain.build_model_data()])
+    assert np.all(np.abs(lnls - lnl_o) <= LNL_RTOL * abs(lnl_o))
+    return lnl, lnl_o
+
+
+def check_coeval_staging_slices(mods, monkeypatch, n=10, nz=3, nwalk=4):
+    """With several redshifts (data sets) and a host batch staged in several slices, box b must be compared with
+    data set b % nsets whatever slice it travels in."""
+    lk_mod, core_mod, chain_mod = mods
+    up = core_mod.UserParams(BOX_LEN=1.5 * n, HII_DIM=n)
+
+    class Sim:
+        def __init__(self):
+            self.seed = 0
+
+        def __call__(self, params):
+            return [synth_box((n, n, n), 10 * self.seed + z) for z in range(nz)]
+
+    sim = Sim()
+    c = core_mod.CoreCoevalModule([7.0, 8.0, 9.0][:nz], sim, up)
+    lk = lk_mod.Likelihood1DPowerCoeval(n_psbins=5, simulate=True, min_k=0.3, max_k=4.0)
+    chain = chain_mod.build_computation_chain(c, lk)
+    ctxs = []
+    for w in range(nwalk):
+        sim.seed = w + 1
+        ctxs.append(chain.build_model_data())
+    single = [lk.computeLikelihood(lk.reduce_data(ctx)) for ctx in ctxs]
+    monkeypatch.setenv("PS21_STAGE_BYTES", str(2 * n * n * n * 4))  # two cubes per slice
+    lnls, _ = lk.likelihood_batch(ctxs)
+    assert np.allclose(lnls, single, rtol=1e-9, atol=0) and len(set(np.round(lnls, 6))) == nwalk

@@ -298,3 +298,183 @@ def test_random_shape_sweep(mods):
     spec.loader.exec_module(mod)
     fails, worst = mod.sweep(120, 31, mods[0])
     assert fails == 0 and worst < POWER_RTOL
+
+
+# ---------------------------------------------------------------------------------------------------------
+# round 2: the holes VERDICT r1 named
+# ---------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("error_on_model", [True, False])
+def test_noise_and_error_on_model_on_the_device(mods, kpath, tmp_path, error_on_model):
+    """k_finalize's noise^2 / error_on_model=False branches and k_chi2_rows on CUDA (were emulator-only)."""
+    PC.check_noise_and_error_on_model(mods, tmp_path, error_on_model, (32, 32, 128), 48.0, 4, 10, 0.2, 3.0)
+
+
+def test_noise_and_error_on_model_fused_shape(mods, tmp_path):
+    """The same through the fused kernels (128 x 128 x 512 lightcone, two 256-slice chunks)."""
+    PC.check_noise_and_error_on_model(mods, tmp_path, False, (128, 128, 512), 192.0, 2, 12, 0.1, 2.0)
+
+
+def test_coeval_data_sets_follow_boxes_across_staging_slices(mods, kpath, monkeypatch):
+    PC.check_coeval_staging_slices(mods, monkeypatch, n=24, nz=3, nwalk=5)
+
+
+def test_host_pointer_entry_points(mods):
+    """ps21_lnl_host_ptrs (per-walker pinned / pageable buffers) == contiguous host batch == device batch, bitwise."""
+    import torch
+
+    from py21cmmc_b200.plan import get_plan, pinned_empty
+
+    shape = (128, 128, 512)
+    bounds, Ls = [(0, 256), (256, 512)], [(192.0, 192.0, 384.0)] * 2
+    plan = get_plan(shape, bounds, Ls, 20, True, True, False, False, "legacy_1.001", "spherical",
+                    torch.cuda.current_device(), "auto")
+    boxes = [synth_box(shape, s) for s in range(5)]
+    for i in (1, 3):
+        pb = pinned_empty(shape)
+        pb[...] = boxes[i]
+        boxes[i] = pb
+    stack = np.stack(boxes)
+    ref = plan.power_host(stack)
+    data = (ref[0] * np.concatenate(list(plan.kcentres)) ** 3 / (2 * np.pi ** 2)).reshape(1, 2, 20) * 1.2
+    plan.set_data(np.nan_to_num(data), None, np.isfinite(data) & (plan.kcentres[None] > 0.1), 0.15, True)
+    l0, d0, _ = plan.lnl_host(stack, want_delta=True)
+    l1, d1, p1 = plan.lnl_host(boxes, want_delta=True, want_power=True)
+    l2 = plan.lnl_device(torch.from_numpy(stack).cuda()).cpu().numpy()
+    assert np.array_equal(l0, l1) and np.array_equal(l0, l2) and np.all(np.isfinite(l0)) and np.all(l0 < 0)
+    assert np.array_equal(d0, d1, equal_nan=True) and np.array_equal(p1, ref, equal_nan=True)
+
+
+def test_cuda_graph_replay_is_bitwise_identical(mods, kpath):
+    """A step replayed from its captured CUDA graph gives the bits of the directly launched step, is re-captured
+    when the buffers change and follows new data tables (ps21_set_data invalidates the captured launches)."""
+    import torch
+
+    from py21cmmc_b200.plan import PowerPlan
+
+    shape = (128, 128, 512) if kpath == "auto" else (48, 48, 100)
+    nzc = shape[2] // 2
+    L = 1.5 * shape[0]
+    plan = PowerPlan(shape, [(0, nzc), (nzc, shape[2])], [(L, L, 1.5 * nzc)] * 2, 14, device=torch.cuda.current_device(),
+                     path=kpath)
+    t = torch.from_numpy(np.stack([synth_box(shape, s) for s in range(4)])).cuda()
+    pw = plan.power_device(t).cpu().numpy()
+    data = (pw[0] * np.concatenate(list(plan.kcentres)) ** 3 / (2 * np.pi ** 2)).reshape(1, 2, 14)
+    mask = np.isfinite(data)
+    plan.set_data(np.nan_to_num(data), None, mask, 0.15, True)
+    lnl = torch.empty(4, dtype=torch.float64, device="cuda")
+    delta = torch.empty((4, plan.out_per_box), dtype=torch.float64, device="cuda")
+    plan.lnl_device(t, lnl=lnl, delta=delta)
+    want_l, want_d = lnl.cpu().numpy().copy(), delta.cpu().numpy().copy()
+    plan.set_graphs(True)
+    for _ in range(3):
+        lnl.zero_()
+        delta.zero_()
+        plan.lnl_device(t, lnl=lnl, delta=delta)
+        same = (lambda a, b: np.array_equal(a, b, equal_nan=True)) if plan.path == "fused" else \
+            (lambda a, b: np.allclose(a, b, rtol=1e-9, atol=1e-12, equal_nan=True))
+        assert same(lnl.cpu().numpy(), want_l) and same(delta.cpu().numpy(), want_d)
+    st = plan.graph_stats()
+    assert st["captures"] == 1 and st["replays"] == 3
+    assert abs(want_l[0]) < 1e-12 and np.all(want_l[1:] < 0)
+    # other buffers -> another capture; new data tables -> the old graphs are not replayed
+    t2 = t.clone()
+    plan.lnl_device(t2, lnl=lnl)
+    assert plan.graph_stats()["captures"] == 2
+    plan.set_data(np.nan_to_num(data) * 1.5, None, mask, 0.15, True)
+    plan.lnl_device(t, lnl=lnl)
+    assert plan.graph_stats()["captures"] == 3 and lnl.cpu().numpy()[0] < -1e-3
+    plan.set_graphs(False)
+    l_direct = plan.lnl_device(t).cpu().numpy()
+    assert (np.array_equal if plan.path == "fused" else np.allclose)(l_direct, lnl.cpu().numpy())
+    plan.close()
+
+
+def test_config4_512_cube_counts_and_power_elementwise(mods):
+    """512^3 (BASELINE config 4): per-bin mode counts bit-equal to np.bincount(np.digitize(|k|, edges), weights) on the
+    full grid (powerbox's form), and per-bin power against the fp64 oracle on the host (half-spectrum form, which
+    tests/test_oracle.py pins to the full-grid one)."""
+    import torch
+
+    from oracle import ps_oracle as O
+    from py21cmmc_b200.plan import get_plan
+
+    n, L, nb = 512, 768.0, 20
+    plan = get_plan((n, n, n), [(0, n)], [(L, L, L)], nb, True, True, False, False, "legacy_1.001", "spherical",
+                    torch.cuda.current_device(), "auto")
+    freq = [O.fftfreq(n, d=L / n)] * 3
+    kmag = O.magnitude_grid(freq)
+    edges = O.get_bins(nb, kmag, True, "legacy_1.001")
+    assert np.array_equal(edges, plan.edges[0])
+    indx = np.digitize(kmag.ravel(), edges)
+    del kmag
+    w = O.k_weights_coeval((n, n, n), True, False, False)
+    counts = np.bincount(indx, weights=w.ravel(), minlength=nb + 2)[1:-1]
+    del indx, w
+    assert np.array_equal(plan.counts, counts.astype(np.int64))
+    box = synth_box((n, n, n), 21)
+    got = plan.power_host(box)[0]
+    want, sw = O.half_spectrum_power(box, L, edges, (True, False, False))
+    assert np.array_equal(sw.astype(np.int64), plan.counts)
+    assert rel_err(got, want) < POWER_RTOL
+
+
+def test_full_benchmark_lightcone_lnl_vs_oracle(mods):
+    """One whole 256 x 256 x 1024 lightcone (BASELINE config 3 walker) through the plugin chain: Delta^2 of all four
+    chunks and lnL element-wise against the fp64 oracle."""
+    from oracle import ps_oracle as O
+
+    lk_mod, core_mod, chain_mod = mods
+    shape, box_len, nchunks, nb = (256, 256, 1024), 384.0, 4, 20
+    chain, lk, state = PC.make_lightcone_chain(lk_mod, core_mod, chain_mod, shape, box_len, nchunks, nb,
+                                               min_k=0.1, max_k=1.0)
+    assert lk._geometry(chain.build_model_data())[1].path == "fused"
+    cell = box_len / shape[0]
+    data_o = O.reduce_data_lightcone(state["box"], box_len, cell, nchunks, nb)
+    for d, do in zip(lk.data, data_o):
+        assert np.array_equal(d["k"], do["k"]) and rel_err(d["delta"], do["delta"]) < POWER_RTOL
+    state["box"] = synth_box(shape, seed=7)
+    val, blobs = chain([])
+    model_o = O.reduce_data_lightcone(state["box"], box_len, cell, nchunks, nb)
+    lnl_o = O.compute_likelihood(model_o, data_o, None, 0.1, 1.0, 0.15, True)
+    for i, mo in enumerate(model_o):
+        assert rel_err(blobs[f"delta_{i}"], mo["delta"]) < POWER_RTOL
+    assert np.isfinite(lnl_o) and lnl_o < 0 and abs(val - lnl_o) <= 1e-6 * abs(lnl_o), (val, lnl_o)
+    (lb,), _ = lk.likelihood_batch([chain.build_model_data()])
+    assert abs(lb - lnl_o) <= 1e-6 * abs(lnl_o)
+
+
+@pytest.mark.parametrize("shape,L,index", [
+    ((256, 256, 256), (384.0, 384.0, 384.0), -3.0),
+    ((128, 128, 256), (192.0, 192.0, 384.0), -2.0),
+    ((96, 96, 200), (144.0, 144.0, 300.0), -3.0),      # general path
+])
+def test_steep_spectrum_field_vs_fp64_oracle(mods, shape, L, index):
+    """P ~ k^-3 / k^-2 fields (realistic 21-cm slopes): one bin mixes modes of very different power, which is where
+    fp32 partial sums would show (VERDICT r1 weak #8).  Default bins (116 / 73 / 60) and 20 log bins."""
+    from oracle import ps_oracle as O
+    from tests.helpers import power_law_box
+
+    box = power_law_box(shape, index, seed=3)
+    for nb in (20, None):
+        p, k = mods[0].Likelihood1DPowerLightcone.compute_power(box, L, nb)
+        po, ko = O.compute_power_lightcone(box, L, nb)
+        assert np.array_equal(k, ko)
+        assert rel_err(p, po) < POWER_RTOL
+        fin = np.isfinite(po)
+        assert po[fin].max() / po[fin].min() > 1e3    # the spectrum really is steep
+
+
+def test_release_workspace_and_plan_cache_on_device(mods):
+    import torch
+
+    from py21cmmc_b200.plan import get_plan
+
+    plan = get_plan((64, 64, 128), [(0, 128)], [(96.0, 96.0, 192.0)], 10, True, True, False, False, "legacy_1.001",
+                    "spherical", torch.cuda.current_device(), "auto")
+    box = synth_box((64, 64, 128), 2)
+    a = plan.power_host(box)
+    assert plan.info()["workspace_bytes"] > 0
+    free0 = torch.cuda.mem_get_info()[0]
+    plan.release_workspace()
+    assert plan.info()["workspace_bytes"] == 0 and torch.cuda.mem_get_info()[0] >= free0
+    assert np.array_equal(plan.power_host(box), a, equal_nan=True)

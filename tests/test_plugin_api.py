@@ -123,33 +123,9 @@ def test_setup_errors_like_reference(mods, tmp_path):
 
 @pytest.mark.parametrize("error_on_model", [True, False])
 def test_noise_and_error_on_model_match_oracle(mods, tmp_path, error_on_model):
-    state = {"box": synth_box(SHAPE, 0)}
-    data_o = O.reduce_data_lightcone(state["box"], BOX_LEN, BOX_LEN / SHAPE[0], NCHUNKS, NB)
-    dfiles, nfiles, noise = [], [], []
-    rng = np.random.default_rng(1)
-    for i, d in enumerate(data_o):
-        ok = np.isfinite(d["delta"])
-        f = str(tmp_path / f"d{i}.npz")
-        np.savez(f, k=d["k"][ok], delta=d["delta"][ok] * 1.1)  # data on a *different* k grid than the model
-        dfiles.append(f)
-        n = {"k": np.linspace(0.05, 6.0, 9), "errs": rng.uniform(5.0, 50.0, 9)}
-        nf = str(tmp_path / f"n{i}.npz")
-        np.savez(nf, **n)
-        nfiles.append(nf)
-        noise.append(n)
-    chain, lk = make(mods, state, datafile=dfiles, noisefile=nfiles, error_on_model=error_on_model,
-                     model_uncertainty=0.2)
-    chain.setup()
-    state["box"] = synth_box(SHAPE, 5)
-    model = lk.reduce_data(chain.build_model_data())
-    lnl = lk.computeLikelihood(model)
-    model_o = O.reduce_data_lightcone(state["box"], BOX_LEN, BOX_LEN / SHAPE[0], NCHUNKS, NB)
-    data_read = [dict(np.load(f)) for f in dfiles]
-    lnl_o = O.compute_likelihood(model_o, data_read, noise, 0.3, 4.0, 0.2, error_on_model)
-    assert np.isfinite(lnl_o) and abs(lnl - lnl_o) <= LNL_RTOL * abs(lnl_o)
-    # the fused batched path (tables uploaded once) agrees with the per-model call
-    lnls, _ = lk.likelihood_batch([chain.build_model_data()])
-    assert abs(lnls[0] - lnl_o) <= LNL_RTOL * abs(lnl_o)
+    from tests import parity_cases as PC
+
+    PC.check_noise_and_error_on_model(mods, tmp_path, error_on_model, SHAPE, BOX_LEN, NCHUNKS, NB)
 
 
 def test_equality_and_pickle(mods):
@@ -211,31 +187,10 @@ def test_blob_handoff_matches_reference_storage_layout(mods, tmp_path):
 
 
 def test_coeval_data_sets_follow_boxes_across_staging_slices(mods, monkeypatch):
-    """Regression: with several redshifts (data sets) and a host batch staged in several slices, box b must be
-    compared with data set b % nsets whatever slice it travels in."""
-    lk_mod, core_mod, chain_mod = mods
-    n, nz, nwalk = 10, 3, 4
-    up = core_mod.UserParams(BOX_LEN=15.0, HII_DIM=n)
+    """Regression: box b is compared with data set b % nsets whatever staging slice it travels in."""
+    from tests import parity_cases as PC
 
-    class Sim:
-        def __init__(self):
-            self.seed = 0
-
-        def __call__(self, params):
-            return [synth_box((n, n, n), 10 * self.seed + z) for z in range(nz)]
-
-    sim = Sim()
-    c = core_mod.CoreCoevalModule([7.0, 8.0, 9.0], sim, up)
-    lk = lk_mod.Likelihood1DPowerCoeval(n_psbins=5, simulate=True, min_k=0.3, max_k=4.0)
-    chain = chain_mod.build_computation_chain(c, lk)
-    ctxs = []
-    for w in range(nwalk):
-        sim.seed = w + 1
-        ctxs.append(chain.build_model_data())
-    single = [lk.computeLikelihood(lk.reduce_data(ctx)) for ctx in ctxs]
-    monkeypatch.setenv("PS21_STAGE_BYTES", str(2 * n * n * n * 4))  # two cubes per slice -> six slices
-    lnls, _ = lk.likelihood_batch(ctxs)
-    assert np.allclose(lnls, single, rtol=1e-9, atol=0) and len(set(np.round(lnls, 6))) == nwalk
+    PC.check_coeval_staging_slices(mods, monkeypatch)
 
 
 def test_call_batch_composes_with_upper_limit_and_windowed_likelihoods(mods, tmp_path):
