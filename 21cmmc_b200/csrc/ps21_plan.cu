@@ -134,14 +134,27 @@ k_finalize(const double* __restrict__ partials, int slots_max, long long out_per
     const long long box = blockIdx.x;
     const long long set = (box0 + box) % nsets;  // box0: index of this call's first box in the caller's batch
     double chi = 0.0;
-    // gridDim.y > 1 only without lnL (cylindrical spectra have tens of thousands of outputs per box)
-    for (long long i = (long long)blockIdx.y * blockDim.x + threadIdx.x; i < out_per_box;
-         i += (long long)gridDim.y * blockDim.x) {
+    // Many partial-sum slots (fused path: 43-129 per spectrum): one warp per output, lanes over the slots, fixed-order
+    // shuffle tree -- a thread walking 86 slots alone made this kernel 27 us of pure load latency.  Few slots
+    // (cylindrical records have one): one thread per output.  gridDim.y > 1 only without lnL.
+    const bool by_warp = slots_max >= 8;
+    const int lane = threadIdx.x & 31;
+    const long long first = by_warp ? (long long)blockIdx.y * (blockDim.x >> 5) + (threadIdx.x >> 5)
+                                    : (long long)blockIdx.y * blockDim.x + threadIdx.x;
+    const long long stride = by_warp ? (long long)gridDim.y * (blockDim.x >> 5) : (long long)gridDim.y * blockDim.x;
+    for (long long i = first; i < out_per_box; i += stride) {
         int c = 0;
         while (c + 1 < nchunks && chunks[c + 1].out_off <= i) ++c;
         const ChunkDev ch = chunks[c];
         double s = 0.0;
-        for (int sl = 0; sl < ch.nslots; ++sl) s += partials[(box * slots_max + sl) * out_per_box + i];
+        if (by_warp) {
+            for (int sl = lane; sl < ch.nslots; sl += 32) s += partials[(box * slots_max + sl) * out_per_box + i];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+            if (lane != 0) continue;
+        } else {
+            for (int sl = 0; sl < ch.nslots; ++sl) s += partials[(box * slots_max + sl) * out_per_box + i];
+        }
         if (ch.dc_bin >= 0 && ch.out_off + ch.dc_bin == i) {
             // restore the k=0 power removed by the offset subtraction: |F'(0) + N c|^2 - |F'(0)|^2
             const float2 f0 = dc[box * nchunks + c];
