@@ -17,6 +17,7 @@ PS21_MODE_CYLINDRICAL = 1
 PS21_PATH_AUTO = 0
 PS21_PATH_GENERAL = 1
 PS21_PATH_FUSED = 2
+PS21_PATH_TWOPASS = 3
 
 EXPORTS = (
     "ps21_last_error", "ps21_version", "ps21_plan_create", "ps21_plan_destroy", "ps21_plan_info",

@@ -279,6 +279,86 @@ __device__ __forceinline__ void small_dft<32>(float2 (&v)[32]) {
     }
 }
 
+
+// Odd prime radices 7, 11, 13 (lightcone chunk lengths are arbitrary: 2 * 7 * 13 = 182, 2 * 11 * 13 = 286, ...):
+// X_k = v_0 + sum_m (v_m + v_{P-m}) cos(2 pi m k / P) - i (v_m - v_{P-m}) sin(2 pi m k / P),  X_{P-k} = conj-pair form.
+template <int P>
+__device__ __forceinline__ void odd_roots(float (&C)[P], float (&S)[P]);   // cos / sin of 2 pi m / P
+template <>
+__device__ __forceinline__ void odd_roots<7>(float (&C)[7], float (&S)[7]) {
+    C[0] = 1.00000000000000000000f; S[0] = 0.00000000000000000000f;
+    C[1] = 0.62348980185873359439f; S[1] = 0.78183148246802980363f;
+    C[2] = -0.22252093395631433737f; S[2] = 0.97492791218182361934f;
+    C[3] = -0.90096886790241903498f; S[3] = 0.43388373911755823142f;
+    C[4] = -0.90096886790241914600f; S[4] = -0.43388373911755800938f;
+    C[5] = -0.22252093395631458717f; S[5] = -0.97492791218182361934f;
+    C[6] = 0.62348980185873337234f; S[6] = -0.78183148246802991466f;
+}
+template <>
+__device__ __forceinline__ void odd_roots<11>(float (&C)[11], float (&S)[11]) {
+    C[0] = 1.00000000000000000000f; S[0] = 0.00000000000000000000f;
+    C[1] = 0.84125353283118120551f; S[1] = 0.54064081745559755543f;
+    C[2] = 0.41541501300188643508f; S[2] = 0.90963199535451833011f;
+    C[3] = -0.14231483827328500480f; S[3] = 0.98982144188093279524f;
+    C[4] = -0.65486073394528498959f; S[4] = 0.75574957435425826890f;
+    C[5] = -0.95949297361449736865f; S[5] = 0.28173255684142967104f;
+    C[6] = -0.95949297361449747967f; S[6] = -0.28173255684142939348f;
+    C[7] = -0.65486073394528521163f; S[7] = -0.75574957435425815788f;
+    C[8] = -0.14231483827328522684f; S[8] = -0.98982144188093268422f;
+    C[9] = 0.41541501300188604651f; S[9] = -0.90963199535451855215f;
+    C[10] = 0.84125353283118120551f; S[10] = -0.54064081745559744441f;
+}
+template <>
+__device__ __forceinline__ void odd_roots<13>(float (&C)[13], float (&S)[13]) {
+    C[0] = 1.00000000000000000000f; S[0] = 0.00000000000000000000f;
+    C[1] = 0.88545602565320991051f; S[1] = 0.46472317204376850652f;
+    C[2] = 0.56806474673115592289f; S[2] = 0.82298386589365635224f;
+    C[3] = 0.12053668025532300601f; S[3] = 0.99270887409805397272f;
+    C[4] = -0.35460488704253545489f; S[4] = 0.93501624268541483342f;
+    C[5] = -0.74851074817110119231f; S[5] = 0.66312265824079519305f;
+    C[6] = -0.97094181742605201180f; S[6] = 0.23931566428755768339f;
+    C[7] = -0.97094181742605212282f; S[7] = -0.23931566428755743359f;
+    C[8] = -0.74851074817110130333f; S[8] = -0.66312265824079497101f;
+    C[9] = -0.35460488704253589898f; S[9] = -0.93501624268541472240f;
+    C[10] = 0.12053668025532320029f; S[10] = -0.99270887409805397272f;
+    C[11] = 0.56806474673115481266f; S[11] = -0.82298386589365701838f;
+    C[12] = 0.88545602565321002153f; S[12] = -0.46472317204376839550f;
+}
+template <int P>
+__device__ __forceinline__ void small_dft_odd(float2 (&v)[P]) {
+    constexpr int H = (P - 1) / 2;
+    float C[P], S[P];   // literal tables: folded into immediates once the loops below are unrolled
+    odd_roots<P>(C, S);
+    float2 a[H], b[H];
+#pragma unroll
+    for (int m = 1; m <= H; ++m) {
+        a[m - 1] = cadd(v[m], v[P - m]);
+        b[m - 1] = csub(v[m], v[P - m]);
+    }
+    const float2 v0 = v[0];
+    float2 s0 = v0;
+#pragma unroll
+    for (int m = 0; m < H; ++m) s0 = cadd(s0, a[m]);
+    v[0] = s0;
+#pragma unroll
+    for (int k = 1; k <= H; ++k) {
+        float2 re = v0, im = make_float2(0.f, 0.f);
+#pragma unroll
+        for (int m = 1; m <= H; ++m) {
+            re = caxpy(C[(m * k) % P], a[m - 1], re);
+            im = caxpy(S[(m * k) % P], b[m - 1], im);
+        }
+        v[k] = cadd_mi(re, im);       // re - i im
+        v[P - k] = csub_mi(re, im);   // re + i im
+    }
+}
+template <>
+__device__ __forceinline__ void small_dft<7>(float2 (&v)[7]) { small_dft_odd<7>(v); }
+template <>
+__device__ __forceinline__ void small_dft<11>(float2 (&v)[11]) { small_dft_odd<11>(v); }
+template <>
+__device__ __forceinline__ void small_dft<13>(float2 (&v)[13]) { small_dft_odd<13>(v); }
+
 // One Stockham stage of radix R over 2^lc columns (lc = log2 of the tile width; ragged tiles still run all
 // columns of the tile -- columns are independent, the surplus ones are never stored).  Ns = product of the
 // radices already applied.  No integer division: the column split is a shift, j % Ns a multiply-shift.

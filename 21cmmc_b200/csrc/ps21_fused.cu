@@ -26,6 +26,7 @@
 #include <cmath>
 
 #include "ps21_internal.cuh"
+#include "ptx_sm100.cuh"
 #include "../../include/ps21.h"
 
 namespace ps21 {
@@ -73,107 +74,6 @@ struct FusedShape {
     long long cylpart_items = 0;
     float4* tw256 = nullptr;   // w = exp(-2 pi i q / 256) stored as (w.x, w.y, -w.y, w.x) for cmul_tw
 };
-
-// ------------------------------------------------------------------------------------------------
-// PTX helpers: mbarrier + bulk async copy (TMA, 1-D) global -> shared
-// ------------------------------------------------------------------------------------------------
-#ifndef PS21_EMU
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-    uint32_t done;
-    const uint32_t addr = smem_u32(bar);
-    do {
-        asm volatile(
-            "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-            "selp.u32 %0, 1, 0, p;\n\t}"
-            : "=r"(done)
-            : "r"(addr), "r"(parity)
-            : "memory");
-    } while (!done);
-}
-__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                     smem_u32(dst)),
-                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
-                 : "memory");
-}
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-// barrier over `nthreads` threads of the CTA (named barrier `id`, 1..15)
-__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
-    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
-}
-// non-blocking arrival at named barrier `id` (the warps that call named_bar_sync on it wait for `nthreads` arrivals)
-__device__ __forceinline__ void named_bar_arrive(int id, int nthreads) {
-    asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
-}
-// L2 eviction policies: streamed data must not push the (re-used) bin-index table out of L2
-__device__ __forceinline__ uint64_t l2_policy_evict_first() {
-    uint64_t pol;
-    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
-    return pol;
-}
-__device__ __forceinline__ uint64_t l2_policy_evict_last() {
-    uint64_t pol;
-    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
-    return pol;
-}
-__device__ __forceinline__ void bulk_g2s_hint(void* dst, const void* src, uint32_t bytes, uint64_t* bar, uint64_t pol) {
-    asm volatile(
-        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
-            smem_u32(dst)),
-        "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(pol)
-        : "memory");
-}
-
-#else
-// emulated build (tests only): the bulk copy is a synchronous memcpy; the mbarrier is modelled as
-// {pending bytes, arrived flag, phase bit} packed in its 8 bytes
-struct EmuBar {
-    int pending;
-    unsigned short arrived, phase;
-};
-__device__ __forceinline__ void emu_bar_check(EmuBar* b) {
-    if (b->arrived && b->pending == 0) {
-        b->arrived = 0;
-        b->phase ^= 1;
-    }
-}
-__device__ __forceinline__ void mbar_init(uint64_t* bar, int) { *bar = 0; }
-__device__ __forceinline__ void mbar_fence_init() {}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-    EmuBar* b = reinterpret_cast<EmuBar*>(bar);
-    b->pending += (int)bytes;
-    b->arrived = 1;
-    emu_bar_check(b);
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-    EmuBar* b = reinterpret_cast<EmuBar*>(bar);
-    while (b->phase == parity) ps21emu::spin_yield();
-}
-__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
-    std::memcpy(dst, src, bytes);
-    EmuBar* b = reinterpret_cast<EmuBar*>(bar);
-    b->pending -= (int)bytes;
-    emu_bar_check(b);
-}
-__device__ __forceinline__ void fence_proxy_async() {}
-__device__ __forceinline__ void named_bar_sync(int, int) { __syncthreads(); }  // stronger, same result
-__device__ __forceinline__ void named_bar_arrive(int, int) { __syncthreads(); }
-__device__ __forceinline__ uint64_t l2_policy_evict_first() { return 0; }
-__device__ __forceinline__ uint64_t l2_policy_evict_last() { return 0; }
-__device__ __forceinline__ void bulk_g2s_hint(void* dst, const void* src, uint32_t bytes, uint64_t* bar, uint64_t) {
-    bulk_g2s(dst, src, bytes, bar);
-}
-
-#endif
 
 // ------------------------------------------------------------------------------------------------
 // layout of the half-spectrum scratch ("tile order"), per sky-plane size S (S x S x 256 chunks)
@@ -325,25 +225,6 @@ __device__ __forceinline__ void zfft_row(float2* __restrict__ row, int t, float 
         row[m0 + 16 * u] = a[u];
         row[m1 + 16 * u] = b[u];
     }
-}
-
-// untangle of the (even,odd)-packed real FFT for the column pair (p, 128-p), one row.
-// With E = (C_p + conj C_{N-p})/2 and O = (C_p - conj C_{N-p})/(2i):  A_p = E + w^p O,  A_{N-p} = conj(E - w^p O).
-// `wu` is the table entry of  w_256^p * (-i/2), so that  w^p O = wu * (C_p - conj C_{N-p}).
-__device__ __forceinline__ void untangle(float2 ck, float2 cn, float4 wu, float2& a1, float2& a2) {
-#ifdef PS21_PACKED_F32X2
-    const float2 e2 = __ffma2_rn(cn, make_float2(1.f, -1.f), ck);   // 2E
-    const float2 d = __ffma2_rn(cn, make_float2(-1.f, 1.f), ck);    // C_p - conj C_{N-p}
-    const float2 t = cmul_tw(d, wu);
-    a1 = __ffma2_rn(e2, make_float2(0.5f, 0.5f), t);
-    a2 = __ffma2_rn(e2, make_float2(0.5f, -0.5f), __fmul2_rn(t, make_float2(-1.f, 1.f)));
-#else
-    const float2 e2 = make_float2(ck.x + cn.x, ck.y - cn.y);
-    const float2 d = make_float2(ck.x - cn.x, ck.y + cn.y);
-    const float2 t = cmul_tw(d, wu);
-    a1 = make_float2(0.5f * e2.x + t.x, 0.5f * e2.y + t.y);
-    a2 = make_float2(0.5f * e2.x - t.x, -(0.5f * e2.y - t.y));
-#endif
 }
 
 template <int S>

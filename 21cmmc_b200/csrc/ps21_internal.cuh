@@ -68,7 +68,7 @@ struct ShapePlan {
     int g3_tile = 0;   // (k_y,k_z) columns per CTA in the x pass
     int g3_slots = 0;  // CTAs per spectrum in the x pass (= partial-sum slots)
     // fused path (ps21_fused.cu)
-    void* fused = nullptr;
+    void* fused = nullptr;   // FusedShape (path FUSED) or G2Shape (path TWOPASS)
 };
 
 struct DataTables {
@@ -205,6 +205,25 @@ int fused_forward(ps21_plan* p, ShapePlan& sp, const float* d_boxes, long long b
 long long fused_scratch_elems(const ShapePlan& sp, int n0, int n1);
 // allocations fused_forward would need for `nitems` spectra per launch (none may happen while a graph is captured)
 int fused_reserve(ps21_plan* p, ShapePlan& sp, long long nitems);
+
+// generic two-pass path (ps21_g2.cu); returns 0 and sets sp.fused when the shape is supported
+int g2_try_setup(ps21_plan* p, ShapePlan& sp);
+void g2_destroy(ShapePlan& sp);
+int g2_build_lut(ps21_plan* p, int chunk, const double* d_k0sq, const double* d_k1sq, const double* d_k2sq,
+                 const double* d_edges, cudaStream_t st);
+int g2_forward(ps21_plan* p, ShapePlan& sp, const float* d_boxes, long long batch_stride, long long item0,
+               long long nitems, cudaStream_t st);
+long long g2_scratch_elems(const ShapePlan& sp);
+
+// exact n / d for 0 <= n < 65536, 1 <= d < 65536: q = (n * mul) >> shift with mul = ceil(2^(16+L) / d), L = ceil(log2 d)
+inline FastDiv make_fastdiv(int d) {
+    int L = 0;
+    while ((1 << L) < d) ++L;
+    FastDiv f;
+    f.shift = 16 + L;
+    f.mul = (unsigned)(((1ull << f.shift) + d - 1) / d);
+    return f;
+}
 
 // item -> (box, chunk) for a shape whose chunk-id list is `ids[0..nper)`
 struct ItemMap {

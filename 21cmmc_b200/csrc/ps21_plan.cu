@@ -37,16 +37,6 @@ static int invalid(const std::string& msg) {
     return PS21_ERR_INVALID;
 }
 
-static FastDiv make_fastdiv(int d) {
-    // q = (n * mul) >> shift is exact for 0 <= n < 2^16, 1 <= d < 2^16 (mul = ceil(2^(16+L) / d), L = ceil(log2 d))
-    int L = 0;
-    while ((1 << L) < d) ++L;
-    FastDiv f;
-    f.shift = 16 + L;
-    f.mul = (unsigned)(((1ull << f.shift) + d - 1) / d);
-    return f;
-}
-
 static FftFactors factorize(int n, bool allow32) {
     FftFactors f{};
     f.n = n;
@@ -318,12 +308,24 @@ static int ensure_scratch(ps21_plan* p, long long want_elems) {
     return PS21_OK;
 }
 
+static long long spectrum_elems(const ps21_plan* p, const ShapePlan& sp) {
+    if (sp.path == PS21_PATH_FUSED) return fused_scratch_elems(sp, p->n0, p->n1);
+    if (sp.path == PS21_PATH_TWOPASS) return g2_scratch_elems(sp);
+    return (long long)p->n0 * p->n1 * sp.nh;
+}
+
+static int forward_any(ps21_plan* p, ShapePlan& sp, const float* d_boxes, long long batch_stride, long long i0,
+                       long long n, cudaStream_t st) {
+    if (sp.path == PS21_PATH_FUSED) return fused_forward(p, sp, d_boxes, batch_stride, i0, n, st);
+    if (sp.path == PS21_PATH_TWOPASS) return g2_forward(p, sp, d_boxes, batch_stride, i0, n, st);
+    return general_forward(p, sp, d_boxes, batch_stride, i0, n, st);
+}
+
 // spectra of shape `sp` per scratch slice for a batch of `batch` boxes (equal slices: 256 spectra with room for
 // 121 run as 86 + 85 + 85, not 121 + 121 + 14)
 static long long slice_items(const ps21_plan* p, const ShapePlan& sp, long long batch, long long* spec_out) {
     const long long total = batch * (long long)sp.chunks.size();
-    const long long spec = (sp.path == PS21_PATH_FUSED) ? fused_scratch_elems(sp, p->n0, p->n1)
-                                                         : (long long)p->n0 * p->n1 * sp.nh;
+    const long long spec = spectrum_elems(p, sp);
     long long per = p->workspace_cap / (spec * (long long)sizeof(float2));
     if (per < 1) per = 1;
     if (per > 32768) per = 32768;
@@ -348,8 +350,7 @@ static int issue_launches(ps21_plan* p, const float* d_boxes, long long batch, l
         const long long per = slice_items(p, sp, batch, nullptr);
         for (long long i0 = 0; i0 < total; i0 += per) {
             const long long n = (total - i0 < per) ? (total - i0) : per;
-            rc = (sp.path == PS21_PATH_FUSED) ? fused_forward(p, sp, d_boxes, batch_stride, i0, n, st)
-                                              : general_forward(p, sp, d_boxes, batch_stride, i0, n, st);
+            rc = forward_any(p, sp, d_boxes, batch_stride, i0, n, st);
             if (rc) return rc;
         }
     }
@@ -503,7 +504,8 @@ int ps21_plan_destroy(ps21_plan* p) {
         free_dev(sp.tw_y);
         free_dev(sp.tw_x);
         free_dev(sp.d_chunks);
-        fused_destroy(sp);
+        if (sp.path == PS21_PATH_TWOPASS) g2_destroy(sp);
+        else fused_destroy(sp);
     }
     for (size_t i = 0; i < p->d_lut.size(); ++i)
         if (i < p->lut_owned.size() && p->lut_owned[i]) free_dev(p->d_lut[i]);
@@ -685,11 +687,18 @@ int ps21_plan_create(const ps21_desc* d, ps21_plan** out) {
         if ((rc = upload_twiddles(d->n0, &sp.tw_x))) return fail(rc);
         PS21_CUDA(cudaMalloc((void**)&sp.d_chunks, sizeof(int) * sp.chunks.size()));
         PS21_CUDA(cudaMemcpy(sp.d_chunks, sp.chunks.data(), sizeof(int) * sp.chunks.size(), cudaMemcpyHostToDevice));
+        // fastest first: the hand-tuned fused kernels (256^2 / 128^2 planes, 256-slice chunks), then the generic
+        // two-pass kernels, then the three-pass general path (any size)
         sp.path = PS21_PATH_GENERAL;
-        if (d->path != PS21_PATH_GENERAL && fused_try_setup(p, sp) == 0)
+        if ((d->path == PS21_PATH_AUTO || d->path == PS21_PATH_FUSED) && fused_try_setup(p, sp) == 0)
             sp.path = PS21_PATH_FUSED;
         if (d->path == PS21_PATH_FUSED && sp.path != PS21_PATH_FUSED)
             return fail(invalid("fused path requested but this shape/alignment is not supported by it: " + g_err));
+        if (sp.path == PS21_PATH_GENERAL && (d->path == PS21_PATH_AUTO || d->path == PS21_PATH_TWOPASS) &&
+            !(d->path == PS21_PATH_AUTO && std::getenv("PS21_NO_TWOPASS")) && g2_try_setup(p, sp) == 0)
+            sp.path = PS21_PATH_TWOPASS;
+        if (d->path == PS21_PATH_TWOPASS && sp.path != PS21_PATH_TWOPASS)
+            return fail(invalid("two-pass path requested but this shape is not supported by it: " + g_err));
         const int nb_out = p->chunks[sp.chunks[0]].nbins_out;
         auto none = [](int) { return (size_t)0; };
         sp.g1_cols = pick_tile(sp.nz, none);
@@ -714,9 +723,9 @@ int ps21_plan_create(const ps21_desc* d, ps21_plan** out) {
         sp.g3_slots = (int)(ntiles < cap ? ntiles : cap);
         long long spec = (long long)d->n0 * d->n1 * sp.nh;
         int nslots = sp.g3_slots;
-        if (sp.path == PS21_PATH_FUSED) {
-            spec = fused_scratch_elems(sp, d->n0, d->n1);
-            nslots = p->chunks[sp.chunks[0]].nslots;  // set by fused_try_setup
+        if (sp.path != PS21_PATH_GENERAL) {
+            spec = spectrum_elems(p, sp);
+            nslots = p->chunks[sp.chunks[0]].nslots;  // set by fused_try_setup / g2_try_setup
         }
         for (int c : sp.chunks) p->chunks[c].nslots = nslots;
         if (nslots > p->slots_max) p->slots_max = nslots;
@@ -767,8 +776,8 @@ int ps21_plan_create(const ps21_desc* d, ps21_plan** out) {
                 continue;
             }
             p->lut_owned[c] = 1;
-            const long long spec = (sp.path == PS21_PATH_FUSED) ? fused_scratch_elems(sp, d->n0, d->n1)
-                                                                 : general_lut_elems(d->n0, d->n1, sp.nh, sp.g3_tile);
+            const long long spec = (sp.path != PS21_PATH_GENERAL) ? spectrum_elems(p, sp)
+                                                                   : general_lut_elems(d->n0, d->n1, sp.nh, sp.g3_tile);
             if (cudaMalloc((void**)&p->d_lut[c], sizeof(uint16_t) * spec) != cudaSuccess) {
                 cudaGetLastError();
                 set_error("cannot allocate bin-index table");
@@ -776,8 +785,9 @@ int ps21_plan_create(const ps21_desc* d, ps21_plan** out) {
                 break;
             }
             const double* e = ded + (long long)c * (d->nbins + 1);
-            rc = (sp.path == PS21_PATH_FUSED) ? fused_build_lut(p, c, dk0, dk1, dk2 + k2offs[c], e, 0)
-                                              : general_build_lut(p, c, dk0, dk1, dk2 + k2offs[c], e, 0);
+            rc = (sp.path == PS21_PATH_FUSED)     ? fused_build_lut(p, c, dk0, dk1, dk2 + k2offs[c], e, 0)
+                 : (sp.path == PS21_PATH_TWOPASS) ? g2_build_lut(p, c, dk0, dk1, dk2 + k2offs[c], e, 0)
+                                                  : general_build_lut(p, c, dk0, dk1, dk2 + k2offs[c], e, 0);
         }
         cudaError_t se = cudaDeviceSynchronize();
         for (int c = 0; c < d->nchunks && se == cudaSuccess; ++c)

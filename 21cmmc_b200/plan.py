@@ -31,7 +31,7 @@ class PowerPlan:
     lengths : list of (L0, L1, L2_c) per chunk, Mpc
     nbins, log_bins, ignore_* : as ``compute_power`` (likelihood.py:734-743)
     edge_rule : top-edge rule of the installed powerbox generation ("legacy_1.001" | "inscribed")
-    mode : "spherical" | "cylindrical";  path : "auto" | "general" | "fused"
+    mode : "spherical" | "cylindrical";  path : "auto" | "general" | "fused" | "twopass"
     """
 
     def __init__(self, shape, chunk_bounds, lengths, nbins=None, log_bins=True, ignore_kperp_zero=True,
@@ -97,7 +97,7 @@ class PowerPlan:
         d.mode = _capi.PS21_MODE_CYLINDRICAL if cyl else _capi.PS21_MODE_SPHERICAL
         d.device = self.device
         d.path = {"auto": _capi.PS21_PATH_AUTO, "general": _capi.PS21_PATH_GENERAL,
-                  "fused": _capi.PS21_PATH_FUSED}[path]
+                  "fused": _capi.PS21_PATH_FUSED, "twopass": _capi.PS21_PATH_TWOPASS}[path]
         d.workspace_bytes = int(workspace_bytes)
         h = C.c_void_p()
         _capi.check(self._lib.ps21_plan_create(C.byref(d), C.byref(h)))
@@ -161,7 +161,7 @@ class PowerPlan:
 
     @property
     def path(self):
-        return {1: "general", 2: "fused"}[self.info()["path_of_chunk0"]]
+        return {1: "general", 2: "fused", 3: "twopass"}[self.info()["path_of_chunk0"]]
 
     def chunk_counts(self, c):
         return self._chunk_view(self.counts, c)

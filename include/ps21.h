@@ -36,9 +36,11 @@ extern "C" {
 #define PS21_MODE_SPHERICAL 0     /* 1-D |k| bins: get_power(..., res_ndim=None) */
 #define PS21_MODE_CYLINDRICAL 1   /* (k_perp bin, k_par) : get_power(..., res_ndim=2) */
 
-#define PS21_PATH_AUTO 0          /* fused two-pass kernels when the shape allows, else general */
+#define PS21_PATH_AUTO 0          /* fused kernels when the shape allows, else the generic two-pass ones, else general */
 #define PS21_PATH_GENERAL 1       /* three-pass mixed-radix path (any size) */
 #define PS21_PATH_FUSED 2         /* fail plan creation unless the fused path applies */
+#define PS21_PATH_TWOPASS 3       /* generic two-pass kernels (any axes that factor into radices <= 32 / primes <= 13);
+                                     fail plan creation when the shape is not supported */
 
 typedef struct ps21_plan ps21_plan;
 
@@ -74,7 +76,7 @@ typedef struct ps21_desc {
 
 typedef struct ps21_info {
     int32_t nshapes;              /* distinct chunk lengths */
-    int32_t path_of_chunk0;       /* PS21_PATH_GENERAL or PS21_PATH_FUSED actually chosen for chunk 0 */
+    int32_t path_of_chunk0;       /* PS21_PATH_GENERAL / _FUSED / _TWOPASS actually chosen for chunk 0 */
     int64_t out_per_box;          /* doubles of power per box: sum_c nbins_out_c */
     int64_t workspace_bytes;      /* scratch currently allocated */
     int64_t alg_bytes_per_box;    /* algorithmic HBM bytes per box: sum_c 4N_c + 16 N_h,c */

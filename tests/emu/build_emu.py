@@ -13,7 +13,7 @@ LIB = os.path.join(HERE, "libps21_emu.so")
 def build(force=False):
     if os.environ.get("PS21_EMU_LIBRARY"):   # e.g. an AddressSanitizer build of the same sources
         return os.environ["PS21_EMU_LIBRARY"]
-    srcs = [os.path.join(CSRC, f) for f in ("ps21_plan.cu", "ps21_general.cu", "ps21_fused.cu")]
+    srcs = [os.path.join(CSRC, f) for f in ("ps21_plan.cu", "ps21_general.cu", "ps21_fused.cu", "ps21_g2.cu")]
     deps = srcs + glob.glob(os.path.join(CSRC, "*.cuh")) + glob.glob(os.path.join(HERE, "cuda_emu.*")) + [
         os.path.join(ROOT, "include", "ps21.h")]
     if not force and os.path.exists(LIB) and all(os.path.getmtime(d) <= os.path.getmtime(LIB) for d in deps):

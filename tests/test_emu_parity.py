@@ -112,3 +112,37 @@ def test_lnl_before_data_is_a_state_error(mods):
     with pytest.raises(ValueError):
         pl.power_host(np.zeros((1, 8, 8, 4), np.float32))
     pl.close()
+
+
+@pytest.mark.parametrize("shape,L,nb,log,flags", [
+    ((16, 16, 32), (24.0, 24.0, 48.0), 8, True, (True, False, False)),
+    ((32, 32, 20), (48.0, 48.0, 30.0), 6, False, (False, False, False)),   # DC binned
+    ((40, 40, 40), (60.0, 60.0, 60.0), 9, True, (True, True, False)),      # 40 = 8 * 5
+    ((24, 24, 28), (36.0, 36.0, 42.0), 7, True, (True, False, True)),      # nz / 2 = 14 = 2 * 7
+    ((48, 48, 52), (72.0, 72.0, 78.0), None, True, (True, False, False)),  # 2 * 13
+    ((80, 80, 44), (120.0, 120.0, 66.0), 50, False, (True, False, False)), # 2 * 11, 50 bins: 4-lane-group bin columns
+    ((64, 64, 16), (96.0, 96.0, 24.0), 10, True, (True, False, False)),    # R2 = 4, x = 8 * 8
+    ((200, 200, 8), (300.0, 300.0, 12.0), 20, True, (True, False, False)), # config-2 sky plane: y 50 x 4, x = 8 * 25
+])
+def test_generic_two_pass_kernels(mods, shape, L, nb, log, flags):
+    """ps21_g2.cu (in-place digit-reversed transforms, position-defined tiles) on the emulated device vs the oracle."""
+    from py21cmmc_b200.plan import get_plan
+
+    mods[0].set_defaults(kernel_path="twopass")
+    try:
+        PC.check_compute_power(mods[0], shape, L, nb, log, flags)
+    finally:
+        mods[0].set_defaults(kernel_path="auto")
+
+
+def test_two_pass_rejects_what_it_cannot_factor(mods):
+    from py21cmmc_b200 import Ps21Error
+    from py21cmmc_b200.plan import PowerPlan
+    from py21cmmc_b200 import _capi
+
+    for shape in ((16, 16, 34), (15, 15, 16), (16, 16, 17)):   # 17 prime, odd plane, odd chunk
+        with pytest.raises(Ps21Error):
+            PowerPlan(shape, [(0, shape[2])], [(24.0, 24.0, 30.0)], 4, path="twopass", library=_capi.LIB_PATH)
+    pl = PowerPlan((16, 16, 34), [(0, 34)], [(24.0, 24.0, 51.0)], 4, path="auto", library=_capi.LIB_PATH)
+    assert pl.path == "general"
+    pl.close()

@@ -478,3 +478,63 @@ def test_release_workspace_and_plan_cache_on_device(mods):
     plan.release_workspace()
     assert plan.info()["workspace_bytes"] == 0 and torch.cuda.mem_get_info()[0] >= free0
     assert np.array_equal(plan.power_host(box), a, equal_nan=True)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# generic two-pass kernels (ps21_g2.cu)
+# ---------------------------------------------------------------------------------------------------------
+TWOPASS_CASES = [
+    ((200, 200, 200), (300.0, 300.0, 300.0), 20, True, (True, False, False)),      # BASELINE config 2 cube
+    ((200, 200, 200), (300.0, 300.0, 300.0), None, True, (True, False, False)),    # default 90 bins: group bin mode
+    ((256, 256, 250), (384.0, 384.0, 375.0), 20, True, (True, False, False)),      # 250-slice chunk: M = 125 = 5^3
+    ((256, 256, 300), (384.0, 384.0, 450.0), 24, False, (False, False, False)),    # linear bins, DC binned
+    ((128, 128, 182), (192.0, 192.0, 273.0), 16, True, (True, True, False)),       # M = 91 = 7 * 13
+    ((512, 512, 16), (768.0, 768.0, 24.0), 20, True, (True, False, False)),        # 512^2 plane: R2 = 8, three x stages
+    ((64, 64, 44), (96.0, 96.0, 66.0), 12, True, (True, False, True)),             # M = 22 = 2 * 11
+    ((100, 100, 100), (150.0, 150.0, 150.0), 15, True, (True, False, False)),      # 100 = 4 * 25
+    ((400, 400, 20), (600.0, 600.0, 30.0), 18, True, (True, False, False)),        # 400 = 8 * 2 * 25
+]
+
+
+@pytest.mark.parametrize("shape,L,nb,log,flags", TWOPASS_CASES)
+def test_twopass_path_vs_oracle(mods, shape, L, nb, log, flags):
+    import torch
+
+    from py21cmmc_b200.plan import get_plan
+
+    mods[0].set_defaults(kernel_path="twopass")
+    try:
+        PC.check_compute_power(mods[0], shape, L, nb, log, flags, seed=13)
+        nbins = nb if nb is not None else int(np.prod(shape) ** (1.0 / 3) / 2.2)
+        plan = get_plan(shape, [(0, shape[2])], [L], nbins, log, *flags, "legacy_1.001", "spherical",
+                        torch.cuda.current_device(), "twopass")
+        assert plan.path == "twopass"
+        t = torch.from_numpy(np.stack([synth_box(shape, s) for s in (1, 2)])).cuda()
+        a = plan.power_device(t).cpu().numpy()
+        assert np.array_equal(a, plan.power_device(t).cpu().numpy(), equal_nan=True)          # bitwise reproducible
+        assert np.array_equal(a[1], plan.power_device(t[1:2].contiguous()).cpu().numpy()[0], equal_nan=True)
+    finally:
+        mods[0].set_defaults(kernel_path="auto")
+
+
+def test_auto_prefers_two_pass_kernels_and_falls_back(mods):
+    import torch
+
+    from py21cmmc_b200.plan import get_plan
+
+    dev = torch.cuda.current_device()
+    mk = lambda shape, L: get_plan(shape, [(0, shape[2])], [L], 12, True, True, False, False, "legacy_1.001",
+                                   "spherical", dev, "auto")
+    assert mk((200, 200, 200), (300.0,) * 3).path == "twopass"
+    assert mk((256, 256, 256), (384.0,) * 3).path == "fused"
+    assert mk((64, 64, 334), (96.0, 96.0, 501.0)).path == "general"     # 334 / 2 = 167 is prime
+    assert mk((35, 35, 36), (52.5, 52.5, 54.0)).path == "general"       # odd sky plane
+    with pytest.raises(Exception):
+        get_plan((35, 35, 36), [(0, 36)], [(52.5, 52.5, 54.0)], 12, True, True, False, False, "legacy_1.001",
+                 "spherical", dev, "twopass")
+
+
+def test_twopass_lightcone_with_unequal_chunks(mods):
+    """A 128 x 128 x 500 lightcone in 3 chunks (167, 167, 166 slices): the odd chunks take the general path, the even
+    one the two-pass kernels, inside one plan; lnL against the oracle."""
+    PC.check_lightcone_likelihood(*mods, shape=(64, 64, 500), box_len=96.0, nchunks=3, nb=12, min_k=0.2, max_k=3.0)
