@@ -260,8 +260,8 @@ def test_full_size_properties(mods, kpath):
 
 
 def test_config4_512_cube_properties(mods):
-    """512^3 coeval cube (BASELINE config 4 shape, general path): Parseval with every mode weighted, bit-equal
-    counts against the closed form, batch invariance.  (The fp64 oracle would need ~10 GB and a minute here.)"""
+    """512^3 coeval cube (BASELINE config 4 shape; two-pass kernels, and the general path for comparison): Parseval
+    with every mode weighted, bit-equal counts, batch invariance."""
     import torch
 
     from py21cmmc_b200.plan import get_plan
@@ -270,7 +270,10 @@ def test_config4_512_cube_properties(mods):
     dev = torch.cuda.current_device()
     plan = get_plan((n, n, n), [(0, n)], [(L, L, L)], 20, False, False, False, False, "legacy_1.001", "spherical",
                     dev, "auto")
-    assert plan.path == "general" and int(plan.counts.sum()) == n ** 3
+    assert plan.path == "twopass" and int(plan.counts.sum()) == n ** 3
+    pgen = get_plan((n, n, n), [(0, n)], [(L, L, L)], 20, False, False, False, False, "legacy_1.001", "spherical",
+                    dev, "general")
+    assert pgen.path == "general" and np.array_equal(pgen.counts, plan.counts)
     g = torch.Generator(device="cuda").manual_seed(5)
     boxes = torch.randn((2, n, n, n), generator=g, device="cuda", dtype=torch.float32) * 10 + 20
     p = plan.power_device(boxes).cpu().numpy()
@@ -279,7 +282,9 @@ def test_config4_512_cube_properties(mods):
         got = float(np.nansum(p[b] * plan.counts))
         assert abs(got / expect - 1) < 2e-6
     one = plan.power_device(boxes[1:2].contiguous()).cpu().numpy()[0]
-    assert np.allclose(one, p[1], rtol=1e-12, atol=0, equal_nan=True)
+    assert np.array_equal(one, p[1], equal_nan=True)          # fixed-order reductions: bitwise
+    assert rel_err(pgen.power_device(boxes[:1].contiguous()).cpu().numpy()[0], p[0]) < 2e-6
+    pgen.release_workspace()
     # log bins with the default masks: white noise gives sigma^2 V / N in every well-populated bin
     plan2 = get_plan((n, n, n), [(0, n)], [(L, L, L)], 20, True, True, False, False, "legacy_1.001", "spherical",
                      dev, "auto")

@@ -304,3 +304,82 @@ def test_plan_cache_is_bounded(mods, monkeypatch):
     assert np.isfinite(want).any()
     assert plan_mod.get_plan((8, 8, 14), [(0, 14)], [(12.0, 12.0, 21.0)], 4) is plans[3]
     plan_mod.clear_plans()
+
+
+def _seed_chain(mods, prior_max=50.0):
+    from py21cmmc_b200.chain import Params
+
+    lk_mod, core_mod, chain_mod = mods
+    up = core_mod.UserParams(BOX_LEN=BOX_LEN, HII_DIM=SHAPE[0])
+
+    class SeedSim:
+        def __call__(self, params):
+            return synth_box(SHAPE, int(round(params.seed)) if len(params) else 0)
+
+    c = core_mod.CoreLightConeModule(SeedSim(), up)
+    lk = lk_mod.Likelihood1DPowerLightcone(nchunks=NCHUNKS, n_psbins=NB, simulate=True, min_k=0.3, max_k=4.0)
+    return chain_mod.build_computation_chain(c, lk, params=Params(("seed", [0.0, 0.0, prior_max, 1.0])))
+
+
+def test_vectorised_sampler_entry_points_and_half_ensembles(mods):
+    """zeus ``vectorize=True`` / UltraNest ``vectorized=True`` hand all points of a step to the log-probability at
+    once (mcmc.py:495-511, 517-545); emcee's stretch move evaluates half the ensemble per call (ensemble.py:166-170)."""
+    from py21cmmc_b200.walkers import BatchedWalkerPool, ultranest_prior_transform, vectorized_log_prob
+
+    chain = _seed_chain(mods)
+    f = vectorized_log_prob(chain)
+    P = np.array([[1.0], [2.0], [77.0], [3.0], [4.0]])      # 77: outside the prior -> -inf, cores not run
+    lnl = f(P)
+    assert lnl.shape == (5,) and lnl[2] == -np.inf and np.all(np.isfinite(np.delete(lnl, 2)))
+    for i in (0, 1, 3, 4):
+        one = chain(list(P[i]))[0]                            # chi^2 summed per chunk there, in one tree here
+        assert abs(lnl[i] - one) <= 1e-12 * abs(one)
+    assert f(P[1]) == lnl[1]                                  # a single point works too
+    # zeus with blobs_dtype: (lnL, structured rows)
+    fb = vectorized_log_prob(chain, with_blobs=True)
+    l2, blobs = fb(P)
+    assert np.array_equal(l2, lnl) and blobs.shape == (5,) and np.all(np.isnan(blobs["delta_0"][2]))
+    # (Delta^2 = P k^3 / 2 pi^2 is formed on the device in the batch, by NumPy in the single call: last bits may differ)
+    assert np.allclose(blobs["delta_1"][3], chain([3.0])[1]["delta_1"], rtol=1e-14, atol=0, equal_nan=True)
+    # half-ensemble batches of the stretch move: 5 walkers -> halves of 2 and 3 through the pool interface
+    pool = BatchedWalkerPool(chain)
+    halfk = len(P) // 2
+    first = pool.map(None, [list(p) for p in P[:halfk]])
+    second = pool.map(None, [list(p) for p in P[halfk:]])
+    assert [r[0] for r in first + second] == list(lnl)
+    # UltraNest prior transform (mcmc.py:533-543), vectorised
+    t = ultranest_prior_transform(chain.params)(np.array([[0.0], [0.5], [1.0]]))
+    assert np.array_equal(t, np.array([[0.0], [25.0], [50.0]]))
+    assert np.all(np.isfinite(vectorized_log_prob(chain)(t[1:2])))
+
+
+def test_hdf_storage_layout_contract(mods, tmp_path):
+    """The dataset layout of the reference's HDFStorage (cosmoHammer.py:60-105, 208-295); a real file when h5py is
+    importable, the shape / dtype contract otherwise."""
+    from py21cmmc_b200.walkers import HDFBlobStorage, blob_dtype, blobs_to_structured
+
+    chain = _seed_chain(mods)
+    res = chain.call_batch([[1.0], [2.0], [3.0]])
+    blobs = [r[1] for r in res]
+    lay = HDFBlobStorage.layout(3, 1, blobs[0])
+    assert lay["chain"] == ((0, 3, 1), (None, 3, 1), np.dtype(np.float64))
+    assert lay["accepted"][2] == np.dtype(int) and lay["trial_log_prob"][1] == (None, 3)
+    assert lay["blobs"][2] == blob_dtype(blobs[0]) and lay["blobs"][2]["delta_0"].shape == (NB,)
+    rows = blobs_to_structured(blobs, lay["blobs"][2])
+    assert rows.shape == (3,) and np.array_equal(rows["k_2"][1], blobs[1]["k_2"])
+    try:
+        import h5py
+    except ImportError:
+        with pytest.raises(ImportError):
+            HDFBlobStorage(str(tmp_path / "x.h5"))
+        return
+    st = HDFBlobStorage(str(tmp_path / "x.h5"))
+    st.reset(3, chain.params)
+    coords = np.array([[1.0], [2.0], [3.0]])
+    for it in range(2):
+        st.grow(1, blobs[0])
+        st.save_step(coords, [r[0] for r in res], blobs, coords, [r[0] for r in res], [True] * 3)
+    with h5py.File(str(tmp_path / "x.h5")) as f:
+        g = f["sample_0"]
+        assert g.attrs["iteration"] == 2 and g["blobs"].shape == (2, 3) and g["chain"].shape == (2, 3, 1)
+        assert np.array_equal(g["blobs"]["delta_0"][1, 2], blobs[2]["delta_0"], equal_nan=True)
