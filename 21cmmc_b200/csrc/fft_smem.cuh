@@ -280,6 +280,114 @@ __device__ __forceinline__ void small_dft<32>(float2 (&v)[32]) {
 }
 
 
+
+// Composite radices 6, 9, 10, 12, 15 (two-factor Cooley-Tukey in registers): i = j + B i2, k = q + A p,
+// w_N^(ik) = w_N^(jq) w_B^(jp) w_A^(i2 q).  They keep 100 = 10 * 10, 50 = 5 * 10, 150 = 10 * 15 ... at two stages.
+template <int N>
+__device__ __forceinline__ void lit_roots(float (&C)[N], float (&S)[N]);   // cos / sin of 2 pi m / N
+template <>
+__device__ __forceinline__ void lit_roots<6>(float (&C)[6], float (&S)[6]) {
+    C[0] = 1.00000000000000000000f; S[0] = 0.00000000000000000000f;
+    C[1] = 0.50000000000000011102f; S[1] = 0.86602540378443859659f;
+    C[2] = -0.49999999999999977796f; S[2] = 0.86602540378443870761f;
+    C[3] = -1.00000000000000000000f; S[3] = 0.00000000000000012246f;
+    C[4] = -0.50000000000000044409f; S[4] = -0.86602540378443837454f;
+    C[5] = 0.50000000000000011102f; S[5] = -0.86602540378443859659f;
+}
+template <>
+__device__ __forceinline__ void lit_roots<9>(float (&C)[9], float (&S)[9]) {
+    C[0] = 1.00000000000000000000f; S[0] = 0.00000000000000000000f;
+    C[1] = 0.76604444311897801345f; S[1] = 0.64278760968653925190f;
+    C[2] = 0.17364817766693041445f; S[2] = 0.98480775301220802032f;
+    C[3] = -0.49999999999999977796f; S[3] = 0.86602540378443870761f;
+    C[4] = -0.93969262078590831688f; S[4] = 0.34202014332566887944f;
+    C[5] = -0.93969262078590842791f; S[5] = -0.34202014332566865740f;
+    C[6] = -0.50000000000000044409f; S[6] = -0.86602540378443837454f;
+    C[7] = 0.17364817766692997036f; S[7] = -0.98480775301220813134f;
+    C[8] = 0.76604444311897779141f; S[8] = -0.64278760968653958496f;
+}
+template <>
+__device__ __forceinline__ void lit_roots<10>(float (&C)[10], float (&S)[10]) {
+    C[0] = 1.00000000000000000000f; S[0] = 0.00000000000000000000f;
+    C[1] = 0.80901699437494745126f; S[1] = 0.58778525229247313710f;
+    C[2] = 0.30901699437494745126f; S[2] = 0.95105651629515353118f;
+    C[3] = -0.30901699437494734024f; S[3] = 0.95105651629515364220f;
+    C[4] = -0.80901699437494734024f; S[4] = 0.58778525229247324813f;
+    C[5] = -1.00000000000000000000f; S[5] = 0.00000000000000012246f;
+    C[6] = -0.80901699437494756229f; S[6] = -0.58778525229247302608f;
+    C[7] = -0.30901699437494756229f; S[7] = -0.95105651629515353118f;
+    C[8] = 0.30901699437494722922f; S[8] = -0.95105651629515364220f;
+    C[9] = 0.80901699437494734024f; S[9] = -0.58778525229247335915f;
+}
+template <>
+__device__ __forceinline__ void lit_roots<12>(float (&C)[12], float (&S)[12]) {
+    C[0] = 1.00000000000000000000f; S[0] = 0.00000000000000000000f;
+    C[1] = 0.86602540378443870761f; S[1] = 0.49999999999999994449f;
+    C[2] = 0.50000000000000011102f; S[2] = 0.86602540378443859659f;
+    C[3] = 0.00000000000000006123f; S[3] = 1.00000000000000000000f;
+    C[4] = -0.49999999999999977796f; S[4] = 0.86602540378443870761f;
+    C[5] = -0.86602540378443870761f; S[5] = 0.49999999999999994449f;
+    C[6] = -1.00000000000000000000f; S[6] = 0.00000000000000012246f;
+    C[7] = -0.86602540378443881863f; S[7] = -0.49999999999999972244f;
+    C[8] = -0.50000000000000044409f; S[8] = -0.86602540378443837454f;
+    C[9] = -0.00000000000000018370f; S[9] = -1.00000000000000000000f;
+    C[10] = 0.50000000000000011102f; S[10] = -0.86602540378443859659f;
+    C[11] = 0.86602540378443837454f; S[11] = -0.50000000000000044409f;
+}
+template <>
+__device__ __forceinline__ void lit_roots<15>(float (&C)[15], float (&S)[15]) {
+    C[0] = 1.00000000000000000000f; S[0] = 0.00000000000000000000f;
+    C[1] = 0.91354545764260086660f; S[1] = 0.40673664307580015276f;
+    C[2] = 0.66913060635885823757f; S[2] = 0.74314482547739413310f;
+    C[3] = 0.30901699437494745126f; S[3] = 0.95105651629515353118f;
+    C[4] = -0.10452846326765333207f; S[4] = 0.99452189536827340088f;
+    C[5] = -0.49999999999999977796f; S[5] = 0.86602540378443870761f;
+    C[6] = -0.80901699437494734024f; S[6] = 0.58778525229247324813f;
+    C[7] = -0.97814760073380568883f; S[7] = 0.20791169081775931482f;
+    C[8] = -0.97814760073380568883f; S[8] = -0.20791169081775906502f;
+    C[9] = -0.80901699437494756229f; S[9] = -0.58778525229247302608f;
+    C[10] = -0.50000000000000044409f; S[10] = -0.86602540378443837454f;
+    C[11] = -0.10452846326765423413f; S[11] = -0.99452189536827328986f;
+    C[12] = 0.30901699437494722922f; S[12] = -0.95105651629515364220f;
+    C[13] = 0.66913060635885845961f; S[13] = -0.74314482547739402207f;
+    C[14] = 0.91354545764260097762f; S[14] = -0.40673664307580015276f;
+}
+template <int A, int B>
+__device__ __forceinline__ void small_dft_ct(float2 (&v)[A * B]) {
+    constexpr int N = A * B;
+    float C[N], S[N];   // literal tables: folded into immediates once the loops are unrolled
+    lit_roots<N>(C, S);
+    float2 a[B][A];
+#pragma unroll
+    for (int j = 0; j < B; ++j) {
+        float2 t[A];
+#pragma unroll
+        for (int i2 = 0; i2 < A; ++i2) t[i2] = v[j + B * i2];
+        small_dft<A>(t);
+#pragma unroll
+        for (int q = 0; q < A; ++q) a[j][q] = (j * q == 0) ? t[q] : crot(t[q], C[(j * q) % N], S[(j * q) % N]);
+    }
+#pragma unroll
+    for (int q = 0; q < A; ++q) {
+        float2 t[B];
+#pragma unroll
+        for (int j = 0; j < B; ++j) t[j] = a[j][q];
+        small_dft<B>(t);
+#pragma unroll
+        for (int p = 0; p < B; ++p) v[q + A * p] = t[p];
+    }
+}
+template <>
+__device__ __forceinline__ void small_dft<6>(float2 (&v)[6]) { small_dft_ct<2, 3>(v); }
+template <>
+__device__ __forceinline__ void small_dft<9>(float2 (&v)[9]) { small_dft_ct<3, 3>(v); }
+template <>
+__device__ __forceinline__ void small_dft<10>(float2 (&v)[10]) { small_dft_ct<2, 5>(v); }
+template <>
+__device__ __forceinline__ void small_dft<12>(float2 (&v)[12]) { small_dft_ct<4, 3>(v); }
+template <>
+__device__ __forceinline__ void small_dft<15>(float2 (&v)[15]) { small_dft_ct<3, 5>(v); }
+
 // Odd prime radices 7, 11, 13 (lightcone chunk lengths are arbitrary: 2 * 7 * 13 = 182, 2 * 11 * 13 = 286, ...):
 // X_k = v_0 + sum_m (v_m + v_{P-m}) cos(2 pi m k / P) - i (v_m - v_{P-m}) sin(2 pi m k / P),  X_{P-k} = conj-pair form.
 template <int P>

@@ -24,6 +24,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdlib>
+#include <functional>
 #include <vector>
 
 #include "ps21_internal.cuh"
@@ -54,6 +55,9 @@ struct G2Dev {
     int nzt, ntiles;            // z tiles per ky_a position, tiles per spectrum
     int slots;                  // pass-2 CTAs per spectrum
     int p2_threads;
+    int nbuf;                   // pass 1: shared-memory row buffers (2: the next unit streams in during this one's FFTs)
+    int slabs;                  // pass 1: consecutive x slabs per CTA
+    int fuse_first, fuse_last;  // pass 1: untangle inside the first y stage / HBM store inside the last y stage
     IpFft fz, fy, fx;
     FastDiv div_M, div_R1, div_nh;
     const float2 *tw_z, *tw_y, *tw_x;   // exp(-2 pi i q / n) for n = nz, n1, n0
@@ -78,24 +82,27 @@ struct G2Shape {
 // One stage of radix R over `ncols` independent sequences: element i of column c lives at buf[addr(i, c)].
 // Stage geometry: sub-blocks of L = q R consecutive indices; butterfly (b, o) takes i = b L + o + m q, m = 0..R-1,
 // and leaves output m' (multiplied by w_L^(o m')) where input m' was.
+// `sub` (pass 1, first z stage): the chunk's offset estimate is subtracted from both halves of every packed pair as
+// the data is read -- before any butterfly, so the fp32 transform never sees the large mean.
 template <int R, class Addr>
 __device__ __forceinline__ void ip_stage(float2* __restrict__ buf, const IpStage st, int nbf, int ncols, FastDiv div_cols,
-                                         const Addr addr, const float2* __restrict__ tw) {
+                                         const Addr addr, const float2* __restrict__ tw, float sub = 0.f) {
     const int ntasks = nbf * ncols;
+    const float2 sub2 = make_float2(sub, sub);
     for (int task = threadIdx.x; task < ntasks; task += blockDim.x) {
         const int bf = fast_div(task, div_cols), c = task - bf * ncols;
         const int b = fast_div(bf, st.div_q), o = bf - b * st.q;
         const int i0 = b * st.q * R + o;
         float2 v[R];
 #pragma unroll
-        for (int m = 0; m < R; ++m) v[m] = buf[addr(i0 + m * st.q, c)];
+        for (int m = 0; m < R; ++m) v[m] = csub(buf[addr(i0 + m * st.q, c)], sub2);
         small_dft<R>(v);
         if (st.q > 1) {
             const int step = o * st.twmul;
             int idx = step;
 #pragma unroll
             for (int m = 1; m < R; ++m) {
-                v[m] = cmul_w2(v[m], __ldg(tw + idx));
+                v[m] = cmul_w2(v[m], tw[idx]);
                 idx += step;
             }
         }
@@ -106,21 +113,18 @@ __device__ __forceinline__ void ip_stage(float2* __restrict__ buf, const IpStage
 
 template <bool BIG, class Addr>
 __device__ __forceinline__ void ip_stage_any(float2* buf, const IpStage st, int n, int ncols, FastDiv div_cols,
-                                             const Addr addr, const float2* tw) {
+                                             const Addr addr, const float2* tw, float sub = 0.f) {
     const int nbf = n / st.radix;
+#define PS21_IP_CASE(R) case R: ip_stage<R>(buf, st, nbf, ncols, div_cols, addr, tw, sub); break
     switch (st.radix) {
-        case 2: ip_stage<2>(buf, st, nbf, ncols, div_cols, addr, tw); break;
-        case 3: ip_stage<3>(buf, st, nbf, ncols, div_cols, addr, tw); break;
-        case 4: ip_stage<4>(buf, st, nbf, ncols, div_cols, addr, tw); break;
-        case 5: ip_stage<5>(buf, st, nbf, ncols, div_cols, addr, tw); break;
-        case 7: ip_stage<7>(buf, st, nbf, ncols, div_cols, addr, tw); break;
-        case 8: ip_stage<8>(buf, st, nbf, ncols, div_cols, addr, tw); break;
-        case 11: ip_stage<11>(buf, st, nbf, ncols, div_cols, addr, tw); break;
-        case 13: ip_stage<13>(buf, st, nbf, ncols, div_cols, addr, tw); break;
-        case 16: ip_stage<16>(buf, st, nbf, ncols, div_cols, addr, tw); break;
-        case 25: if (BIG) ip_stage<25>(buf, st, nbf, ncols, div_cols, addr, tw); break;
-        default: if (BIG) ip_stage<32>(buf, st, nbf, ncols, div_cols, addr, tw); break;
+        PS21_IP_CASE(2); PS21_IP_CASE(3); PS21_IP_CASE(4); PS21_IP_CASE(5); PS21_IP_CASE(6); PS21_IP_CASE(7);
+        PS21_IP_CASE(8); PS21_IP_CASE(9); PS21_IP_CASE(10); PS21_IP_CASE(11); PS21_IP_CASE(12); PS21_IP_CASE(13);
+        PS21_IP_CASE(15); PS21_IP_CASE(16);
+        case 25: if (BIG) ip_stage<25>(buf, st, nbf, ncols, div_cols, addr, tw, sub); break;
+        case 32: if (BIG) ip_stage<32>(buf, st, nbf, ncols, div_cols, addr, tw, sub); break;
+        default: break;
     }
+#undef PS21_IP_CASE
 }
 
 struct AddrStrided {   // pass 1: index stride si, column stride sc
@@ -175,87 +179,225 @@ __global__ void k_g2_lut(uint8_t* __restrict__ lut, unsigned long long* __restri
 // ------------------------------------------------------------------------------------------------
 // pass 1
 // ------------------------------------------------------------------------------------------------
+struct P1Smem {   // views into the dynamic shared memory of k_g2_p1
+    float2* buf[2];
+    float2 *twz, *twy;       // w_nz^q (nz entries), w_n1^q (n1 entries)
+    uint16_t *rowz, *kya;    // copies of G2Dev::rowz_of_k / kya_of_jp
+};
+
+// untangle of the packed real FFT for pair p of one butterfly leg: rows r1 = row(p), r2 = row(M - p)
+template <int R>
+__device__ __forceinline__ void p1_y_first(float2* __restrict__ buf, const G2Dev& g, const P1Smem& sm) {
+    // first y stage (radix R over j = o + m q) of the row pair (p, M - p), with the untangle of that pair done on
+    // the values as they are read: one pass over shared memory and one barrier instead of two
+    const IpStage st = g.fy.st[0];
+    const int q = st.q, M = g.M, ld = g.ld;
+    const int ntasks = (M / 2 + 1) * q;
+    for (int task = threadIdx.x; task < ntasks; task += blockDim.x) {
+        const int p = fast_div(task, st.div_q), o = task - p * q;   // o fastest: lanes along contiguous j
+        float2 a1[R], a2[R];
+        float2 *q1, *q2;
+        const bool self = (2 * p == M);
+        if (p == 0) {
+            q1 = buf + o;                 // frequency 0 stays in row 0
+            q2 = buf + M * ld + o;        // the Nyquist row is created here
+#pragma unroll
+            for (int m = 0; m < R; ++m) {
+                const float2 c0 = q1[m * q];
+                a1[m] = make_float2(c0.x + c0.y, 0.f);
+                a2[m] = make_float2(c0.x - c0.y, 0.f);
+            }
+        } else if (self) {
+            q1 = q2 = buf + sm.rowz[p] * ld + o;
+#pragma unroll
+            for (int m = 0; m < R; ++m) {
+                const float2 c0 = q1[m * q];
+                a1[m] = make_float2(c0.x, -c0.y);
+                a2[m] = a1[m];
+            }
+        } else {
+            q1 = buf + sm.rowz[p] * ld + o;
+            q2 = buf + sm.rowz[M - p] * ld + o;
+            const float2 w = sm.twz[p];   // w_nz^p; times -i/2 -> (wy/2, -wx/2)
+            const float4 wu = make_float4(0.5f * w.y, -0.5f * w.x, 0.5f * w.x, 0.5f * w.y);
+#pragma unroll
+            for (int m = 0; m < R; ++m) untangle(q1[m * q], q2[m * q], wu, a1[m], a2[m]);
+        }
+        small_dft<R>(a1);
+        small_dft<R>(a2);
+        if (q > 1) {
+            const int step = o * st.twmul;
+            int idx = step;
+#pragma unroll
+            for (int m = 1; m < R; ++m) {
+                const float2 w = sm.twy[idx];
+                idx += step;
+                a1[m] = cmul_w2(a1[m], w);
+                a2[m] = cmul_w2(a2[m], w);
+            }
+        }
+#pragma unroll
+        for (int m = 0; m < R; ++m) q1[m * q] = a1[m];
+        if (!self) {
+#pragma unroll
+            for (int m = 0; m < R; ++m) q2[m * q] = a2[m];
+        }
+    }
+}
+
+// last y stage (radix R over contiguous j) of every row, results times w_n1^(yl ky_a) straight to HBM in tile order
+template <int R>
+__device__ __forceinline__ void p1_y_last_store(const float2* __restrict__ buf, float2* __restrict__ dst,
+                                                const G2Dev& g, const P1Smem& sm, int yl, long long inner) {
+    const int nh = g.nh, ld = g.ld, nsub = g.R1 / R;
+    const long long tile_elems = (long long)g.n0 * 32;
+    for (int task = threadIdx.x; task < nsub * nh; task += blockDim.x) {
+        const int b = fast_div(task, g.div_nh), r = task - b * nh;   // r fastest: lanes along rows
+        float2 v[R];
+        const float2* src = buf + r * ld + b * R;
+#pragma unroll
+        for (int m = 0; m < R; ++m) v[m] = src[m];
+        small_dft<R>(v);
+        float2* out = dst + (long long)(r >> g.lgT) * tile_elems + inner + (r & (g.T - 1));
+#pragma unroll
+        for (int m = 0; m < R; ++m) {
+            const int jp = b * R + m;
+            const float2 o = yl ? cmul_w2(v[m], sm.twy[yl * sm.kya[jp]]) : v[m];   // yl ky_a < n1: no reduction needed
+            out[(long long)jp * g.nzt * tile_elems] = o;
+        }
+    }
+}
+
 template <int THREADS, int MINB>
 __global__ void __launch_bounds__(THREADS, MINB)
 k_g2_p1(const float* __restrict__ boxes, long long batch_stride, int n2_total, ItemMap im,
                         const ChunkDev* __restrict__ chunks, int nchunks, const double* __restrict__ mean_parts,
                         float2* __restrict__ scratch, G2Dev g, int aligned8) {
-    PS21_DYN_SMEM(float2, buf);   // [nh][ld]
+    PS21_DYN_SMEM(float2, smem);
     const int tid = threadIdx.x, nthr = blockDim.x;
+    const int M = g.M, R1 = g.R1, ld = g.ld, nh = g.nh;
+    P1Smem sm;
+    sm.buf[0] = smem;
+    sm.buf[1] = smem + (g.nbuf - 1) * nh * ld;
+    sm.twz = smem + g.nbuf * nh * ld;
+    sm.twy = sm.twz + g.nz;
+    sm.rowz = reinterpret_cast<uint16_t*>(sm.twy + g.n1);
+    sm.kya = sm.rowz + M;
     long long box;
     int cid;
     item_to_box_chunk(im, blockIdx.y, box, cid);
     const ChunkDev ch = chunks[cid];
     const float mean = chunk_offset(mean_parts, box * nchunks + cid, g.n1, ch.nz);
-    const int x = blockIdx.x;
-    const int M = g.M, R1 = g.R1, ld = g.ld, nh = g.nh;
-    const float* slab = boxes + box * batch_stride + ch.start + (long long)x * g.n1 * n2_total;
+    const int x0 = blockIdx.x * g.slabs;
+    const float* spec = boxes + box * batch_stride + ch.start;
     float2* dst = scratch + (long long)blockIdx.y * ((long long)g.ntiles * g.n0 * 32);
     const AddrStrided az{ld, 1};    // z transform: index = row (z pair / k_z), column = j
     const AddrStrided ay{1, ld};    // y transform: index = j, column = row
-    for (int yl = 0; yl < g.R2; ++yl) {
-        // ---- rows y = yl + R2 j as packed (even, odd) pairs: buf[zc][j]; lanes along z -> coalesced, conflict free
+    for (int i = tid; i < g.nz; i += nthr) sm.twz[i] = g.tw_z[i];
+    for (int i = tid; i < g.n1; i += nthr) sm.twy[i] = g.tw_y[i];
+    for (int i = tid; i < M; i += nthr) sm.rowz[i] = g.rowz_of_k[i];
+    for (int i = tid; i < R1; i += nthr) sm.kya[i] = g.kya_of_jp[i];
+    // rows y = yl + R2 j of slab x as packed (even, odd) pairs: buf[zc][j]; asynchronous copies (LDGSTS), lanes along z
+    // -> coalesced reads, conflict-free writes (ld is odd)
+    auto issue_unit = [&](int u, float2* buf) {
+        const int x = x0 + u / g.R2, yl = u - (u / g.R2) * g.R2;
+        const float* slab = spec + (long long)x * g.n1 * n2_total + (long long)yl * n2_total;
         for (int e = tid; e < R1 * M; e += nthr) {
             const int j = fast_div(e, g.div_M), zc = e - j * M;
-            const float* row = slab + (long long)(yl + g.R2 * j) * n2_total;
-            float2 v;
+            const float* src = slab + (long long)(g.R2 * j) * n2_total + 2 * zc;
+            float2* d = buf + zc * ld + j;
             if (aligned8) {
-                v = *reinterpret_cast<const float2*>(row + 2 * zc);
+                cp_async8(d, src);
             } else {
-                v.x = row[2 * zc];
-                v.y = row[2 * zc + 1];
+                cp_async4(&d->x, src);
+                cp_async4(&d->y, src + 1);
             }
-            buf[zc * ld + j] = make_float2(v.x - mean, v.y - mean);
         }
-        __syncthreads();
-        // ---- z: complex FFT of length M over the row index, in place
+        cp_async_commit();
+    };
+    const int nunits = g.slabs * g.R2;
+    issue_unit(0, sm.buf[0]);
+    for (int u = 0; u < nunits; ++u) {
+        float2* buf = sm.buf[u % g.nbuf];
+        const int x = x0 + u / g.R2, yl = u - (u / g.R2) * g.R2;
+        cp_async_wait<0>();
+        __syncthreads();   // unit u has landed; everybody is done with unit u - 1 (tables ready on the first turn)
+        if (g.nbuf == 2 && u + 1 < nunits) issue_unit(u + 1, sm.buf[(u + 1) % 2]);
+        // ---- z: complex FFT of length M over the row index, in place; the offset is subtracted as stage 0 reads
         for (int s = 0; s < g.fz.nstages; ++s) {
-            ip_stage_any<false>(buf, g.fz.st[s], M, R1, g.div_R1, az, g.tw_z);
+            ip_stage_any<false>(buf, g.fz.st[s], M, R1, g.div_R1, az, sm.twz, s == 0 ? mean : 0.f);
             __syncthreads();
         }
-        // ---- untangle: pairs (p, M - p) -> A_p, A_{M-p}; p = 0 also yields the Nyquist row M; p = M/2 is its own pair
-        {
+        // ---- untangle (pairs (p, M - p) -> A_p, A_{M-p}; p = 0 also yields the Nyquist row M) + first y stage
+        if (g.fuse_first) {
+            switch (g.fy.st[0].radix) {
+                case 2: p1_y_first<2>(buf, g, sm); break;
+                case 3: p1_y_first<3>(buf, g, sm); break;
+                case 4: p1_y_first<4>(buf, g, sm); break;
+                case 5: p1_y_first<5>(buf, g, sm); break;
+                case 6: p1_y_first<6>(buf, g, sm); break;
+                case 8: p1_y_first<8>(buf, g, sm); break;
+                default: p1_y_first<10>(buf, g, sm); break;
+            }
+            __syncthreads();
+        } else {
             const int npair = M / 2 + 1;
             for (int e = tid; e < npair * R1; e += nthr) {
                 const int p = fast_div(e, g.div_R1), j = e - p * R1;
                 if (p == 0) {
-                    const float2 c0 = buf[j];   // frequency 0 stays in row 0
+                    const float2 c0 = buf[j];
                     buf[j] = make_float2(c0.x + c0.y, 0.f);
                     buf[M * ld + j] = make_float2(c0.x - c0.y, 0.f);
                 } else if (2 * p == M) {
-                    float2* q = buf + g.rowz_of_k[p] * ld + j;
+                    float2* q = buf + sm.rowz[p] * ld + j;
                     const float2 c0 = *q;
                     *q = make_float2(c0.x, -c0.y);
-                } else if (2 * p < M) {
-                    float2* q1 = buf + g.rowz_of_k[p] * ld + j;
-                    float2* q2 = buf + g.rowz_of_k[M - p] * ld + j;
-                    const float2 w = __ldg(g.tw_z + p);   // w_nz^p; times -i/2 -> (wy/2, -wx/2)
+                } else {
+                    float2* q1 = buf + sm.rowz[p] * ld + j;
+                    float2* q2 = buf + sm.rowz[M - p] * ld + j;
+                    const float2 w = sm.twz[p];
                     float2 a1, a2;
                     untangle(*q1, *q2, make_float4(0.5f * w.y, -0.5f * w.x, 0.5f * w.x, 0.5f * w.y), a1, a2);
                     *q1 = a1;
                     *q2 = a2;
                 }
             }
-        }
-        __syncthreads();
-        // ---- y: FFT of length R1 over j for every one of the nh rows, in place
-        for (int s = 0; s < g.fy.nstages; ++s) {
-            ip_stage_any<false>(buf, g.fy.st[s], R1, nh, g.div_nh, ay, g.tw_y);
+            __syncthreads();
+            ip_stage_any<false>(buf, g.fy.st[0], R1, nh, g.div_nh, ay, sm.twy);
             __syncthreads();
         }
-        // ---- times w_n1^(yl ky_a), to HBM in tile order: runs of T consecutive rows
-        {
-            const int slot = (yl ^ (x & (g.R2 - 1)));
-            const long long inner = ((long long)x * g.R2 + slot) << g.lgT;
+        // ---- middle y stages, in place
+        const int ylast = g.fy.nstages - 1;
+        for (int s = 1; s < (g.fuse_last ? ylast : g.fy.nstages); ++s) {
+            ip_stage_any<false>(buf, g.fy.st[s], R1, nh, g.div_nh, ay, sm.twy);
+            __syncthreads();
+        }
+        // ---- last y stage, times w_n1^(yl ky_a), to HBM in tile order: runs of T consecutive rows
+        const int slot = (yl ^ (x & (g.R2 - 1)));
+        const long long inner = ((long long)x * g.R2 + slot) << g.lgT;
+        if (g.fuse_last) {
+            switch (g.fy.st[ylast].radix) {
+                case 2: p1_y_last_store<2>(buf, dst, g, sm, yl, inner); break;
+                case 3: p1_y_last_store<3>(buf, dst, g, sm, yl, inner); break;
+                case 4: p1_y_last_store<4>(buf, dst, g, sm, yl, inner); break;
+                case 5: p1_y_last_store<5>(buf, dst, g, sm, yl, inner); break;
+                case 6: p1_y_last_store<6>(buf, dst, g, sm, yl, inner); break;
+                case 8: p1_y_last_store<8>(buf, dst, g, sm, yl, inner); break;
+                default: p1_y_last_store<10>(buf, dst, g, sm, yl, inner); break;
+            }
+        } else {
+            const long long tile_elems = (long long)g.n0 * 32;
             for (int e = tid; e < R1 * nh; e += nthr) {
                 const int jp = fast_div(e, g.div_nh), r = e - jp * nh;
                 float2 v = buf[r * ld + jp];
-                if (yl) v = cmul_w2(v, __ldg(g.tw_y + (yl * g.kya_of_jp[jp]) % g.n1));
-                const long long tile = (long long)jp * g.nzt + (r >> g.lgT);
-                dst[tile * ((long long)g.n0 * 32) + inner + (r & (g.T - 1))] = v;
+                if (yl) v = cmul_w2(v, sm.twy[yl * sm.kya[jp]]);
+                dst[((long long)jp * g.nzt + (r >> g.lgT)) * tile_elems + inner + (r & (g.T - 1))] = v;
             }
         }
-        __syncthreads();
+        if (g.nbuf == 1 && u + 1 < nunits) {
+            __syncthreads();
+            issue_unit(u + 1, sm.buf[0]);
+        }
     }
 }
 
@@ -294,7 +436,7 @@ __device__ __forceinline__ void p2_first_stage(float2* __restrict__ tile, const 
 #pragma unroll
         for (int m = 0; m < R0; ++m) {
             const int x = o + m * q0;
-            const float2 w = __ldg(tw + idx);
+            const float2 w = tw[idx];
             idx += step;
 #pragma unroll
             for (int kyb = 0; kyb < R2; ++kyb)
@@ -365,10 +507,19 @@ __device__ __forceinline__ void p2_last_stage(const float2* __restrict__ tile, c
 #pragma unroll
             for (int w4 = 0; w4 < RL / 4; ++w4) {
                 const uint32_t word = lw[w4];
+                float pw[4];
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
                     const float2 o = v[visit_order(4 * w4 + i, RL)];
-                    bw.add((word >> (8 * i)) & 255u, o.x * o.x + o.y * o.y);
+                    pw[i] = o.x * o.x + o.y * o.y;
+                }
+                // the bin changes rarely along |k_x|: a whole word of four outputs usually stays in the current bin
+                const bool same = word == bw.cur * 0x01010101u;
+                if (NSHARE == 1 ? same : (bool)__all_sync(0xffffffffu, same)) {
+                    bw.acc += (pw[0] + pw[1]) + (pw[2] + pw[3]);
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) bw.add((word >> (8 * i)) & 255u, pw[i]);
                 }
             }
         } else {
@@ -394,7 +545,8 @@ k_g2_p2(const float2* __restrict__ scratch, ItemMap im, const ChunkDev* __restri
     uint8_t* lutb = reinterpret_cast<uint8_t*>(tile + tile_elems);           // [n0 * 32]
     uint64_t* bar = reinterpret_cast<uint64_t*>(lutb + tile_elems);
     double* cbins = reinterpret_cast<double*>(bar + 2);                      // [nbins] fp64 bins of the CTA
-    float* lbins = reinterpret_cast<float*>(cbins + MAX_BINS);               // [nbins][ncol]
+    float2* twx = reinterpret_cast<float2*>(cbins + MAX_BINS);               // [n0] w_n0^q
+    float* lbins = reinterpret_cast<float*>(twx + g.n0);                     // [nbins][ncol]
     const int tid = threadIdx.x, nthr = blockDim.x;
     const int ncol = nthr / NSHARE;
     long long box;
@@ -405,6 +557,7 @@ k_g2_p2(const float2* __restrict__ scratch, ItemMap im, const ChunkDev* __restri
     const float2* src = scratch + (long long)blockIdx.y * ((long long)g.ntiles * tile_elems);
     for (int i = tid; i < nbins * ncol; i += nthr) lbins[i] = 0.f;
     for (int i = tid; i < nbins; i += nthr) cbins[i] = 0.0;
+    for (int i = tid; i < g.n0; i += nthr) twx[i] = g.tw_x[i];
     if (tid == 0) {
         mbar_init(bar, 1);
         mbar_fence_init();
@@ -432,10 +585,10 @@ k_g2_p2(const float2* __restrict__ scratch, ItemMap im, const ChunkDev* __restri
     for (; tl < g.ntiles; tl += g.slots, ++it) {
         mbar_wait(bar, phase);
         phase ^= 1;
-        p2_first_stage<R0, R2>(tile, g, g.tw_x);
+        p2_first_stage<R0, R2>(tile, g, twx);
         __syncthreads();
         for (int s = 1; s + 1 < g.fx.nstages; ++s) {
-            ip_stage_any<true>(tile, g.fx.st[s], g.n0, 32, div32, addr, g.tw_x);
+            ip_stage_any<true>(tile, g.fx.st[s], g.n0, 32, div32, addr, twx);
             __syncthreads();
         }
         {
@@ -481,26 +634,45 @@ k_g2_p2(const float2* __restrict__ scratch, ItemMap im, const ChunkDev* __restri
 // ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
-static bool split_radices(int n, std::vector<int>& out, bool big = true) {
-    // radices of the in-place engine: 25s, then the power of two in pieces of at most 5 bits (as even as possible),
-    // then 5, 3, 7, 11, 13; false when another prime remains.  big = false: no 25- and 32-point butterflies (pass 1
-    // keeps its registers for occupancy: 16-point pieces, 25 = 5 * 5)
+// Fewest stages first, then the smallest largest radix (balanced stages: 64 = 8 * 8 rather than 16 * 4), radices taken
+// from `allowed`; false when n has a prime factor outside the set.
+static bool split_radices(int n, const std::vector<int>& allowed, std::vector<int>& out) {
     out.clear();
-    int m = n, a = 0;
-    while (m % 2 == 0) { m /= 2; ++a; }
-    while (big && m % 25 == 0) { out.push_back(25); m /= 25; }
-    if (a > 0) {
-        const int mb = big ? 5 : 4;
-        const int pieces = (a + mb - 1) / mb, base = a / pieces, extra = a % pieces;
-        for (int i = 0; i < pieces; ++i) out.push_back(1 << (base + (i < extra ? 1 : 0)));
-    }
-    for (int p : {5, 3, 7, 11, 13})
-        while (m % p == 0) { out.push_back(p); m /= p; }
-    if (m != 1 || (int)out.size() > kMaxStages) return false;
-    if (out.empty()) out.push_back(1);
+    if (n == 1) return true;
+    struct Best { int stages, maxr; std::vector<int> r; };
+    std::vector<Best> memo(n + 1, Best{-1, 0, {}});
+    std::vector<char> seen(n + 1, 0);
+    std::function<const Best&(int)> go = [&](int m) -> const Best& {
+        if (seen[m]) return memo[m];
+        seen[m] = 1;
+        Best best{1 << 20, 0, {}};
+        if (m == 1) best = Best{0, 0, {}};
+        else
+            for (int r : allowed) {
+                if (r > m || m % r) continue;
+                const Best& sub = go(m / r);
+                if (sub.stages >= (1 << 20)) continue;
+                const int st = sub.stages + 1, mx = std::max(sub.maxr, r);
+                if (st < best.stages || (st == best.stages && mx < best.maxr)) {
+                    best.stages = st;
+                    best.maxr = mx;
+                    best.r = sub.r;
+                    best.r.push_back(r);
+                }
+            }
+        memo[m] = best;
+        return memo[m];
+    };
+    const Best& b = go(n);
+    if (b.stages >= (1 << 20) || b.stages > kMaxStages) return false;
+    out = b.r;
     std::sort(out.begin(), out.end(), [](int x, int y) { return x > y; });
     return true;
 }
+static const std::vector<int> kRadZ = {16, 15, 13, 12, 11, 10, 9, 8, 7, 6, 5, 4, 3, 2};   // pass 1, z (<= 32 data registers)
+static const std::vector<int> kRadY = {13, 12, 11, 10, 9, 8, 7, 6, 5, 4, 3, 2};           // pass 1, y (two rows per task)
+static const std::vector<int> kRadX = {32, 25, 16, 15, 13, 12, 11, 10, 9, 8, 7, 6, 5, 4, 3, 2};   // pass 2
+static bool is_fusable_y(int r) { return r == 2 || r == 3 || r == 4 || r == 5 || r == 6 || r == 8 || r == 10; }
 
 static void make_ipfft(int n, const std::vector<int>& radices, int twscale, IpFft& f) {
     f = IpFft{};
@@ -542,9 +714,13 @@ static int upload(const std::vector<T>& v, T** d) {
     return PS21_OK;
 }
 
-static size_t p1_smem(const G2Dev& g) { return (size_t)g.nh * g.ld * sizeof(float2); }
+static size_t p1_smem(const G2Dev& g) {
+    return (size_t)g.nbuf * g.nh * g.ld * sizeof(float2) + (size_t)(g.nz + g.n1) * sizeof(float2) +
+           (size_t)(g.M + g.R1) * 2 + 64;
+}
 static size_t p2_smem(const G2Dev& g, int nbins, int nshare) {
-    return (size_t)g.n0 * 32 * 9 + 16 + (size_t)MAX_BINS * 8 + (size_t)nbins * (g.p2_threads / nshare) * 4;
+    return (size_t)g.n0 * 32 * 9 + 16 + (size_t)MAX_BINS * 8 + (size_t)g.n0 * 8 +
+           (size_t)nbins * (g.p2_threads / nshare) * 4;
 }
 
 template <int R0, int R2, int NSHARE>
@@ -585,44 +761,56 @@ int g2_try_setup(ps21_plan* p, ShapePlan& sp) {
     G2Dev g{};
     g.n0 = n0; g.n1 = n1; g.nz = nz; g.M = nz / 2; g.nh = g.M + 1;
     std::vector<int> rz, ry, rx;
-    if (!split_radices(g.M, rz, false)) return no("chunk length / 2 has a prime factor above 13");
-    // y split: R2 = 4 (64-byte runs) while the pass-1 buffer leaves two CTAs per SM, else 8
-    int R2 = 0;
-    const size_t budget2 = 110 * 1024, budget1 = 220 * 1024;
-    int force_r2 = 0;
+    if (!split_radices(g.M, kRadZ, rz)) return no("chunk length / 2 has a prime factor above 13");
+    // y split n1 = R1 R2.  Pass 1 keeps nh x R1 coefficients per buffer and wants two buffers (the next unit streams in
+    // while this one is transformed) and two CTAs per SM; R2 = 4 gives 64-byte runs in the scratch, R2 = 8 halves the
+    // buffer (32-byte runs).  Preference: (R2 4, 2 buffers), (R2 8, 2 buffers), (R2 4, 1 buffer), (R2 8, 1 buffer).
+    int R2 = 0, nbuf = 0;
+    int force_r2 = 0, force_nbuf = 0;
     if (const char* e = std::getenv("PS21_G2_R2")) force_r2 = std::atoi(e);
-    for (int cand : {4, 8}) {
-        if (force_r2 && cand != force_r2) continue;
-        if (n1 % cand) continue;
-        const int R1 = n1 / cand;
-        std::vector<int> tmp;
-        if (R1 < 2 || !split_radices(R1, tmp, false)) continue;
-        const size_t need = (size_t)g.nh * (R1 | 1) * sizeof(float2);
-        if (need <= (cand == 4 && !force_r2 ? budget2 : budget1)) { R2 = cand; break; }
-    }
-    if (!R2)
-        for (int cand : {4, 8}) {   // second chance: R2 = 4 with one CTA per SM
-            if (force_r2 && cand != force_r2) continue;
-            if (n1 % cand) continue;
-            std::vector<int> tmp;
-            if (n1 / cand >= 2 && split_radices(n1 / cand, tmp, false) &&
-                (size_t)g.nh * ((n1 / cand) | 1) * sizeof(float2) <= budget1) { R2 = cand; break; }
+    if (const char* e = std::getenv("PS21_G2_NBUF")) force_nbuf = std::atoi(e);
+    auto extra1 = [&](int R1) { return (size_t)(nz + n1) * sizeof(float2) + (size_t)(g.M + R1) * 2 + 64; };
+    auto buf1 = [&](int R1) { return (size_t)g.nh * (R1 | 1) * sizeof(float2); };
+    const size_t budget_two = 112 * 1024, budget_one = 224 * 1024;
+    for (int pass = 0; pass < 2 && !R2; ++pass)
+        for (int nb : {2, 1}) {
+            for (int cand : {4, 8}) {
+                if ((force_r2 && cand != force_r2) || (force_nbuf && nb != force_nbuf) || n1 % cand) continue;
+                const int R1 = n1 / cand;
+                std::vector<int> tmp;
+                if (R1 < 2 || !split_radices(R1, kRadY, tmp)) continue;
+                if (nb * buf1(R1) + extra1(R1) <= (pass == 0 ? budget_two : budget_one)) {
+                    R2 = cand;
+                    nbuf = nb;
+                    break;
+                }
+            }
+            if (R2) break;
         }
     if (!R2) return no("no y split fits the shared memory");
     g.R2 = R2; g.R1 = n1 / R2; g.T = 32 / R2; g.lgT = (g.T == 8) ? 3 : 2;
     g.ld = g.R1 | 1;
-    split_radices(g.R1, ry, false);
+    g.nbuf = nbuf;
+    split_radices(g.R1, kRadY, ry);
+    if (ry.size() >= 2) std::swap(ry.front(), ry.back());   // smallest radix first: the fused first stage holds 2 R values
+    g.fuse_first = is_fusable_y(ry.front()) ? 1 : 0;
+    g.fuse_last = (ry.size() >= 2 && is_fusable_y(ry.back())) ? 1 : 0;
+    if (std::getenv("PS21_G2_NOFUSE")) g.fuse_first = g.fuse_last = 0;
+    g.slabs = (n0 % 2 == 0 && n0 >= 64) ? 2 : 1;
     // x: first stage R0 with R0 * R2 <= 32 values per thread, the largest remaining radix last (it feeds the bins)
     int R0 = 0;
     for (int cand : (R2 == 4 ? std::vector<int>{8, 4, 2} : std::vector<int>{4, 2})) {
         if (n0 % cand) continue;
+        if (n0 / cand < 2) continue;
+        // the last stage feeds the bins: it must be one of the instantiated ones, the larger the better
+        int last = 0;
         std::vector<int> rest;
-        if (n0 / cand < 2 || !split_radices(n0 / cand, rest)) continue;
-        const int last = rest.front();   // sorted descending
-        if (last != 32 && last != 25 && last != 16 && last != 8 && last != 5 && last != 4) continue;
+        for (int want : {32, 25, 16, 8, 5, 4})
+            if (!last && (n0 / cand) % want == 0 && split_radices(n0 / cand / want, kRadX, rest)) last = want;
+        if (!last) continue;
         rx.clear();
         rx.push_back(cand);
-        for (size_t i = 1; i < rest.size(); ++i) rx.push_back(rest[i]);
+        for (int r : rest) rx.push_back(r);
         rx.push_back(last);
         R0 = cand;
         break;
@@ -669,7 +857,7 @@ int g2_try_setup(ps21_plan* p, ShapePlan& sp) {
     gs->dev = g;
     gs->smem1 = p1_smem(g);
     gs->smem2 = p2_smem(g, p->nbins, gs->nshare);
-    gs->p1_threads = (gs->smem1 > 72 * 1024) ? 512 : 256;   // one or two big CTAs per SM get 512 threads
+    gs->p1_threads = (gs->smem1 > 112 * 1024) ? 512 : 256;   // a CTA that has the SM to itself gets 512 threads
     if (gs->smem2 > 227 * 1024 || gs->smem1 > 227 * 1024) {
         sp.fused = gs;
         g2_destroy(sp);
@@ -677,6 +865,7 @@ int g2_try_setup(ps21_plan* p, ShapePlan& sp) {
     }
 #ifndef PS21_EMU
     if (cudaFuncSetAttribute(k_g2_p1<256, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess ||
+        cudaFuncSetAttribute(k_g2_p1<256, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess ||
         cudaFuncSetAttribute(k_g2_p1<512, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) {
         cudaGetLastError();
         sp.fused = gs;
@@ -742,11 +931,14 @@ int g2_forward(ps21_plan* p, ShapePlan& sp, const float* d_boxes, long long batc
         if (p->chunks[c].start % 2) aligned8 = 0;
     {
         ProfScope ps(p, KK_PASS1, st);
-        if (gs->p1_threads == 256)
-            PS21_LAUNCH((k_g2_p1<256, 3>), dim3(g.n0, (unsigned)nitems), dim3(256), gs->smem1, st, d_boxes, batch_stride,
+        if (gs->p1_threads == 256 && gs->smem1 <= 74 * 1024)   // three CTAs per SM: 80 registers
+            PS21_LAUNCH((k_g2_p1<256, 3>), dim3(g.n0 / g.slabs, (unsigned)nitems), dim3(256), gs->smem1, st, d_boxes, batch_stride,
+                        p->n2_total, im, p->d_chunks, p->nchunks, p->d_mean_parts, p->d_scratch, g, aligned8);
+        else if (gs->p1_threads == 256)                          // two CTAs per SM: 128 registers
+            PS21_LAUNCH((k_g2_p1<256, 2>), dim3(g.n0 / g.slabs, (unsigned)nitems), dim3(256), gs->smem1, st, d_boxes, batch_stride,
                         p->n2_total, im, p->d_chunks, p->nchunks, p->d_mean_parts, p->d_scratch, g, aligned8);
         else
-            PS21_LAUNCH((k_g2_p1<512, 1>), dim3(g.n0, (unsigned)nitems), dim3(512), gs->smem1, st, d_boxes, batch_stride,
+            PS21_LAUNCH((k_g2_p1<512, 1>), dim3(g.n0 / g.slabs, (unsigned)nitems), dim3(512), gs->smem1, st, d_boxes, batch_stride,
                         p->n2_total, im, p->d_chunks, p->nchunks, p->d_mean_parts, p->d_scratch, g, aligned8);
         PS21_CUDA(cudaGetLastError());
     }

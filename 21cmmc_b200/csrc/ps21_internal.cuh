@@ -166,6 +166,15 @@ __device__ __forceinline__ void cp_async8(void* smem_dst, const void* gsrc) {
                  : "memory");
 #endif
 }
+__device__ __forceinline__ void cp_async4(void* smem_dst, const void* gsrc) {
+#ifdef PS21_EMU
+    *reinterpret_cast<float*>(smem_dst) = *reinterpret_cast<const float*>(gsrc);
+#else
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)),
+                 "l"(gsrc)
+                 : "memory");
+#endif
+}
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
 #ifdef PS21_EMU
     *reinterpret_cast<float4*>(smem_dst) = *reinterpret_cast<const float4*>(gsrc);
