@@ -28,8 +28,23 @@ class NotAChain(AttributeError):
                          "to enable this method/attribute!")
 
 
-class ModuleBase:
-    """Base of cores and likelihoods (core.py:50-138)."""
+def _reference_core():
+    """``py21cmmc.core`` when the reference is installed next to this package (a drop-in must
+    plug into the reference's own chain), else None."""
+    try:
+        import py21cmmc.core as rc
+
+        return rc if hasattr(rc, "ModuleBase") and hasattr(rc, "CoreBase") else None
+    except Exception:
+        return None
+
+
+_REF = _reference_core()
+
+
+class _ModuleBase:
+    """Base of cores and likelihoods -- the plugin contract of core.py:50-138, used when py21cmmc is not importable
+    (it needs py21cmfast / cosmoHammer / powerbox); with the reference installed its own class is the base."""
 
     _extra_defining_attributes = ()
     _ignore_attributes = ()
@@ -99,8 +114,11 @@ class ModuleBase:
         self._check_required_cores()
 
 
-class CoreBase(ModuleBase):
-    """core.py:148-223."""
+ModuleBase = _REF.ModuleBase if _REF is not None else _ModuleBase
+
+
+class _CoreBase(ModuleBase):
+    """core.py:148-223 (fallback, see _ModuleBase)."""
 
     def __init__(self, store=None):
         super().__init__()
@@ -125,6 +143,9 @@ class CoreBase(ModuleBase):
 
     def __call__(self, ctx):
         self.build_model_data(ctx)
+
+
+CoreBase = _REF.CoreBase if _REF is not None else _CoreBase
 
 
 class UserParams:
@@ -190,3 +211,11 @@ class CoreCoevalModule(CoreBase):
         if len(boxes) != len(self.redshift):
             raise ValueError("simulator must return one cube per redshift")
         ctx.add("brightness_temp", [np.asarray(b) for b in boxes])
+
+
+# What the likelihoods accept as their ``required_cores`` / ``paired_core``: the box-providing cores of this module
+# and, when the reference is importable, its own 21cmFAST-running ones (likelihood.py:340, :695, :666-682, :878-892).
+LIGHTCONE_CORES = (CoreLightConeModule,) + ((_REF.CoreLightConeModule,) if _REF is not None and
+                                             hasattr(_REF, "CoreLightConeModule") else ())
+COEVAL_CORES = (CoreCoevalModule,) + ((_REF.CoreCoevalModule,) if _REF is not None and
+                                       hasattr(_REF, "CoreCoevalModule") else ())

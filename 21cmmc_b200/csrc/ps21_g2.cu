@@ -762,31 +762,30 @@ int g2_try_setup(ps21_plan* p, ShapePlan& sp) {
     g.n0 = n0; g.n1 = n1; g.nz = nz; g.M = nz / 2; g.nh = g.M + 1;
     std::vector<int> rz, ry, rx;
     if (!split_radices(g.M, kRadZ, rz)) return no("chunk length / 2 has a prime factor above 13");
-    // y split n1 = R1 R2.  Pass 1 keeps nh x R1 coefficients per buffer and wants two buffers (the next unit streams in
-    // while this one is transformed) and two CTAs per SM; R2 = 4 gives 64-byte runs in the scratch, R2 = 8 halves the
-    // buffer (32-byte runs).  Preference: (R2 4, 2 buffers), (R2 8, 2 buffers), (R2 4, 1 buffer), (R2 8, 1 buffer).
+    // y split n1 = R1 R2.  Pass 1 keeps nh x R1 coefficients per buffer; with two buffers the next unit streams in while
+    // this one is transformed.  R2 = 4 gives 64-byte runs in the scratch, R2 = 8 halves the buffer (32-byte runs).
     int R2 = 0, nbuf = 0;
     int force_r2 = 0, force_nbuf = 0;
     if (const char* e = std::getenv("PS21_G2_R2")) force_r2 = std::atoi(e);
     if (const char* e = std::getenv("PS21_G2_NBUF")) force_nbuf = std::atoi(e);
     auto extra1 = [&](int R1) { return (size_t)(nz + n1) * sizeof(float2) + (size_t)(g.M + R1) * 2 + 64; };
     auto buf1 = [&](int R1) { return (size_t)g.nh * (R1 | 1) * sizeof(float2); };
-    const size_t budget_two = 112 * 1024, budget_one = 224 * 1024;
-    for (int pass = 0; pass < 2 && !R2; ++pass)
-        for (int nb : {2, 1}) {
-            for (int cand : {4, 8}) {
-                if ((force_r2 && cand != force_r2) || (force_nbuf && nb != force_nbuf) || n1 % cand) continue;
-                const int R1 = n1 / cand;
-                std::vector<int> tmp;
-                if (R1 < 2 || !split_radices(R1, kRadY, tmp)) continue;
-                if (nb * buf1(R1) + extra1(R1) <= (pass == 0 ? budget_two : budget_one)) {
-                    R2 = cand;
-                    nbuf = nb;
-                    break;
-                }
-            }
-            if (R2) break;
+    // measured on 200^3 (B200): one buffer with three CTAs per SM 4.83 ms, two buffers with two CTAs 5.24 ms -- occupancy
+    // beats overlap inside a CTA, so: three resident CTAs first, then two with the prefetch buffer, then whatever fits
+    struct Try { int r2, nb; size_t budget; };
+    const Try order[] = {{4, 1, 74 * 1024},  {8, 1, 74 * 1024},  {4, 2, 112 * 1024}, {8, 2, 112 * 1024},
+                         {4, 1, 112 * 1024}, {8, 1, 112 * 1024}, {4, 1, 224 * 1024}, {8, 1, 224 * 1024}};
+    for (const Try& t : order) {
+        if ((force_r2 && t.r2 != force_r2) || (force_nbuf && t.nb != force_nbuf) || n1 % t.r2) continue;
+        const int R1 = n1 / t.r2;
+        std::vector<int> tmp;
+        if (R1 < 2 || !split_radices(R1, kRadY, tmp)) continue;
+        if (t.nb * buf1(R1) + extra1(R1) <= t.budget) {
+            R2 = t.r2;
+            nbuf = t.nb;
+            break;
         }
+    }
     if (!R2) return no("no y split fits the shared memory");
     g.R2 = R2; g.R1 = n1 / R2; g.T = 32 / R2; g.lgT = (g.T == 8) ? 3 : 2;
     g.ld = g.R1 | 1;

@@ -69,6 +69,26 @@ def set_defaults(device=None, edge_rule=None, kernel_path=None):
         _DEFAULTS["kernel_path"] = kernel_path
 
 
+def builtin_data_dir():
+    """Directory of the built-in data files (``from_builtin_data``, likelihood.py:702-707, :2192-2197): PS21_DATA_DIR,
+    else the reference's own ``py21cmmc/data`` when it is installed (this package ships no observational data), else
+    ``21cmmc_b200/data``."""
+    import importlib.util
+    import os
+
+    if os.environ.get("PS21_DATA_DIR"):
+        return os.environ["PS21_DATA_DIR"]
+    try:
+        spec = importlib.util.find_spec("py21cmmc")
+        if spec is not None and spec.submodule_search_locations:
+            cand = path.join(list(spec.submodule_search_locations)[0], "data")
+            if path.isdir(cand):
+                return cand
+    except Exception:
+        pass
+    return path.join(path.dirname(__file__), "data")
+
+
 def _device(dev=None):
     if dev is not None:
         return int(dev)
@@ -195,7 +215,7 @@ class LikelihoodBaseFile(LikelihoodBase):
 class Likelihood1DPowerCoeval(LikelihoodBaseFile):
     """Gaussian likelihood on the spherically averaged Delta^2(k) of coeval cubes (likelihood.py:269-682)."""
 
-    required_cores = ((core.CoreCoevalModule,),)
+    required_cores = (core.COEVAL_CORES,)
     _variant = "coeval"
 
     def __init__(self, n_psbins=None, min_k=0.1, max_k=1.0, logk=True, model_uncertainty=0.15,
@@ -277,7 +297,7 @@ class Likelihood1DPowerCoeval(LikelihoodBaseFile):
 
     @cached_property
     def paired_core(self):
-        paired = [c for c in self._cores if isinstance(c, core.CoreCoevalModule)]
+        paired = [c for c in self._cores if isinstance(c, core.COEVAL_CORES)]
         if len(paired) > 1:
             raise ValueError("You've got more than one CoreCoevalModule -- they will overwrite each other!")
         return paired[0]
@@ -436,13 +456,18 @@ class Likelihood1DPowerCoeval(LikelihoodBaseFile):
 class Likelihood1DPowerLightcone(Likelihood1DPowerCoeval):
     """The same likelihood on a lightcone cut into ``nchunks`` line-of-sight chunks (likelihood.py:685-892)."""
 
-    required_cores = ((core.CoreLightConeModule,),)
+    required_cores = (core.LIGHTCONE_CORES,)
     _variant = "lightcone"
 
     def __init__(self, *args, datafile="", nchunks=1, **kwargs):
         super().__init__(*args, **kwargs)
         self.nchunks = nchunks
         self.datafile = [datafile] if isinstance(datafile, (str, Path)) else datafile
+
+    @classmethod
+    def from_builtin_data(cls, datafile="", **kwargs):
+        """Create the class loading in built-in data (likelihood.py:702-707): ``<data dir>/<datafile>.npz``."""
+        return cls(datafile=path.join(builtin_data_dir(), datafile + ".npz"), **kwargs)
 
     def _n_expected(self):
         return self.nchunks
@@ -462,7 +487,7 @@ class Likelihood1DPowerLightcone(Likelihood1DPowerCoeval):
 
     @cached_property
     def paired_core(self):
-        paired = [c for c in self._cores if isinstance(c, core.CoreLightConeModule) and c.name == self.name]
+        paired = [c for c in self._cores if isinstance(c, core.LIGHTCONE_CORES) and c.name == self.name]
         if len(paired) > 1:
             raise ValueError("You've got more than one CoreLightConeModule with the same name -- "
                              "they will overwrite each other!")

@@ -383,3 +383,85 @@ def test_hdf_storage_layout_contract(mods, tmp_path):
         g = f["sample_0"]
         assert g.attrs["iteration"] == 2 and g["blobs"].shape == (2, 3) and g["chain"].shape == (2, 3, 1)
         assert np.array_equal(g["blobs"]["delta_0"][1, 2], blobs[2]["delta_0"], equal_nan=True)
+
+
+def test_reference_core_classes_are_used_when_py21cmmc_imports(monkeypatch):
+    """Drop-in boundary: with the reference importable, ModuleBase / CoreBase are ITS classes and its
+    CoreLightConeModule / CoreCoevalModule satisfy required_cores / paired_core (likelihood.py:340, :695)."""
+    import importlib.util
+    import sys
+    import types
+
+    import py21cmmc_b200.core as here   # imported without the reference: the local fallback classes serve
+
+    assert here.LIGHTCONE_CORES == (here.CoreLightConeModule,) and here.ModuleBase is here._ModuleBase
+    ref = types.ModuleType("py21cmmc.core")
+
+    class RefModuleBase:
+        required_cores = ()
+
+        def __init__(self):
+            self._is_setup = False
+
+    class RefCoreBase(RefModuleBase):
+        def __init__(self, store=None):
+            super().__init__()
+            self.store = store or {}
+
+    class RefLightCone(RefCoreBase):
+        pass
+
+    class RefCoeval(RefCoreBase):
+        pass
+
+    ref.ModuleBase, ref.CoreBase = RefModuleBase, RefCoreBase
+    ref.CoreLightConeModule, ref.CoreCoevalModule = RefLightCone, RefCoeval
+    pkg = types.ModuleType("py21cmmc")
+    pkg.core = ref
+    monkeypatch.setitem(sys.modules, "py21cmmc", pkg)
+    monkeypatch.setitem(sys.modules, "py21cmmc.core", ref)
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("ps21_core_probe", os.path.join(root, "21cmmc_b200", "core.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    assert mod.ModuleBase is RefModuleBase and mod.CoreBase is RefCoreBase
+    assert issubclass(mod.CoreLightConeModule, RefCoreBase)
+    assert mod.LIGHTCONE_CORES == (mod.CoreLightConeModule, RefLightCone)
+    assert mod.COEVAL_CORES == (mod.CoreCoevalModule, RefCoeval)
+
+
+HERA_FILE = "/root/reference/src/py21cmmc/data/HERA_H1C_IDR3.npz"
+
+
+@pytest.mark.skipif(not os.path.exists(HERA_FILE), reason="the reference tree (and its HERA data file) is not on this box")
+def test_upper_limit_likelihood_on_the_reference_hera_file(mods, monkeypatch):
+    """f-2 on the reference's real data file (src/py21cmmc/data/HERA_H1C_IDR3.npz: band8 (5,16,3), band10 (5,19,3),
+    window functions 32 / 37 wide, z_bands (2,)) through ``from_builtin_data``, against the oracle's restatement of
+    likelihood.py:2249-2335."""
+    lk_mod, core_mod, chain_mod = mods
+    monkeypatch.setenv("PS21_DATA_DIR", os.path.dirname(HERA_FILE))
+    shape, box_len, nchunks, nb = (24, 24, 96), 240.0, 2, 14     # 10 Mpc cells: k reaches the HERA window (0.18-1.7 /Mpc)
+    up = core_mod.UserParams(BOX_LEN=box_len, HII_DIM=shape[0])
+    state = {"box": synth_box(shape, 3)}
+    lk = lk_mod.Likelihood1DPowerLightconeUpper.from_builtin_data("HERA_H1C_IDR3", nchunks=nchunks, n_psbins=nb,
+                                                                   band_chunks=[1, 0])
+    chain = chain_mod.build_computation_chain(core_mod.CoreLightConeModule(lambda p: state["box"], up), lk)
+    assert lk.datafile == [HERA_FILE] and list(np.round(lk.redshifts, 2)) == [10.37, 7.93] and lk.k_len == 37
+    model = lk.reduce_data(chain.build_model_data())
+    assert model[0]["delta"].shape == (1, 2, 37)
+    hera = dict(np.load(HERA_FILE, allow_pickle=True))
+    rng = np.random.default_rng(2)
+    # many models spanning "far below every limit" to "far above": the erf saturates on both sides
+    delta = np.abs(model[0]["delta"]) * rng.uniform(1e-2, 1e5, (12, 1, 1)) + rng.uniform(0.0, 50.0, (12, 2, 37))
+    got = lk.computeLikelihood([{"k": lk.k, "delta": delta}])
+    want = O.upper_limit_likelihood(hera, hera["z_bands"], delta)
+    assert np.all(np.isfinite(want)) and np.ptp(want) > 10     # the models really differ in likelihood
+    assert np.allclose(got, want, rtol=1e-9, atol=1e-9)
+    err = np.abs(delta[0]) * 0.3
+    got_e = lk.computeLikelihood([{"k": lk.k, "delta": delta, "delta_err": err}])
+    want_e = O.upper_limit_likelihood(hera, hera["z_bands"], delta, err)
+    assert np.allclose(got_e, want_e, rtol=1e-9, atol=1e-9) and not np.allclose(got_e, got)
+    # and through the batched chain
+    lnl, _ = chain([])
+    lnl_b = chain.call_batch([[], []])
+    assert np.isfinite(lnl) and lnl_b[0][0] == lnl_b[1][0] and abs(lnl_b[0][0] - lnl) <= 1e-12 * abs(lnl)
