@@ -140,19 +140,27 @@ struct AddrTile {      // pass 2: row x holds 32 columns (ky_b, t); the ky_b slo
 // LUT (one byte per mode, in the order pass 2 visits its outputs) + counts
 // ------------------------------------------------------------------------------------------------
 __host__ __device__ __forceinline__ int visit_order(int v, int R) { return (v & 1) ? R - 1 - (v >> 1) : (v >> 1); }
+// bin indices of one butterfly's RL outputs occupy RL rounded up to whole 32-bit words (25 -> 28): the walk reads words
+__host__ __device__ __forceinline__ int lut_row(int RL) { return (RL + 3) & ~3; }
+__host__ __device__ __forceinline__ long long lut_tile_bytes(int n0, int RL) { return (long long)(n0 / RL) * 32 * lut_row(RL); }
 
 __global__ void k_g2_lut(uint8_t* __restrict__ lut, unsigned long long* __restrict__ counts, G2Dev g, int RL,
                          const uint16_t* __restrict__ kx_of_pos, const uint16_t* __restrict__ kz_of_row,
                          const double* __restrict__ k0sq, const double* __restrict__ k1sq,
                          const double* __restrict__ k2sq, const double* __restrict__ edges, int nbins, int ig_kperp,
                          int ig_kpar, int ig_k0) {
-    const long long tile_elems = (long long)g.n0 * 32;
-    const long long total = (long long)g.ntiles * tile_elems;
+    const int RLP = lut_row(RL);
+    const long long tile_bytes = lut_tile_bytes(g.n0, RL);
+    const long long total = (long long)g.ntiles * tile_bytes;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
          i += (long long)gridDim.x * blockDim.x) {
-        const int tile = (int)(i / tile_elems), e = (int)(i % tile_elems);
-        // e = (bf * 32 + c) * RL + v : butterfly bf of the last x stage, column c = (ky_b, t), output in visiting order
-        const int v = e % RL, task = e / RL, c = task & 31, bf = task >> 5;
+        const int tile = (int)(i / tile_bytes), e = (int)(i % tile_bytes);
+        // e = (bf * 32 + c) * RLP + v : butterfly bf of the last x stage, column c = (ky_b, t), output in visiting order
+        const int v = e % RLP, task = e / RLP, c = task & 31, bf = task >> 5;
+        if (v >= RL) {   // padding of the row
+            lut[i] = 255;
+            continue;
+        }
         const int kx = kx_of_pos[bf * RL + visit_order(v, RL)];
         const int kyb = c >> g.lgT, t = c & (g.T - 1);
         const int jp = tile / g.nzt, zt = tile - jp * g.nzt;
@@ -179,15 +187,14 @@ __global__ void k_g2_lut(uint8_t* __restrict__ lut, unsigned long long* __restri
 // ------------------------------------------------------------------------------------------------
 // pass 1
 // ------------------------------------------------------------------------------------------------
-struct P1Smem {   // views into the dynamic shared memory of k_g2_p1
-    float2* buf[2];
-    float2 *twz, *twy;       // w_nz^q (nz entries), w_n1^q (n1 entries)
-    uint16_t *rowz, *kya;    // copies of G2Dev::rowz_of_k / kya_of_jp
-};
+// NOTE: every shared-memory pointer below is formed as `smem + integer` inside the kernel and handed down by value.
+// (A struct holding a dynamically indexed pointer array cost the address-space inference: ncu showed LD.E / ST.E
+// generic accesses, 30 % excess wavefronts and long-scoreboard stalls where LDS / STS were meant.)
 
 // untangle of the packed real FFT for pair p of one butterfly leg: rows r1 = row(p), r2 = row(M - p)
 template <int R>
-__device__ __forceinline__ void p1_y_first(float2* __restrict__ buf, const G2Dev& g, const P1Smem& sm) {
+__device__ __forceinline__ void p1_y_first(float2* __restrict__ buf, const G2Dev& g, const float2* __restrict__ twz,
+                                           const float2* __restrict__ twy, const uint16_t* __restrict__ rowz) {
     // first y stage (radix R over j = o + m q) of the row pair (p, M - p), with the untangle of that pair done on
     // the values as they are read: one pass over shared memory and one barrier instead of two
     const IpStage st = g.fy.st[0];
@@ -208,7 +215,7 @@ __device__ __forceinline__ void p1_y_first(float2* __restrict__ buf, const G2Dev
                 a2[m] = make_float2(c0.x - c0.y, 0.f);
             }
         } else if (self) {
-            q1 = q2 = buf + sm.rowz[p] * ld + o;
+            q1 = q2 = buf + rowz[p] * ld + o;
 #pragma unroll
             for (int m = 0; m < R; ++m) {
                 const float2 c0 = q1[m * q];
@@ -216,9 +223,9 @@ __device__ __forceinline__ void p1_y_first(float2* __restrict__ buf, const G2Dev
                 a2[m] = a1[m];
             }
         } else {
-            q1 = buf + sm.rowz[p] * ld + o;
-            q2 = buf + sm.rowz[M - p] * ld + o;
-            const float2 w = sm.twz[p];   // w_nz^p; times -i/2 -> (wy/2, -wx/2)
+            q1 = buf + rowz[p] * ld + o;
+            q2 = buf + rowz[M - p] * ld + o;
+            const float2 w = twz[p];   // w_nz^p; times -i/2 -> (wy/2, -wx/2)
             const float4 wu = make_float4(0.5f * w.y, -0.5f * w.x, 0.5f * w.x, 0.5f * w.y);
 #pragma unroll
             for (int m = 0; m < R; ++m) untangle(q1[m * q], q2[m * q], wu, a1[m], a2[m]);
@@ -230,7 +237,7 @@ __device__ __forceinline__ void p1_y_first(float2* __restrict__ buf, const G2Dev
             int idx = step;
 #pragma unroll
             for (int m = 1; m < R; ++m) {
-                const float2 w = sm.twy[idx];
+                const float2 w = twy[idx];
                 idx += step;
                 a1[m] = cmul_w2(a1[m], w);
                 a2[m] = cmul_w2(a2[m], w);
@@ -248,7 +255,8 @@ __device__ __forceinline__ void p1_y_first(float2* __restrict__ buf, const G2Dev
 // last y stage (radix R over contiguous j) of every row, results times w_n1^(yl ky_a) straight to HBM in tile order
 template <int R>
 __device__ __forceinline__ void p1_y_last_store(const float2* __restrict__ buf, float2* __restrict__ dst,
-                                                const G2Dev& g, const P1Smem& sm, int yl, long long inner) {
+                                                const G2Dev& g, const float2* __restrict__ twy,
+                                                const uint16_t* __restrict__ kya, int yl, long long inner) {
     const int nh = g.nh, ld = g.ld, nsub = g.R1 / R;
     const long long tile_elems = (long long)g.n0 * 32;
     for (int task = threadIdx.x; task < nsub * nh; task += blockDim.x) {
@@ -258,12 +266,13 @@ __device__ __forceinline__ void p1_y_last_store(const float2* __restrict__ buf, 
 #pragma unroll
         for (int m = 0; m < R; ++m) v[m] = src[m];
         small_dft<R>(v);
-        float2* out = dst + (long long)(r >> g.lgT) * tile_elems + inner + (r & (g.T - 1));
+        const long long jstride = (long long)g.nzt * tile_elems;
+        float2* out = dst + (long long)(r >> g.lgT) * tile_elems + inner + (r & (g.T - 1)) + (long long)(b * R) * jstride;
 #pragma unroll
         for (int m = 0; m < R; ++m) {
-            const int jp = b * R + m;
-            const float2 o = yl ? cmul_w2(v[m], sm.twy[yl * sm.kya[jp]]) : v[m];   // yl ky_a < n1: no reduction needed
-            out[(long long)jp * g.nzt * tile_elems] = o;
+            const float2 o = yl ? cmul_w2(v[m], twy[yl * kya[b * R + m]]) : v[m];   // yl ky_a < n1: no reduction
+            *out = o;
+            out += jstride;
         }
     }
 }
@@ -276,13 +285,11 @@ k_g2_p1(const float* __restrict__ boxes, long long batch_stride, int n2_total, I
     PS21_DYN_SMEM(float2, smem);
     const int tid = threadIdx.x, nthr = blockDim.x;
     const int M = g.M, R1 = g.R1, ld = g.ld, nh = g.nh;
-    P1Smem sm;
-    sm.buf[0] = smem;
-    sm.buf[1] = smem + (g.nbuf - 1) * nh * ld;
-    sm.twz = smem + g.nbuf * nh * ld;
-    sm.twy = sm.twz + g.nz;
-    sm.rowz = reinterpret_cast<uint16_t*>(sm.twy + g.n1);
-    sm.kya = sm.rowz + M;
+    const int bufstride = nh * ld;
+    float2* const twz = smem + g.nbuf * bufstride;                       // [nz]  w_nz^q
+    float2* const twy = twz + g.nz;                                      // [n1]  w_n1^q
+    uint16_t* const rowz = reinterpret_cast<uint16_t*>(twy + g.n1);      // [M]   copy of G2Dev::rowz_of_k
+    uint16_t* const kya = rowz + M;                                      // [R1]  copy of G2Dev::kya_of_jp
     long long box;
     int cid;
     item_to_box_chunk(im, blockIdx.y, box, cid);
@@ -293,51 +300,55 @@ k_g2_p1(const float* __restrict__ boxes, long long batch_stride, int n2_total, I
     float2* dst = scratch + (long long)blockIdx.y * ((long long)g.ntiles * g.n0 * 32);
     const AddrStrided az{ld, 1};    // z transform: index = row (z pair / k_z), column = j
     const AddrStrided ay{1, ld};    // y transform: index = j, column = row
-    for (int i = tid; i < g.nz; i += nthr) sm.twz[i] = g.tw_z[i];
-    for (int i = tid; i < g.n1; i += nthr) sm.twy[i] = g.tw_y[i];
-    for (int i = tid; i < M; i += nthr) sm.rowz[i] = g.rowz_of_k[i];
-    for (int i = tid; i < R1; i += nthr) sm.kya[i] = g.kya_of_jp[i];
+    for (int i = tid; i < g.nz; i += nthr) twz[i] = g.tw_z[i];
+    for (int i = tid; i < g.n1; i += nthr) twy[i] = g.tw_y[i];
+    for (int i = tid; i < M; i += nthr) rowz[i] = g.rowz_of_k[i];
+    for (int i = tid; i < R1; i += nthr) kya[i] = g.kya_of_jp[i];
     // rows y = yl + R2 j of slab x as packed (even, odd) pairs: buf[zc][j]; asynchronous copies (LDGSTS), lanes along z
     // -> coalesced reads, conflict-free writes (ld is odd)
     auto issue_unit = [&](int u, float2* buf) {
         const int x = x0 + u / g.R2, yl = u - (u / g.R2) * g.R2;
         const float* slab = spec + (long long)x * g.n1 * n2_total + (long long)yl * n2_total;
-        for (int e = tid; e < R1 * M; e += nthr) {
-            const int j = fast_div(e, g.div_M), zc = e - j * M;
-            const float* src = slab + (long long)(g.R2 * j) * n2_total + 2 * zc;
-            float2* d = buf + zc * ld + j;
+        // one row per warp turn, lanes along z: the row pointer is formed once per row
+        const int warp = tid >> 5, lane = tid & 31, nwarps = nthr >> 5;
+        const long long rstride = (long long)g.R2 * n2_total;
+        for (int j = warp; j < R1; j += nwarps) {
+            const float* src = slab + j * rstride;
+            float2* d = buf + j;
             if (aligned8) {
-                cp_async8(d, src);
+                for (int zc = lane; zc < M; zc += 32) cp_async8(d + zc * ld, src + 2 * zc);
             } else {
-                cp_async4(&d->x, src);
-                cp_async4(&d->y, src + 1);
+                for (int zc = lane; zc < M; zc += 32) {
+                    cp_async4(&d[zc * ld].x, src + 2 * zc);
+                    cp_async4(&d[zc * ld].y, src + 2 * zc + 1);
+                }
             }
         }
         cp_async_commit();
     };
     const int nunits = g.slabs * g.R2;
-    issue_unit(0, sm.buf[0]);
+    issue_unit(0, smem);
     for (int u = 0; u < nunits; ++u) {
-        float2* buf = sm.buf[u % g.nbuf];
+        float2* buf = smem + (u % g.nbuf) * bufstride;
         const int x = x0 + u / g.R2, yl = u - (u / g.R2) * g.R2;
         cp_async_wait<0>();
         __syncthreads();   // unit u has landed; everybody is done with unit u - 1 (tables ready on the first turn)
-        if (g.nbuf == 2 && u + 1 < nunits) issue_unit(u + 1, sm.buf[(u + 1) % 2]);
+        if (g.nbuf == 2 && u + 1 < nunits) issue_unit(u + 1, smem + ((u + 1) % 2) * bufstride);
         // ---- z: complex FFT of length M over the row index, in place; the offset is subtracted as stage 0 reads
         for (int s = 0; s < g.fz.nstages; ++s) {
-            ip_stage_any<false>(buf, g.fz.st[s], M, R1, g.div_R1, az, sm.twz, s == 0 ? mean : 0.f);
+            ip_stage_any<false>(buf, g.fz.st[s], M, R1, g.div_R1, az, twz, s == 0 ? mean : 0.f);
             __syncthreads();
         }
         // ---- untangle (pairs (p, M - p) -> A_p, A_{M-p}; p = 0 also yields the Nyquist row M) + first y stage
         if (g.fuse_first) {
             switch (g.fy.st[0].radix) {
-                case 2: p1_y_first<2>(buf, g, sm); break;
-                case 3: p1_y_first<3>(buf, g, sm); break;
-                case 4: p1_y_first<4>(buf, g, sm); break;
-                case 5: p1_y_first<5>(buf, g, sm); break;
-                case 6: p1_y_first<6>(buf, g, sm); break;
-                case 8: p1_y_first<8>(buf, g, sm); break;
-                default: p1_y_first<10>(buf, g, sm); break;
+                case 2: p1_y_first<2>(buf, g, twz, twy, rowz); break;
+                case 3: p1_y_first<3>(buf, g, twz, twy, rowz); break;
+                case 4: p1_y_first<4>(buf, g, twz, twy, rowz); break;
+                case 5: p1_y_first<5>(buf, g, twz, twy, rowz); break;
+                case 6: p1_y_first<6>(buf, g, twz, twy, rowz); break;
+                case 8: p1_y_first<8>(buf, g, twz, twy, rowz); break;
+                default: p1_y_first<10>(buf, g, twz, twy, rowz); break;
             }
             __syncthreads();
         } else {
@@ -349,13 +360,13 @@ k_g2_p1(const float* __restrict__ boxes, long long batch_stride, int n2_total, I
                     buf[j] = make_float2(c0.x + c0.y, 0.f);
                     buf[M * ld + j] = make_float2(c0.x - c0.y, 0.f);
                 } else if (2 * p == M) {
-                    float2* q = buf + sm.rowz[p] * ld + j;
+                    float2* q = buf + rowz[p] * ld + j;
                     const float2 c0 = *q;
                     *q = make_float2(c0.x, -c0.y);
                 } else {
-                    float2* q1 = buf + sm.rowz[p] * ld + j;
-                    float2* q2 = buf + sm.rowz[M - p] * ld + j;
-                    const float2 w = sm.twz[p];
+                    float2* q1 = buf + rowz[p] * ld + j;
+                    float2* q2 = buf + rowz[M - p] * ld + j;
+                    const float2 w = twz[p];
                     float2 a1, a2;
                     untangle(*q1, *q2, make_float4(0.5f * w.y, -0.5f * w.x, 0.5f * w.x, 0.5f * w.y), a1, a2);
                     *q1 = a1;
@@ -363,13 +374,13 @@ k_g2_p1(const float* __restrict__ boxes, long long batch_stride, int n2_total, I
                 }
             }
             __syncthreads();
-            ip_stage_any<false>(buf, g.fy.st[0], R1, nh, g.div_nh, ay, sm.twy);
+            ip_stage_any<false>(buf, g.fy.st[0], R1, nh, g.div_nh, ay, twy);
             __syncthreads();
         }
         // ---- middle y stages, in place
         const int ylast = g.fy.nstages - 1;
         for (int s = 1; s < (g.fuse_last ? ylast : g.fy.nstages); ++s) {
-            ip_stage_any<false>(buf, g.fy.st[s], R1, nh, g.div_nh, ay, sm.twy);
+            ip_stage_any<false>(buf, g.fy.st[s], R1, nh, g.div_nh, ay, twy);
             __syncthreads();
         }
         // ---- last y stage, times w_n1^(yl ky_a), to HBM in tile order: runs of T consecutive rows
@@ -377,26 +388,26 @@ k_g2_p1(const float* __restrict__ boxes, long long batch_stride, int n2_total, I
         const long long inner = ((long long)x * g.R2 + slot) << g.lgT;
         if (g.fuse_last) {
             switch (g.fy.st[ylast].radix) {
-                case 2: p1_y_last_store<2>(buf, dst, g, sm, yl, inner); break;
-                case 3: p1_y_last_store<3>(buf, dst, g, sm, yl, inner); break;
-                case 4: p1_y_last_store<4>(buf, dst, g, sm, yl, inner); break;
-                case 5: p1_y_last_store<5>(buf, dst, g, sm, yl, inner); break;
-                case 6: p1_y_last_store<6>(buf, dst, g, sm, yl, inner); break;
-                case 8: p1_y_last_store<8>(buf, dst, g, sm, yl, inner); break;
-                default: p1_y_last_store<10>(buf, dst, g, sm, yl, inner); break;
+                case 2: p1_y_last_store<2>(buf, dst, g, twy, kya, yl, inner); break;
+                case 3: p1_y_last_store<3>(buf, dst, g, twy, kya, yl, inner); break;
+                case 4: p1_y_last_store<4>(buf, dst, g, twy, kya, yl, inner); break;
+                case 5: p1_y_last_store<5>(buf, dst, g, twy, kya, yl, inner); break;
+                case 6: p1_y_last_store<6>(buf, dst, g, twy, kya, yl, inner); break;
+                case 8: p1_y_last_store<8>(buf, dst, g, twy, kya, yl, inner); break;
+                default: p1_y_last_store<10>(buf, dst, g, twy, kya, yl, inner); break;
             }
         } else {
             const long long tile_elems = (long long)g.n0 * 32;
             for (int e = tid; e < R1 * nh; e += nthr) {
                 const int jp = fast_div(e, g.div_nh), r = e - jp * nh;
                 float2 v = buf[r * ld + jp];
-                if (yl) v = cmul_w2(v, sm.twy[yl * sm.kya[jp]]);
+                if (yl) v = cmul_w2(v, twy[yl * kya[jp]]);
                 dst[((long long)jp * g.nzt + (r >> g.lgT)) * tile_elems + inner + (r & (g.T - 1))] = v;
             }
         }
         if (g.nbuf == 1 && u + 1 < nunits) {
             __syncthreads();
-            issue_unit(u + 1, sm.buf[0]);
+            issue_unit(u + 1, smem);
         }
     }
 }
@@ -488,45 +499,47 @@ struct BinWalk {
     }
 };
 
-// last x stage (radix RL, contiguous sub-blocks) -> |delta_k|^2 -> bins, straight from registers
-template <int RL, int NSHARE>
+// last x stage (radix RL, contiguous sub-blocks) -> |delta_k|^2 -> bins, straight from registers.
+// `release`: called by every thread once its inputs and bin indices sit in registers when the whole stage is one task
+// per thread (the usual case: (n0 / RL) * 32 tasks = block size) -- the tile buffers are dead from then on, and the
+// bulk copy of the next tile overlaps the butterflies and the binning of this one.
+template <int RL, int NSHARE, bool EARLY, class Release>
 __device__ __forceinline__ void p2_last_stage(const float2* __restrict__ tile, const uint8_t* __restrict__ lutb,
                                               const G2Dev& g, const AddrTile addr, BinWalk<NSHARE>& bw,
-                                              float2* __restrict__ dc_out) {
-    const int ntasks = (g.n0 / RL) * 32;
+                                              float2* __restrict__ dc_out, Release release) {
+    constexpr int NW = (RL + 3) / 4;
+    const int ntasks = (g.n0 / RL) * 32;   // EARLY: == blockDim.x, the loop body runs once in every thread
     for (int task = threadIdx.x; task < ntasks; task += blockDim.x) {
         const int c = task & 31, bf = task >> 5;
         float2 v[RL];
+        uint32_t lw[NW];
 #pragma unroll
         for (int m = 0; m < RL; ++m) v[m] = tile[addr(bf * RL + m, c)];
+        const uint32_t* lp = reinterpret_cast<const uint32_t*>(lutb) + task * NW;
+#pragma unroll
+        for (int w4 = 0; w4 < NW; ++w4) lw[w4] = lp[w4];
+        if (EARLY) release();
         small_dft<RL>(v);
         if (dc_out && task == 0) *dc_out = v[0];
-        const uint8_t* lp = lutb + task * RL;
-        if (RL % 4 == 0) {
-            const uint32_t* lw = reinterpret_cast<const uint32_t*>(lp);
 #pragma unroll
-            for (int w4 = 0; w4 < RL / 4; ++w4) {
-                const uint32_t word = lw[w4];
-                float pw[4];
+        for (int w4 = 0; w4 < NW; ++w4) {
+            const uint32_t word = lw[w4];
+            const int cnt = (4 * w4 + 4 <= RL) ? 4 : RL - 4 * w4;   // the last word of a 25-point row holds one output
+            float pw[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-                for (int i = 0; i < 4; ++i) {
+            for (int i = 0; i < 4; ++i)
+                if (i < cnt) {
                     const float2 o = v[visit_order(4 * w4 + i, RL)];
                     pw[i] = o.x * o.x + o.y * o.y;
                 }
-                // the bin changes rarely along |k_x|: a whole word of four outputs usually stays in the current bin
-                const bool same = word == bw.cur * 0x01010101u;
-                if (NSHARE == 1 ? same : (bool)__all_sync(0xffffffffu, same)) {
-                    bw.acc += (pw[0] + pw[1]) + (pw[2] + pw[3]);
-                } else {
+            // the bin changes rarely along |k_x|: a whole word of four outputs usually stays in the current bin
+            const bool same = cnt == 4 && word == bw.cur * 0x01010101u;
+            if (NSHARE == 1 ? same : (bool)__all_sync(0xffffffffu, same)) {
+                bw.acc += (pw[0] + pw[1]) + (pw[2] + pw[3]);
+            } else {
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) bw.add((word >> (8 * i)) & 255u, pw[i]);
-                }
-            }
-        } else {
-#pragma unroll
-            for (int i = 0; i < RL; ++i) {
-                const float2 o = v[visit_order(i, RL)];
-                bw.add(lp[i], o.x * o.x + o.y * o.y);
+                for (int i = 0; i < 4; ++i)
+                    if (i < cnt) bw.add((word >> (8 * i)) & 255u, pw[i]);
             }
         }
         bw.flush();   // at most RL fp32 terms per register sum
@@ -542,8 +555,10 @@ k_g2_p2(const float2* __restrict__ scratch, ItemMap im, const ChunkDev* __restri
     constexpr int lgT = (T == 16) ? 4 : (T == 8) ? 3 : (T == 4) ? 2 : 1;
     const int tile_elems = g.n0 * 32;
     PS21_DYN_SMEM(float2, tile);                                            // [n0][32]
-    uint8_t* lutb = reinterpret_cast<uint8_t*>(tile + tile_elems);           // [n0 * 32]
-    uint64_t* bar = reinterpret_cast<uint64_t*>(lutb + tile_elems);
+    const int RLk = g.fx.st[g.fx.nstages - 1].radix;
+    const uint32_t lut_bytes = (uint32_t)lut_tile_bytes(g.n0, RLk);          // multiple of 128
+    uint8_t* lutb = reinterpret_cast<uint8_t*>(tile + tile_elems);           // [lut_bytes]
+    uint64_t* bar = reinterpret_cast<uint64_t*>(lutb + lut_bytes);
     double* cbins = reinterpret_cast<double*>(bar + 2);                      // [nbins] fp64 bins of the CTA
     float2* twx = reinterpret_cast<float2*>(cbins + MAX_BINS);               // [n0] w_n0^q
     float* lbins = reinterpret_cast<float*>(twx + g.n0);                     // [nbins][ncol]
@@ -565,9 +580,9 @@ k_g2_p2(const float2* __restrict__ scratch, ItemMap im, const ChunkDev* __restri
     __syncthreads();
     const uint64_t pol_stream = l2_policy_evict_first(), pol_keep = l2_policy_evict_last();
     auto issue_tile = [&](int tl) {
-        mbar_expect_tx(bar, (uint32_t)tile_elems * 9u);
+        mbar_expect_tx(bar, (uint32_t)tile_elems * 8u + lut_bytes);
         bulk_g2s_hint(tile, src + (long long)tl * tile_elems, (uint32_t)tile_elems * 8u, bar, pol_stream);
-        bulk_g2s_hint(lutb, lut + (long long)tl * tile_elems, (uint32_t)tile_elems, bar, pol_keep);
+        bulk_g2s_hint(lutb, lut + (long long)tl * lut_bytes, lut_bytes, bar, pol_keep);
     };
     const AddrTile addr{R2 - 1, lgT};
     FastDiv div32;
@@ -595,22 +610,50 @@ k_g2_p2(const float2* __restrict__ scratch, ItemMap im, const ChunkDev* __restri
             const int zt = tl % g.nzt;
             bw.mult = (float)g.zmult[zt * T + (tid & (T - 1))];
             float2* dc_out = (tl == 0) ? dc + (box * nchunks + cid) : nullptr;
-            switch (g.fx.st[g.fx.nstages - 1].radix) {
-                case 32: p2_last_stage<32, NSHARE>(tile, lutb, g, addr, bw, dc_out); break;
-                case 25: p2_last_stage<25, NSHARE>(tile, lutb, g, addr, bw, dc_out); break;
-                case 16: p2_last_stage<16, NSHARE>(tile, lutb, g, addr, bw, dc_out); break;
-                case 8: p2_last_stage<8, NSHARE>(tile, lutb, g, addr, bw, dc_out); break;
-                case 5: p2_last_stage<5, NSHARE>(tile, lutb, g, addr, bw, dc_out); break;
-                default: p2_last_stage<4, NSHARE>(tile, lutb, g, addr, bw, dc_out); break;
+            const bool have_next = tl + g.slots < g.ntiles;
+            // one task per thread and whole warps busy or idle together (the group bin mode votes per warp)
+            const int ntasks_last = (g.n0 / RLk) * 32;
+            const bool early = ntasks_last == nthr;
+            auto release = [&]() {   // warps 1.. signal without waiting, warp 0 waits for them and starts the copy
+                if (!have_next) return;
+                if (tid >= 32) {
+                    named_bar_arrive(3, nthr);
+                } else {
+                    named_bar_sync(3, nthr);
+                    if (tid == 0) {
+                        fence_proxy_async();
+                        issue_tile(tl + g.slots);
+                    }
+                }
+            };
+#define PS21_G2_LAST(RL)                                                                                   \
+    case RL:                                                                                               \
+        if (early) p2_last_stage<RL, NSHARE, true>(tile, lutb, g, addr, bw, dc_out, release);             \
+        else p2_last_stage<RL, NSHARE, false>(tile, lutb, g, addr, bw, dc_out, release);                  \
+        break
+            switch (RLk) {
+                PS21_G2_LAST(32);
+                PS21_G2_LAST(25);
+                PS21_G2_LAST(16);
+                PS21_G2_LAST(8);
+                PS21_G2_LAST(5);
+                default:
+                    if (early) p2_last_stage<4, NSHARE, true>(tile, lutb, g, addr, bw, dc_out, release);
+                    else p2_last_stage<4, NSHARE, false>(tile, lutb, g, addr, bw, dc_out, release);
+                    break;
             }
-        }
-        __syncthreads();   // tile and table buffers are dead, lane bins of this tile complete
-        if (tid == 0 && tl + g.slots < g.ntiles) {
-            fence_proxy_async();
-            issue_tile(tl + g.slots);
+#undef PS21_G2_LAST
+            if (!early) {
+                __syncthreads();   // tile and table buffers are dead
+                if (tid == 0 && have_next) {
+                    fence_proxy_async();
+                    issue_tile(tl + g.slots);
+                }
+            }
         }
         if ((it % FLUSH_EVERY) == FLUSH_EVERY - 1 || tl + g.slots >= g.ntiles) {
             // fixed-order fp32 -> fp64 flush; a lane bin then holds at most RL * tasks * FLUSH_EVERY fp32 terms
+            __syncthreads();   // every thread's bins of this tile are complete
             const int warp = tid >> 5, lane = tid & 31;
             for (int b = warp; b < nbins; b += nthr >> 5) {
                 double a = 0.0;
@@ -719,7 +762,8 @@ static size_t p1_smem(const G2Dev& g) {
            (size_t)(g.M + g.R1) * 2 + 64;
 }
 static size_t p2_smem(const G2Dev& g, int nbins, int nshare) {
-    return (size_t)g.n0 * 32 * 9 + 16 + (size_t)MAX_BINS * 8 + (size_t)g.n0 * 8 +
+    const int RL = g.fx.st[g.fx.nstages - 1].radix;
+    return (size_t)g.n0 * 32 * 8 + (size_t)lut_tile_bytes(g.n0, RL) + 16 + (size_t)MAX_BINS * 8 + (size_t)g.n0 * 8 +
            (size_t)nbins * (g.p2_threads / nshare) * 4;
 }
 
@@ -828,7 +872,10 @@ int g2_try_setup(ps21_plan* p, ShapePlan& sp) {
         g.slots = (g.ntiles + per - 1) / per;
         if (g.slots < 1) g.slots = 1;
     }
-    g.p2_threads = (n0 * 32 >= 12288) ? 512 : 256;
+    {   // one last-stage butterfly per thread when that gives a sensible block (enables the early tile hand-over)
+        const int last_tasks = (n0 / rx.back()) * 32;
+        g.p2_threads = (last_tasks >= 128 && last_tasks <= 512) ? last_tasks : ((n0 * 32 >= 12288) ? 512 : 256);
+    }
     auto* gs = new G2Shape();
     gs->R0 = R0;
     gs->nshare = p->nbins <= MAX_BINS_LANE ? 1 : 4;
