@@ -58,6 +58,10 @@ struct G2Dev {
     int nbuf;                   // pass 1: shared-memory row buffers (2: the next unit streams in during this one's FFTs)
     int slabs;                  // pass 1: consecutive x slabs per CTA
     int fuse_first, fuse_last;  // pass 1: untangle inside the first y stage / HBM store inside the last y stage
+    int bluestein, Lc;          // pass 1: z transform of length M as a chirp convolution of length Lc (M has a big prime)
+    int zrows;                  // pass 1: rows per buffer = max(nh, Lc)
+    IpFft fzb;                  // ... the convolution's transform of length Lc
+    const float2 *tw_c, *chirp, *bhat;   // w_Lc^q [Lc]; exp(-i pi n^2 / M) [M]; FFT of the chirp / Lc, position order [Lc]
     IpFft fz, fy, fx;
     FastDiv div_M, div_R1, div_nh;
     const float2 *tw_z, *tw_y, *tw_x;   // exp(-2 pi i q / n) for n = nz, n1, n0
@@ -70,6 +74,7 @@ struct G2Shape {
     G2Dev dev{};
     uint16_t *d_rowz = nullptr, *d_kya = nullptr, *d_kxpos = nullptr, *d_kzrow = nullptr;
     uint8_t* d_zmult = nullptr;
+    float2 *d_twc = nullptr, *d_chirp = nullptr, *d_bhat = nullptr;   // Bluestein tables
     int R0 = 0;                 // radix of the first x stage (fused with the y_lo transform)
     int nshare = 1;             // lanes per fp32 bin column: 1 (<= 40 bins) or 4
     size_t smem1 = 0, smem2 = 0;
@@ -82,20 +87,43 @@ struct G2Shape {
 // One stage of radix R over `ncols` independent sequences: element i of column c lives at buf[addr(i, c)].
 // Stage geometry: sub-blocks of L = q R consecutive indices; butterfly (b, o) takes i = b L + o + m q, m = 0..R-1,
 // and leaves output m' (multiplied by w_L^(o m')) where input m' was.
-// `sub` (pass 1, first z stage): the chunk's offset estimate is subtracted from both halves of every packed pair as
-// the data is read -- before any butterfly, so the fp32 transform never sees the large mean.
-template <int R, class Addr>
-__device__ __forceinline__ void ip_stage(float2* __restrict__ buf, const IpStage st, int nbf, int ncols, FastDiv div_cols,
-                                         const Addr addr, const float2* __restrict__ tw, float sub = 0.f) {
+// `pre(i, v)` transforms a value as it is read (index i along the transform axis):
+//   PreSub    pass 1, first z stage: the chunk's offset estimate is subtracted from both halves of every packed pair
+//             before any butterfly, so the fp32 transform never sees the large mean;
+//   PreChirp  the same, times the chirp exp(-i pi i^2 / M), zero beyond M (Bluestein input);
+//   PreBhat   times the chirp's spectrum, conjugated (Bluestein: first stage of the inverse transform).
+struct PreSub {
+    float2 s;
+    __device__ __forceinline__ float2 operator()(int, float2 v) const { return csub(v, s); }
+};
+struct PreChirp {
+    float2 s;
+    const float2* chirp;
+    int M;
+    __device__ __forceinline__ float2 operator()(int i, float2 v) const {
+        return i < M ? cmul_w2(csub(v, s), chirp[i]) : make_float2(0.f, 0.f);
+    }
+};
+struct PreBhat {
+    const float2* bhat;
+    __device__ __forceinline__ float2 operator()(int i, float2 v) const {
+        const float2 t = cmul_w2(v, bhat[i]);
+        return make_float2(t.x, -t.y);
+    }
+};
+
+// `addr(i, c)` is the 32-bit shared-memory byte address of element i of column c.
+template <int R, class Addr, class Pre>
+__device__ __forceinline__ void ip_stage(const IpStage st, int nbf, int ncols, FastDiv div_cols,
+                                         const Addr addr, const float2* __restrict__ tw, const Pre pre) {
     const int ntasks = nbf * ncols;
-    const float2 sub2 = make_float2(sub, sub);
     for (int task = threadIdx.x; task < ntasks; task += blockDim.x) {
         const int bf = fast_div(task, div_cols), c = task - bf * ncols;
         const int b = fast_div(bf, st.div_q), o = bf - b * st.q;
         const int i0 = b * st.q * R + o;
         float2 v[R];
 #pragma unroll
-        for (int m = 0; m < R; ++m) v[m] = csub(buf[addr(i0 + m * st.q, c)], sub2);
+        for (int m = 0; m < R; ++m) v[m] = pre(i0 + m * st.q, lds64(addr(i0 + m * st.q, c)));
         small_dft<R>(v);
         if (st.q > 1) {
             const int step = o * st.twmul;
@@ -107,33 +135,70 @@ __device__ __forceinline__ void ip_stage(float2* __restrict__ buf, const IpStage
             }
         }
 #pragma unroll
-        for (int m = 0; m < R; ++m) buf[addr(i0 + m * st.q, c)] = v[m];
+        for (int m = 0; m < R; ++m) sts64(addr(i0 + m * st.q, c), v[m]);
     }
 }
 
-template <bool BIG, class Addr>
-__device__ __forceinline__ void ip_stage_any(float2* buf, const IpStage st, int n, int ncols, FastDiv div_cols,
-                                             const Addr addr, const float2* tw, float sub = 0.f) {
+// The transposed stage (twiddle on the inputs, then the butterfly).  Running the stages of a forward plan transposed
+// and in reverse order takes digit-reversed input to natural-order output: the DFT matrix is symmetric, so
+// W = (P^T S_last ... S_0)^T = S_0^T ... S_last^T P.  Used by the Bluestein path for the inverse transform
+// (on conjugated data).
+template <int R, class Addr, class Pre>
+__device__ __forceinline__ void ip_stage_T(const IpStage st, int nbf, int ncols, FastDiv div_cols,
+                                           const Addr addr, const float2* __restrict__ tw, const Pre pre) {
+    const int ntasks = nbf * ncols;
+    for (int task = threadIdx.x; task < ntasks; task += blockDim.x) {
+        const int bf = fast_div(task, div_cols), c = task - bf * ncols;
+        const int b = fast_div(bf, st.div_q), o = bf - b * st.q;
+        const int i0 = b * st.q * R + o;
+        float2 v[R];
+#pragma unroll
+        for (int m = 0; m < R; ++m) v[m] = pre(i0 + m * st.q, lds64(addr(i0 + m * st.q, c)));
+        if (st.q > 1) {
+            const int step = o * st.twmul;
+            int idx = step;
+#pragma unroll
+            for (int m = 1; m < R; ++m) {
+                v[m] = cmul_w2(v[m], tw[idx]);
+                idx += step;
+            }
+        }
+        small_dft<R>(v);
+#pragma unroll
+        for (int m = 0; m < R; ++m) sts64(addr(i0 + m * st.q, c), v[m]);
+    }
+}
+
+template <bool BIG, bool TRANSPOSED = false, class Addr, class Pre>
+__device__ __forceinline__ void ip_stage_any(const IpStage st, int n, int ncols, FastDiv div_cols,
+                                             const Addr addr, const float2* tw, const Pre pre) {
     const int nbf = n / st.radix;
-#define PS21_IP_CASE(R) case R: ip_stage<R>(buf, st, nbf, ncols, div_cols, addr, tw, sub); break
+#define PS21_IP_CASE(R)                                                        \
+    case R:                                                                    \
+        if (TRANSPOSED) ip_stage_T<R>(st, nbf, ncols, div_cols, addr, tw, pre);      \
+        else ip_stage<R>(st, nbf, ncols, div_cols, addr, tw, pre);             \
+        break
     switch (st.radix) {
         PS21_IP_CASE(2); PS21_IP_CASE(3); PS21_IP_CASE(4); PS21_IP_CASE(5); PS21_IP_CASE(6); PS21_IP_CASE(7);
         PS21_IP_CASE(8); PS21_IP_CASE(9); PS21_IP_CASE(10); PS21_IP_CASE(11); PS21_IP_CASE(12); PS21_IP_CASE(13);
         PS21_IP_CASE(15); PS21_IP_CASE(16);
-        case 25: if (BIG) ip_stage<25>(buf, st, nbf, ncols, div_cols, addr, tw, sub); break;
-        case 32: if (BIG) ip_stage<32>(buf, st, nbf, ncols, div_cols, addr, tw, sub); break;
+        case 25: if (BIG) ip_stage<25>(st, nbf, ncols, div_cols, addr, tw, pre); break;
+        case 32: if (BIG) ip_stage<32>(st, nbf, ncols, div_cols, addr, tw, pre); break;
         default: break;
     }
 #undef PS21_IP_CASE
 }
 
-struct AddrStrided {   // pass 1: index stride si, column stride sc
-    int si, sc;
-    __device__ __forceinline__ int operator()(int i, int c) const { return i * si + c * sc; }
+struct AddrStrided {   // pass 1: byte strides of the index and of the column
+    uint32_t base, si, sc;
+    __device__ __forceinline__ uint32_t operator()(int i, int c) const { return base + i * si + c * sc; }
 };
 struct AddrTile {      // pass 2: row x holds 32 columns (ky_b, t); the ky_b slot is XOR-ed with the low bits of x
-    int swmask, lgT;   // swmask = R2 - 1
-    __device__ __forceinline__ int operator()(int i, int c) const { return i * 32 + (c ^ ((i & swmask) << lgT)); }
+    uint32_t base;     // 256-byte aligned
+    int swmask, sh;    // swmask = R2 - 1, sh = log2(T) + 3
+    __device__ __forceinline__ uint32_t operator()(int i, int c) const {
+        return base + i * 256 + ((c << 3) ^ ((i & swmask) << sh));
+    }
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -192,43 +257,53 @@ __global__ void k_g2_lut(uint8_t* __restrict__ lut, unsigned long long* __restri
 // generic accesses, 30 % excess wavefronts and long-scoreboard stalls where LDS / STS were meant.)
 
 // untangle of the packed real FFT for pair p of one butterfly leg: rows r1 = row(p), r2 = row(M - p)
-template <int R>
-__device__ __forceinline__ void p1_y_first(float2* __restrict__ buf, const G2Dev& g, const float2* __restrict__ twz,
-                                           const float2* __restrict__ twy, const uint16_t* __restrict__ rowz) {
+// BLU: the rows hold the conjugate of the chirp convolution; C_p = chirp[p] * conj(row p) is formed as they are read
+template <bool BLU>
+__device__ __forceinline__ float2 zfix(float2 v, const float2* __restrict__ chirp, int p) {
+    return BLU ? cmul_w2(make_float2(v.x, -v.y), chirp[p]) : v;
+}
+
+template <int R, bool BLU>
+__device__ __forceinline__ void p1_y_first(uint32_t buf, const G2Dev& g, const float2* __restrict__ twz,
+                                           const float2* __restrict__ twy, const uint16_t* __restrict__ rowz,
+                                           const float2* __restrict__ chirp) {
     // first y stage (radix R over j = o + m q) of the row pair (p, M - p), with the untangle of that pair done on
     // the values as they are read: one pass over shared memory and one barrier instead of two
     const IpStage st = g.fy.st[0];
-    const int q = st.q, M = g.M, ld = g.ld;
+    const int q = st.q, M = g.M;
+    const uint32_t ldb = g.ld * 8, qb = q * 8;
     const int ntasks = (M / 2 + 1) * q;
     for (int task = threadIdx.x; task < ntasks; task += blockDim.x) {
         const int p = fast_div(task, st.div_q), o = task - p * q;   // o fastest: lanes along contiguous j
         float2 a1[R], a2[R];
-        float2 *q1, *q2;
+        uint32_t q1, q2;
         const bool self = (2 * p == M);
         if (p == 0) {
-            q1 = buf + o;                 // frequency 0 stays in row 0
-            q2 = buf + M * ld + o;        // the Nyquist row is created here
+            q1 = buf + o * 8;                 // frequency 0 stays in row 0
+            q2 = buf + M * ldb + o * 8;       // the Nyquist row is created here
 #pragma unroll
             for (int m = 0; m < R; ++m) {
-                const float2 c0 = q1[m * q];
+                const float2 c0 = zfix<BLU>(lds64(q1 + m * qb), chirp, 0);
                 a1[m] = make_float2(c0.x + c0.y, 0.f);
                 a2[m] = make_float2(c0.x - c0.y, 0.f);
             }
         } else if (self) {
-            q1 = q2 = buf + rowz[p] * ld + o;
+            q1 = q2 = buf + rowz[p] * ldb + o * 8;
 #pragma unroll
             for (int m = 0; m < R; ++m) {
-                const float2 c0 = q1[m * q];
+                const float2 c0 = zfix<BLU>(lds64(q1 + m * qb), chirp, p);
                 a1[m] = make_float2(c0.x, -c0.y);
                 a2[m] = a1[m];
             }
         } else {
-            q1 = buf + rowz[p] * ld + o;
-            q2 = buf + rowz[M - p] * ld + o;
+            q1 = buf + rowz[p] * ldb + o * 8;
+            q2 = buf + rowz[M - p] * ldb + o * 8;
             const float2 w = twz[p];   // w_nz^p; times -i/2 -> (wy/2, -wx/2)
             const float4 wu = make_float4(0.5f * w.y, -0.5f * w.x, 0.5f * w.x, 0.5f * w.y);
 #pragma unroll
-            for (int m = 0; m < R; ++m) untangle(q1[m * q], q2[m * q], wu, a1[m], a2[m]);
+            for (int m = 0; m < R; ++m)
+                untangle(zfix<BLU>(lds64(q1 + m * qb), chirp, p), zfix<BLU>(lds64(q2 + m * qb), chirp, M - p), wu,
+                         a1[m], a2[m]);
         }
         small_dft<R>(a1);
         small_dft<R>(a2);
@@ -244,27 +319,28 @@ __device__ __forceinline__ void p1_y_first(float2* __restrict__ buf, const G2Dev
             }
         }
 #pragma unroll
-        for (int m = 0; m < R; ++m) q1[m * q] = a1[m];
+        for (int m = 0; m < R; ++m) sts64(q1 + m * qb, a1[m]);
         if (!self) {
 #pragma unroll
-            for (int m = 0; m < R; ++m) q2[m * q] = a2[m];
+            for (int m = 0; m < R; ++m) sts64(q2 + m * qb, a2[m]);
         }
     }
 }
 
 // last y stage (radix R over contiguous j) of every row, results times w_n1^(yl ky_a) straight to HBM in tile order
 template <int R>
-__device__ __forceinline__ void p1_y_last_store(const float2* __restrict__ buf, float2* __restrict__ dst,
+__device__ __forceinline__ void p1_y_last_store(uint32_t buf, float2* __restrict__ dst,
                                                 const G2Dev& g, const float2* __restrict__ twy,
                                                 const uint16_t* __restrict__ kya, int yl, long long inner) {
-    const int nh = g.nh, ld = g.ld, nsub = g.R1 / R;
+    const int nh = g.nh, nsub = g.R1 / R;
+    const uint32_t ldb = g.ld * 8;
     const long long tile_elems = (long long)g.n0 * 32;
     for (int task = threadIdx.x; task < nsub * nh; task += blockDim.x) {
         const int b = fast_div(task, g.div_nh), r = task - b * nh;   // r fastest: lanes along rows
         float2 v[R];
-        const float2* src = buf + r * ld + b * R;
+        const uint32_t src = buf + r * ldb + b * (R * 8);
 #pragma unroll
-        for (int m = 0; m < R; ++m) v[m] = src[m];
+        for (int m = 0; m < R; ++m) v[m] = lds64(src + m * 8);
         small_dft<R>(v);
         const long long jstride = (long long)g.nzt * tile_elems;
         float2* out = dst + (long long)(r >> g.lgT) * tile_elems + inner + (r & (g.T - 1)) + (long long)(b * R) * jstride;
@@ -285,10 +361,13 @@ k_g2_p1(const float* __restrict__ boxes, long long batch_stride, int n2_total, I
     PS21_DYN_SMEM(float2, smem);
     const int tid = threadIdx.x, nthr = blockDim.x;
     const int M = g.M, R1 = g.R1, ld = g.ld, nh = g.nh;
-    const int bufstride = nh * ld;
+    const int bufstride = g.zrows * ld;
     float2* const twz = smem + g.nbuf * bufstride;                       // [nz]  w_nz^q
     float2* const twy = twz + g.nz;                                      // [n1]  w_n1^q
-    uint16_t* const rowz = reinterpret_cast<uint16_t*>(twy + g.n1);      // [M]   copy of G2Dev::rowz_of_k
+    float2* const twc = twy + g.n1;                                      // [Lc]  w_Lc^q            (Bluestein only)
+    float2* const chirp = twc + g.Lc;                                    // [M]   exp(-i pi n^2/M)  (Bluestein only)
+    float2* const bhat = chirp + (g.bluestein ? M : 0);                  // [Lc]  chirp spectrum    (Bluestein only)
+    uint16_t* const rowz = reinterpret_cast<uint16_t*>(bhat + g.Lc);     // [M]   copy of G2Dev::rowz_of_k
     uint16_t* const kya = rowz + M;                                      // [R1]  copy of G2Dev::kya_of_jp
     long long box;
     int cid;
@@ -298,12 +377,18 @@ k_g2_p1(const float* __restrict__ boxes, long long batch_stride, int n2_total, I
     const int x0 = blockIdx.x * g.slabs;
     const float* spec = boxes + box * batch_stride + ch.start;
     float2* dst = scratch + (long long)blockIdx.y * ((long long)g.ntiles * g.n0 * 32);
-    const AddrStrided az{ld, 1};    // z transform: index = row (z pair / k_z), column = j
-    const AddrStrided ay{1, ld};    // y transform: index = j, column = row
+    const uint32_t smem32 = smem_u32(smem), ldb = (uint32_t)ld * 8u;
     for (int i = tid; i < g.nz; i += nthr) twz[i] = g.tw_z[i];
     for (int i = tid; i < g.n1; i += nthr) twy[i] = g.tw_y[i];
     for (int i = tid; i < M; i += nthr) rowz[i] = g.rowz_of_k[i];
     for (int i = tid; i < R1; i += nthr) kya[i] = g.kya_of_jp[i];
+    if (g.bluestein) {
+        for (int i = tid; i < g.Lc; i += nthr) {
+            twc[i] = g.tw_c[i];
+            bhat[i] = g.bhat[i];
+        }
+        for (int i = tid; i < M; i += nthr) chirp[i] = g.chirp[i];
+    }
     // rows y = yl + R2 j of slab x as packed (even, odd) pairs: buf[zc][j]; asynchronous copies (LDGSTS), lanes along z
     // -> coalesced reads, conflict-free writes (ld is odd)
     auto issue_unit = [&](int u, float2* buf) {
@@ -330,57 +415,89 @@ k_g2_p1(const float* __restrict__ boxes, long long batch_stride, int n2_total, I
     issue_unit(0, smem);
     for (int u = 0; u < nunits; ++u) {
         float2* buf = smem + (u % g.nbuf) * bufstride;
+        const uint32_t buf32 = smem32 + (uint32_t)(u % g.nbuf) * (uint32_t)bufstride * 8u;
+        const AddrStrided az{buf32, ldb, 8u};    // z transform: index = row (z pair / k_z), column = j
+        const AddrStrided ay{buf32, 8u, ldb};    // y transform: index = j, column = row
         const int x = x0 + u / g.R2, yl = u - (u / g.R2) * g.R2;
         cp_async_wait<0>();
         __syncthreads();   // unit u has landed; everybody is done with unit u - 1 (tables ready on the first turn)
         if (g.nbuf == 2 && u + 1 < nunits) issue_unit(u + 1, smem + ((u + 1) % 2) * bufstride);
         // ---- z: complex FFT of length M over the row index, in place; the offset is subtracted as stage 0 reads
-        for (int s = 0; s < g.fz.nstages; ++s) {
-            ip_stage_any<false>(buf, g.fz.st[s], M, R1, g.div_R1, az, twz, s == 0 ? mean : 0.f);
-            __syncthreads();
+        const float2 mean2 = make_float2(mean, mean);
+        if (!g.bluestein) {
+            for (int s = 0; s < g.fz.nstages; ++s) {
+                ip_stage_any<false>(g.fz.st[s], M, R1, g.div_R1, az, twz, PreSub{s == 0 ? mean2 : make_float2(0.f, 0.f)});
+                __syncthreads();
+            }
+        } else {
+            // M has a prime factor the butterflies do not cover: X_k = c_k sum_n (x_n c_n) conj(c)_{k-n}, c_n = exp(-i pi n^2/M),
+            // as a circular convolution of length Lc >= 2M - 1: forward transform (chirp and zero padding applied as
+            // stage 0 reads), times the chirp's spectrum (applied, conjugated, as the inverse's first stage reads),
+            // inverse transform = the forward plan transposed and reversed on conjugated data -> natural order;
+            // the last factor c_k and the conjugation are applied where the untangle reads the rows.
+            const int ns = g.fzb.nstages;
+            for (int s = 0; s < ns; ++s) {
+                if (s == 0) ip_stage_any<false>(g.fzb.st[0], g.Lc, R1, g.div_R1, az, twc, PreChirp{mean2, chirp, M});
+                else ip_stage_any<false>(g.fzb.st[s], g.Lc, R1, g.div_R1, az, twc, PreSub{make_float2(0.f, 0.f)});
+                __syncthreads();
+            }
+            for (int s = ns - 1; s >= 0; --s) {
+                if (s == ns - 1) ip_stage_any<false, true>(g.fzb.st[s], g.Lc, R1, g.div_R1, az, twc, PreBhat{bhat});
+                else ip_stage_any<false, true>(g.fzb.st[s], g.Lc, R1, g.div_R1, az, twc, PreSub{make_float2(0.f, 0.f)});
+                __syncthreads();
+            }
         }
         // ---- untangle (pairs (p, M - p) -> A_p, A_{M-p}; p = 0 also yields the Nyquist row M) + first y stage
         if (g.fuse_first) {
+#define PS21_G2_YFIRST(R)                                                        \
+    do {                                                                         \
+        if (g.bluestein) p1_y_first<R, true>(buf32, g, twz, twy, rowz, chirp);   \
+        else p1_y_first<R, false>(buf32, g, twz, twy, rowz, chirp);              \
+    } while (0)
             switch (g.fy.st[0].radix) {
-                case 2: p1_y_first<2>(buf, g, twz, twy, rowz); break;
-                case 3: p1_y_first<3>(buf, g, twz, twy, rowz); break;
-                case 4: p1_y_first<4>(buf, g, twz, twy, rowz); break;
-                case 5: p1_y_first<5>(buf, g, twz, twy, rowz); break;
-                case 6: p1_y_first<6>(buf, g, twz, twy, rowz); break;
-                case 8: p1_y_first<8>(buf, g, twz, twy, rowz); break;
-                default: p1_y_first<10>(buf, g, twz, twy, rowz); break;
+                case 2: PS21_G2_YFIRST(2); break;
+                case 3: PS21_G2_YFIRST(3); break;
+                case 4: PS21_G2_YFIRST(4); break;
+                case 5: PS21_G2_YFIRST(5); break;
+                case 6: PS21_G2_YFIRST(6); break;
+                case 8: PS21_G2_YFIRST(8); break;
+                default: PS21_G2_YFIRST(10); break;
             }
+#undef PS21_G2_YFIRST
             __syncthreads();
         } else {
             const int npair = M / 2 + 1;
             for (int e = tid; e < npair * R1; e += nthr) {
                 const int p = fast_div(e, g.div_R1), j = e - p * R1;
+                auto fix = [&](float2 v, int row) {   // Bluestein: C_p = chirp[p] conj(row p)
+                    return g.bluestein ? cmul_w2(make_float2(v.x, -v.y), chirp[row]) : v;
+                };
                 if (p == 0) {
-                    const float2 c0 = buf[j];
+                    const float2 c0 = fix(buf[j], 0);
                     buf[j] = make_float2(c0.x + c0.y, 0.f);
                     buf[M * ld + j] = make_float2(c0.x - c0.y, 0.f);
                 } else if (2 * p == M) {
                     float2* q = buf + rowz[p] * ld + j;
-                    const float2 c0 = *q;
+                    const float2 c0 = fix(*q, p);
                     *q = make_float2(c0.x, -c0.y);
                 } else {
                     float2* q1 = buf + rowz[p] * ld + j;
                     float2* q2 = buf + rowz[M - p] * ld + j;
                     const float2 w = twz[p];
                     float2 a1, a2;
-                    untangle(*q1, *q2, make_float4(0.5f * w.y, -0.5f * w.x, 0.5f * w.x, 0.5f * w.y), a1, a2);
+                    untangle(fix(*q1, p), fix(*q2, M - p), make_float4(0.5f * w.y, -0.5f * w.x, 0.5f * w.x, 0.5f * w.y), a1, a2);
                     *q1 = a1;
                     *q2 = a2;
                 }
             }
             __syncthreads();
-            ip_stage_any<false>(buf, g.fy.st[0], R1, nh, g.div_nh, ay, twy);
+            ip_stage_any<false>(g.fy.st[0], R1, nh, g.div_nh, ay, twy, PreSub{make_float2(0.f, 0.f)});
             __syncthreads();
         }
         // ---- middle y stages, in place
         const int ylast = g.fy.nstages - 1;
         for (int s = 1; s < (g.fuse_last ? ylast : g.fy.nstages); ++s) {
-            ip_stage_any<false>(buf, g.fy.st[s], R1, nh, g.div_nh, ay, twy);
+            ip_stage_any<false>(g.fy.st[s], R1, nh, g.div_nh, ay, twy, PreSub{make_float2(0.f, 0.f)});
             __syncthreads();
         }
         // ---- last y stage, times w_n1^(yl ky_a), to HBM in tile order: runs of T consecutive rows
@@ -388,13 +505,13 @@ k_g2_p1(const float* __restrict__ boxes, long long batch_stride, int n2_total, I
         const long long inner = ((long long)x * g.R2 + slot) << g.lgT;
         if (g.fuse_last) {
             switch (g.fy.st[ylast].radix) {
-                case 2: p1_y_last_store<2>(buf, dst, g, twy, kya, yl, inner); break;
-                case 3: p1_y_last_store<3>(buf, dst, g, twy, kya, yl, inner); break;
-                case 4: p1_y_last_store<4>(buf, dst, g, twy, kya, yl, inner); break;
-                case 5: p1_y_last_store<5>(buf, dst, g, twy, kya, yl, inner); break;
-                case 6: p1_y_last_store<6>(buf, dst, g, twy, kya, yl, inner); break;
-                case 8: p1_y_last_store<8>(buf, dst, g, twy, kya, yl, inner); break;
-                default: p1_y_last_store<10>(buf, dst, g, twy, kya, yl, inner); break;
+                case 2: p1_y_last_store<2>(buf32, dst, g, twy, kya, yl, inner); break;
+                case 3: p1_y_last_store<3>(buf32, dst, g, twy, kya, yl, inner); break;
+                case 4: p1_y_last_store<4>(buf32, dst, g, twy, kya, yl, inner); break;
+                case 5: p1_y_last_store<5>(buf32, dst, g, twy, kya, yl, inner); break;
+                case 6: p1_y_last_store<6>(buf32, dst, g, twy, kya, yl, inner); break;
+                case 8: p1_y_last_store<8>(buf32, dst, g, twy, kya, yl, inner); break;
+                default: p1_y_last_store<10>(buf32, dst, g, twy, kya, yl, inner); break;
             }
         } else {
             const long long tile_elems = (long long)g.n0 * 32;
@@ -415,21 +532,26 @@ k_g2_p1(const float* __restrict__ boxes, long long batch_stride, int n2_total, I
 // ------------------------------------------------------------------------------------------------
 // pass 2
 // ------------------------------------------------------------------------------------------------
-// first x stage (radix R0, sub-block = the whole axis) fused with the R2-point transform over y_lo
+// first x stage (radix R0, sub-block = the whole axis) fused with the R2-point transform over y_lo.
+// `tile32` is 256-byte aligned: row x starts at tile32 + 256 x, and inside the row the (slot, t) offset
+// ((yl ^ (x & (R2-1))) << (lgT+3)) | (t << 3) is a pure XOR of bit fields, so one row term per m and one XOR per value.
 template <int R0, int R2>
-__device__ __forceinline__ void p2_first_stage(float2* __restrict__ tile, const G2Dev& g, const float2* __restrict__ tw) {
+__device__ __forceinline__ void p2_first_stage(uint32_t tile32, const G2Dev& g, const float2* __restrict__ tw) {
     constexpr int T = 32 / R2;
     constexpr int lgT = (T == 16) ? 4 : (T == 8) ? 3 : (T == 4) ? 2 : 1;
+    constexpr int SH = lgT + 3;
     const int q0 = g.n0 / R0;
     const int ntasks = q0 * T;
     for (int task = threadIdx.x; task < ntasks; task += blockDim.x) {
         const int t = task & (T - 1), o = task >> lgT;
         float2 v[R0][R2];
+        uint32_t row[R0];
 #pragma unroll
         for (int m = 0; m < R0; ++m) {
             const int x = o + m * q0;
+            row[m] = (tile32 + x * 256 + (t << 3)) ^ ((x & (R2 - 1)) << SH);
 #pragma unroll
-            for (int yl = 0; yl < R2; ++yl) v[m][yl] = tile[x * 32 + (((yl ^ (x & (R2 - 1))) << lgT) | t)];
+            for (int yl = 0; yl < R2; ++yl) v[m][yl] = lds64(row[m] ^ (yl << SH));
         }
 #pragma unroll
         for (int m = 0; m < R0; ++m) small_dft<R2>(v[m]);
@@ -446,12 +568,11 @@ __device__ __forceinline__ void p2_first_stage(float2* __restrict__ tile, const 
         int idx = 0;
 #pragma unroll
         for (int m = 0; m < R0; ++m) {
-            const int x = o + m * q0;
             const float2 w = tw[idx];
             idx += step;
 #pragma unroll
             for (int kyb = 0; kyb < R2; ++kyb)
-                tile[x * 32 + (((kyb ^ (x & (R2 - 1))) << lgT) | t)] = (m == 0) ? v[m][kyb] : cmul_w2(v[m][kyb], w);
+                sts64(row[m] ^ (kyb << SH), (m == 0) ? v[m][kyb] : cmul_w2(v[m][kyb], w));
         }
     }
 }
@@ -503,8 +624,8 @@ struct BinWalk {
 // `release`: called by every thread once its inputs and bin indices sit in registers when the whole stage is one task
 // per thread (the usual case: (n0 / RL) * 32 tasks = block size) -- the tile buffers are dead from then on, and the
 // bulk copy of the next tile overlaps the butterflies and the binning of this one.
-template <int RL, int NSHARE, bool EARLY, class Release>
-__device__ __forceinline__ void p2_last_stage(const float2* __restrict__ tile, const uint8_t* __restrict__ lutb,
+template <int RL, int R2, int NSHARE, bool EARLY, class Release>
+__device__ __forceinline__ void p2_last_stage(const uint8_t* __restrict__ lutb,
                                               const G2Dev& g, const AddrTile addr, BinWalk<NSHARE>& bw,
                                               float2* __restrict__ dc_out, Release release) {
     constexpr int NW = (RL + 3) / 4;
@@ -513,8 +634,16 @@ __device__ __forceinline__ void p2_last_stage(const float2* __restrict__ tile, c
         const int c = task & 31, bf = task >> 5;
         float2 v[RL];
         uint32_t lw[NW];
+        {   // x = bf RL + m: the XOR term of the address depends on x & (R2 - 1) only -> R2 row-relative offsets,
+            // rotated by (bf RL) & (R2 - 1), and compile-time displacements m * 256
+            const uint32_t base = addr.base + (uint32_t)(bf * RL) * 256u;
+            const int rot = (bf * RL) & (R2 - 1);
+            uint32_t off[R2];
 #pragma unroll
-        for (int m = 0; m < RL; ++m) v[m] = tile[addr(bf * RL + m, c)];
+            for (int k = 0; k < R2; ++k) off[k] = base + (uint32_t)((c << 3) ^ (((k + rot) & (R2 - 1)) << addr.sh));
+#pragma unroll
+            for (int m = 0; m < RL; ++m) v[m] = lds64(off[m & (R2 - 1)] + m * 256);
+        }
         const uint32_t* lp = reinterpret_cast<const uint32_t*>(lutb) + task * NW;
 #pragma unroll
         for (int w4 = 0; w4 < NW; ++w4) lw[w4] = lp[w4];
@@ -554,7 +683,9 @@ k_g2_p2(const float2* __restrict__ scratch, ItemMap im, const ChunkDev* __restri
     constexpr int T = 32 / R2;
     constexpr int lgT = (T == 16) ? 4 : (T == 8) ? 3 : (T == 4) ? 2 : 1;
     const int tile_elems = g.n0 * 32;
-    PS21_DYN_SMEM(float2, tile);                                            // [n0][32]
+    PS21_DYN_SMEM(float2, smem_raw);
+    // the tile starts on a 256-byte boundary of the shared window (the first-stage addressing XORs bit fields)
+    float2* tile = smem_raw + ((256u - (smem_u32(smem_raw) & 255u)) & 255u) / 8u;   // [n0][32]
     const int RLk = g.fx.st[g.fx.nstages - 1].radix;
     const uint32_t lut_bytes = (uint32_t)lut_tile_bytes(g.n0, RLk);          // multiple of 128
     uint8_t* lutb = reinterpret_cast<uint8_t*>(tile + tile_elems);           // [lut_bytes]
@@ -584,7 +715,7 @@ k_g2_p2(const float2* __restrict__ scratch, ItemMap im, const ChunkDev* __restri
         bulk_g2s_hint(tile, src + (long long)tl * tile_elems, (uint32_t)tile_elems * 8u, bar, pol_stream);
         bulk_g2s_hint(lutb, lut + (long long)tl * lut_bytes, lut_bytes, bar, pol_keep);
     };
-    const AddrTile addr{R2 - 1, lgT};
+    const AddrTile addr{smem_u32(tile), R2 - 1, lgT + 3};
     FastDiv div32;
     div32.mul = 1u << 11;   // x / 32 for x < 65536: (x * 2^11) >> 16
     div32.shift = 16;
@@ -600,10 +731,10 @@ k_g2_p2(const float2* __restrict__ scratch, ItemMap im, const ChunkDev* __restri
     for (; tl < g.ntiles; tl += g.slots, ++it) {
         mbar_wait(bar, phase);
         phase ^= 1;
-        p2_first_stage<R0, R2>(tile, g, twx);
+        p2_first_stage<R0, R2>(addr.base, g, twx);
         __syncthreads();
         for (int s = 1; s + 1 < g.fx.nstages; ++s) {
-            ip_stage_any<true>(tile, g.fx.st[s], g.n0, 32, div32, addr, twx);
+            ip_stage_any<true>(g.fx.st[s], g.n0, 32, div32, addr, twx, PreSub{make_float2(0.f, 0.f)});
             __syncthreads();
         }
         {
@@ -628,8 +759,8 @@ k_g2_p2(const float2* __restrict__ scratch, ItemMap im, const ChunkDev* __restri
             };
 #define PS21_G2_LAST(RL)                                                                                   \
     case RL:                                                                                               \
-        if (early) p2_last_stage<RL, NSHARE, true>(tile, lutb, g, addr, bw, dc_out, release);             \
-        else p2_last_stage<RL, NSHARE, false>(tile, lutb, g, addr, bw, dc_out, release);                  \
+        if (early) p2_last_stage<RL, R2, NSHARE, true>(lutb, g, addr, bw, dc_out, release);                   \
+        else p2_last_stage<RL, R2, NSHARE, false>(lutb, g, addr, bw, dc_out, release);                        \
         break
             switch (RLk) {
                 PS21_G2_LAST(32);
@@ -638,8 +769,8 @@ k_g2_p2(const float2* __restrict__ scratch, ItemMap im, const ChunkDev* __restri
                 PS21_G2_LAST(8);
                 PS21_G2_LAST(5);
                 default:
-                    if (early) p2_last_stage<4, NSHARE, true>(tile, lutb, g, addr, bw, dc_out, release);
-                    else p2_last_stage<4, NSHARE, false>(tile, lutb, g, addr, bw, dc_out, release);
+                    if (early) p2_last_stage<4, R2, NSHARE, true>(lutb, g, addr, bw, dc_out, release);
+                    else p2_last_stage<4, R2, NSHARE, false>(lutb, g, addr, bw, dc_out, release);
                     break;
             }
 #undef PS21_G2_LAST
@@ -758,12 +889,12 @@ static int upload(const std::vector<T>& v, T** d) {
 }
 
 static size_t p1_smem(const G2Dev& g) {
-    return (size_t)g.nbuf * g.nh * g.ld * sizeof(float2) + (size_t)(g.nz + g.n1) * sizeof(float2) +
-           (size_t)(g.M + g.R1) * 2 + 64;
+    return (size_t)g.nbuf * g.zrows * g.ld * sizeof(float2) +
+           (size_t)(g.nz + g.n1 + 2 * g.Lc + (g.bluestein ? g.M : 0)) * sizeof(float2) + (size_t)(g.M + g.R1) * 2 + 64;
 }
 static size_t p2_smem(const G2Dev& g, int nbins, int nshare) {
     const int RL = g.fx.st[g.fx.nstages - 1].radix;
-    return (size_t)g.n0 * 32 * 8 + (size_t)lut_tile_bytes(g.n0, RL) + 16 + (size_t)MAX_BINS * 8 + (size_t)g.n0 * 8 +
+    return 256 + (size_t)g.n0 * 32 * 8 + (size_t)lut_tile_bytes(g.n0, RL) + 16 + (size_t)MAX_BINS * 8 + (size_t)g.n0 * 8 +
            (size_t)nbins * (g.p2_threads / nshare) * 4;
 }
 
@@ -805,15 +936,25 @@ int g2_try_setup(ps21_plan* p, ShapePlan& sp) {
     G2Dev g{};
     g.n0 = n0; g.n1 = n1; g.nz = nz; g.M = nz / 2; g.nh = g.M + 1;
     std::vector<int> rz, ry, rx;
-    if (!split_radices(g.M, kRadZ, rz)) return no("chunk length / 2 has a prime factor above 13");
+    std::vector<int> rzb;   // Bluestein: radices of the convolution length
+    if (!split_radices(g.M, kRadZ, rz) || std::getenv("PS21_G2_FORCE_BLUESTEIN")) {
+        // nz / 2 has a prime factor above 13 (334 = 2 * 167, ...): chirp convolution of the smallest length >= 2M - 1
+        // that the butterflies cover
+        g.bluestein = 1;
+        for (g.Lc = 2 * g.M - 1; !split_radices(g.Lc, kRadZ, rzb); ++g.Lc) {}
+        if (g.Lc > 4096) return no("chunk too long for the chirp convolution");
+    }
+    g.zrows = std::max(g.nh, g.Lc);
     // y split n1 = R1 R2.  Pass 1 keeps nh x R1 coefficients per buffer; with two buffers the next unit streams in while
     // this one is transformed.  R2 = 4 gives 64-byte runs in the scratch, R2 = 8 halves the buffer (32-byte runs).
     int R2 = 0, nbuf = 0;
     int force_r2 = 0, force_nbuf = 0;
     if (const char* e = std::getenv("PS21_G2_R2")) force_r2 = std::atoi(e);
     if (const char* e = std::getenv("PS21_G2_NBUF")) force_nbuf = std::atoi(e);
-    auto extra1 = [&](int R1) { return (size_t)(nz + n1) * sizeof(float2) + (size_t)(g.M + R1) * 2 + 64; };
-    auto buf1 = [&](int R1) { return (size_t)g.nh * (R1 | 1) * sizeof(float2); };
+    auto extra1 = [&](int R1) {
+        return (size_t)(nz + n1 + 2 * g.Lc + (g.bluestein ? g.M : 0)) * sizeof(float2) + (size_t)(g.M + R1) * 2 + 64;
+    };
+    auto buf1 = [&](int R1) { return (size_t)g.zrows * (R1 | 1) * sizeof(float2); };
     // measured on 200^3 (B200): one buffer with three CTAs per SM 4.83 ms, two buffers with two CTAs 5.24 ms -- occupancy
     // beats overlap inside a CTA, so: three resident CTAs first, then two with the prefetch buffer, then whatever fits
     struct Try { int r2, nb; size_t budget; };
@@ -859,9 +1000,11 @@ int g2_try_setup(ps21_plan* p, ShapePlan& sp) {
         break;
     }
     if (!R0) return no("sky-plane size does not split into the x radices");
-    if ((long long)g.R1 * g.M >= 65536 || (long long)g.R1 * g.nh >= 65536 || (long long)(g.M / 2 + 1) * g.R1 >= 65536)
+    if ((long long)g.R1 * g.M >= 65536 || (long long)g.R1 * g.nh >= 65536 || (long long)(g.M / 2 + 1) * g.R1 >= 65536 ||
+        (long long)g.R1 * g.Lc >= 65536)
         return no("unit too large for the index arithmetic");
-    make_ipfft(g.M, rz, 2, g.fz);          // w_M^q = w_nz^(2q)
+    if (!g.bluestein) make_ipfft(g.M, rz, 2, g.fz);          // w_M^q = w_nz^(2q)
+    else make_ipfft(g.Lc, rzb, 1, g.fzb);
     make_ipfft(g.R1, ry, R2, g.fy);        // w_R1^q = w_n1^(R2 q)
     make_ipfft(n0, rx, 1, g.fx);
     g.div_M = make_fastdiv(g.M); g.div_R1 = make_fastdiv(g.R1); g.div_nh = make_fastdiv(g.nh);
@@ -881,7 +1024,10 @@ int g2_try_setup(ps21_plan* p, ShapePlan& sp) {
     gs->nshare = p->nbins <= MAX_BINS_LANE ? 1 : 4;
     g.tw_z = sp.tw_z; g.tw_y = sp.tw_y; g.tw_x = sp.tw_x;
     // tables
-    const std::vector<int> fz_pos = freq_of_pos(g.M, g.fz), fy_pos = freq_of_pos(g.R1, g.fy), fx_pos = freq_of_pos(n0, g.fx);
+    std::vector<int> fz_pos = freq_of_pos(g.M, g.fz);
+    if (g.bluestein)   // the inverse transform of the convolution leaves the rows in natural order
+        for (int r = 0; r < g.M; ++r) fz_pos[r] = r;
+    const std::vector<int> fy_pos = freq_of_pos(g.R1, g.fy), fx_pos = freq_of_pos(n0, g.fx);
     std::vector<uint16_t> rowz(g.M), kya(g.R1), kxpos(n0), kzrow((size_t)g.nzt * g.T, 0xFFFF);
     std::vector<uint8_t> zmult((size_t)g.nzt * g.T, 0);
     for (int r = 0; r < g.M; ++r) {
@@ -898,6 +1044,49 @@ int g2_try_setup(ps21_plan* p, ShapePlan& sp) {
         sp.fused = gs;
         g2_destroy(sp);
         return no("table upload failed");
+    }
+    if (g.bluestein) {
+        const int M = g.M, Lc = g.Lc;
+        const double PI = 3.14159265358979323846;
+        std::vector<float2> twc(Lc), chirp(M), bhat(Lc);
+        std::vector<double> wr(Lc), wi(Lc);
+        for (int q = 0; q < Lc; ++q) {
+            wr[q] = std::cos(-2.0 * PI * q / Lc);
+            wi[q] = std::sin(-2.0 * PI * q / Lc);
+            twc[q] = make_float2((float)wr[q], (float)wi[q]);
+        }
+        // c_n = exp(-i pi n^2 / M); n^2 is reduced mod 2M in integers, so the angle stays small and exact
+        std::vector<double> br(Lc, 0.0), bi(Lc, 0.0);   // b_ext = conj(c) wrapped around the convolution length
+        for (int n = 0; n < M; ++n) {
+            const long long r = ((long long)n * n) % (2LL * M);
+            const double a = PI * (double)r / (double)M;
+            chirp[n] = make_float2((float)std::cos(a), (float)-std::sin(a));
+            br[n] = std::cos(a);
+            bi[n] = std::sin(a);
+            if (n) {
+                br[Lc - n] = br[n];
+                bi[Lc - n] = bi[n];
+            }
+        }
+        // its spectrum (direct sum in double, roots by index), divided by Lc, in the position order of the forward plan
+        const std::vector<int> fpos = freq_of_pos(Lc, g.fzb);
+        for (int pos = 0; pos < Lc; ++pos) {
+            const int f = fpos[pos];
+            double sr = 0.0, si = 0.0;
+            for (int m = 0; m < Lc; ++m) {
+                if (br[m] == 0.0 && bi[m] == 0.0) continue;
+                const int q = (int)(((long long)m * f) % Lc);
+                sr += br[m] * wr[q] - bi[m] * wi[q];
+                si += br[m] * wi[q] + bi[m] * wr[q];
+            }
+            bhat[pos] = make_float2((float)(sr / Lc), (float)(si / Lc));
+        }
+        if ((rc = upload(twc, &gs->d_twc)) || (rc = upload(chirp, &gs->d_chirp)) || (rc = upload(bhat, &gs->d_bhat))) {
+            sp.fused = gs;
+            g2_destroy(sp);
+            return no("table upload failed");
+        }
+        g.tw_c = gs->d_twc; g.chirp = gs->d_chirp; g.bhat = gs->d_bhat;
     }
     g.rowz_of_k = gs->d_rowz; g.kya_of_jp = gs->d_kya; g.zmult = gs->d_zmult;
     gs->dev = g;
@@ -944,6 +1133,9 @@ void g2_destroy(ShapePlan& sp) {
     if (gs->d_kxpos) cudaFree(gs->d_kxpos);
     if (gs->d_kzrow) cudaFree(gs->d_kzrow);
     if (gs->d_zmult) cudaFree(gs->d_zmult);
+    if (gs->d_twc) cudaFree(gs->d_twc);
+    if (gs->d_chirp) cudaFree(gs->d_chirp);
+    if (gs->d_bhat) cudaFree(gs->d_bhat);
     delete gs;
     sp.fused = nullptr;
 }

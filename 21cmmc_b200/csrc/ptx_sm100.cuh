@@ -6,8 +6,28 @@
 
 namespace ps21 {
 
+// 32-bit shared-memory addressing: the generic kernels (ps21_g2.cu) form their addresses as 32-bit byte offsets in the
+// shared window and access them with explicit ld.shared / st.shared -- pointer arithmetic on 64-bit generic pointers
+// cost three integer instructions per access there (ncu: half of all instructions were address arithmetic).
 #ifndef PS21_EMU
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ float2 lds64(uint32_t a) {
+    float2 v;
+    asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ void sts64(uint32_t a, float2 v) {
+    asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(a), "f"(v.x), "f"(v.y) : "memory");
+}
+#else
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+    return (uint32_t)(reinterpret_cast<const char*>(p) - ps21emu::g_dyn_smem);
+}
+__device__ __forceinline__ float2 lds64(uint32_t a) { return *reinterpret_cast<const float2*>(ps21emu::g_dyn_smem + a); }
+__device__ __forceinline__ void sts64(uint32_t a, float2 v) { *reinterpret_cast<float2*>(ps21emu::g_dyn_smem + a) = v; }
+#endif
+
+#ifndef PS21_EMU
 __device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
 }

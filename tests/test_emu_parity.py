@@ -123,6 +123,9 @@ def test_lnl_before_data_is_a_state_error(mods):
     ((80, 80, 44), (120.0, 120.0, 66.0), 50, False, (True, False, False)), # 2 * 11, 50 bins: 4-lane-group bin columns
     ((64, 64, 16), (96.0, 96.0, 24.0), 10, True, (True, False, False)),    # R2 = 4, x = 8 * 8
     ((200, 200, 8), (300.0, 300.0, 12.0), 20, True, (True, False, False)), # config-2 sky plane: y 50 x 4, x = 8 * 25
+    ((16, 16, 34), (24.0, 24.0, 51.0), 8, True, (True, False, False)),     # nz / 2 = 17: Bluestein (chirp convolution)
+    ((32, 32, 38), (48.0, 48.0, 57.0), 6, False, (False, False, False)),   # 19, DC binned
+    ((64, 64, 334), (96.0, 96.0, 501.0), 12, True, (True, False, False)),  # 167: the 334-slice chunk of a 1002-slice lightcone
 ])
 def test_generic_two_pass_kernels(mods, shape, L, nb, log, flags):
     """ps21_g2.cu (in-place digit-reversed transforms, position-defined tiles) on the emulated device vs the oracle."""
@@ -140,9 +143,9 @@ def test_two_pass_rejects_what_it_cannot_factor(mods):
     from py21cmmc_b200.plan import PowerPlan
     from py21cmmc_b200 import _capi
 
-    for shape in ((16, 16, 34), (15, 15, 16), (16, 16, 17)):   # 17 prime, odd plane, odd chunk
+    for shape in ((15, 15, 16), (16, 16, 17)):   # odd plane, odd chunk
         with pytest.raises(Ps21Error):
             PowerPlan(shape, [(0, shape[2])], [(24.0, 24.0, 30.0)], 4, path="twopass", library=_capi.LIB_PATH)
-    pl = PowerPlan((16, 16, 34), [(0, 34)], [(24.0, 24.0, 51.0)], 4, path="auto", library=_capi.LIB_PATH)
+    pl = PowerPlan((16, 16, 17), [(0, 17)], [(24.0, 24.0, 25.5)], 4, path="auto", library=_capi.LIB_PATH)
     assert pl.path == "general"
     pl.close()

@@ -498,6 +498,9 @@ TWOPASS_CASES = [
     ((64, 64, 44), (96.0, 96.0, 66.0), 12, True, (True, False, True)),             # M = 22 = 2 * 11
     ((100, 100, 100), (150.0, 150.0, 150.0), 15, True, (True, False, False)),      # 100 = 4 * 25
     ((400, 400, 20), (600.0, 600.0, 30.0), 18, True, (True, False, False)),        # 400 = 8 * 2 * 25
+    ((256, 256, 334), (384.0, 384.0, 501.0), 20, True, (True, False, False)),      # M = 167 prime: Bluestein, Lc = 336
+    ((128, 128, 38), (192.0, 192.0, 57.0), 10, False, (False, False, False)),      # M = 19: Bluestein, DC binned
+    ((64, 64, 202), (96.0, 96.0, 303.0), None, True, (True, True, False)),         # M = 101: Bluestein, group bins
 ]
 
 
@@ -532,7 +535,8 @@ def test_auto_prefers_two_pass_kernels_and_falls_back(mods):
                                    "spherical", dev, "auto")
     assert mk((200, 200, 200), (300.0,) * 3).path == "twopass"
     assert mk((256, 256, 256), (384.0,) * 3).path == "fused"
-    assert mk((64, 64, 334), (96.0, 96.0, 501.0)).path == "general"     # 334 / 2 = 167 is prime
+    assert mk((64, 64, 334), (96.0, 96.0, 501.0)).path == "twopass"     # 334 / 2 = 167 is prime: chirp convolution
+    assert mk((64, 64, 333), (96.0, 96.0, 499.5)).path == "general"     # odd chunk length
     assert mk((35, 35, 36), (52.5, 52.5, 54.0)).path == "general"       # odd sky plane
     with pytest.raises(Exception):
         get_plan((35, 35, 36), [(0, 36)], [(52.5, 52.5, 54.0)], 12, True, True, False, False, "legacy_1.001",
