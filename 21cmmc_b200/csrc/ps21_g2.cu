@@ -330,8 +330,8 @@ __device__ __forceinline__ void p1_y_first(uint32_t buf, const G2Dev& g, const f
 // last y stage (radix R over contiguous j) of every row, results times w_n1^(yl ky_a) straight to HBM in tile order
 template <int R>
 __device__ __forceinline__ void p1_y_last_store(uint32_t buf, float2* __restrict__ dst,
-                                                const G2Dev& g, const float2* __restrict__ twy,
-                                                const uint16_t* __restrict__ kya, int yl, long long inner) {
+                                                const G2Dev& g, const float2* __restrict__ twu, int yl,
+                                                long long inner) {
     const int nh = g.nh, nsub = g.R1 / R;
     const uint32_t ldb = g.ld * 8;
     const long long tile_elems = (long long)g.n0 * 32;
@@ -346,7 +346,7 @@ __device__ __forceinline__ void p1_y_last_store(uint32_t buf, float2* __restrict
         float2* out = dst + (long long)(r >> g.lgT) * tile_elems + inner + (r & (g.T - 1)) + (long long)(b * R) * jstride;
 #pragma unroll
         for (int m = 0; m < R; ++m) {
-            const float2 o = yl ? cmul_w2(v[m], twy[yl * kya[b * R + m]]) : v[m];   // yl ky_a < n1: no reduction
+            const float2 o = yl ? cmul_w2(v[m], twu[b * R + m]) : v[m];
             *out = o;
             out += jstride;
         }
@@ -362,12 +362,14 @@ k_g2_p1(const float* __restrict__ boxes, long long batch_stride, int n2_total, I
     const int tid = threadIdx.x, nthr = blockDim.x;
     const int M = g.M, R1 = g.R1, ld = g.ld, nh = g.nh;
     const int bufstride = g.zrows * ld;
+    const uint32_t smem32 = smem_u32(smem), ldb = (uint32_t)ld * 8u;
     float2* const twz = smem + g.nbuf * bufstride;                       // [nz]  w_nz^q
     float2* const twy = twz + g.nz;                                      // [n1]  w_n1^q
     float2* const twc = twy + g.n1;                                      // [Lc]  w_Lc^q            (Bluestein only)
     float2* const chirp = twc + g.Lc;                                    // [M]   exp(-i pi n^2/M)  (Bluestein only)
     float2* const bhat = chirp + (g.bluestein ? M : 0);                  // [Lc]  chirp spectrum    (Bluestein only)
-    uint16_t* const rowz = reinterpret_cast<uint16_t*>(bhat + g.Lc);     // [M]   copy of G2Dev::rowz_of_k
+    float2* const twu = bhat + g.Lc;                                     // [R1]  w_n1^(yl ky_a) of the current unit
+    uint16_t* const rowz = reinterpret_cast<uint16_t*>(twu + R1);        // [M]   copy of G2Dev::rowz_of_k
     uint16_t* const kya = rowz + M;                                      // [R1]  copy of G2Dev::kya_of_jp
     long long box;
     int cid;
@@ -377,7 +379,7 @@ k_g2_p1(const float* __restrict__ boxes, long long batch_stride, int n2_total, I
     const int x0 = blockIdx.x * g.slabs;
     const float* spec = boxes + box * batch_stride + ch.start;
     float2* dst = scratch + (long long)blockIdx.y * ((long long)g.ntiles * g.n0 * 32);
-    const uint32_t smem32 = smem_u32(smem), ldb = (uint32_t)ld * 8u;
+
     for (int i = tid; i < g.nz; i += nthr) twz[i] = g.tw_z[i];
     for (int i = tid; i < g.n1; i += nthr) twy[i] = g.tw_y[i];
     for (int i = tid; i < M; i += nthr) rowz[i] = g.rowz_of_k[i];
@@ -391,28 +393,29 @@ k_g2_p1(const float* __restrict__ boxes, long long batch_stride, int n2_total, I
     }
     // rows y = yl + R2 j of slab x as packed (even, odd) pairs: buf[zc][j]; asynchronous copies (LDGSTS), lanes along z
     // -> coalesced reads, conflict-free writes (ld is odd)
-    auto issue_unit = [&](int u, float2* buf) {
+    auto issue_unit = [&](int u, uint32_t buf32) {
         const int x = x0 + u / g.R2, yl = u - (u / g.R2) * g.R2;
         const float* slab = spec + (long long)x * g.n1 * n2_total + (long long)yl * n2_total;
-        // one row per warp turn, lanes along z: the row pointer is formed once per row
+        // one row per warp turn, lanes along z: row pointer and shared address are formed once per row and stepped
         const int warp = tid >> 5, lane = tid & 31, nwarps = nthr >> 5;
         const long long rstride = (long long)g.R2 * n2_total;
+        const uint32_t dstep = 32u * ldb;
         for (int j = warp; j < R1; j += nwarps) {
-            const float* src = slab + j * rstride;
-            float2* d = buf + j;
+            const float* src = slab + j * rstride + 2 * lane;
+            uint32_t d = buf32 + (uint32_t)j * 8u + (uint32_t)lane * ldb;
             if (aligned8) {
-                for (int zc = lane; zc < M; zc += 32) cp_async8(d + zc * ld, src + 2 * zc);
+                for (int zc = lane; zc < M; zc += 32, d += dstep, src += 64) cp_async8_s32(d, src);
             } else {
-                for (int zc = lane; zc < M; zc += 32) {
-                    cp_async4(&d[zc * ld].x, src + 2 * zc);
-                    cp_async4(&d[zc * ld].y, src + 2 * zc + 1);
+                for (int zc = lane; zc < M; zc += 32, d += dstep, src += 64) {
+                    cp_async4_s32(d, src);
+                    cp_async4_s32(d + 4, src + 1);
                 }
             }
         }
         cp_async_commit();
     };
     const int nunits = g.slabs * g.R2;
-    issue_unit(0, smem);
+    issue_unit(0, smem32);
     for (int u = 0; u < nunits; ++u) {
         float2* buf = smem + (u % g.nbuf) * bufstride;
         const uint32_t buf32 = smem32 + (uint32_t)(u % g.nbuf) * (uint32_t)bufstride * 8u;
@@ -421,7 +424,8 @@ k_g2_p1(const float* __restrict__ boxes, long long batch_stride, int n2_total, I
         const int x = x0 + u / g.R2, yl = u - (u / g.R2) * g.R2;
         cp_async_wait<0>();
         __syncthreads();   // unit u has landed; everybody is done with unit u - 1 (tables ready on the first turn)
-        if (g.nbuf == 2 && u + 1 < nunits) issue_unit(u + 1, smem + ((u + 1) % 2) * bufstride);
+        if (g.nbuf == 2 && u + 1 < nunits) issue_unit(u + 1, smem32 + (uint32_t)((u + 1) % 2) * (uint32_t)bufstride * 8u);
+        for (int jp = tid; jp < R1; jp += nthr) twu[jp] = twy[yl * kya[jp]];   // yl ky_a < n1: no reduction needed
         // ---- z: complex FFT of length M over the row index, in place; the offset is subtracted as stage 0 reads
         const float2 mean2 = make_float2(mean, mean);
         if (!g.bluestein) {
@@ -505,26 +509,26 @@ k_g2_p1(const float* __restrict__ boxes, long long batch_stride, int n2_total, I
         const long long inner = ((long long)x * g.R2 + slot) << g.lgT;
         if (g.fuse_last) {
             switch (g.fy.st[ylast].radix) {
-                case 2: p1_y_last_store<2>(buf32, dst, g, twy, kya, yl, inner); break;
-                case 3: p1_y_last_store<3>(buf32, dst, g, twy, kya, yl, inner); break;
-                case 4: p1_y_last_store<4>(buf32, dst, g, twy, kya, yl, inner); break;
-                case 5: p1_y_last_store<5>(buf32, dst, g, twy, kya, yl, inner); break;
-                case 6: p1_y_last_store<6>(buf32, dst, g, twy, kya, yl, inner); break;
-                case 8: p1_y_last_store<8>(buf32, dst, g, twy, kya, yl, inner); break;
-                default: p1_y_last_store<10>(buf32, dst, g, twy, kya, yl, inner); break;
+                case 2: p1_y_last_store<2>(buf32, dst, g, twu, yl, inner); break;
+                case 3: p1_y_last_store<3>(buf32, dst, g, twu, yl, inner); break;
+                case 4: p1_y_last_store<4>(buf32, dst, g, twu, yl, inner); break;
+                case 5: p1_y_last_store<5>(buf32, dst, g, twu, yl, inner); break;
+                case 6: p1_y_last_store<6>(buf32, dst, g, twu, yl, inner); break;
+                case 8: p1_y_last_store<8>(buf32, dst, g, twu, yl, inner); break;
+                default: p1_y_last_store<10>(buf32, dst, g, twu, yl, inner); break;
             }
         } else {
             const long long tile_elems = (long long)g.n0 * 32;
             for (int e = tid; e < R1 * nh; e += nthr) {
                 const int jp = fast_div(e, g.div_nh), r = e - jp * nh;
                 float2 v = buf[r * ld + jp];
-                if (yl) v = cmul_w2(v, twy[yl * kya[jp]]);
+                if (yl) v = cmul_w2(v, twu[jp]);
                 dst[((long long)jp * g.nzt + (r >> g.lgT)) * tile_elems + inner + (r & (g.T - 1))] = v;
             }
         }
         if (g.nbuf == 1 && u + 1 < nunits) {
             __syncthreads();
-            issue_unit(u + 1, smem);
+            issue_unit(u + 1, smem32);
         }
     }
 }
@@ -890,7 +894,8 @@ static int upload(const std::vector<T>& v, T** d) {
 
 static size_t p1_smem(const G2Dev& g) {
     return (size_t)g.nbuf * g.zrows * g.ld * sizeof(float2) +
-           (size_t)(g.nz + g.n1 + 2 * g.Lc + (g.bluestein ? g.M : 0)) * sizeof(float2) + (size_t)(g.M + g.R1) * 2 + 64;
+           (size_t)(g.nz + g.n1 + g.R1 + 2 * g.Lc + (g.bluestein ? g.M : 0)) * sizeof(float2) +
+           (size_t)(g.M + g.R1) * 2 + 64;
 }
 static size_t p2_smem(const G2Dev& g, int nbins, int nshare) {
     const int RL = g.fx.st[g.fx.nstages - 1].radix;
@@ -952,7 +957,7 @@ int g2_try_setup(ps21_plan* p, ShapePlan& sp) {
     if (const char* e = std::getenv("PS21_G2_R2")) force_r2 = std::atoi(e);
     if (const char* e = std::getenv("PS21_G2_NBUF")) force_nbuf = std::atoi(e);
     auto extra1 = [&](int R1) {
-        return (size_t)(nz + n1 + 2 * g.Lc + (g.bluestein ? g.M : 0)) * sizeof(float2) + (size_t)(g.M + R1) * 2 + 64;
+        return (size_t)(nz + n1 + R1 + 2 * g.Lc + (g.bluestein ? g.M : 0)) * sizeof(float2) + (size_t)(g.M + R1) * 2 + 64;
     };
     auto buf1 = [&](int R1) { return (size_t)g.zrows * (R1 | 1) * sizeof(float2); };
     // measured on 200^3 (B200): one buffer with three CTAs per SM 4.83 ms, two buffers with two CTAs 5.24 ms -- occupancy

@@ -184,6 +184,21 @@ __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
                  : "memory");
 #endif
 }
+// the same with a 32-bit shared-window address (ptx_sm100.cuh: smem_u32)
+__device__ __forceinline__ void cp_async8_s32(unsigned smem_addr, const void* gsrc) {
+#ifdef PS21_EMU
+    *reinterpret_cast<float2*>(ps21emu::g_dyn_smem + smem_addr) = *reinterpret_cast<const float2*>(gsrc);
+#else
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_addr), "l"(gsrc) : "memory");
+#endif
+}
+__device__ __forceinline__ void cp_async4_s32(unsigned smem_addr, const void* gsrc) {
+#ifdef PS21_EMU
+    *reinterpret_cast<float*>(ps21emu::g_dyn_smem + smem_addr) = *reinterpret_cast<const float*>(gsrc);
+#else
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_addr), "l"(gsrc) : "memory");
+#endif
+}
 __device__ __forceinline__ void cp_async_commit() {
 #ifndef PS21_EMU
     asm volatile("cp.async.commit_group;" ::: "memory");
