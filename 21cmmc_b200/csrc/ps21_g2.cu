@@ -49,7 +49,9 @@ struct IpFft {
 };
 
 struct G2Dev {
-    int n0, n1, nz, M, nh;      // M = nz / 2 complex points per packed row, nh = M + 1 half-spectrum rows
+    int n0, n1, nz, M, nh;      // M = length of the complex z transform, nh = nz / 2 + 1 half-spectrum rows
+    int pair, zcols;            // even nz: M = nz / 2 on (even, odd)-packed rows, zcols = R1 columns (pair = 0);
+                                // odd nz:  M = nz on row PAIRS (row j + i row j + R1/2), zcols = R1 / 2 columns (pair = 1)
     int R1, R2, T, lgT;         // n1 = R1 R2, T = 32 / R2 k_z rows per tile
     int ld;                     // pass 1: complex slots per shared-memory row (odd -> conflict free both ways)
     int nzt, ntiles;            // z tiles per ky_a position, tiles per spectrum
@@ -63,16 +65,17 @@ struct G2Dev {
     IpFft fzb;                  // ... the convolution's transform of length Lc
     const float2 *tw_c, *chirp, *bhat;   // w_Lc^q [Lc]; exp(-i pi n^2 / M) [M]; FFT of the chirp / Lc, position order [Lc]
     IpFft fz, fy, fx;
-    FastDiv div_M, div_R1, div_nh;
+    FastDiv div_M, div_R1, div_nh, div_zcols;
     const float2 *tw_z, *tw_y, *tw_x;   // exp(-2 pi i q / n) for n = nz, n1, n0
     const uint16_t* rowz_of_k;          // [M]   row that holds frequency k after the in-place z transform
     const uint16_t* kya_of_jp;          // [R1]  ky_a at position jp after the in-place y transform
+    const uint16_t* prow_of_row;        // [nh]  pair mode: physical row of logical half-spectrum row r
     const uint8_t* zmult;               // [nzt T] Hermitian multiplicity of the k_z in row r (0: padding row)
 };
 
 struct G2Shape {
     G2Dev dev{};
-    uint16_t *d_rowz = nullptr, *d_kya = nullptr, *d_kxpos = nullptr, *d_kzrow = nullptr;
+    uint16_t *d_rowz = nullptr, *d_kya = nullptr, *d_kxpos = nullptr, *d_kzrow = nullptr, *d_prow = nullptr;
     uint8_t* d_zmult = nullptr;
     float2 *d_twc = nullptr, *d_chirp = nullptr, *d_bhat = nullptr;   // Bluestein tables
     int R0 = 0;                 // radix of the first x stage (fused with the y_lo transform)
@@ -112,7 +115,7 @@ struct PreBhat {
     }
 };
 
-// `addr(i, c)` is the 32-bit shared-memory byte address of element i of column c.
+// `addr.at(addr.col(c), i)` is the 32-bit shared-memory byte address of element i of column c.
 template <int R, class Addr, class Pre>
 __device__ __forceinline__ void ip_stage(const IpStage st, int nbf, int ncols, FastDiv div_cols,
                                          const Addr addr, const float2* __restrict__ tw, const Pre pre) {
@@ -122,8 +125,9 @@ __device__ __forceinline__ void ip_stage(const IpStage st, int nbf, int ncols, F
         const int b = fast_div(bf, st.div_q), o = bf - b * st.q;
         const int i0 = b * st.q * R + o;
         float2 v[R];
+        const uint32_t cb = addr.col(c);
 #pragma unroll
-        for (int m = 0; m < R; ++m) v[m] = pre(i0 + m * st.q, lds64(addr(i0 + m * st.q, c)));
+        for (int m = 0; m < R; ++m) v[m] = pre(i0 + m * st.q, lds64(addr.at(cb, i0 + m * st.q)));
         small_dft<R>(v);
         if (st.q > 1) {
             const int step = o * st.twmul;
@@ -135,7 +139,7 @@ __device__ __forceinline__ void ip_stage(const IpStage st, int nbf, int ncols, F
             }
         }
 #pragma unroll
-        for (int m = 0; m < R; ++m) sts64(addr(i0 + m * st.q, c), v[m]);
+        for (int m = 0; m < R; ++m) sts64(addr.at(cb, i0 + m * st.q), v[m]);
     }
 }
 
@@ -152,8 +156,9 @@ __device__ __forceinline__ void ip_stage_T(const IpStage st, int nbf, int ncols,
         const int b = fast_div(bf, st.div_q), o = bf - b * st.q;
         const int i0 = b * st.q * R + o;
         float2 v[R];
+        const uint32_t cb = addr.col(c);
 #pragma unroll
-        for (int m = 0; m < R; ++m) v[m] = pre(i0 + m * st.q, lds64(addr(i0 + m * st.q, c)));
+        for (int m = 0; m < R; ++m) v[m] = pre(i0 + m * st.q, lds64(addr.at(cb, i0 + m * st.q)));
         if (st.q > 1) {
             const int step = o * st.twmul;
             int idx = step;
@@ -165,7 +170,7 @@ __device__ __forceinline__ void ip_stage_T(const IpStage st, int nbf, int ncols,
         }
         small_dft<R>(v);
 #pragma unroll
-        for (int m = 0; m < R; ++m) sts64(addr(i0 + m * st.q, c), v[m]);
+        for (int m = 0; m < R; ++m) sts64(addr.at(cb, i0 + m * st.q), v[m]);
     }
 }
 
@@ -189,15 +194,23 @@ __device__ __forceinline__ void ip_stage_any(const IpStage st, int n, int ncols,
 #undef PS21_IP_CASE
 }
 
-struct AddrStrided {   // pass 1: byte strides of the index and of the column
+struct AddrStrided {   // pass 1, z transform: byte strides of the index (row) and of the column (j)
     uint32_t base, si, sc;
-    __device__ __forceinline__ uint32_t operator()(int i, int c) const { return base + i * si + c * sc; }
+    __device__ __forceinline__ uint32_t col(int c) const { return base + c * sc; }
+    __device__ __forceinline__ uint32_t at(uint32_t cb, int i) const { return cb + i * si; }
+};
+struct AddrRows {      // pass 1, y transform: index = j (8 bytes apart), column = logical row -> physical row prow[c]
+    uint32_t base, ldb;
+    const uint16_t* prow;   // nullptr: rows are stored in logical order
+    __device__ __forceinline__ uint32_t col(int c) const { return base + (prow ? (uint32_t)prow[c] : (uint32_t)c) * ldb; }
+    __device__ __forceinline__ uint32_t at(uint32_t cb, int i) const { return cb + i * 8; }
 };
 struct AddrTile {      // pass 2: row x holds 32 columns (ky_b, t); the ky_b slot is XOR-ed with the low bits of x
     uint32_t base;     // 256-byte aligned
     int swmask, sh;    // swmask = R2 - 1, sh = log2(T) + 3
-    __device__ __forceinline__ uint32_t operator()(int i, int c) const {
-        return base + i * 256 + ((c << 3) ^ ((i & swmask) << sh));
+    __device__ __forceinline__ uint32_t col(int c) const { return (uint32_t)(c << 3); }
+    __device__ __forceinline__ uint32_t at(uint32_t cb, int i) const {
+        return base + i * 256 + (cb ^ ((i & swmask) << sh));
     }
 };
 
@@ -330,15 +343,15 @@ __device__ __forceinline__ void p1_y_first(uint32_t buf, const G2Dev& g, const f
 // last y stage (radix R over contiguous j) of every row, results times w_n1^(yl ky_a) straight to HBM in tile order
 template <int R>
 __device__ __forceinline__ void p1_y_last_store(uint32_t buf, float2* __restrict__ dst,
-                                                const G2Dev& g, const float2* __restrict__ twu, int yl,
-                                                long long inner) {
+                                                const G2Dev& g, const float2* __restrict__ twu,
+                                                const uint16_t* __restrict__ prow, int yl, long long inner) {
     const int nh = g.nh, nsub = g.R1 / R;
     const uint32_t ldb = g.ld * 8;
     const long long tile_elems = (long long)g.n0 * 32;
     for (int task = threadIdx.x; task < nsub * nh; task += blockDim.x) {
         const int b = fast_div(task, g.div_nh), r = task - b * nh;   // r fastest: lanes along rows
         float2 v[R];
-        const uint32_t src = buf + r * ldb + b * (R * 8);
+        const uint32_t src = buf + (prow ? (uint32_t)prow[r] : (uint32_t)r) * ldb + b * (R * 8);
 #pragma unroll
         for (int m = 0; m < R; ++m) v[m] = lds64(src + m * 8);
         small_dft<R>(v);
@@ -371,6 +384,7 @@ k_g2_p1(const float* __restrict__ boxes, long long batch_stride, int n2_total, I
     float2* const twu = bhat + g.Lc;                                     // [R1]  w_n1^(yl ky_a) of the current unit
     uint16_t* const rowz = reinterpret_cast<uint16_t*>(twu + R1);        // [M]   copy of G2Dev::rowz_of_k
     uint16_t* const kya = rowz + M;                                      // [R1]  copy of G2Dev::kya_of_jp
+    uint16_t* const prow = kya + R1;                                     // [nh]  copy of G2Dev::prow_of_row (pair mode)
     long long box;
     int cid;
     item_to_box_chunk(im, blockIdx.y, box, cid);
@@ -384,6 +398,8 @@ k_g2_p1(const float* __restrict__ boxes, long long batch_stride, int n2_total, I
     for (int i = tid; i < g.n1; i += nthr) twy[i] = g.tw_y[i];
     for (int i = tid; i < M; i += nthr) rowz[i] = g.rowz_of_k[i];
     for (int i = tid; i < R1; i += nthr) kya[i] = g.kya_of_jp[i];
+    if (g.pair)
+        for (int i = tid; i < nh; i += nthr) prow[i] = g.prow_of_row[i];
     if (g.bluestein) {
         for (int i = tid; i < g.Lc; i += nthr) {
             twc[i] = g.tw_c[i];
@@ -400,16 +416,25 @@ k_g2_p1(const float* __restrict__ boxes, long long batch_stride, int n2_total, I
         const int warp = tid >> 5, lane = tid & 31, nwarps = nthr >> 5;
         const long long rstride = (long long)g.R2 * n2_total;
         const uint32_t dstep = 32u * ldb;
-        for (int j = warp; j < R1; j += nwarps) {
-            const float* src = slab + j * rstride + 2 * lane;
-            uint32_t d = buf32 + (uint32_t)j * 8u + (uint32_t)lane * ldb;
-            if (aligned8) {
-                for (int zc = lane; zc < M; zc += 32, d += dstep, src += 64) cp_async8_s32(d, src);
-            } else {
-                for (int zc = lane; zc < M; zc += 32, d += dstep, src += 64) {
-                    cp_async4_s32(d, src);
-                    cp_async4_s32(d + 4, src + 1);
+        if (!g.pair) {
+            for (int j = warp; j < R1; j += nwarps) {
+                const float* src = slab + j * rstride + 2 * lane;
+                uint32_t d = buf32 + (uint32_t)j * 8u + (uint32_t)lane * ldb;
+                if (aligned8) {
+                    for (int zc = lane; zc < M; zc += 32, d += dstep, src += 64) cp_async8_s32(d, src);
+                } else {
+                    for (int zc = lane; zc < M; zc += 32, d += dstep, src += 64) {
+                        cp_async4_s32(d, src);
+                        cp_async4_s32(d + 4, src + 1);
+                    }
                 }
+            }
+        } else {   // odd nz: column c = row j (real part) + i row j + R1/2 (imaginary part), one complex value per slice
+            for (int j = warp; j < R1; j += nwarps) {
+                const int c = j < g.zcols ? j : j - g.zcols;
+                const float* src = slab + j * rstride + lane;
+                uint32_t d = buf32 + (uint32_t)c * 8u + (j < g.zcols ? 0u : 4u) + (uint32_t)lane * ldb;
+                for (int z = lane; z < M; z += 32, d += dstep, src += 32) cp_async4_s32(d, src);
             }
         }
         cp_async_commit();
@@ -420,7 +445,7 @@ k_g2_p1(const float* __restrict__ boxes, long long batch_stride, int n2_total, I
         float2* buf = smem + (u % g.nbuf) * bufstride;
         const uint32_t buf32 = smem32 + (uint32_t)(u % g.nbuf) * (uint32_t)bufstride * 8u;
         const AddrStrided az{buf32, ldb, 8u};    // z transform: index = row (z pair / k_z), column = j
-        const AddrStrided ay{buf32, 8u, ldb};    // y transform: index = j, column = row
+        const AddrRows ay{buf32, ldb, g.pair ? prow : nullptr};   // y transform: index = j, column = row
         const int x = x0 + u / g.R2, yl = u - (u / g.R2) * g.R2;
         cp_async_wait<0>();
         __syncthreads();   // unit u has landed; everybody is done with unit u - 1 (tables ready on the first turn)
@@ -430,7 +455,7 @@ k_g2_p1(const float* __restrict__ boxes, long long batch_stride, int n2_total, I
         const float2 mean2 = make_float2(mean, mean);
         if (!g.bluestein) {
             for (int s = 0; s < g.fz.nstages; ++s) {
-                ip_stage_any<false>(g.fz.st[s], M, R1, g.div_R1, az, twz, PreSub{s == 0 ? mean2 : make_float2(0.f, 0.f)});
+                ip_stage_any<false>(g.fz.st[s], M, g.zcols, g.div_zcols, az, twz, PreSub{s == 0 ? mean2 : make_float2(0.f, 0.f)});
                 __syncthreads();
             }
         } else {
@@ -441,13 +466,13 @@ k_g2_p1(const float* __restrict__ boxes, long long batch_stride, int n2_total, I
             // the last factor c_k and the conjugation are applied where the untangle reads the rows.
             const int ns = g.fzb.nstages;
             for (int s = 0; s < ns; ++s) {
-                if (s == 0) ip_stage_any<false>(g.fzb.st[0], g.Lc, R1, g.div_R1, az, twc, PreChirp{mean2, chirp, M});
-                else ip_stage_any<false>(g.fzb.st[s], g.Lc, R1, g.div_R1, az, twc, PreSub{make_float2(0.f, 0.f)});
+                if (s == 0) ip_stage_any<false>(g.fzb.st[0], g.Lc, g.zcols, g.div_zcols, az, twc, PreChirp{mean2, chirp, M});
+                else ip_stage_any<false>(g.fzb.st[s], g.Lc, g.zcols, g.div_zcols, az, twc, PreSub{make_float2(0.f, 0.f)});
                 __syncthreads();
             }
             for (int s = ns - 1; s >= 0; --s) {
-                if (s == ns - 1) ip_stage_any<false, true>(g.fzb.st[s], g.Lc, R1, g.div_R1, az, twc, PreBhat{bhat});
-                else ip_stage_any<false, true>(g.fzb.st[s], g.Lc, R1, g.div_R1, az, twc, PreSub{make_float2(0.f, 0.f)});
+                if (s == ns - 1) ip_stage_any<false, true>(g.fzb.st[s], g.Lc, g.zcols, g.div_zcols, az, twc, PreBhat{bhat});
+                else ip_stage_any<false, true>(g.fzb.st[s], g.Lc, g.zcols, g.div_zcols, az, twc, PreSub{make_float2(0.f, 0.f)});
                 __syncthreads();
             }
         }
@@ -468,6 +493,23 @@ k_g2_p1(const float* __restrict__ boxes, long long batch_stride, int n2_total, I
                 default: PS21_G2_YFIRST(10); break;
             }
 #undef PS21_G2_YFIRST
+            __syncthreads();
+        } else if (g.pair) {
+            // odd nz: Z = FFT(row_a + i row_b);  A_a(k) = (Z_k + conj Z_{nz-k}) / 2,  A_b(k) = (Z_k - conj Z_{nz-k}) / 2i.
+            // A_a replaces Z_k, A_b goes to the (unused) right half of the same row; the rows of Z_{nz-k} are dead after.
+            for (int e = tid; e < nh * g.zcols; e += nthr) {
+                const int k = fast_div(e, g.div_zcols), c = e - k * g.zcols;
+                auto fix = [&](float2 v, int row) {   // Bluestein: Z_k = chirp[k] conj(row k)
+                    return g.bluestein ? cmul_w2(make_float2(v.x, -v.y), chirp[row]) : v;
+                };
+                float2* qk = buf + rowz[k] * ld + c;
+                const float2 zk = fix(*qk, k);
+                const float2 zn = (k == 0) ? zk : fix(buf[rowz[M - k] * ld + c], M - k);
+                qk[0] = make_float2(0.5f * (zk.x + zn.x), 0.5f * (zk.y - zn.y));
+                qk[g.zcols] = make_float2(0.5f * (zk.y + zn.y), -0.5f * (zk.x - zn.x));
+            }
+            __syncthreads();
+            ip_stage_any<false>(g.fy.st[0], R1, nh, g.div_nh, ay, twy, PreSub{make_float2(0.f, 0.f)});
             __syncthreads();
         } else {
             const int npair = M / 2 + 1;
@@ -509,19 +551,19 @@ k_g2_p1(const float* __restrict__ boxes, long long batch_stride, int n2_total, I
         const long long inner = ((long long)x * g.R2 + slot) << g.lgT;
         if (g.fuse_last) {
             switch (g.fy.st[ylast].radix) {
-                case 2: p1_y_last_store<2>(buf32, dst, g, twu, yl, inner); break;
-                case 3: p1_y_last_store<3>(buf32, dst, g, twu, yl, inner); break;
-                case 4: p1_y_last_store<4>(buf32, dst, g, twu, yl, inner); break;
-                case 5: p1_y_last_store<5>(buf32, dst, g, twu, yl, inner); break;
-                case 6: p1_y_last_store<6>(buf32, dst, g, twu, yl, inner); break;
-                case 8: p1_y_last_store<8>(buf32, dst, g, twu, yl, inner); break;
-                default: p1_y_last_store<10>(buf32, dst, g, twu, yl, inner); break;
+                case 2: p1_y_last_store<2>(buf32, dst, g, twu, g.pair ? prow : nullptr, yl, inner); break;
+                case 3: p1_y_last_store<3>(buf32, dst, g, twu, g.pair ? prow : nullptr, yl, inner); break;
+                case 4: p1_y_last_store<4>(buf32, dst, g, twu, g.pair ? prow : nullptr, yl, inner); break;
+                case 5: p1_y_last_store<5>(buf32, dst, g, twu, g.pair ? prow : nullptr, yl, inner); break;
+                case 6: p1_y_last_store<6>(buf32, dst, g, twu, g.pair ? prow : nullptr, yl, inner); break;
+                case 8: p1_y_last_store<8>(buf32, dst, g, twu, g.pair ? prow : nullptr, yl, inner); break;
+                default: p1_y_last_store<10>(buf32, dst, g, twu, g.pair ? prow : nullptr, yl, inner); break;
             }
         } else {
             const long long tile_elems = (long long)g.n0 * 32;
             for (int e = tid; e < R1 * nh; e += nthr) {
                 const int jp = fast_div(e, g.div_nh), r = e - jp * nh;
-                float2 v = buf[r * ld + jp];
+                float2 v = buf[(g.pair ? (int)prow[r] : r) * ld + jp];
                 if (yl) v = cmul_w2(v, twu[jp]);
                 dst[((long long)jp * g.nzt + (r >> g.lgT)) * tile_elems + inner + (r & (g.T - 1))] = v;
             }
@@ -895,7 +937,7 @@ static int upload(const std::vector<T>& v, T** d) {
 static size_t p1_smem(const G2Dev& g) {
     return (size_t)g.nbuf * g.zrows * g.ld * sizeof(float2) +
            (size_t)(g.nz + g.n1 + g.R1 + 2 * g.Lc + (g.bluestein ? g.M : 0)) * sizeof(float2) +
-           (size_t)(g.M + g.R1) * 2 + 64;
+           (size_t)(g.M + g.R1 + g.nh) * 2 + 64;
 }
 static size_t p2_smem(const G2Dev& g, int nbins, int nshare) {
     const int RL = g.fx.st[g.fx.nstages - 1].radix;
@@ -936,10 +978,14 @@ int g2_try_setup(ps21_plan* p, ShapePlan& sp) {
     if (p->mode != PS21_MODE_SPHERICAL) return no("spherical bins only");
     if (p->nbins > MAX_BINS) return no("n_psbins <= 254");
     const int n0 = p->n0, n1 = p->n1, nz = sp.nz;
-    if (nz % 2 || nz < 4) return no("even chunk length >= 4 needed");
+    if (nz < 4) return no("chunk length >= 4 needed");
     if (n0 < 8 || n1 < 8 || n0 > 2048 || n1 > 2048 || nz > 4096) return no("axis length out of range");
     G2Dev g{};
-    g.n0 = n0; g.n1 = n1; g.nz = nz; g.M = nz / 2; g.nh = g.M + 1;
+    // even nz: (even, odd)-packed rows, complex transform of length nz / 2 + untangle; odd nz: complex transform of
+    // length nz on pairs of rows + separation
+    g.pair = nz % 2;
+    if (std::getenv("PS21_G2_NOPAIR") && g.pair) return no("odd chunk lengths disabled");
+    g.n0 = n0; g.n1 = n1; g.nz = nz; g.M = g.pair ? nz : nz / 2; g.nh = nz / 2 + 1;
     std::vector<int> rz, ry, rx;
     std::vector<int> rzb;   // Bluestein: radices of the convolution length
     if (!split_radices(g.M, kRadZ, rz) || std::getenv("PS21_G2_FORCE_BLUESTEIN")) {
@@ -949,7 +995,7 @@ int g2_try_setup(ps21_plan* p, ShapePlan& sp) {
         for (g.Lc = 2 * g.M - 1; !split_radices(g.Lc, kRadZ, rzb); ++g.Lc) {}
         if (g.Lc > 4096) return no("chunk too long for the chirp convolution");
     }
-    g.zrows = std::max(g.nh, g.Lc);
+    g.zrows = std::max(g.pair ? g.M : g.nh, g.Lc);
     // y split n1 = R1 R2.  Pass 1 keeps nh x R1 coefficients per buffer; with two buffers the next unit streams in while
     // this one is transformed.  R2 = 4 gives 64-byte runs in the scratch, R2 = 8 halves the buffer (32-byte runs).
     int R2 = 0, nbuf = 0;
@@ -957,7 +1003,8 @@ int g2_try_setup(ps21_plan* p, ShapePlan& sp) {
     if (const char* e = std::getenv("PS21_G2_R2")) force_r2 = std::atoi(e);
     if (const char* e = std::getenv("PS21_G2_NBUF")) force_nbuf = std::atoi(e);
     auto extra1 = [&](int R1) {
-        return (size_t)(nz + n1 + R1 + 2 * g.Lc + (g.bluestein ? g.M : 0)) * sizeof(float2) + (size_t)(g.M + R1) * 2 + 64;
+        return (size_t)(nz + n1 + R1 + 2 * g.Lc + (g.bluestein ? g.M : 0)) * sizeof(float2) +
+               (size_t)(g.M + R1 + g.nh) * 2 + 64;
     };
     auto buf1 = [&](int R1) { return (size_t)g.zrows * (R1 | 1) * sizeof(float2); };
     // measured on 200^3 (B200): one buffer with three CTAs per SM 4.83 ms, two buffers with two CTAs 5.24 ms -- occupancy
@@ -969,7 +1016,7 @@ int g2_try_setup(ps21_plan* p, ShapePlan& sp) {
         if ((force_r2 && t.r2 != force_r2) || (force_nbuf && t.nb != force_nbuf) || n1 % t.r2) continue;
         const int R1 = n1 / t.r2;
         std::vector<int> tmp;
-        if (R1 < 2 || !split_radices(R1, kRadY, tmp)) continue;
+        if (R1 < 2 || !split_radices(R1, kRadY, tmp) || (g.pair && R1 % 2)) continue;
         if (t.nb * buf1(R1) + extra1(R1) <= t.budget) {
             R2 = t.r2;
             nbuf = t.nb;
@@ -982,7 +1029,8 @@ int g2_try_setup(ps21_plan* p, ShapePlan& sp) {
     g.nbuf = nbuf;
     split_radices(g.R1, kRadY, ry);
     if (ry.size() >= 2) std::swap(ry.front(), ry.back());   // smallest radix first: the fused first stage holds 2 R values
-    g.fuse_first = is_fusable_y(ry.front()) ? 1 : 0;
+    g.fuse_first = (!g.pair && is_fusable_y(ry.front())) ? 1 : 0;   // the fused stage untangles packed rows only
+    g.zcols = g.pair ? g.R1 / 2 : g.R1;
     g.fuse_last = (ry.size() >= 2 && is_fusable_y(ry.back())) ? 1 : 0;
     if (std::getenv("PS21_G2_NOFUSE")) g.fuse_first = g.fuse_last = 0;
     g.slabs = (n0 % 2 == 0 && n0 >= 64) ? 2 : 1;
@@ -1008,11 +1056,12 @@ int g2_try_setup(ps21_plan* p, ShapePlan& sp) {
     if ((long long)g.R1 * g.M >= 65536 || (long long)g.R1 * g.nh >= 65536 || (long long)(g.M / 2 + 1) * g.R1 >= 65536 ||
         (long long)g.R1 * g.Lc >= 65536)
         return no("unit too large for the index arithmetic");
-    if (!g.bluestein) make_ipfft(g.M, rz, 2, g.fz);          // w_M^q = w_nz^(2q)
+    if (!g.bluestein) make_ipfft(g.M, rz, g.pair ? 1 : 2, g.fz);   // packed rows: w_M^q = w_nz^(2q)
     else make_ipfft(g.Lc, rzb, 1, g.fzb);
     make_ipfft(g.R1, ry, R2, g.fy);        // w_R1^q = w_n1^(R2 q)
     make_ipfft(n0, rx, 1, g.fx);
     g.div_M = make_fastdiv(g.M); g.div_R1 = make_fastdiv(g.R1); g.div_nh = make_fastdiv(g.nh);
+    g.div_zcols = make_fastdiv(g.zcols);
     g.nzt = (g.nh + g.T - 1) / g.T;
     g.ntiles = g.R1 * g.nzt;
     {   // pass-2 CTAs per spectrum: about 12 tiles each
@@ -1033,19 +1082,29 @@ int g2_try_setup(ps21_plan* p, ShapePlan& sp) {
     if (g.bluestein)   // the inverse transform of the convolution leaves the rows in natural order
         for (int r = 0; r < g.M; ++r) fz_pos[r] = r;
     const std::vector<int> fy_pos = freq_of_pos(g.R1, g.fy), fx_pos = freq_of_pos(n0, g.fx);
-    std::vector<uint16_t> rowz(g.M), kya(g.R1), kxpos(n0), kzrow((size_t)g.nzt * g.T, 0xFFFF);
+    std::vector<uint16_t> rowz(g.M), kya(g.R1), kxpos(n0), kzrow((size_t)g.nzt * g.T, 0xFFFF), prow(g.nh);
     std::vector<uint8_t> zmult((size_t)g.nzt * g.T, 0);
-    for (int r = 0; r < g.M; ++r) {
-        rowz[fz_pos[r]] = (uint16_t)r;
-        kzrow[r] = (uint16_t)fz_pos[r];
+    for (int r = 0; r < g.M; ++r) rowz[fz_pos[r]] = (uint16_t)r;
+    if (!g.pair) {
+        for (int r = 0; r < g.M; ++r) kzrow[r] = (uint16_t)fz_pos[r];
+        kzrow[g.M] = (uint16_t)g.M;   // the Nyquist row
+        for (int r = 0; r < g.nh; ++r) prow[r] = (uint16_t)r;
+    } else {
+        // the separated spectrum A(k), k = 0 .. nz/2, stays in the physical row of Z_k; logical rows in physical order
+        std::vector<std::pair<int, int>> used;   // (physical row, k)
+        for (int k = 0; k < g.nh; ++k) used.push_back({(int)rowz[k], k});
+        std::sort(used.begin(), used.end());
+        for (int r = 0; r < g.nh; ++r) {
+            prow[r] = (uint16_t)used[r].first;
+            kzrow[r] = (uint16_t)used[r].second;
+        }
     }
-    kzrow[g.M] = (uint16_t)g.M;   // the Nyquist row
     for (int r = 0; r < g.nh; ++r) zmult[r] = (kzrow[r] == 0 || 2 * kzrow[r] == nz) ? 1 : 2;
     for (int j = 0; j < g.R1; ++j) kya[j] = (uint16_t)fy_pos[j];
     for (int x = 0; x < n0; ++x) kxpos[x] = (uint16_t)fx_pos[x];
     int rc = PS21_OK;
     if ((rc = upload(rowz, &gs->d_rowz)) || (rc = upload(kya, &gs->d_kya)) || (rc = upload(kxpos, &gs->d_kxpos)) ||
-        (rc = upload(kzrow, &gs->d_kzrow)) || (rc = upload(zmult, &gs->d_zmult))) {
+        (rc = upload(kzrow, &gs->d_kzrow)) || (rc = upload(zmult, &gs->d_zmult)) || (rc = upload(prow, &gs->d_prow))) {
         sp.fused = gs;
         g2_destroy(sp);
         return no("table upload failed");
@@ -1093,7 +1152,7 @@ int g2_try_setup(ps21_plan* p, ShapePlan& sp) {
         }
         g.tw_c = gs->d_twc; g.chirp = gs->d_chirp; g.bhat = gs->d_bhat;
     }
-    g.rowz_of_k = gs->d_rowz; g.kya_of_jp = gs->d_kya; g.zmult = gs->d_zmult;
+    g.rowz_of_k = gs->d_rowz; g.kya_of_jp = gs->d_kya; g.zmult = gs->d_zmult; g.prow_of_row = gs->d_prow;
     gs->dev = g;
     gs->smem1 = p1_smem(g);
     gs->smem2 = p2_smem(g, p->nbins, gs->nshare);
@@ -1137,6 +1196,7 @@ void g2_destroy(ShapePlan& sp) {
     if (gs->d_kya) cudaFree(gs->d_kya);
     if (gs->d_kxpos) cudaFree(gs->d_kxpos);
     if (gs->d_kzrow) cudaFree(gs->d_kzrow);
+    if (gs->d_prow) cudaFree(gs->d_prow);
     if (gs->d_zmult) cudaFree(gs->d_zmult);
     if (gs->d_twc) cudaFree(gs->d_twc);
     if (gs->d_chirp) cudaFree(gs->d_chirp);

@@ -126,6 +126,10 @@ def test_lnl_before_data_is_a_state_error(mods):
     ((16, 16, 34), (24.0, 24.0, 51.0), 8, True, (True, False, False)),     # nz / 2 = 17: Bluestein (chirp convolution)
     ((32, 32, 38), (48.0, 48.0, 57.0), 6, False, (False, False, False)),   # 19, DC binned
     ((64, 64, 334), (96.0, 96.0, 501.0), 12, True, (True, False, False)),  # 167: the 334-slice chunk of a 1002-slice lightcone
+    ((16, 16, 15), (24.0, 24.0, 22.5), 8, True, (True, False, False)),     # odd chunk length: transform of row pairs
+    ((32, 32, 21), (48.0, 48.0, 31.5), 6, False, (False, False, False)),   # odd, 3 * 7, DC binned
+    ((24, 24, 37), (36.0, 36.0, 55.5), 7, True, (True, False, True)),      # odd and prime: row pairs + Bluestein
+    ((64, 64, 333), (96.0, 96.0, 499.5), 12, True, (True, False, False)),  # 333 = 9 * 37: the other chunks of that lightcone
 ])
 def test_generic_two_pass_kernels(mods, shape, L, nb, log, flags):
     """ps21_g2.cu (in-place digit-reversed transforms, position-defined tiles) on the emulated device vs the oracle."""
@@ -143,9 +147,9 @@ def test_two_pass_rejects_what_it_cannot_factor(mods):
     from py21cmmc_b200.plan import PowerPlan
     from py21cmmc_b200 import _capi
 
-    for shape in ((15, 15, 16), (16, 16, 17)):   # odd plane, odd chunk
+    for shape in ((15, 15, 16), (50, 50, 16)):   # odd sky plane; 50 rows do not split into 4 or 8 units
         with pytest.raises(Ps21Error):
             PowerPlan(shape, [(0, shape[2])], [(24.0, 24.0, 30.0)], 4, path="twopass", library=_capi.LIB_PATH)
-    pl = PowerPlan((16, 16, 17), [(0, 17)], [(24.0, 24.0, 25.5)], 4, path="auto", library=_capi.LIB_PATH)
+    pl = PowerPlan((15, 15, 16), [(0, 16)], [(22.5, 22.5, 24.0)], 4, path="auto", library=_capi.LIB_PATH)
     assert pl.path == "general"
     pl.close()

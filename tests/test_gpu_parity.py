@@ -501,6 +501,9 @@ TWOPASS_CASES = [
     ((256, 256, 334), (384.0, 384.0, 501.0), 20, True, (True, False, False)),      # M = 167 prime: Bluestein, Lc = 336
     ((128, 128, 38), (192.0, 192.0, 57.0), 10, False, (False, False, False)),      # M = 19: Bluestein, DC binned
     ((64, 64, 202), (96.0, 96.0, 303.0), None, True, (True, True, False)),         # M = 101: Bluestein, group bins
+    ((256, 256, 333), (384.0, 384.0, 499.5), 20, True, (True, False, False)),      # odd: row pairs, 333 = 9 * 37 -> Bluestein
+    ((128, 128, 225), (192.0, 192.0, 337.5), 16, False, (False, False, False)),    # odd, 225 = 15 * 15 direct, DC binned
+    ((200, 200, 75), (300.0, 300.0, 112.5), 20, True, (True, False, True)),        # odd on the config-2 plane
 ]
 
 
@@ -536,7 +539,8 @@ def test_auto_prefers_two_pass_kernels_and_falls_back(mods):
     assert mk((200, 200, 200), (300.0,) * 3).path == "twopass"
     assert mk((256, 256, 256), (384.0,) * 3).path == "fused"
     assert mk((64, 64, 334), (96.0, 96.0, 501.0)).path == "twopass"     # 334 / 2 = 167 is prime: chirp convolution
-    assert mk((64, 64, 333), (96.0, 96.0, 499.5)).path == "general"     # odd chunk length
+    assert mk((64, 64, 333), (96.0, 96.0, 499.5)).path == "twopass"     # odd chunk length: row pairs (+ Bluestein: 37)
+    assert mk((100, 100, 33), (150.0, 150.0, 49.5)).path == "general"   # odd length needs an even number of rows per unit
     assert mk((35, 35, 36), (52.5, 52.5, 54.0)).path == "general"       # odd sky plane
     with pytest.raises(Exception):
         get_plan((35, 35, 36), [(0, 36)], [(52.5, 52.5, 54.0)], 12, True, True, False, False, "legacy_1.001",
@@ -544,6 +548,6 @@ def test_auto_prefers_two_pass_kernels_and_falls_back(mods):
 
 
 def test_twopass_lightcone_with_unequal_chunks(mods):
-    """A 128 x 128 x 500 lightcone in 3 chunks (167, 167, 166 slices): the odd chunks take the general path, the even
-    one the two-pass kernels, inside one plan; lnL against the oracle."""
+    """A 64 x 64 x 500 lightcone in 3 chunks (167, 167, 166 slices): odd chunks (row pairs + chirp convolution, 167 is
+    prime) and an even one (166 = 2 * 83, chirp convolution) inside one plan; lnL against the oracle."""
     PC.check_lightcone_likelihood(*mods, shape=(64, 64, 500), box_len=96.0, nchunks=3, nb=12, min_k=0.2, max_k=3.0)
