@@ -964,7 +964,9 @@ static int set_attr(size_t smem) {
         else if (R2 == 8 && R0 == 4 && NSHARE == 1) { WHAT(4, 8, 1); }                          \
         else if (R2 == 8 && R0 == 4) { WHAT(4, 8, 4); }                                         \
         else if (R2 == 8 && R0 == 2 && NSHARE == 1) { WHAT(2, 8, 1); }                          \
-        else { WHAT(2, 8, 4); }                                                                 \
+        else if (R2 == 8 && R0 == 2) { WHAT(2, 8, 4); }                                         \
+        else if (R2 == 16 && NSHARE == 1) { WHAT(2, 16, 1); }                                   \
+        else { WHAT(2, 16, 4); }                                                                \
     } while (0)
 
 }  // namespace g2
@@ -1010,8 +1012,11 @@ int g2_try_setup(ps21_plan* p, ShapePlan& sp) {
     // measured on 200^3 (B200): one buffer with three CTAs per SM 4.83 ms, two buffers with two CTAs 5.24 ms -- occupancy
     // beats overlap inside a CTA, so: three resident CTAs first, then two with the prefetch buffer, then whatever fits
     struct Try { int r2, nb; size_t budget; };
+    // R2 = 16 (T = 2: 16-byte runs, two units complete a 32-byte sector in L2) only where nothing else keeps more than
+    // one CTA per SM resident (512^3: 134 KB per unit at R2 = 8)
     const Try order[] = {{4, 1, 74 * 1024},  {8, 1, 74 * 1024},  {4, 2, 112 * 1024}, {8, 2, 112 * 1024},
-                         {4, 1, 112 * 1024}, {8, 1, 112 * 1024}, {4, 1, 224 * 1024}, {8, 1, 224 * 1024}};
+                         {4, 1, 112 * 1024}, {8, 1, 112 * 1024}, {16, 1, 74 * 1024}, {16, 1, 112 * 1024},
+                         {4, 1, 224 * 1024}, {8, 1, 224 * 1024}, {16, 1, 224 * 1024}};
     for (const Try& t : order) {
         if ((force_r2 && t.r2 != force_r2) || (force_nbuf && t.nb != force_nbuf) || n1 % t.r2) continue;
         const int R1 = n1 / t.r2;
@@ -1024,7 +1029,7 @@ int g2_try_setup(ps21_plan* p, ShapePlan& sp) {
         }
     }
     if (!R2) return no("no y split fits the shared memory");
-    g.R2 = R2; g.R1 = n1 / R2; g.T = 32 / R2; g.lgT = (g.T == 8) ? 3 : 2;
+    g.R2 = R2; g.R1 = n1 / R2; g.T = 32 / R2; g.lgT = (g.T == 8) ? 3 : (g.T == 4) ? 2 : 1;
     g.ld = g.R1 | 1;
     g.nbuf = nbuf;
     split_radices(g.R1, kRadY, ry);
@@ -1036,7 +1041,7 @@ int g2_try_setup(ps21_plan* p, ShapePlan& sp) {
     g.slabs = (n0 % 2 == 0 && n0 >= 64) ? 2 : 1;
     // x: first stage R0 with R0 * R2 <= 32 values per thread, the largest remaining radix last (it feeds the bins)
     int R0 = 0;
-    for (int cand : (R2 == 4 ? std::vector<int>{8, 4, 2} : std::vector<int>{4, 2})) {
+    for (int cand : (R2 == 4 ? std::vector<int>{8, 4, 2} : R2 == 8 ? std::vector<int>{4, 2} : std::vector<int>{2})) {
         if (n0 % cand) continue;
         if (n0 / cand < 2) continue;
         // the last stage feeds the bins: it must be one of the instantiated ones, the larger the better
