@@ -1012,11 +1012,11 @@ int g2_try_setup(ps21_plan* p, ShapePlan& sp) {
     // measured on 200^3 (B200): one buffer with three CTAs per SM 4.83 ms, two buffers with two CTAs 5.24 ms -- occupancy
     // beats overlap inside a CTA, so: three resident CTAs first, then two with the prefetch buffer, then whatever fits
     struct Try { int r2, nb; size_t budget; };
-    // R2 = 16 (T = 2: 16-byte runs, two units complete a 32-byte sector in L2) only where nothing else keeps more than
-    // one CTA per SM resident (512^3: 134 KB per unit at R2 = 8)
+    // R2 = 16 (T = 2: 16-byte runs) is the last resort: measured on 512^3, its three resident CTAs do not make up for
+    // the half-sector writes (pass 1 44.5 ms against 20.6 ms with R2 = 8 and one 134 KB CTA per SM)
     const Try order[] = {{4, 1, 74 * 1024},  {8, 1, 74 * 1024},  {4, 2, 112 * 1024}, {8, 2, 112 * 1024},
-                         {4, 1, 112 * 1024}, {8, 1, 112 * 1024}, {16, 1, 74 * 1024}, {16, 1, 112 * 1024},
-                         {4, 1, 224 * 1024}, {8, 1, 224 * 1024}, {16, 1, 224 * 1024}};
+                         {4, 1, 112 * 1024}, {8, 1, 112 * 1024}, {4, 1, 224 * 1024}, {8, 1, 224 * 1024},
+                         {16, 1, 224 * 1024}};
     for (const Try& t : order) {
         if ((force_r2 && t.r2 != force_r2) || (force_nbuf && t.nb != force_nbuf) || n1 % t.r2) continue;
         const int R1 = n1 / t.r2;
