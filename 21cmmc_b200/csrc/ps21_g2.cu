@@ -1038,7 +1038,11 @@ int g2_try_setup(ps21_plan* p, ShapePlan& sp) {
     g.zcols = g.pair ? g.R1 / 2 : g.R1;
     g.fuse_last = (ry.size() >= 2 && is_fusable_y(ry.back())) ? 1 : 0;
     if (std::getenv("PS21_G2_NOFUSE")) g.fuse_first = g.fuse_last = 0;
-    g.slabs = (n0 % 2 == 0 && n0 >= 64) ? 2 : 1;
+    g.slabs = 1;   // x slabs per CTA (measured on 200^3: 1 -> 4.52 ms, 2 -> 4.67, 4 -> 4.56, 8 -> 4.62)
+    if (const char* e = std::getenv("PS21_G2_SLABS")) {   // tuning sweeps only
+        const int v = std::atoi(e);
+        if (v >= 1 && n0 % v == 0) g.slabs = v;
+    }
     // x: first stage R0 with R0 * R2 <= 32 values per thread, the largest remaining radix last (it feeds the bins)
     int R0 = 0;
     for (int cand : (R2 == 4 ? std::vector<int>{8, 4, 2} : R2 == 8 ? std::vector<int>{4, 2} : std::vector<int>{2})) {
@@ -1071,6 +1075,10 @@ int g2_try_setup(ps21_plan* p, ShapePlan& sp) {
     g.ntiles = g.R1 * g.nzt;
     {   // pass-2 CTAs per spectrum: about 12 tiles each
         int per = 12;
+        if (const char* e = std::getenv("PS21_G2_TILES_PER_CTA")) {   // tuning sweeps only
+            const int v = std::atoi(e);
+            if (v >= 1) per = v;
+        }
         g.slots = (g.ntiles + per - 1) / per;
         if (g.slots < 1) g.slots = 1;
     }
@@ -1170,6 +1178,7 @@ int g2_try_setup(ps21_plan* p, ShapePlan& sp) {
 #ifndef PS21_EMU
     if (cudaFuncSetAttribute(k_g2_p1<256, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess ||
         cudaFuncSetAttribute(k_g2_p1<256, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess ||
+        cudaFuncSetAttribute(k_g2_p1<256, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess ||
         cudaFuncSetAttribute(k_g2_p1<512, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) {
         cudaGetLastError();
         sp.fused = gs;
@@ -1239,7 +1248,11 @@ int g2_forward(ps21_plan* p, ShapePlan& sp, const float* d_boxes, long long batc
         if (p->chunks[c].start % 2) aligned8 = 0;
     {
         ProfScope ps(p, KK_PASS1, st);
-        if (gs->p1_threads == 256 && gs->smem1 <= 74 * 1024)   // three CTAs per SM: 80 registers
+        if (gs->p1_threads == 256 && gs->smem1 <= 55 * 1024 && !std::getenv("PS21_G2_P1_MINB3"))
+            // four CTAs per SM at 64 registers (a few spills) beat three at 80: 4.43 vs 4.67 ms on 200^3
+            PS21_LAUNCH((k_g2_p1<256, 4>), dim3(g.n0 / g.slabs, (unsigned)nitems), dim3(256), gs->smem1, st, d_boxes, batch_stride,
+                        p->n2_total, im, p->d_chunks, p->nchunks, p->d_mean_parts, p->d_scratch, g, aligned8);
+        else if (gs->p1_threads == 256 && gs->smem1 <= 74 * 1024)   // three CTAs per SM: 80 registers
             PS21_LAUNCH((k_g2_p1<256, 3>), dim3(g.n0 / g.slabs, (unsigned)nitems), dim3(256), gs->smem1, st, d_boxes, batch_stride,
                         p->n2_total, im, p->d_chunks, p->nchunks, p->d_mean_parts, p->d_scratch, g, aligned8);
         else if (gs->p1_threads == 256)                          // two CTAs per SM: 128 registers
