@@ -1033,12 +1033,27 @@ int g2_try_setup(ps21_plan* p, ShapePlan& sp) {
     g.ld = g.R1 | 1;
     g.nbuf = nbuf;
     split_radices(g.R1, kRadY, ry);
+    // A unit that has the SM to itself (512^3: 134 KB) hides its latencies with threads instead of CTAs: 1024 threads at
+    // 64 registers, which caps the butterflies at radix 8 (one more z stage for 256 = 8 * 8 * 4)
+    bool big_unit = nbuf * buf1(g.R1) + extra1(g.R1) > 112 * 1024 && !g.bluestein && std::getenv("PS21_G2_P1_1024");
+    if (big_unit) {
+        static const std::vector<int> kRad8 = {8, 7, 6, 5, 4, 3, 2};
+        std::vector<int> rz8, ry8;
+        if (split_radices(g.M, kRad8, rz8) && split_radices(g.R1, kRad8, ry8)) {
+            rz = rz8;
+            ry = ry8;
+        } else {
+            big_unit = false;
+        }
+    }
     if (ry.size() >= 2) std::swap(ry.front(), ry.back());   // smallest radix first: the fused first stage holds 2 R values
     g.fuse_first = (!g.pair && is_fusable_y(ry.front())) ? 1 : 0;   // the fused stage untangles packed rows only
     g.zcols = g.pair ? g.R1 / 2 : g.R1;
     g.fuse_last = (ry.size() >= 2 && is_fusable_y(ry.back())) ? 1 : 0;
     if (std::getenv("PS21_G2_NOFUSE")) g.fuse_first = g.fuse_last = 0;
-    g.slabs = 1;   // x slabs per CTA (measured on 200^3: 1 -> 4.52 ms, 2 -> 4.67, 4 -> 4.56, 8 -> 4.62)
+    // x slabs per CTA and resident CTAs go together (200^3, pass 1, same box): 4 CTAs/SM x 2 slabs 4.41 ms, 3 x 1 4.52,
+    // 3 x 2 4.67, 4 x 1 4.90
+    g.slabs = (n0 % 2 == 0 && nbuf * buf1(g.R1) + extra1(g.R1) <= 55 * 1024) ? 2 : 1;
     if (const char* e = std::getenv("PS21_G2_SLABS")) {   // tuning sweeps only
         const int v = std::atoi(e);
         if (v >= 1 && n0 % v == 0) g.slabs = v;
@@ -1169,7 +1184,7 @@ int g2_try_setup(ps21_plan* p, ShapePlan& sp) {
     gs->dev = g;
     gs->smem1 = p1_smem(g);
     gs->smem2 = p2_smem(g, p->nbins, gs->nshare);
-    gs->p1_threads = (gs->smem1 > 112 * 1024) ? 512 : 256;   // a CTA that has the SM to itself gets 512 threads
+    gs->p1_threads = big_unit ? 1024 : (gs->smem1 > 112 * 1024) ? 512 : 256;   // a CTA that has the SM to itself gets more threads
     if (gs->smem2 > 227 * 1024 || gs->smem1 > 227 * 1024) {
         sp.fused = gs;
         g2_destroy(sp);
@@ -1179,6 +1194,7 @@ int g2_try_setup(ps21_plan* p, ShapePlan& sp) {
     if (cudaFuncSetAttribute(k_g2_p1<256, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess ||
         cudaFuncSetAttribute(k_g2_p1<256, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess ||
         cudaFuncSetAttribute(k_g2_p1<256, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess ||
+        cudaFuncSetAttribute(k_g2_p1<1024, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess ||
         cudaFuncSetAttribute(k_g2_p1<512, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) {
         cudaGetLastError();
         sp.fused = gs;
@@ -1248,7 +1264,10 @@ int g2_forward(ps21_plan* p, ShapePlan& sp, const float* d_boxes, long long batc
         if (p->chunks[c].start % 2) aligned8 = 0;
     {
         ProfScope ps(p, KK_PASS1, st);
-        if (gs->p1_threads == 256 && gs->smem1 <= 55 * 1024 && !std::getenv("PS21_G2_P1_MINB3"))
+        if (gs->p1_threads == 1024)
+            PS21_LAUNCH((k_g2_p1<1024, 1>), dim3(g.n0 / g.slabs, (unsigned)nitems), dim3(1024), gs->smem1, st, d_boxes, batch_stride,
+                        p->n2_total, im, p->d_chunks, p->nchunks, p->d_mean_parts, p->d_scratch, g, aligned8);
+        else if (gs->p1_threads == 256 && gs->smem1 <= 55 * 1024 && !std::getenv("PS21_G2_P1_MINB3"))
             // four CTAs per SM at 64 registers (a few spills) beat three at 80: 4.43 vs 4.67 ms on 200^3
             PS21_LAUNCH((k_g2_p1<256, 4>), dim3(g.n0 / g.slabs, (unsigned)nitems), dim3(256), gs->smem1, st, d_boxes, batch_stride,
                         p->n2_total, im, p->d_chunks, p->nchunks, p->d_mean_parts, p->d_scratch, g, aligned8);

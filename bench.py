@@ -474,6 +474,21 @@ def run_gpu(args):
         if world > 1:
             dist.all_reduce(dt, op=dist.ReduceOp.MAX)
         dt_abi = float(dt.item())
+        # (2b) the same plugin call on ordinary (pageable) NumPy lightcones, as an unmodified simulator returns them
+        sim.boxes = [np.array(h) for h in hboxes[:min(ew, 4)]]
+        plist_p = [[float(w)] for w in range(len(sim.boxes))]
+        ch.call_batch(plist_p)
+        if world > 1:
+            dist.barrier()
+        t0 = time.perf_counter()
+        for _ in range(esteps):
+            ch.call_batch(plist_p)
+        dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+        dt_pageable = float(dt.item())
+        n_pageable = len(sim.boxes)
+        sim.boxes = hboxes
         # (3) the H2D line rate of this box: a plain pinned copy of the same bytes, nothing else
         dst = torch.empty((min(ew, 4),) + SHAPE, dtype=torch.float32, device=dev)
         srcs = [torch.from_numpy(h) for h in hboxes[:dst.shape[0]]]
@@ -502,6 +517,9 @@ def run_gpu(args):
                           "store)",
                "bound": "pcie", "h2d_gbs_per_gpu": ew * esteps * box_bytes / dt_plugin / 1e9,
                "h2d_line_rate_gbs_per_gpu": line_rate,
+               "pageable": {"value": world * n_pageable * esteps / dt_pageable, "unit": UNIT,
+                            "h2d_gbs_per_gpu": n_pageable * esteps * box_bytes / dt_pageable / 1e9,
+                            "through": "the same plugin call on pageable NumPy lightcones (staged by the library)"},
                "c_abi": {"value": world * ew * esteps / dt_abi, "unit": UNIT,
                          "h2d_gbs_per_gpu": ew * esteps * box_bytes / dt_abi / 1e9,
                          "through": "ps21_lnl_host_ptrs on the same buffers"},
