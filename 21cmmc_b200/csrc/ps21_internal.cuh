@@ -121,6 +121,11 @@ struct ps21_plan {
     void* stage_stream[2] = {nullptr, nullptr};
     void* stage_ev[4] = {nullptr, nullptr, nullptr, nullptr};   // copy done [2], compute done [2]
     double* d_res[3] = {nullptr, nullptr, nullptr};             // power, Delta^2, lnL of a *_host call
+    // pageable host inputs: page-locked ring the staging threads copy through (2 slots per thread) + "slot free" events
+    static constexpr int kStageThreads = 6;
+    static constexpr long long kStageSlotBytes = 16LL << 20;
+    char* h_ring = nullptr;
+    void* ring_ev[2 * kStageThreads] = {};
     long long res_boxes = 0;
     // CUDA graphs of whole calls (ps21_plan_set_graphs)
     struct GraphKey {

@@ -4,6 +4,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <map>
+#include <thread>
 
 #include "ps21_internal.cuh"
 #include "../../include/ps21.h"
@@ -485,6 +486,14 @@ static void release_workspace(ps21_plan* p) {
         p->d_res[i] = nullptr;
     }
     p->res_boxes = 0;
+#ifndef PS21_EMU
+    if (p->h_ring) cudaFreeHost(p->h_ring);
+    p->h_ring = nullptr;
+    for (auto& e : p->ring_ev) {
+        if (e) cudaEventDestroy((cudaEvent_t)e);
+        e = nullptr;
+    }
+#endif
 }
 
 }  // namespace ps21
@@ -903,6 +912,79 @@ int ps21_lnl_batched(ps21_plan* p, const float* d_boxes, int64_t batch, int64_t 
     return run_device(p, d_boxes, batch, batch_stride, d_power, d_delta, d_lnl, (cudaStream_t)stream);
 }
 
+#ifndef PS21_EMU
+// H2D of `nboxes` host boxes into `d_dst` on stream `st`.  Page-locked sources (cudaHostAlloc / cudaHostRegister:
+// ps21_host_alloc, ps21_host_register, torch pinned memory) are handed to the DMA engine as they are.  PAGEABLE
+// sources -- what an unmodified simulator returns -- would make cudaMemcpyAsync stage them synchronously through the
+// driver's bounce buffer on the calling thread (measured 10.8 GB/s); instead kStageThreads threads copy 16 MiB
+// pieces into a page-locked ring (two slots per thread) and issue the DMA of each piece themselves, so the host
+// memcpy of one piece overlaps the DMA of the others.
+static int stage_boxes_h2d(ps21_plan* p, float* d_dst, const float* const* h_ptrs, const float* h_boxes,
+                           long long first, long long batch_stride, long long nboxes, long long box_elems,
+                           cudaStream_t st) {
+    const long long box_bytes = box_elems * (long long)sizeof(float);
+    auto src_of = [&](long long i) { return h_ptrs ? h_ptrs[first + i] : h_boxes + (first + i) * batch_stride; };
+    bool pageable = false;
+    for (long long i = 0; i < nboxes && !pageable; ++i) {
+        cudaPointerAttributes at{};
+        if (cudaPointerGetAttributes(&at, src_of(i)) != cudaSuccess) {
+            cudaGetLastError();
+            pageable = true;
+        } else if (at.type == cudaMemoryTypeUnregistered) {
+            pageable = true;
+        }
+    }
+    if (!pageable || std::getenv("PS21_NO_STAGING_THREADS")) {
+        if (!h_ptrs && batch_stride == box_elems) {
+            PS21_CUDA(cudaMemcpyAsync(d_dst, h_boxes + first * batch_stride, (size_t)(nboxes * box_bytes),
+                                      cudaMemcpyHostToDevice, st));
+        } else {
+            for (long long i = 0; i < nboxes; ++i)
+                PS21_CUDA(cudaMemcpyAsync(d_dst + i * box_elems, src_of(i), (size_t)box_bytes, cudaMemcpyHostToDevice, st));
+        }
+        return PS21_OK;
+    }
+    constexpr int NT = ps21_plan::kStageThreads;
+    const long long SLOT = ps21_plan::kStageSlotBytes;
+    if (!p->h_ring) {
+        PS21_CUDA(cudaHostAlloc((void**)&p->h_ring, (size_t)(2 * NT * SLOT), cudaHostAllocPortable));
+        for (auto& e : p->ring_ev) {
+            cudaEvent_t ev;
+            PS21_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+            e = (void*)ev;
+        }
+    }
+    const long long per_box = (box_bytes + SLOT - 1) / SLOT, npieces = nboxes * per_box;
+    cudaError_t errs[NT];
+    std::thread th[NT];
+    for (int t = 0; t < NT; ++t) {
+        errs[t] = cudaSuccess;
+        th[t] = std::thread([&, t]() {
+            cudaError_t e = cudaSetDevice(p->device);
+            int turn = 0;
+            for (long long pc = t; pc < npieces && e == cudaSuccess; pc += NT, ++turn) {
+                const int slot = 2 * t + (turn & 1);
+                const long long i = pc / per_box, off = (pc % per_box) * SLOT;
+                const long long n = (box_bytes - off < SLOT) ? box_bytes - off : SLOT;
+                char* ring = p->h_ring + (long long)slot * SLOT;
+                cudaEvent_t ev = (cudaEvent_t)p->ring_ev[slot];
+                e = cudaEventSynchronize(ev);   // the DMA that last read this slot (this call or an earlier one) is done
+                if (e != cudaSuccess) break;
+                std::memcpy(ring, reinterpret_cast<const char*>(src_of(i)) + off, (size_t)n);
+                e = cudaMemcpyAsync(reinterpret_cast<char*>(d_dst + i * box_elems) + off, ring, (size_t)n,
+                                    cudaMemcpyHostToDevice, st);
+                if (e == cudaSuccess) e = cudaEventRecord(ev, st);
+            }
+            errs[t] = e;
+        });
+    }
+    for (int t = 0; t < NT; ++t) th[t].join();
+    for (int t = 0; t < NT; ++t)
+        if (errs[t] != cudaSuccess) return cuda_fail(errs[t], "host staging thread");
+    return PS21_OK;
+}
+#endif
+
 // Host-buffer variants: boxes are staged through two device buffers; the copy of slice i+1 overlaps the kernels
 // of slice i.  Box b is read from h_ptrs[b] when a pointer array is given (walker-owned buffers, no gather on the
 // host), else from h_boxes + b * batch_stride.  Staging buffers, result buffers, streams and events belong to
@@ -974,15 +1056,15 @@ static int run_host(ps21_plan* p, const float* const* h_ptrs, const float* h_box
         const long long n = (batch - done < per) ? (batch - done) : per;
         const int b = sl & 1;
         if (sl >= 2) cudaStreamWaitEvent(s_copy, ev_comp[b], 0);
-        if (!h_ptrs && batch_stride == box_elems) {
-            cudaMemcpyAsync(p->d_stage[b], h_boxes + done * batch_stride, sizeof(float) * n * box_elems,
-                            cudaMemcpyHostToDevice, s_copy);
-        } else {
-            for (long long i = 0; i < n; ++i)
-                cudaMemcpyAsync(p->d_stage[b] + i * box_elems,
-                                h_ptrs ? h_ptrs[done + i] : h_boxes + (done + i) * batch_stride,
-                                sizeof(float) * box_elems, cudaMemcpyHostToDevice, s_copy);
-        }
+#ifndef PS21_EMU
+        rc = stage_boxes_h2d(p, p->d_stage[b], h_ptrs, h_boxes, done, batch_stride, n, box_elems, s_copy);
+        if (rc) break;
+#else
+        for (long long i = 0; i < n; ++i)
+            cudaMemcpyAsync(p->d_stage[b] + i * box_elems,
+                            h_ptrs ? h_ptrs[done + i] : h_boxes + (done + i) * batch_stride,
+                            sizeof(float) * box_elems, cudaMemcpyHostToDevice, s_copy);
+#endif
         cudaEventRecord(ev_copy[b], s_copy);
         cudaStreamWaitEvent(s_comp, ev_copy[b], 0);
         rc = run_device(p, p->d_stage[b], n, box_elems, d_res_p + done * p->out_per_box,

@@ -551,3 +551,33 @@ def test_twopass_lightcone_with_unequal_chunks(mods):
     """A 64 x 64 x 500 lightcone in 3 chunks (167, 167, 166 slices): odd chunks (row pairs + chirp convolution, 167 is
     prime) and an even one (166 = 2 * 83, chirp convolution) inside one plan; lnL against the oracle."""
     PC.check_lightcone_likelihood(*mods, shape=(64, 64, 500), box_len=96.0, nchunks=3, nb=12, min_k=0.2, max_k=3.0)
+
+
+def test_pageable_host_boxes_go_through_the_staging_threads(mods, monkeypatch):
+    """Ordinary (pageable) NumPy lightcones -- what an unmodified simulator returns -- are copied through the
+    page-locked ring by the staging threads; the result is bitwise the one of page-locked and device inputs, for
+    boxes that are not a multiple of the 16 MiB ring slot and across several staging slices."""
+    import torch
+
+    from py21cmmc_b200.plan import PowerPlan, pinned_empty
+
+    shape = (128, 128, 300)                                  # 19.7 MB per box: one full ring slot + a ragged piece
+    plan = PowerPlan(shape, [(0, 150), (150, 300)], [(192.0, 192.0, 225.0)] * 2, 16, device=torch.cuda.current_device())
+    pageable = [synth_box(shape, s) for s in range(7)]
+    pinned = []
+    for b in pageable:
+        pb = pinned_empty(shape)
+        pb[...] = b
+        pinned.append(pb)
+    want = plan.power_device(torch.from_numpy(np.stack(pageable)).cuda()).cpu().numpy()
+    same = (lambda a, b: np.array_equal(a, b, equal_nan=True)) if plan.path != "general" else \
+        (lambda a, b: np.allclose(a, b, rtol=1e-12, atol=0, equal_nan=True))
+    assert same(plan.power_host(pinned), want)
+    assert same(plan.power_host(pageable), want)
+    assert same(plan.power_host(np.stack(pageable)), want)            # one contiguous pageable batch
+    monkeypatch.setenv("PS21_STAGE_BYTES", str(3 * 4 * int(np.prod(shape))))   # three boxes per slice -> three slices
+    assert same(plan.power_host(pageable), want)
+    assert same(plan.power_host(pageable[:1] + pinned[1:]), want)     # mixed: treated as pageable
+    monkeypatch.setenv("PS21_NO_STAGING_THREADS", "1")
+    assert same(plan.power_host(pageable), want)
+    plan.close()
