@@ -122,7 +122,7 @@ struct ps21_plan {
     void* stage_ev[4] = {nullptr, nullptr, nullptr, nullptr};   // copy done [2], compute done [2]
     double* d_res[3] = {nullptr, nullptr, nullptr};             // power, Delta^2, lnL of a *_host call
     // pageable host inputs: page-locked ring the staging threads copy through (2 slots per thread) + "slot free" events
-    static constexpr int kStageThreads = 6;
+    static constexpr int kStageThreads = 16;   // at most; PS21_STAGE_THREADS or half of the hardware threads are used
     static constexpr long long kStageSlotBytes = 16LL << 20;
     char* h_ring = nullptr;
     void* ring_ev[2 * kStageThreads] = {};
