@@ -217,18 +217,20 @@ __global__ void k_chi2_rows(const double* __restrict__ delta, long long n, long 
     lnl[r] = total;
 }
 
-// one thread per model: nk window-function rows of length nkwf (tens of values each)
+// one CTA per model, one thread per window-function row k (tens of rows of tens of values each); the per-row terms are
+// summed by a fixed-order tree, so lnL is bitwise reproducible
 // gauss = 0: one-sided erf likelihood of upper limits (likelihood.py:2324-2328);
 // gauss = 1: Gaussian -0.5 (after - value)^2 / err^2 of measured band powers (likelihood.py:569-583)
-__global__ void k_upper_limit(const double* __restrict__ model, long long nrec, int nk, int nkwf,
-                              const double* __restrict__ wf, const double* __restrict__ limit,
-                              const double* __restrict__ var, const double* __restrict__ model_err, double frac,
-                              int gauss, double* __restrict__ lnl) {
-    const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (r >= nrec) return;
+__global__ void __launch_bounds__(128)
+k_upper_limit(const double* __restrict__ model, long long nrec, int nk, int nkwf,
+              const double* __restrict__ wf, const double* __restrict__ limit,
+              const double* __restrict__ var, const double* __restrict__ model_err, double frac,
+              int gauss, double* __restrict__ lnl) {
+    __shared__ double red[128];
+    const long long r = blockIdx.x;
     const double* m = model + r * nkwf;
     double total = 0.0;
-    for (int k = 0; k < nk; ++k) {
+    for (int k = threadIdx.x; k < nk; k += blockDim.x) {
         double after = 0.0, up = 0.0, lo = 0.0;
         for (int j = 0; j < nkwf; ++j) {
             const double w = wf[(long long)k * nkwf + j];
@@ -253,7 +255,13 @@ __global__ void k_upper_limit(const double* __restrict__ model, long long nrec, 
         const double l = log(like);
         if (l == l) total += l;  // nansum
     }
-    lnl[r] += total;
+    red[threadIdx.x] = total;
+    __syncthreads();
+    for (int s = 64; s > 0; s >>= 1) {
+        if ((int)threadIdx.x < s) red[threadIdx.x] += red[threadIdx.x + s];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) lnl[r] += red[0];
 }
 
 static void free_dev(void* p) {
@@ -1183,31 +1191,58 @@ int ps21_chi2_host(int32_t device, int64_t nrec, int64_t n, const double* delta,
     return PS21_OK;
 }
 
+// Grow-only device scratch of the plan-free entry points (one per host thread): ps21_upper_limit_host is called once
+// per (band, field) block -- ten times per evaluation with the HERA file -- and used to pay six cudaMalloc / cudaFree
+// pairs and six copies each time.
+struct ScratchArena {
+    void* d = nullptr;
+    size_t cap = 0;
+    int device = -1;
+    std::vector<double> h;
+    int ensure(int dev, size_t bytes) {
+        if (dev == device && bytes <= cap) return PS21_OK;
+        if (d) {
+            cudaSetDevice(device);
+            cudaFree(d);
+            d = nullptr;
+            cap = 0;
+        }
+        PS21_CUDA(cudaSetDevice(dev));
+        const size_t want = bytes < (1u << 20) ? (1u << 20) : bytes * 2;
+        PS21_CUDA(cudaMalloc(&d, want));
+        cap = want;
+        device = dev;
+        return PS21_OK;
+    }
+};
+static thread_local ScratchArena g_arena;
+
 static int windowed_host(int32_t device, int64_t nrec, int64_t nk, int64_t nkwf, const double* model,
                          const double* wf, const double* limit, const double* var, const double* model_err,
                          double frac, int gauss, double* lnl) {
     if (!model || !wf || !limit || !var || !lnl || nrec < 0 || nk < 0 || nkwf < 0) return invalid("null argument");
     if (nrec == 0 || nk == 0) return PS21_OK;
     PS21_CUDA(cudaSetDevice(device));
-    double *dm = nullptr, *dw = nullptr, *dl = nullptr, *dv = nullptr, *de = nullptr, *dout = nullptr;
-    cudaError_t e = cudaSuccess;
-    auto up = [&](double** dst, const double* src, size_t n) {
-        if (e == cudaSuccess) e = cudaMalloc((void**)dst, sizeof(double) * (n ? n : 1));
-        if (e == cudaSuccess && n) e = cudaMemcpy(*dst, src, sizeof(double) * n, cudaMemcpyHostToDevice);
-    };
-    up(&dm, model, (size_t)(nrec * nkwf));
-    up(&dw, wf, (size_t)(nk * nkwf));
-    up(&dl, limit, (size_t)nk);
-    up(&dv, var, (size_t)nk);
-    if (model_err) up(&de, model_err, (size_t)nkwf);
-    up(&dout, lnl, (size_t)nrec);
-    if (e == cudaSuccess) {
-        PS21_LAUNCH(k_upper_limit, dim3((unsigned)((nrec + 63) / 64)), dim3(64), 0, (cudaStream_t)0, dm, (long long)nrec,
-                    (int)nk, (int)nkwf, dw, dl, dv, de, frac, gauss, dout);
-        e = cudaGetLastError();
-    }
-    if (e == cudaSuccess) e = cudaMemcpy(lnl, dout, sizeof(double) * nrec, cudaMemcpyDeviceToHost);
-    free_dev(dm); free_dev(dw); free_dev(dl); free_dev(dv); free_dev(de); free_dev(dout);
+    // one packed buffer: [model nrec*nkwf][wf nk*nkwf][limit nk][var nk][model_err nkwf | -][lnl nrec]
+    const size_t n_model = (size_t)(nrec * nkwf), n_wf = (size_t)(nk * nkwf), n_err = model_err ? (size_t)nkwf : 0;
+    const size_t o_wf = n_model, o_lim = o_wf + n_wf, o_var = o_lim + (size_t)nk, o_err = o_var + (size_t)nk,
+                 o_out = o_err + n_err, total = o_out + (size_t)nrec;
+    ScratchArena& A = g_arena;
+    int rc = A.ensure(device, total * sizeof(double));
+    if (rc) return rc;
+    A.h.resize(total);
+    std::memcpy(A.h.data(), model, n_model * sizeof(double));
+    std::memcpy(A.h.data() + o_wf, wf, n_wf * sizeof(double));
+    std::memcpy(A.h.data() + o_lim, limit, (size_t)nk * sizeof(double));
+    std::memcpy(A.h.data() + o_var, var, (size_t)nk * sizeof(double));
+    if (model_err) std::memcpy(A.h.data() + o_err, model_err, n_err * sizeof(double));
+    std::memcpy(A.h.data() + o_out, lnl, (size_t)nrec * sizeof(double));
+    double* d = static_cast<double*>(A.d);
+    PS21_CUDA(cudaMemcpy(d, A.h.data(), total * sizeof(double), cudaMemcpyHostToDevice));
+    PS21_LAUNCH(k_upper_limit, dim3((unsigned)nrec), dim3(128), 0, (cudaStream_t)0, d, (long long)nrec, (int)nk, (int)nkwf,
+                d + o_wf, d + o_lim, d + o_var, model_err ? d + o_err : nullptr, frac, gauss, d + o_out);
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaMemcpy(lnl, d + o_out, sizeof(double) * nrec, cudaMemcpyDeviceToHost);
     if (e != cudaSuccess) return cuda_fail(e, gauss ? "ps21_windowed_gauss_host" : "ps21_upper_limit_host");
     return PS21_OK;
 }
