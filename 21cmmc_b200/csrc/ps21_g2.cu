@@ -60,6 +60,7 @@ struct G2Dev {
     int nbuf;                   // pass 1: shared-memory row buffers (2: the next unit streams in during this one's FFTs)
     int slabs;                  // pass 1: consecutive x slabs per CTA
     int fuse_first, fuse_last;  // pass 1: untangle inside the first y stage / HBM store inside the last y stage
+    int dbg_skip;               // timing experiments only (PS21_G2_DBG_SKIP): bit 0 skip the z stages, bit 1 the y stages
     int bluestein, Lc;          // pass 1: z transform of length M as a chirp convolution of length Lc (M has a big prime)
     int zrows;                  // pass 1: rows per buffer = max(nh, Lc)
     IpFft fzb;                  // ... the convolution's transform of length Lc
@@ -453,7 +454,8 @@ k_g2_p1(const float* __restrict__ boxes, long long batch_stride, int n2_total, I
         for (int jp = tid; jp < R1; jp += nthr) twu[jp] = twy[yl * kya[jp]];   // yl ky_a < n1: no reduction needed
         // ---- z: complex FFT of length M over the row index, in place; the offset is subtracted as stage 0 reads
         const float2 mean2 = make_float2(mean, mean);
-        if (!g.bluestein) {
+        if (g.dbg_skip & 1) {   // timing experiment: rows in, tiles out (profiles/r02_g2_experiments.md)
+        } else if (!g.bluestein) {
             for (int s = 0; s < g.fz.nstages; ++s) {
                 ip_stage_any<false>(g.fz.st[s], M, g.zcols, g.div_zcols, az, twz, PreSub{s == 0 ? mean2 : make_float2(0.f, 0.f)});
                 __syncthreads();
@@ -477,7 +479,8 @@ k_g2_p1(const float* __restrict__ boxes, long long batch_stride, int n2_total, I
             }
         }
         // ---- untangle (pairs (p, M - p) -> A_p, A_{M-p}; p = 0 also yields the Nyquist row M) + first y stage
-        if (g.fuse_first) {
+        if (g.dbg_skip & 2) {
+        } else if (g.fuse_first) {
 #define PS21_G2_YFIRST(R)                                                        \
     do {                                                                         \
         if (g.bluestein) p1_y_first<R, true>(buf32, g, twz, twy, rowz, chirp);   \
@@ -998,6 +1001,7 @@ int g2_try_setup(ps21_plan* p, ShapePlan& sp) {
         if (g.Lc > 4096) return no("chunk too long for the chirp convolution");
     }
     g.zrows = std::max(g.pair ? g.M : g.nh, g.Lc);
+    if (const char* e = std::getenv("PS21_G2_DBG_SKIP")) g.dbg_skip = std::atoi(e);
     // y split n1 = R1 R2.  Pass 1 keeps nh x R1 coefficients per buffer; with two buffers the next unit streams in while
     // this one is transformed.  R2 = 4 gives 64-byte runs in the scratch, R2 = 8 halves the buffer (32-byte runs).
     int R2 = 0, nbuf = 0;
