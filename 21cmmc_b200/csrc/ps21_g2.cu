@@ -7,8 +7,8 @@
 //
 //   y = y_lo + R2 j,  k_y = ky_a + R1 ky_b   (n1 = R1 R2, R2 = 4 or 8, T = 32 / R2)
 //
-//   pass 1  k_g2_p1   CTA = one x slab, R2 units (y_lo) of R1 z-rows each.  Rows land in shared memory as packed
-//                     (even, odd) complex pairs [z/2][j]; z: complex FFT of length nz/2 over the rows + untangle
+//   pass 1  k_g2_p1   CTA = x slabs x R2 units (y_lo) of R1 z-rows each.  Rows land in shared memory as packed
+//                     (even, odd) complex pairs [j][z/2] (odd row stride); z: complex FFT of length nz/2 + untangle
 //                     (real-FFT post-processing); y: FFT of length R1 over j; times w_n1^(y_lo ky_a); stored to HBM in
 //                     tile order: tile = (ky_a position, T consecutive k_z rows), inner [x][y_lo][T] -> runs of T
 //                     coefficients (64 bytes for R2 = 4).
@@ -53,7 +53,7 @@ struct G2Dev {
     int pair, zcols;            // even nz: M = nz / 2 on (even, odd)-packed rows, zcols = R1 columns (pair = 0);
                                 // odd nz:  M = nz on row PAIRS (row j + i row j + R1/2), zcols = R1 / 2 columns (pair = 1)
     int R1, R2, T, lgT;         // n1 = R1 R2, T = 32 / R2 k_z rows per tile
-    int ld;                     // pass 1: complex slots per shared-memory row (odd -> conflict free both ways)
+    int ld;                     // pass 1: complex slots per shared-memory row [j][z slot] (odd -> conflict free both ways)
     int nzt, ntiles;            // z tiles per ky_a position, tiles per spectrum
     int slots;                  // pass-2 CTAs per spectrum
     int p2_threads;
@@ -195,16 +195,16 @@ __device__ __forceinline__ void ip_stage_any(const IpStage st, int n, int ncols,
 #undef PS21_IP_CASE
 }
 
-struct AddrStrided {   // pass 1, z transform: byte strides of the index (row) and of the column (j)
+struct AddrStrided {   // pass 1, z transform: byte strides of the index (z pair / k_z: 8) and of the column (j: one row)
     uint32_t base, si, sc;
     __device__ __forceinline__ uint32_t col(int c) const { return base + c * sc; }
     __device__ __forceinline__ uint32_t at(uint32_t cb, int i) const { return cb + i * si; }
 };
-struct AddrRows {      // pass 1, y transform: index = j (8 bytes apart), column = logical row -> physical row prow[c]
+struct AddrRows {      // pass 1, y transform: index = j (one buffer row each), column = logical k_z row -> slot prow[c]
     uint32_t base, ldb;
-    const uint16_t* prow;   // nullptr: rows are stored in logical order
-    __device__ __forceinline__ uint32_t col(int c) const { return base + (prow ? (uint32_t)prow[c] : (uint32_t)c) * ldb; }
-    __device__ __forceinline__ uint32_t at(uint32_t cb, int i) const { return cb + i * 8; }
+    const uint16_t* prow;   // nullptr: the k_z rows are stored in logical order
+    __device__ __forceinline__ uint32_t col(int c) const { return base + (prow ? (uint32_t)prow[c] : (uint32_t)c) * 8u; }
+    __device__ __forceinline__ uint32_t at(uint32_t cb, int i) const { return cb + i * ldb; }
 };
 struct AddrTile {      // pass 2: row x holds 32 columns (ky_b, t); the ky_b slot is XOR-ed with the low bits of x
     uint32_t base;     // 256-byte aligned
@@ -285,16 +285,16 @@ __device__ __forceinline__ void p1_y_first(uint32_t buf, const G2Dev& g, const f
     // the values as they are read: one pass over shared memory and one barrier instead of two
     const IpStage st = g.fy.st[0];
     const int q = st.q, M = g.M;
-    const uint32_t ldb = g.ld * 8, qb = q * 8;
+    const uint32_t ldb = g.ld * 8, qb = q * ldb;   // element (k_z slot r, row j) lives at buf + j ldb + 8 r
     const int ntasks = (M / 2 + 1) * q;
     for (int task = threadIdx.x; task < ntasks; task += blockDim.x) {
-        const int p = fast_div(task, st.div_q), o = task - p * q;   // o fastest: lanes along contiguous j
+        const int p = fast_div(task, st.div_q), o = task - p * q;   // o fastest: lanes along j (odd row stride)
         float2 a1[R], a2[R];
         uint32_t q1, q2;
         const bool self = (2 * p == M);
         if (p == 0) {
-            q1 = buf + o * 8;                 // frequency 0 stays in row 0
-            q2 = buf + M * ldb + o * 8;       // the Nyquist row is created here
+            q1 = buf + o * ldb;               // frequency 0 stays in slot 0
+            q2 = buf + o * ldb + M * 8;       // the Nyquist slot M is created here
 #pragma unroll
             for (int m = 0; m < R; ++m) {
                 const float2 c0 = zfix<BLU>(lds64(q1 + m * qb), chirp, 0);
@@ -302,7 +302,7 @@ __device__ __forceinline__ void p1_y_first(uint32_t buf, const G2Dev& g, const f
                 a2[m] = make_float2(c0.x - c0.y, 0.f);
             }
         } else if (self) {
-            q1 = q2 = buf + rowz[p] * ldb + o * 8;
+            q1 = q2 = buf + o * ldb + rowz[p] * 8;
 #pragma unroll
             for (int m = 0; m < R; ++m) {
                 const float2 c0 = zfix<BLU>(lds64(q1 + m * qb), chirp, p);
@@ -310,8 +310,8 @@ __device__ __forceinline__ void p1_y_first(uint32_t buf, const G2Dev& g, const f
                 a2[m] = a1[m];
             }
         } else {
-            q1 = buf + rowz[p] * ldb + o * 8;
-            q2 = buf + rowz[M - p] * ldb + o * 8;
+            q1 = buf + o * ldb + rowz[p] * 8;
+            q2 = buf + o * ldb + rowz[M - p] * 8;
             const float2 w = twz[p];   // w_nz^p; times -i/2 -> (wy/2, -wx/2)
             const float4 wu = make_float4(0.5f * w.y, -0.5f * w.x, 0.5f * w.x, 0.5f * w.y);
 #pragma unroll
@@ -341,28 +341,53 @@ __device__ __forceinline__ void p1_y_first(uint32_t buf, const G2Dev& g, const f
     }
 }
 
-// last y stage (radix R over contiguous j) of every row, results times w_n1^(yl ky_a) straight to HBM in tile order
-template <int R>
+// last y stage (radix R over R consecutive buffer rows) for every k_z slot, results times w_n1^(yl ky_a) straight to
+// HBM in tile order.  Tasks run sub-block by sub-block; the warp that completes a sub-block (shared-memory counter, no
+// CTA barrier) calls `reload(b)`: the R buffer rows of that sub-block are dead, so the rows of the NEXT unit stream
+// into them while the remaining sub-blocks are still being stored -- the load of unit u+1 overlaps the store of unit u.
+template <int R, class Reload>
 __device__ __forceinline__ void p1_y_last_store(uint32_t buf, float2* __restrict__ dst,
                                                 const G2Dev& g, const float2* __restrict__ twu,
-                                                const uint16_t* __restrict__ prow, int yl, long long inner) {
-    const int nh = g.nh, nsub = g.R1 / R;
+                                                const uint16_t* __restrict__ prow, int yl, long long inner,
+                                                int* __restrict__ done, bool have_next, Reload reload) {
+    const int nh = g.nh, nsub = g.R1 / R, ntasks = nsub * nh;
     const uint32_t ldb = g.ld * 8;
     const long long tile_elems = (long long)g.n0 * 32;
-    for (int task = threadIdx.x; task < nsub * nh; task += blockDim.x) {
-        const int b = fast_div(task, g.div_nh), r = task - b * nh;   // r fastest: lanes along rows
-        float2 v[R];
-        const uint32_t src = buf + (prow ? (uint32_t)prow[r] : (uint32_t)r) * ldb + b * (R * 8);
+    const int lane = threadIdx.x & 31;
+    for (int task0 = threadIdx.x - lane; task0 < ntasks; task0 += blockDim.x) {   // whole warps: the tail votes too
+        const int task = task0 + lane;
+        const bool live = task < ntasks;
+        const int b = live ? fast_div(task, g.div_nh) : 0, r = task - b * nh;   // r fastest: lanes along k_z slots
+        if (live) {
+            float2 v[R];
+            const uint32_t src = buf + (prow ? (uint32_t)prow[r] : (uint32_t)r) * 8u + (uint32_t)(b * R) * ldb;
 #pragma unroll
-        for (int m = 0; m < R; ++m) v[m] = lds64(src + m * 8);
-        small_dft<R>(v);
-        const long long jstride = (long long)g.nzt * tile_elems;
-        float2* out = dst + (long long)(r >> g.lgT) * tile_elems + inner + (r & (g.T - 1)) + (long long)(b * R) * jstride;
+            for (int m = 0; m < R; ++m) v[m] = lds64(src + m * ldb);
+            small_dft<R>(v);
+            const long long jstride = (long long)g.nzt * tile_elems;
+            float2* out = dst + (long long)(r >> g.lgT) * tile_elems + inner + (r & (g.T - 1)) + (long long)(b * R) * jstride;
 #pragma unroll
-        for (int m = 0; m < R; ++m) {
-            const float2 o = yl ? cmul_w2(v[m], twu[b * R + m]) : v[m];
-            *out = o;
-            out += jstride;
+            for (int m = 0; m < R; ++m) {
+                const float2 o = yl ? cmul_w2(v[m], twu[b * R + m]) : v[m];
+                *out = o;
+                out += jstride;
+            }
+        }
+        if (have_next) {
+            // count the finished butterflies of every sub-block this warp touched (at most two: nh >= 32 or not, the
+            // loop below takes whatever the ballot says)
+            bool last = false;
+            if (live) {
+                __threadfence_block();
+                last = atomicAdd(&done[b], 1) == nh - 1;
+            }
+            unsigned fin = __ballot_sync(0xffffffffu, last);
+            if (fin) __threadfence_block();   // the other warps' reads of that sub-block are ordered before our copies
+            while (fin) {
+                const int src_lane = __ffs(fin) - 1;
+                fin &= fin - 1;
+                reload(__shfl_sync(0xffffffffu, b, src_lane));
+            }
         }
     }
 }
@@ -375,7 +400,7 @@ k_g2_p1(const float* __restrict__ boxes, long long batch_stride, int n2_total, I
     PS21_DYN_SMEM(float2, smem);
     const int tid = threadIdx.x, nthr = blockDim.x;
     const int M = g.M, R1 = g.R1, ld = g.ld, nh = g.nh;
-    const int bufstride = g.zrows * ld;
+    const int bufstride = R1 * ld;
     const uint32_t smem32 = smem_u32(smem), ldb = (uint32_t)ld * 8u;
     float2* const twz = smem + g.nbuf * bufstride;                       // [nz]  w_nz^q
     float2* const twy = twz + g.nz;                                      // [n1]  w_n1^q
@@ -386,6 +411,7 @@ k_g2_p1(const float* __restrict__ boxes, long long batch_stride, int n2_total, I
     uint16_t* const rowz = reinterpret_cast<uint16_t*>(twu + R1);        // [M]   copy of G2Dev::rowz_of_k
     uint16_t* const kya = rowz + M;                                      // [R1]  copy of G2Dev::kya_of_jp
     uint16_t* const prow = kya + R1;                                     // [nh]  copy of G2Dev::prow_of_row (pair mode)
+    int* const done = reinterpret_cast<int*>((reinterpret_cast<uintptr_t>(prow + nh) + 3) & ~(uintptr_t)3);   // [R1] butterflies done per sub-block
     long long box;
     int cid;
     item_to_box_chunk(im, blockIdx.y, box, cid);
@@ -408,48 +434,50 @@ k_g2_p1(const float* __restrict__ boxes, long long batch_stride, int n2_total, I
         }
         for (int i = tid; i < M; i += nthr) chirp[i] = g.chirp[i];
     }
-    // rows y = yl + R2 j of slab x as packed (even, odd) pairs: buf[zc][j]; asynchronous copies (LDGSTS), lanes along z
-    // -> coalesced reads, conflict-free writes (ld is odd)
-    auto issue_unit = [&](int u, uint32_t buf32) {
+    // rows y = yl + R2 j of slab x as packed (even, odd) pairs: buf[j][zc]; asynchronous copies (LDGSTS), lanes along z:
+    // coalesced reads, contiguous writes.  `load_rows` is called by whole warps: rows j0 .. j1-1 of unit u, one row
+    // per warp turn starting at `w0` of `nw` warps.
+    auto load_rows = [&](int u, uint32_t buf32, int j0, int j1, int w0, int nw) {
         const int x = x0 + u / g.R2, yl = u - (u / g.R2) * g.R2;
         const float* slab = spec + (long long)x * g.n1 * n2_total + (long long)yl * n2_total;
-        // one row per warp turn, lanes along z: row pointer and shared address are formed once per row and stepped
-        const int warp = tid >> 5, lane = tid & 31, nwarps = nthr >> 5;
+        const int lane = tid & 31;
         const long long rstride = (long long)g.R2 * n2_total;
-        const uint32_t dstep = 32u * ldb;
         if (!g.pair) {
-            for (int j = warp; j < R1; j += nwarps) {
+            for (int j = j0 + w0; j < j1; j += nw) {
                 const float* src = slab + j * rstride + 2 * lane;
-                uint32_t d = buf32 + (uint32_t)j * 8u + (uint32_t)lane * ldb;
+                uint32_t d = buf32 + (uint32_t)j * ldb + (uint32_t)lane * 8u;
                 if (aligned8) {
-                    for (int zc = lane; zc < M; zc += 32, d += dstep, src += 64) cp_async8_s32(d, src);
+                    for (int zc = lane; zc < M; zc += 32, d += 256u, src += 64) cp_async8_s32(d, src);
                 } else {
-                    for (int zc = lane; zc < M; zc += 32, d += dstep, src += 64) {
+                    for (int zc = lane; zc < M; zc += 32, d += 256u, src += 64) {
                         cp_async4_s32(d, src);
                         cp_async4_s32(d + 4, src + 1);
                     }
                 }
             }
         } else {   // odd nz: column c = row j (real part) + i row j + R1/2 (imaginary part), one complex value per slice
-            for (int j = warp; j < R1; j += nwarps) {
+            for (int j = j0 + w0; j < j1; j += nw) {
                 const int c = j < g.zcols ? j : j - g.zcols;
                 const float* src = slab + j * rstride + lane;
-                uint32_t d = buf32 + (uint32_t)c * 8u + (j < g.zcols ? 0u : 4u) + (uint32_t)lane * ldb;
-                for (int z = lane; z < M; z += 32, d += dstep, src += 32) cp_async4_s32(d, src);
+                uint32_t d = buf32 + (uint32_t)c * ldb + (j < g.zcols ? 0u : 4u) + (uint32_t)lane * 8u;
+                for (int z = lane; z < M; z += 32, d += 256u, src += 32) cp_async4_s32(d, src);
             }
         }
         cp_async_commit();
     };
+    auto issue_unit = [&](int u, uint32_t buf32) { load_rows(u, buf32, 0, R1, tid >> 5, nthr >> 5); };
     const int nunits = g.slabs * g.R2;
     issue_unit(0, smem32);
     for (int u = 0; u < nunits; ++u) {
         float2* buf = smem + (u % g.nbuf) * bufstride;
         const uint32_t buf32 = smem32 + (uint32_t)(u % g.nbuf) * (uint32_t)bufstride * 8u;
-        const AddrStrided az{buf32, ldb, 8u};    // z transform: index = row (z pair / k_z), column = j
+        const AddrStrided az{buf32, 8u, ldb};    // z transform: index = z pair / k_z slot, column = j
         const AddrRows ay{buf32, ldb, g.pair ? prow : nullptr};   // y transform: index = j, column = row
         const int x = x0 + u / g.R2, yl = u - (u / g.R2) * g.R2;
         cp_async_wait<0>();
         __syncthreads();   // unit u has landed; everybody is done with unit u - 1 (tables ready on the first turn)
+        if (tid < R1) done[tid] = 0;   // (after the barrier: slower warps were still counting unit u - 1; the stage
+                                       //  barriers below order the reset before this unit's last y stage)
         if (g.nbuf == 2 && u + 1 < nunits) issue_unit(u + 1, smem32 + (uint32_t)((u + 1) % 2) * (uint32_t)bufstride * 8u);
         for (int jp = tid; jp < R1; jp += nthr) twu[jp] = twy[yl * kya[jp]];   // yl ky_a < n1: no reduction needed
         // ---- z: complex FFT of length M over the row index, in place; the offset is subtracted as stage 0 reads
@@ -499,17 +527,17 @@ k_g2_p1(const float* __restrict__ boxes, long long batch_stride, int n2_total, I
             __syncthreads();
         } else if (g.pair) {
             // odd nz: Z = FFT(row_a + i row_b);  A_a(k) = (Z_k + conj Z_{nz-k}) / 2,  A_b(k) = (Z_k - conj Z_{nz-k}) / 2i.
-            // A_a replaces Z_k, A_b goes to the (unused) right half of the same row; the rows of Z_{nz-k} are dead after.
+            // A_a replaces Z_k, A_b goes to the same slot of buffer row c + R1/2 (unused so far); the slots of Z_{nz-k} are dead after.
             for (int e = tid; e < nh * g.zcols; e += nthr) {
                 const int k = fast_div(e, g.div_zcols), c = e - k * g.zcols;
                 auto fix = [&](float2 v, int row) {   // Bluestein: Z_k = chirp[k] conj(row k)
                     return g.bluestein ? cmul_w2(make_float2(v.x, -v.y), chirp[row]) : v;
                 };
-                float2* qk = buf + rowz[k] * ld + c;
+                float2* qk = buf + c * ld + rowz[k];
                 const float2 zk = fix(*qk, k);
-                const float2 zn = (k == 0) ? zk : fix(buf[rowz[M - k] * ld + c], M - k);
+                const float2 zn = (k == 0) ? zk : fix(buf[c * ld + rowz[M - k]], M - k);
                 qk[0] = make_float2(0.5f * (zk.x + zn.x), 0.5f * (zk.y - zn.y));
-                qk[g.zcols] = make_float2(0.5f * (zk.y + zn.y), -0.5f * (zk.x - zn.x));
+                qk[g.zcols * ld] = make_float2(0.5f * (zk.y + zn.y), -0.5f * (zk.x - zn.x));
             }
             __syncthreads();
             ip_stage_any<false>(g.fy.st[0], R1, nh, g.div_nh, ay, twy, PreSub{make_float2(0.f, 0.f)});
@@ -522,16 +550,16 @@ k_g2_p1(const float* __restrict__ boxes, long long batch_stride, int n2_total, I
                     return g.bluestein ? cmul_w2(make_float2(v.x, -v.y), chirp[row]) : v;
                 };
                 if (p == 0) {
-                    const float2 c0 = fix(buf[j], 0);
-                    buf[j] = make_float2(c0.x + c0.y, 0.f);
-                    buf[M * ld + j] = make_float2(c0.x - c0.y, 0.f);
+                    const float2 c0 = fix(buf[j * ld], 0);
+                    buf[j * ld] = make_float2(c0.x + c0.y, 0.f);
+                    buf[j * ld + M] = make_float2(c0.x - c0.y, 0.f);
                 } else if (2 * p == M) {
-                    float2* q = buf + rowz[p] * ld + j;
+                    float2* q = buf + j * ld + rowz[p];
                     const float2 c0 = fix(*q, p);
                     *q = make_float2(c0.x, -c0.y);
                 } else {
-                    float2* q1 = buf + rowz[p] * ld + j;
-                    float2* q2 = buf + rowz[M - p] * ld + j;
+                    float2* q1 = buf + j * ld + rowz[p];
+                    float2* q2 = buf + j * ld + rowz[M - p];
                     const float2 w = twz[p];
                     float2 a1, a2;
                     untangle(fix(*q1, p), fix(*q2, M - p), make_float4(0.5f * w.y, -0.5f * w.x, 0.5f * w.x, 0.5f * w.y), a1, a2);
@@ -552,26 +580,31 @@ k_g2_p1(const float* __restrict__ boxes, long long batch_stride, int n2_total, I
         // ---- last y stage, times w_n1^(yl ky_a), to HBM in tile order: runs of T consecutive rows
         const int slot = (yl ^ (x & (g.R2 - 1)));
         const long long inner = ((long long)x * g.R2 + slot) << g.lgT;
+        // progressive reload (one buffer, packed rows): as a sub-block of buffer rows has been stored, the warp that
+        // finished it streams the same rows of the next unit in
+        const bool progressive = g.fuse_last && g.nbuf == 1 && !g.pair;
+        const int RL = g.fy.st[ylast].radix;
+        auto reload = [&](int b) { load_rows(u + 1, smem32, b * RL, b * RL + RL, 0, 1); };
         if (g.fuse_last) {
-            switch (g.fy.st[ylast].radix) {
-                case 2: p1_y_last_store<2>(buf32, dst, g, twu, g.pair ? prow : nullptr, yl, inner); break;
-                case 3: p1_y_last_store<3>(buf32, dst, g, twu, g.pair ? prow : nullptr, yl, inner); break;
-                case 4: p1_y_last_store<4>(buf32, dst, g, twu, g.pair ? prow : nullptr, yl, inner); break;
-                case 5: p1_y_last_store<5>(buf32, dst, g, twu, g.pair ? prow : nullptr, yl, inner); break;
-                case 6: p1_y_last_store<6>(buf32, dst, g, twu, g.pair ? prow : nullptr, yl, inner); break;
-                case 8: p1_y_last_store<8>(buf32, dst, g, twu, g.pair ? prow : nullptr, yl, inner); break;
-                default: p1_y_last_store<10>(buf32, dst, g, twu, g.pair ? prow : nullptr, yl, inner); break;
+            switch (RL) {
+                case 2: p1_y_last_store<2>(buf32, dst, g, twu, g.pair ? prow : nullptr, yl, inner, done, progressive && u + 1 < nunits, reload); break;
+                case 3: p1_y_last_store<3>(buf32, dst, g, twu, g.pair ? prow : nullptr, yl, inner, done, progressive && u + 1 < nunits, reload); break;
+                case 4: p1_y_last_store<4>(buf32, dst, g, twu, g.pair ? prow : nullptr, yl, inner, done, progressive && u + 1 < nunits, reload); break;
+                case 5: p1_y_last_store<5>(buf32, dst, g, twu, g.pair ? prow : nullptr, yl, inner, done, progressive && u + 1 < nunits, reload); break;
+                case 6: p1_y_last_store<6>(buf32, dst, g, twu, g.pair ? prow : nullptr, yl, inner, done, progressive && u + 1 < nunits, reload); break;
+                case 8: p1_y_last_store<8>(buf32, dst, g, twu, g.pair ? prow : nullptr, yl, inner, done, progressive && u + 1 < nunits, reload); break;
+                default: p1_y_last_store<10>(buf32, dst, g, twu, g.pair ? prow : nullptr, yl, inner, done, progressive && u + 1 < nunits, reload); break;
             }
         } else {
             const long long tile_elems = (long long)g.n0 * 32;
             for (int e = tid; e < R1 * nh; e += nthr) {
                 const int jp = fast_div(e, g.div_nh), r = e - jp * nh;
-                float2 v = buf[(g.pair ? (int)prow[r] : r) * ld + jp];
+                float2 v = buf[jp * ld + (g.pair ? (int)prow[r] : r)];
                 if (yl) v = cmul_w2(v, twu[jp]);
                 dst[((long long)jp * g.nzt + (r >> g.lgT)) * tile_elems + inner + (r & (g.T - 1))] = v;
             }
         }
-        if (g.nbuf == 1 && u + 1 < nunits) {
+        if (g.nbuf == 1 && !progressive && u + 1 < nunits) {
             __syncthreads();
             issue_unit(u + 1, smem32);
         }
@@ -938,9 +971,9 @@ static int upload(const std::vector<T>& v, T** d) {
 }
 
 static size_t p1_smem(const G2Dev& g) {
-    return (size_t)g.nbuf * g.zrows * g.ld * sizeof(float2) +
+    return (size_t)g.nbuf * g.R1 * g.ld * sizeof(float2) +
            (size_t)(g.nz + g.n1 + g.R1 + 2 * g.Lc + (g.bluestein ? g.M : 0)) * sizeof(float2) +
-           (size_t)(g.M + g.R1 + g.nh) * 2 + 64;
+           (size_t)(g.M + g.R1 + g.nh + 2) * 2 + (size_t)g.R1 * 4 + 64;
 }
 static size_t p2_smem(const G2Dev& g, int nbins, int nshare) {
     const int RL = g.fx.st[g.fx.nstages - 1].radix;
@@ -1010,9 +1043,9 @@ int g2_try_setup(ps21_plan* p, ShapePlan& sp) {
     if (const char* e = std::getenv("PS21_G2_NBUF")) force_nbuf = std::atoi(e);
     auto extra1 = [&](int R1) {
         return (size_t)(nz + n1 + R1 + 2 * g.Lc + (g.bluestein ? g.M : 0)) * sizeof(float2) +
-               (size_t)(g.M + R1 + g.nh) * 2 + 64;
+               (size_t)(g.M + R1 + g.nh + 2) * 2 + (size_t)R1 * 4 + 64;
     };
-    auto buf1 = [&](int R1) { return (size_t)g.zrows * (R1 | 1) * sizeof(float2); };
+    auto buf1 = [&](int R1) { return (size_t)R1 * (g.zrows | 1) * sizeof(float2); };
     // measured on 200^3 (B200): one buffer with three CTAs per SM 4.83 ms, two buffers with two CTAs 5.24 ms -- occupancy
     // beats overlap inside a CTA, so: three resident CTAs first, then two with the prefetch buffer, then whatever fits
     struct Try { int r2, nb; size_t budget; };
@@ -1034,7 +1067,7 @@ int g2_try_setup(ps21_plan* p, ShapePlan& sp) {
     }
     if (!R2) return no("no y split fits the shared memory");
     g.R2 = R2; g.R1 = n1 / R2; g.T = 32 / R2; g.lgT = (g.T == 8) ? 3 : (g.T == 4) ? 2 : 1;
-    g.ld = g.R1 | 1;
+    g.ld = g.zrows | 1;   // complex slots per buffer row (odd: lanes along j and lanes along k_z are both conflict free)
     g.nbuf = nbuf;
     split_radices(g.R1, kRadY, ry);
     // A unit that has the SM to itself (512^3: 134 KB) hides its latencies with threads instead of CTAs: 1024 threads at
