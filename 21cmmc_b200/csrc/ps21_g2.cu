@@ -60,7 +60,8 @@ struct G2Dev {
     int nbuf;                   // pass 1: shared-memory row buffers (2: the next unit streams in during this one's FFTs)
     int slabs;                  // pass 1: consecutive x slabs per CTA
     int fuse_first, fuse_last;  // pass 1: untangle inside the first y stage / HBM store inside the last y stage
-    int dbg_skip;               // timing experiments only (PS21_G2_DBG_SKIP): bit 0 skip the z stages, bit 1 the y stages
+    int dbg_skip;               // experiments only (PS21_G2_DBG_SKIP): bit 0 skip the z stages, bit 1 the first y stage
+                                // (timing, results are garbage); bit 4: progressive reload of the row buffer (correct)
     int bluestein, Lc;          // pass 1: z transform of length M as a chirp convolution of length Lc (M has a big prime)
     int zrows;                  // pass 1: rows per buffer = max(nh, Lc)
     IpFft fzb;                  // ... the convolution's transform of length Lc
@@ -581,8 +582,10 @@ k_g2_p1(const float* __restrict__ boxes, long long batch_stride, int n2_total, I
         const int slot = (yl ^ (x & (g.R2 - 1)));
         const long long inner = ((long long)x * g.R2 + slot) << g.lgT;
         // progressive reload (one buffer, packed rows): as a sub-block of buffer rows has been stored, the warp that
-        // finished it streams the same rows of the next unit in
-        const bool progressive = g.fuse_last && g.nbuf == 1 && !g.pair;
+        // finished it streams the same rows of the next unit in.  Measured SLOWER than loading after the store phase
+        // (200^3 pass 1: 5.34 vs 4.38 ms; 512^3: 20.8 vs 19.4 ms -- one warp issues a whole sub-block's copies while
+        // the others wait at the next barrier), so it is an experiment switch only (PS21_G2_DBG_SKIP bit 4).
+        const bool progressive = g.fuse_last && g.nbuf == 1 && !g.pair && (g.dbg_skip & 16);
         const int RL = g.fy.st[ylast].radix;
         auto reload = [&](int b) { load_rows(u + 1, smem32, b * RL, b * RL + RL, 0, 1); };
         if (g.fuse_last) {
