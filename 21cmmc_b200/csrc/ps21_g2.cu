@@ -61,7 +61,7 @@ struct G2Dev {
     int slabs;                  // pass 1: consecutive x slabs per CTA
     int fuse_first, fuse_last;  // pass 1: untangle inside the first y stage / HBM store inside the last y stage
     int dbg_skip;               // experiments only (PS21_G2_DBG_SKIP): bit 0 skip the z stages, bit 1 the first y stage
-                                // (timing, results are garbage); bit 4: progressive reload of the row buffer (correct)
+                                // (timing, results are garbage); bit 4: no two-half reload of the row buffer (correct)
     int bluestein, Lc;          // pass 1: z transform of length M as a chirp convolution of length Lc (M has a big prime)
     int zrows;                  // pass 1: rows per buffer = max(nh, Lc)
     IpFft fzb;                  // ... the convolution's transform of length Lc
@@ -343,52 +343,30 @@ __device__ __forceinline__ void p1_y_first(uint32_t buf, const G2Dev& g, const f
 }
 
 // last y stage (radix R over R consecutive buffer rows) for every k_z slot, results times w_n1^(yl ky_a) straight to
-// HBM in tile order.  Tasks run sub-block by sub-block; the warp that completes a sub-block (shared-memory counter, no
-// CTA barrier) calls `reload(b)`: the R buffer rows of that sub-block are dead, so the rows of the NEXT unit stream
-// into them while the remaining sub-blocks are still being stored -- the load of unit u+1 overlaps the store of unit u.
-template <int R, class Reload>
+// HBM in tile order; sub-blocks b0 .. b1-1 (the caller runs the stage in two halves and reloads the buffer rows of the
+// first half while the second is being stored)
+template <int R>
 __device__ __forceinline__ void p1_y_last_store(uint32_t buf, float2* __restrict__ dst,
                                                 const G2Dev& g, const float2* __restrict__ twu,
                                                 const uint16_t* __restrict__ prow, int yl, long long inner,
-                                                int* __restrict__ done, bool have_next, Reload reload) {
-    const int nh = g.nh, nsub = g.R1 / R, ntasks = nsub * nh;
+                                                int b0, int b1) {
+    const int nh = g.nh;
     const uint32_t ldb = g.ld * 8;
     const long long tile_elems = (long long)g.n0 * 32;
-    const int lane = threadIdx.x & 31;
-    for (int task0 = threadIdx.x - lane; task0 < ntasks; task0 += blockDim.x) {   // whole warps: the tail votes too
-        const int task = task0 + lane;
-        const bool live = task < ntasks;
-        const int b = live ? fast_div(task, g.div_nh) : 0, r = task - b * nh;   // r fastest: lanes along k_z slots
-        if (live) {
-            float2 v[R];
-            const uint32_t src = buf + (prow ? (uint32_t)prow[r] : (uint32_t)r) * 8u + (uint32_t)(b * R) * ldb;
+    for (int task = b0 * nh + threadIdx.x; task < b1 * nh; task += blockDim.x) {
+        const int b = fast_div(task, g.div_nh), r = task - b * nh;   // r fastest: lanes along k_z slots
+        float2 v[R];
+        const uint32_t src = buf + (prow ? (uint32_t)prow[r] : (uint32_t)r) * 8u + (uint32_t)(b * R) * ldb;
 #pragma unroll
-            for (int m = 0; m < R; ++m) v[m] = lds64(src + m * ldb);
-            small_dft<R>(v);
-            const long long jstride = (long long)g.nzt * tile_elems;
-            float2* out = dst + (long long)(r >> g.lgT) * tile_elems + inner + (r & (g.T - 1)) + (long long)(b * R) * jstride;
+        for (int m = 0; m < R; ++m) v[m] = lds64(src + m * ldb);
+        small_dft<R>(v);
+        const long long jstride = (long long)g.nzt * tile_elems;
+        float2* out = dst + (long long)(r >> g.lgT) * tile_elems + inner + (r & (g.T - 1)) + (long long)(b * R) * jstride;
 #pragma unroll
-            for (int m = 0; m < R; ++m) {
-                const float2 o = yl ? cmul_w2(v[m], twu[b * R + m]) : v[m];
-                *out = o;
-                out += jstride;
-            }
-        }
-        if (have_next) {
-            // count the finished butterflies of every sub-block this warp touched (at most two: nh >= 32 or not, the
-            // loop below takes whatever the ballot says)
-            bool last = false;
-            if (live) {
-                __threadfence_block();
-                last = atomicAdd(&done[b], 1) == nh - 1;
-            }
-            unsigned fin = __ballot_sync(0xffffffffu, last);
-            if (fin) __threadfence_block();   // the other warps' reads of that sub-block are ordered before our copies
-            while (fin) {
-                const int src_lane = __ffs(fin) - 1;
-                fin &= fin - 1;
-                reload(__shfl_sync(0xffffffffu, b, src_lane));
-            }
+        for (int m = 0; m < R; ++m) {
+            const float2 o = yl ? cmul_w2(v[m], twu[b * R + m]) : v[m];
+            *out = o;
+            out += jstride;
         }
     }
 }
@@ -412,7 +390,6 @@ k_g2_p1(const float* __restrict__ boxes, long long batch_stride, int n2_total, I
     uint16_t* const rowz = reinterpret_cast<uint16_t*>(twu + R1);        // [M]   copy of G2Dev::rowz_of_k
     uint16_t* const kya = rowz + M;                                      // [R1]  copy of G2Dev::kya_of_jp
     uint16_t* const prow = kya + R1;                                     // [nh]  copy of G2Dev::prow_of_row (pair mode)
-    int* const done = reinterpret_cast<int*>((reinterpret_cast<uintptr_t>(prow + nh) + 3) & ~(uintptr_t)3);   // [R1] butterflies done per sub-block
     long long box;
     int cid;
     item_to_box_chunk(im, blockIdx.y, box, cid);
@@ -477,8 +454,6 @@ k_g2_p1(const float* __restrict__ boxes, long long batch_stride, int n2_total, I
         const int x = x0 + u / g.R2, yl = u - (u / g.R2) * g.R2;
         cp_async_wait<0>();
         __syncthreads();   // unit u has landed; everybody is done with unit u - 1 (tables ready on the first turn)
-        if (tid < R1) done[tid] = 0;   // (after the barrier: slower warps were still counting unit u - 1; the stage
-                                       //  barriers below order the reset before this unit's last y stage)
         if (g.nbuf == 2 && u + 1 < nunits) issue_unit(u + 1, smem32 + (uint32_t)((u + 1) % 2) * (uint32_t)bufstride * 8u);
         for (int jp = tid; jp < R1; jp += nthr) twu[jp] = twy[yl * kya[jp]];   // yl ky_a < n1: no reduction needed
         // ---- z: complex FFT of length M over the row index, in place; the offset is subtracted as stage 0 reads
@@ -581,23 +556,40 @@ k_g2_p1(const float* __restrict__ boxes, long long batch_stride, int n2_total, I
         // ---- last y stage, times w_n1^(yl ky_a), to HBM in tile order: runs of T consecutive rows
         const int slot = (yl ^ (x & (g.R2 - 1)));
         const long long inner = ((long long)x * g.R2 + slot) << g.lgT;
-        // progressive reload (one buffer, packed rows): as a sub-block of buffer rows has been stored, the warp that
-        // finished it streams the same rows of the next unit in.  Measured SLOWER than loading after the store phase
-        // (200^3 pass 1: 5.34 vs 4.38 ms; 512^3: 20.8 vs 19.4 ms -- one warp issues a whole sub-block's copies while
-        // the others wait at the next barrier), so it is an experiment switch only (PS21_G2_DBG_SKIP bit 4).
-        const bool progressive = g.fuse_last && g.nbuf == 1 && !g.pair && (g.dbg_skip & 16);
+        // A CTA that has the SM to itself (512^3 units) runs the last y stage in two halves of sub-blocks: after the
+        // first half (one more barrier) its buffer rows are dead and ALL warps issue the copies of those rows of the
+        // next unit, which then overlap the stores of the second half; the remaining rows follow after the stage.
+        // Measured: 512^3 pass 1 19.6 -> 18.2 ms; with several resident CTAs the other CTAs already hide the loads and
+        // the extra barrier costs (200^3: 4.36 -> 4.69 ms), so small units load after the stage.  (A finer scheme -- a
+        // counter per sub-block, the warp that completes it issues the copies -- measured slower still:
+        // profiles/r02_g2_experiments.md.)
         const int RL = g.fy.st[ylast].radix;
-        auto reload = [&](int b) { load_rows(u + 1, smem32, b * RL, b * RL + RL, 0, 1); };
+        const int nsub = R1 / RL;
+        const bool halves = MINB == 1 && g.fuse_last && g.nbuf == 1 && !g.pair && nsub >= 2 && u + 1 < nunits &&
+                            !(g.dbg_skip & 16);
+        const int bh = halves ? nsub / 2 : nsub;
         if (g.fuse_last) {
-            switch (RL) {
-                case 2: p1_y_last_store<2>(buf32, dst, g, twu, g.pair ? prow : nullptr, yl, inner, done, progressive && u + 1 < nunits, reload); break;
-                case 3: p1_y_last_store<3>(buf32, dst, g, twu, g.pair ? prow : nullptr, yl, inner, done, progressive && u + 1 < nunits, reload); break;
-                case 4: p1_y_last_store<4>(buf32, dst, g, twu, g.pair ? prow : nullptr, yl, inner, done, progressive && u + 1 < nunits, reload); break;
-                case 5: p1_y_last_store<5>(buf32, dst, g, twu, g.pair ? prow : nullptr, yl, inner, done, progressive && u + 1 < nunits, reload); break;
-                case 6: p1_y_last_store<6>(buf32, dst, g, twu, g.pair ? prow : nullptr, yl, inner, done, progressive && u + 1 < nunits, reload); break;
-                case 8: p1_y_last_store<8>(buf32, dst, g, twu, g.pair ? prow : nullptr, yl, inner, done, progressive && u + 1 < nunits, reload); break;
-                default: p1_y_last_store<10>(buf32, dst, g, twu, g.pair ? prow : nullptr, yl, inner, done, progressive && u + 1 < nunits, reload); break;
+#define PS21_G2_YLAST(R, B0, B1) p1_y_last_store<R>(buf32, dst, g, twu, g.pair ? prow : nullptr, yl, inner, B0, B1)
+#define PS21_G2_YLAST_ANY(B0, B1)                        \
+    switch (RL) {                                        \
+        case 2: PS21_G2_YLAST(2, B0, B1); break;         \
+        case 3: PS21_G2_YLAST(3, B0, B1); break;         \
+        case 4: PS21_G2_YLAST(4, B0, B1); break;         \
+        case 5: PS21_G2_YLAST(5, B0, B1); break;         \
+        case 6: PS21_G2_YLAST(6, B0, B1); break;         \
+        case 8: PS21_G2_YLAST(8, B0, B1); break;         \
+        default: PS21_G2_YLAST(10, B0, B1); break;       \
+    }
+            PS21_G2_YLAST_ANY(0, bh);
+            if (halves) {
+                __syncthreads();
+                load_rows(u + 1, smem32, 0, bh * RL, tid >> 5, nthr >> 5);
+                PS21_G2_YLAST_ANY(bh, nsub);
+                __syncthreads();
+                load_rows(u + 1, smem32, bh * RL, R1, tid >> 5, nthr >> 5);
             }
+#undef PS21_G2_YLAST_ANY
+#undef PS21_G2_YLAST
         } else {
             const long long tile_elems = (long long)g.n0 * 32;
             for (int e = tid; e < R1 * nh; e += nthr) {
@@ -607,7 +599,7 @@ k_g2_p1(const float* __restrict__ boxes, long long batch_stride, int n2_total, I
                 dst[((long long)jp * g.nzt + (r >> g.lgT)) * tile_elems + inner + (r & (g.T - 1))] = v;
             }
         }
-        if (g.nbuf == 1 && !progressive && u + 1 < nunits) {
+        if (g.nbuf == 1 && !halves && u + 1 < nunits) {
             __syncthreads();
             issue_unit(u + 1, smem32);
         }
@@ -976,7 +968,7 @@ static int upload(const std::vector<T>& v, T** d) {
 static size_t p1_smem(const G2Dev& g) {
     return (size_t)g.nbuf * g.R1 * g.ld * sizeof(float2) +
            (size_t)(g.nz + g.n1 + g.R1 + 2 * g.Lc + (g.bluestein ? g.M : 0)) * sizeof(float2) +
-           (size_t)(g.M + g.R1 + g.nh + 2) * 2 + (size_t)g.R1 * 4 + 64;
+           (size_t)(g.M + g.R1 + g.nh + 2) * 2 + 64;
 }
 static size_t p2_smem(const G2Dev& g, int nbins, int nshare) {
     const int RL = g.fx.st[g.fx.nstages - 1].radix;
@@ -1046,7 +1038,7 @@ int g2_try_setup(ps21_plan* p, ShapePlan& sp) {
     if (const char* e = std::getenv("PS21_G2_NBUF")) force_nbuf = std::atoi(e);
     auto extra1 = [&](int R1) {
         return (size_t)(nz + n1 + R1 + 2 * g.Lc + (g.bluestein ? g.M : 0)) * sizeof(float2) +
-               (size_t)(g.M + R1 + g.nh + 2) * 2 + (size_t)R1 * 4 + 64;
+               (size_t)(g.M + R1 + g.nh + 2) * 2 + 64;
     };
     auto buf1 = [&](int R1) { return (size_t)R1 * (g.zrows | 1) * sizeof(float2); };
     // measured on 200^3 (B200): one buffer with three CTAs per SM 4.83 ms, two buffers with two CTAs 5.24 ms -- occupancy
