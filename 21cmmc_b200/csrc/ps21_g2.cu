@@ -60,6 +60,7 @@ struct G2Dev {
     int nbuf;                   // pass 1: shared-memory row buffers (2: the next unit streams in during this one's FFTs)
     int slabs;                  // pass 1: consecutive x slabs per CTA
     int fuse_first, fuse_last;  // pass 1: untangle inside the first y stage / HBM store inside the last y stage
+    int parts;                  // pass 1, units alone on an SM: pieces the last y stage is cut into for the row reload
     int dbg_skip;               // experiments only (PS21_G2_DBG_SKIP): bit 0 skip the z stages, bit 1 the first y stage
                                 // (timing, results are garbage); bit 4: no two-half reload of the row buffer (correct)
     int bluestein, Lc;          // pass 1: z transform of length M as a chirp convolution of length Lc (M has a big prime)
@@ -567,7 +568,6 @@ k_g2_p1(const float* __restrict__ boxes, long long batch_stride, int n2_total, I
         const int nsub = R1 / RL;
         const bool halves = MINB == 1 && g.fuse_last && g.nbuf == 1 && !g.pair && nsub >= 2 && u + 1 < nunits &&
                             !(g.dbg_skip & 16);
-        const int bh = halves ? nsub / 2 : nsub;
         if (g.fuse_last) {
 #define PS21_G2_YLAST(R, B0, B1) p1_y_last_store<R>(buf32, dst, g, twu, g.pair ? prow : nullptr, yl, inner, B0, B1)
 #define PS21_G2_YLAST_ANY(B0, B1)                        \
@@ -580,13 +580,16 @@ k_g2_p1(const float* __restrict__ boxes, long long batch_stride, int n2_total, I
         case 8: PS21_G2_YLAST(8, B0, B1); break;         \
         default: PS21_G2_YLAST(10, B0, B1); break;       \
     }
-            PS21_G2_YLAST_ANY(0, bh);
-            if (halves) {
-                __syncthreads();
-                load_rows(u + 1, smem32, 0, bh * RL, tid >> 5, nthr >> 5);
-                PS21_G2_YLAST_ANY(bh, nsub);
-                __syncthreads();
-                load_rows(u + 1, smem32, bh * RL, R1, tid >> 5, nthr >> 5);
+            if (!halves) {
+                PS21_G2_YLAST_ANY(0, nsub);
+            } else {
+                const int parts = (g.parts < nsub) ? g.parts : nsub;
+                for (int pt = 0; pt < parts; ++pt) {
+                    const int pb0 = nsub * pt / parts, pb1 = nsub * (pt + 1) / parts;
+                    PS21_G2_YLAST_ANY(pb0, pb1);
+                    __syncthreads();
+                    load_rows(u + 1, smem32, pb0 * RL, pb1 * RL, tid >> 5, nthr >> 5);
+                }
             }
 #undef PS21_G2_YLAST_ANY
 #undef PS21_G2_YLAST
@@ -1030,6 +1033,8 @@ int g2_try_setup(ps21_plan* p, ShapePlan& sp) {
     }
     g.zrows = std::max(g.pair ? g.M : g.nh, g.Lc);
     if (const char* e = std::getenv("PS21_G2_DBG_SKIP")) g.dbg_skip = std::atoi(e);
+    g.parts = 2;
+    if (const char* e = std::getenv("PS21_G2_PARTS")) g.parts = std::max(1, std::atoi(e));
     // y split n1 = R1 R2.  Pass 1 keeps nh x R1 coefficients per buffer; with two buffers the next unit streams in while
     // this one is transformed.  R2 = 4 gives 64-byte runs in the scratch, R2 = 8 halves the buffer (32-byte runs).
     int R2 = 0, nbuf = 0;
