@@ -114,14 +114,15 @@ __device__ __forceinline__ double chi2_term(double delta, double data, double no
     return d * d / (mod * mod + noise2);
 }
 
-__global__ void __launch_bounds__(128)
+constexpr int kFinalizeThreads = 512;   // 16 warps: one output per warp and round (80 outputs per config-3 box)
+__global__ void __launch_bounds__(kFinalizeThreads)
 k_finalize(const double* __restrict__ partials, int slots_max, long long out_per_box,
            const ChunkDev* __restrict__ chunks, int nchunks, const long long* __restrict__ counts,
            const double* __restrict__ kfac, const double* __restrict__ mean_parts, int n1,
            const float2* __restrict__ dc, double* __restrict__ power, double* __restrict__ delta,
            double* __restrict__ lnl, const double* __restrict__ data, const double* __restrict__ noise2,
            const uint8_t* __restrict__ mask, int nsets, double mu, int err_on_model, long long box0) {
-    __shared__ double red[128];
+    __shared__ double red[kFinalizeThreads];
     const long long box = blockIdx.x;
     const long long set = (box0 + box) % nsets;  // box0: index of this call's first box in the caller's batch
     double chi = 0.0;
@@ -164,10 +165,10 @@ k_finalize(const double* __restrict__ partials, int slots_max, long long out_per
             }
         }
     }
-    if (lnl) {   // fixed-order tree sum over the 128 threads (gridDim.y == 1): bitwise reproducible
+    if (lnl) {   // fixed-order tree sum over the block (gridDim.y == 1): bitwise reproducible
         red[threadIdx.x] = chi;
         __syncthreads();
-        for (int s = 64; s > 0; s >>= 1) {
+        for (int s = kFinalizeThreads / 2; s > 0; s >>= 1) {
             if ((int)threadIdx.x < s) red[threadIdx.x] += red[threadIdx.x + s];
             __syncthreads();
         }
@@ -367,7 +368,7 @@ static int issue_launches(ps21_plan* p, const float* d_boxes, long long batch, l
     ProfScope psf(p, KK_FINALIZE, st);
     unsigned fparts = want_lnl ? 1u : (unsigned)((p->out_per_box + 1023) / 1024);
     if (fparts > 64u) fparts = 64u;
-    PS21_LAUNCH(k_finalize, dim3((unsigned)batch, fparts), dim3(128), 0, st, p->d_partials, p->slots_max,
+    PS21_LAUNCH(k_finalize, dim3((unsigned)batch, fparts), dim3(kFinalizeThreads), 0, st, p->d_partials, p->slots_max,
                 p->out_per_box, p->d_chunks, p->nchunks, p->d_counts,
                 p->mode == PS21_MODE_SPHERICAL ? p->d_kfac : nullptr, p->d_mean_parts, p->n1, p->d_dc, d_power,
                 d_delta, d_lnl, p->data.d_data, p->data.d_noise2, p->data.d_mask,
