@@ -301,6 +301,29 @@ k_fused_p1(const float* __restrict__ boxes, long long batch_stride, int n2_total
     uint32_t phase = 0;
     for (; x < x_end; ++x, src += (long long)S * n2_total)
     for (int yl = 0; yl < R2S; ++yl) {
+        // ---- L2 prefetch of the rows whose bulk copies are issued at the end of this unit (the next unit of this
+        //      CTA, or the first unit of the CTA that will take its place): by then they come from L2, not DRAM
+        if (im.pf && tid >= 192) {   // 64 threads, one 1 KB row each
+            const float* nsrc = nullptr;
+            int nyl = 0;
+            if (yl + 1 < R2S) {
+                nsrc = src;
+                nyl = yl + 1;
+            } else if (x + 1 < x_end) {
+                nsrc = src + (long long)S * n2_total;
+            } else if (im.pf & 2) {
+                const long long n = (long long)blockIdx.y * gridDim.x + blockIdx.x + im.pf_ahead;
+                const long long it2 = n / gridDim.x;
+                if (it2 < (long long)gridDim.y) {
+                    long long b2;
+                    int c2;
+                    item_to_box_chunk(im, it2, b2, c2);
+                    nsrc = boxes + b2 * batch_stride + chunks[c2].start +
+                           (long long)((int)(n % gridDim.x) * P1_SLABS) * S * n2_total;
+                }
+            }
+            if (nsrc) bulk_prefetch_l2(nsrc + (long long)(nyl + R2S * (tid - 192)) * n2_total, NZ * 4);
+        }
         // ---- z: one 128-point FFT per row, 8 threads per row; rows 0..31 as soon as they have landed
         // thread tid owns rows tid/8 (groups 0..3) and 32 + tid/8 (groups 4..7)
         mbar_wait(bar + (tid >> 6), phase);
@@ -438,10 +461,21 @@ k_fused_p2(const float2* __restrict__ scratch, ItemMap im, const ChunkDev* __res
         count = 1;
     }
     const uint64_t pol_stream = l2_policy_evict_first(), pol_keep = l2_policy_evict_last();
+    const int t_end = tl + stride * count;   // first tile past this CTA's sequence
     auto issue_tile = [&](int t_next) {
         mbar_expect_tx(bar, TILE * 8 + TILE);
         bulk_g2s_hint(tile, src + (long long)t_next * TILE, TILE * 8, bar, pol_stream);
         bulk_g2s_hint(lutb, lut + (long long)t_next * TILE, TILE, bar, pol_keep);
+        if (im.pf) {   // the tile after it -> L2 (or the first tile of the CTA that will take this one's place)
+            if (stride > 0 && t_next + stride < t_end) {
+                bulk_prefetch_l2(src + (long long)(t_next + stride) * TILE, TILE * 8);
+            } else if ((im.pf & 2) && !CYL) {
+                const long long n = (long long)blockIdx.y * gridDim.x + blockIdx.x + im.pf_ahead;
+                const long long it2 = n / gridDim.x;
+                if (it2 < (long long)gridDim.y)
+                    bulk_prefetch_l2(scratch + it2 * ((long long)NTILES * TILE) + (n % gridDim.x) * TILE, TILE * 8);
+            }
+        }
     };
     if (tid == 0) issue_tile(tl);
     uint32_t phase = 0;
@@ -919,8 +953,11 @@ int fused_forward(ps21_plan* p, ShapePlan& sp, const float* d_boxes, long long b
         return PS21_ERR_INVALID;
     }
     ItemMap im{sp.d_chunks, (int)sp.chunks.size(), item0};
+    im.pf = l2_prefetch_mode();
+    const int sms = sm_count(p->device);
     {
         ProfScope ps(p, KK_PASS1, st);
+        im.pf_ahead = prefetch_ahead(3 * sms);
         if (fs->S == 256)
             PS21_LAUNCH(k_fused_p1<256>, dim3(256 / Geo<256>::P1_SLABS, (unsigned)nitems), dim3(P1_THREADS), p1_smem(), st, d_boxes,
                         batch_stride, p->n2_total, im, p->d_chunks, p->nchunks, p->d_mean_parts, p->d_scratch, fs->tw256);
@@ -935,6 +972,7 @@ int fused_forward(ps21_plan* p, ShapePlan& sp, const float* d_boxes, long long b
         // request the next tile inside S2: -8 % in the lane and cylindrical modes, +1.5 % in the vote-heavy group and
         // warp modes (measured), which therefore keep the request after the binning
         const int early = bm == BM_LANE || bm == BM_CYL;
+        im.pf_ahead = prefetch_ahead(2 * sms);
 #define PS21_P2_LAUNCH(BM, NSLOTS, ...)                                                                           \
     do {                                                                                                          \
         if (early)                                                                                                \

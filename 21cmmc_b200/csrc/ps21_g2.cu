@@ -456,6 +456,29 @@ k_g2_p1(const float* __restrict__ boxes, long long batch_stride, int n2_total, I
         cp_async_wait<0>();
         __syncthreads();   // unit u has landed; everybody is done with unit u - 1 (tables ready on the first turn)
         if (g.nbuf == 2 && u + 1 < nunits) issue_unit(u + 1, smem32 + (uint32_t)((u + 1) % 2) * (uint32_t)bufstride * 8u);
+        if (im.pf) {
+            // L2 prefetch of the rows whose copies are issued one unit from now (the next unit of this CTA, or the first
+            // unit of the CTA that will take its place): by then they come from L2, not DRAM
+            const int un = u + g.nbuf;
+            const float* nslab = nullptr;
+            if (un < nunits) {
+                const int xn = x0 + un / g.R2, yn = un - (un / g.R2) * g.R2;
+                nslab = spec + (long long)xn * g.n1 * n2_total + (long long)yn * n2_total;
+            } else if ((im.pf & 2) && un == nunits) {
+                const long long n = (long long)blockIdx.y * gridDim.x + blockIdx.x + im.pf_ahead;
+                const long long it2 = n / gridDim.x;
+                if (it2 < (long long)gridDim.y) {
+                    long long b2;
+                    int c2;
+                    item_to_box_chunk(im, it2, b2, c2);
+                    nslab = boxes + b2 * batch_stride + chunks[c2].start +
+                            (long long)((int)(n % gridDim.x) * g.slabs) * g.n1 * n2_total;
+                }
+            }
+            if (nslab)
+                for (int j = tid; j < R1; j += nthr)
+                    bulk_prefetch_l2(nslab + (long long)j * g.R2 * n2_total, (uint32_t)g.nz * 4u);
+        }
         for (int jp = tid; jp < R1; jp += nthr) twu[jp] = twy[yl * kya[jp]];   // yl ky_a < n1: no reduction needed
         // ---- z: complex FFT of length M over the row index, in place; the offset is subtracted as stage 0 reads
         const float2 mean2 = make_float2(mean, mean);
@@ -787,6 +810,14 @@ k_g2_p2(const float2* __restrict__ scratch, ItemMap im, const ChunkDev* __restri
     if (tid == 0) {
         mbar_init(bar, 1);
         mbar_fence_init();
+        bar[1] = 0;   // address of the first tile of the CTA `pf_ahead` later in launch order (L2 prefetch), or 0
+        if (im.pf & 2) {
+            const long long n = (long long)blockIdx.y * gridDim.x + blockIdx.x + im.pf_ahead;
+            const long long it2 = n / gridDim.x;
+            if (it2 < (long long)gridDim.y)
+                bar[1] = reinterpret_cast<uint64_t>(scratch + it2 * ((long long)g.ntiles * tile_elems) +
+                                                    (n % gridDim.x) * tile_elems);
+        }
     }
     __syncthreads();
     const uint64_t pol_stream = l2_policy_evict_first(), pol_keep = l2_policy_evict_last();
@@ -794,6 +825,11 @@ k_g2_p2(const float2* __restrict__ scratch, ItemMap im, const ChunkDev* __restri
         mbar_expect_tx(bar, (uint32_t)tile_elems * 8u + lut_bytes);
         bulk_g2s_hint(tile, src + (long long)tl * tile_elems, (uint32_t)tile_elems * 8u, bar, pol_stream);
         bulk_g2s_hint(lutb, lut + (long long)tl * lut_bytes, lut_bytes, bar, pol_keep);
+        if (im.pf) {   // the tile after it -> L2 (or the first tile of the CTA that will take this one's place: bar[1])
+            const float2* nx = (tl + g.slots < g.ntiles) ? src + (long long)(tl + g.slots) * tile_elems
+                                                         : reinterpret_cast<const float2*>(bar[1]);
+            if (nx) bulk_prefetch_l2(nx, (uint32_t)tile_elems * 8u);
+        }
     };
     const AddrTile addr{smem_u32(tile), R2 - 1, lgT + 3};
     FastDiv div32;
@@ -1296,11 +1332,17 @@ int g2_forward(ps21_plan* p, ShapePlan& sp, const float* d_boxes, long long batc
     auto* gs = static_cast<G2Shape*>(sp.fused);
     const G2Dev& g = gs->dev;
     ItemMap im{sp.d_chunks, (int)sp.chunks.size(), item0};
+    im.pf = l2_prefetch_mode();
+    const int sms = sm_count(p->device);
     int aligned8 = ((reinterpret_cast<uintptr_t>(d_boxes) & 7) == 0 && batch_stride % 2 == 0 && p->n2_total % 2 == 0) ? 1 : 0;
     for (int c : sp.chunks)
         if (p->chunks[c].start % 2) aligned8 = 0;
     {
         ProfScope ps(p, KK_PASS1, st);
+        const int minb = gs->p1_threads != 256 ? 1
+                         : (gs->smem1 <= 55 * 1024 && !std::getenv("PS21_G2_P1_MINB3")) ? 4
+                         : gs->smem1 <= 74 * 1024 ? 3 : 2;
+        im.pf_ahead = prefetch_ahead(minb * sms);
         if (gs->p1_threads == 1024)
             PS21_LAUNCH((k_g2_p1<1024, 1>), dim3(g.n0 / g.slabs, (unsigned)nitems), dim3(1024), gs->smem1, st, d_boxes, batch_stride,
                         p->n2_total, im, p->d_chunks, p->nchunks, p->d_mean_parts, p->d_scratch, g, aligned8);
@@ -1322,6 +1364,10 @@ int g2_forward(ps21_plan* p, ShapePlan& sp, const float* d_boxes, long long batc
     {
         ProfScope ps(p, KK_PASS_BIN, st);
         const int r0 = gs->R0, r2 = g.R2, ns = gs->nshare;
+        {   // resident pass-2 CTAs per SM: shared memory, or 128 registers per thread
+            const int by_smem = (int)((227 * 1024) / (gs->smem2 + 1024)), by_regs = 65536 / (128 * g.p2_threads);
+            im.pf_ahead = prefetch_ahead(std::max(1, std::min(by_smem, by_regs)) * sms);
+        }
 #define PS21_G2_LAUNCH(A, B, C)                                                                                      \
     PS21_LAUNCH((k_g2_p2<A, B, C>), dim3(g.slots, (unsigned)nitems), dim3(g.p2_threads), gs->smem2, st, p->d_scratch, im, \
                 p->d_chunks, (const uint16_t* const*)p->d_lut_table, p->d_partials, p->out_per_box, p->slots_max,   \

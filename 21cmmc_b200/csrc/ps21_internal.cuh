@@ -259,7 +259,14 @@ struct ItemMap {
     const int* ids;
     int nper;
     long long item0;
+    // L2 prefetch (two-pass kernels): bit 0 = the CTA's own next unit / tile but one, bit 1 = the first unit / tile of
+    // the CTA that will take this CTA's place (`pf_ahead` CTAs later in launch order).  Set per launch by the host.
+    int pf = 0;
+    int pf_ahead = 0;
 };
+int l2_prefetch_mode();              // PS21_L2_PREFETCH (default in ps21_plan.cu)
+int prefetch_ahead(int resident);    // launch-order distance to the CTA that takes a finishing CTA's place
+int sm_count(int device);
 __device__ __forceinline__ void item_to_box_chunk(const ItemMap& m, long long local, long long& box, int& chunk) {
     const long long it = m.item0 + local;
     box = it / m.nper;

@@ -11,6 +11,38 @@
 
 namespace ps21 {
 
+// L2 prefetch in the two-pass kernels (see ItemMap): PS21_L2_PREFETCH = 0 off, 1 own next unit / tile, 3 also the first
+// unit / tile of the succeeding CTA.  PS21_PF_AHEAD overrides the launch-order distance to that CTA.
+int l2_prefetch_mode() {
+    static const int mode = [] {
+        const char* e = std::getenv("PS21_L2_PREFETCH");
+        return e ? std::atoi(e) : 0;
+    }();
+    return mode;
+}
+int prefetch_ahead(int resident) {
+    static const int forced = [] {
+        const char* e = std::getenv("PS21_PF_AHEAD");
+        return e ? std::atoi(e) : 0;
+    }();
+    return forced > 0 ? forced : resident;
+}
+int sm_count(int device) {
+#ifdef PS21_EMU
+    (void)device;
+    return 148;
+#else
+    static int cached[64] = {0};
+    if (device < 0 || device >= 64) return 148;
+    if (!cached[device]) {
+        int v = 0;
+        if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, device) != cudaSuccess || v <= 0) v = 148;
+        cached[device] = v;
+    }
+    return cached[device];
+#endif
+}
+
 static thread_local std::string g_err;
 void set_error(const std::string& msg) { g_err = msg; }
 int cuda_fail(cudaError_t e, const char* what) {

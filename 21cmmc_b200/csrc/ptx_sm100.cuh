@@ -82,9 +82,19 @@ __device__ __forceinline__ void bulk_g2s_hint(void* dst, const void* src, uint32
         : "memory");
 }
 
+// contiguous bytes -> L2 only (no shared-memory destination, no completion to wait for); the range is widened to
+// 16-byte boundaries, which the instruction requires
+__device__ __forceinline__ void bulk_prefetch_l2(const void* src, uint32_t bytes) {
+    const unsigned long long a = reinterpret_cast<unsigned long long>(src);
+    const unsigned long long a0 = a & ~15ull;
+    const uint32_t n = (uint32_t)(((a + bytes + 15ull) & ~15ull) - a0);
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(a0), "r"(n) : "memory");
+}
+
 #else
 // emulated build (tests only): the bulk copy is a synchronous memcpy; the mbarrier is modelled as
-// {pending bytes, arrived flag, phase bit} packed in its 8 bytes
+// {pending bytes, arrived flag, phase bit} packed in its 8 bytes; an L2 prefetch is nothing
+__device__ __forceinline__ void bulk_prefetch_l2(const void*, uint32_t) {}
 struct EmuBar {
     int pending;
     unsigned short arrived, phase;
