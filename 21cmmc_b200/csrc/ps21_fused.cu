@@ -953,7 +953,7 @@ int fused_forward(ps21_plan* p, ShapePlan& sp, const float* d_boxes, long long b
         return PS21_ERR_INVALID;
     }
     ItemMap im{sp.d_chunks, (int)sp.chunks.size(), item0};
-    im.pf = l2_prefetch_mode();
+    im.pf = std::max(0, l2_prefetch_mode());
     const int sms = sm_count(p->device);
     {
         ProfScope ps(p, KK_PASS1, st);

@@ -456,9 +456,11 @@ k_g2_p1(const float* __restrict__ boxes, long long batch_stride, int n2_total, I
         cp_async_wait<0>();
         __syncthreads();   // unit u has landed; everybody is done with unit u - 1 (tables ready on the first turn)
         if (g.nbuf == 2 && u + 1 < nunits) issue_unit(u + 1, smem32 + (uint32_t)((u + 1) % 2) * (uint32_t)bufstride * 8u);
-        if (im.pf) {
-            // L2 prefetch of the rows whose copies are issued one unit from now (the next unit of this CTA, or the first
-            // unit of the CTA that will take its place): by then they come from L2, not DRAM
+        // L2 prefetch of the rows whose copies are issued next (the next unit of this CTA, or the first unit of the CTA
+        // that will take its place): by then they come from L2, not DRAM.  Issued `pf_where` stages before the loads: too
+        // early and the scratch stream has flushed them out of L2 again (ncu: +37 % DRAM reads when issued a whole
+        // 512^3 unit = 37 us ahead).
+        auto prefetch_next = [&]() {
             const int un = u + g.nbuf;
             const float* nslab = nullptr;
             if (un < nunits) {
@@ -478,7 +480,8 @@ k_g2_p1(const float* __restrict__ boxes, long long batch_stride, int n2_total, I
             if (nslab)
                 for (int j = tid; j < R1; j += nthr)
                     bulk_prefetch_l2(nslab + (long long)j * g.R2 * n2_total, (uint32_t)g.nz * 4u);
-        }
+        };
+        if (im.pf && im.pf_where == 0) prefetch_next();
         for (int jp = tid; jp < R1; jp += nthr) twu[jp] = twy[yl * kya[jp]];   // yl ky_a < n1: no reduction needed
         // ---- z: complex FFT of length M over the row index, in place; the offset is subtracted as stage 0 reads
         const float2 mean2 = make_float2(mean, mean);
@@ -506,6 +509,7 @@ k_g2_p1(const float* __restrict__ boxes, long long batch_stride, int n2_total, I
                 __syncthreads();
             }
         }
+        if (im.pf && im.pf_where == 1) prefetch_next();
         // ---- untangle (pairs (p, M - p) -> A_p, A_{M-p}; p = 0 also yields the Nyquist row M) + first y stage
         if (g.dbg_skip & 2) {
         } else if (g.fuse_first) {
@@ -577,6 +581,7 @@ k_g2_p1(const float* __restrict__ boxes, long long batch_stride, int n2_total, I
             ip_stage_any<false>(g.fy.st[s], R1, nh, g.div_nh, ay, twy, PreSub{make_float2(0.f, 0.f)});
             __syncthreads();
         }
+        if (im.pf && im.pf_where == 2) prefetch_next();
         // ---- last y stage, times w_n1^(yl ky_a), to HBM in tile order: runs of T consecutive rows
         const int slot = (yl ^ (x & (g.R2 - 1)));
         const long long inner = ((long long)x * g.R2 + slot) << g.lgT;
@@ -1108,12 +1113,13 @@ int g2_try_setup(ps21_plan* p, ShapePlan& sp) {
     split_radices(g.R1, kRadY, ry);
     // A unit that has the SM to itself (512^3: 134 KB) hides its latencies with threads instead of CTAs: 1024 threads at
     // 64 registers, which caps the butterflies at radix 8 (one more z stage for 256 = 8 * 8 * 4)
-    bool big_unit = nbuf * buf1(g.R1) + extra1(g.R1) > 112 * 1024 && !g.bluestein && std::getenv("PS21_G2_P1_1024");
+    bool big_unit = nbuf * buf1(g.R1) + extra1(g.R1) > 112 * 1024 && std::getenv("PS21_G2_P1_1024");
     if (big_unit) {
         static const std::vector<int> kRad8 = {8, 7, 6, 5, 4, 3, 2};
         std::vector<int> rz8, ry8;
-        if (split_radices(g.M, kRad8, rz8) && split_radices(g.R1, kRad8, ry8)) {
-            rz = rz8;
+        // (chirp convolution: only when its length also splits into the small radices, e.g. 336 = 8 * 7 * 6)
+        if (split_radices(g.bluestein ? g.Lc : g.M, kRad8, rz8) && split_radices(g.R1, kRad8, ry8)) {
+            (g.bluestein ? rzb : rz) = rz8;
             ry = ry8;
         } else {
             big_unit = false;
@@ -1332,7 +1338,7 @@ int g2_forward(ps21_plan* p, ShapePlan& sp, const float* d_boxes, long long batc
     auto* gs = static_cast<G2Shape*>(sp.fused);
     const G2Dev& g = gs->dev;
     ItemMap im{sp.d_chunks, (int)sp.chunks.size(), item0};
-    im.pf = l2_prefetch_mode();
+    const int pf_mode = l2_prefetch_mode();
     const int sms = sm_count(p->device);
     int aligned8 = ((reinterpret_cast<uintptr_t>(d_boxes) & 7) == 0 && batch_stride % 2 == 0 && p->n2_total % 2 == 0) ? 1 : 0;
     for (int c : sp.chunks)
@@ -1342,6 +1348,8 @@ int g2_forward(ps21_plan* p, ShapePlan& sp, const float* d_boxes, long long batc
         const int minb = gs->p1_threads != 256 ? 1
                          : (gs->smem1 <= 55 * 1024 && !std::getenv("PS21_G2_P1_MINB3")) ? 4
                          : gs->smem1 <= 74 * 1024 ? 3 : 2;
+        im.pf = pf_mode >= 0 ? pf_mode : (minb == 1 ? 1 : 0);
+        if (const char* e = std::getenv("PS21_PF_WHERE")) im.pf_where = std::atoi(e);
         im.pf_ahead = prefetch_ahead(minb * sms);
         if (gs->p1_threads == 1024)
             PS21_LAUNCH((k_g2_p1<1024, 1>), dim3(g.n0 / g.slabs, (unsigned)nitems), dim3(1024), gs->smem1, st, d_boxes, batch_stride,
@@ -1366,6 +1374,7 @@ int g2_forward(ps21_plan* p, ShapePlan& sp, const float* d_boxes, long long batc
         const int r0 = gs->R0, r2 = g.R2, ns = gs->nshare;
         {   // resident pass-2 CTAs per SM: shared memory, or 128 registers per thread
             const int by_smem = (int)((227 * 1024) / (gs->smem2 + 1024)), by_regs = 65536 / (128 * g.p2_threads);
+            im.pf = std::max(0, pf_mode);
             im.pf_ahead = prefetch_ahead(std::max(1, std::min(by_smem, by_regs)) * sms);
         }
 #define PS21_G2_LAUNCH(A, B, C)                                                                                      \

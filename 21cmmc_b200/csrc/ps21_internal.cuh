@@ -263,6 +263,7 @@ struct ItemMap {
     // the CTA that will take this CTA's place (`pf_ahead` CTAs later in launch order).  Set per launch by the host.
     int pf = 0;
     int pf_ahead = 0;
+    int pf_where = 0;   // generic pass 1: 0 = at the top of a unit, 1 = after the z stages, 2 = before the last y stage
 };
 int l2_prefetch_mode();              // PS21_L2_PREFETCH (default in ps21_plan.cu)
 int prefetch_ahead(int resident);    // launch-order distance to the CTA that takes a finishing CTA's place

@@ -12,11 +12,15 @@
 namespace ps21 {
 
 // L2 prefetch in the two-pass kernels (see ItemMap): PS21_L2_PREFETCH = 0 off, 1 own next unit / tile, 3 also the first
-// unit / tile of the succeeding CTA.  PS21_PF_AHEAD overrides the launch-order distance to that CTA.
+// unit / tile of the succeeding CTA; unset (-1) = the measured default of each kernel: on (1) only in generic pass-1
+// kernels whose units have the SM to themselves (512^3: 18.2 -> 16.6 ms) -- with several resident CTAs the kernels are
+// bound by DRAM throughput, not latency, and the extra requests cost 1.5 % (256^3 fused), 3 % (200^3) of pass 1;
+// pass 2 does not react at all (profiles/r02_g2_experiments.md).  PS21_PF_AHEAD overrides the launch-order distance to
+// the succeeding CTA.
 int l2_prefetch_mode() {
     static const int mode = [] {
         const char* e = std::getenv("PS21_L2_PREFETCH");
-        return e ? std::atoi(e) : 0;
+        return e ? std::atoi(e) : -1;
     }();
     return mode;
 }

@@ -18,6 +18,7 @@ idx = binning.chunk_indices(ns, nchunks)
 bounds = [(idx[i], idx[i + 1]) for i in range(nchunks)]
 lengths = [(n0 * cell, n0 * cell, (b - a) * cell) for a, b in bounds]
 plan = get_plan((n0, n0, ns), bounds, lengths, nbins, True)
+torch.manual_seed(1)
 x = torch.randn((walkers, n0, n0, ns), device="cuda:0") * 10 + 20
 plan.set_profiling(True)
 for _ in range(3):
@@ -32,4 +33,4 @@ b.record()
 torch.cuda.synchronize()
 ms = a.elapsed_time(b) / reps
 print(f"{n0}x{n0}x{ns}, {nchunks} chunks {[e - s for s, e in bounds]}, path {plan.path}: {ms:.3f} ms per {walkers} walkers = "
-      f"{1e3 * walkers / ms:.1f} evals/s; kernels {plan.profile()}")
+      f"{1e3 * walkers / ms:.1f} evals/s; kernels {plan.profile()}; checksum {float(torch.nan_to_num(out.double()).sum()):.10e}")
