@@ -61,6 +61,9 @@ struct G2Dev {
     int slabs;                  // pass 1: consecutive x slabs per CTA
     int fuse_first, fuse_last;  // pass 1: untangle inside the first y stage / HBM store inside the last y stage
     int parts;                  // pass 1, units alone on an SM: pieces the last y stage is cut into for the row reload
+    int mapb, lgR2, swshift;    // pass 2, last stage: lanes = (k_z, R2 consecutive x blocks) instead of (k_z, ky_b) so that
+                                // the lanes of a warp meet their bin changes together; swshift: the ky_b slot of row x is
+                                // XOR-ed with (x ^ (x >> swshift)) & (R2 - 1) (31: plain x & (R2 - 1))
     int dbg_skip;               // experiments only (PS21_G2_DBG_SKIP): bit 0 skip the z stages, bit 1 the first y stage
                                 // (timing, results are garbage); bit 4: no two-half reload of the row buffer (correct)
     int bluestein, Lc;          // pass 1: z transform of length M as a chirp convolution of length Lc (M has a big prime)
@@ -211,11 +214,28 @@ struct AddrRows {      // pass 1, y transform: index = j (one buffer row each), 
 struct AddrTile {      // pass 2: row x holds 32 columns (ky_b, t); the ky_b slot is XOR-ed with the low bits of x
     uint32_t base;     // 256-byte aligned
     int swmask, sh;    // swmask = R2 - 1, sh = log2(T) + 3
+    int swshift;       // G2Dev::swshift
     __device__ __forceinline__ uint32_t col(int c) const { return (uint32_t)(c << 3); }
     __device__ __forceinline__ uint32_t at(uint32_t cb, int i) const {
-        return base + i * 256 + (cb ^ ((i & swmask) << sh));
+        return base + i * 256 + (cb ^ (((i ^ (i >> swshift)) & swmask) << sh));
     }
 };
+// slot swizzle of row x (see G2Dev::swshift)
+__host__ __device__ __forceinline__ int sw_of_x(int x, int swshift, int R2) { return (x ^ (x >> swshift)) & (R2 - 1); }
+// last x stage of pass 2: task -> (column c = (ky_b, t), butterfly bf).  mapb: lane = (t, low bits of bf), warp = (ky_b,
+// high bits of bf): the lanes of a warp then differ by a few k_z and a few k_x only, so |k| and with it the bin changes
+// along the walk nearly coincide (with ky_b in the lane index they differ by n1 / R2 rows of k_y and every warp took the
+// slow path of the walk at almost every word: ncu, 27 % of all pass-2 instructions).
+__host__ __device__ __forceinline__ void last_task_map(int task, int mapb, int lgT, int lgR2, int& c, int& bf) {
+    if (!mapb) {
+        c = task & 31;
+        bf = task >> 5;
+    } else {
+        const int t = task & ((1 << lgT) - 1), bfl = (task >> lgT) & ((1 << lgR2) - 1), w = task >> 5;
+        c = ((w & ((1 << lgR2) - 1)) << lgT) | t;
+        bf = ((w >> lgR2) << lgR2) | bfl;
+    }
+}
 
 // ------------------------------------------------------------------------------------------------
 // LUT (one byte per mode, in the order pass 2 visits its outputs) + counts
@@ -237,7 +257,9 @@ __global__ void k_g2_lut(uint8_t* __restrict__ lut, unsigned long long* __restri
          i += (long long)gridDim.x * blockDim.x) {
         const int tile = (int)(i / tile_bytes), e = (int)(i % tile_bytes);
         // e = (bf * 32 + c) * RLP + v : butterfly bf of the last x stage, column c = (ky_b, t), output in visiting order
-        const int v = e % RLP, task = e / RLP, c = task & 31, bf = task >> 5;
+        const int v = e % RLP, task = e / RLP;
+        int c, bf;
+        last_task_map(task, g.mapb, g.lgT, g.lgR2, c, bf);
         if (v >= RL) {   // padding of the row
             lut[i] = 255;
             continue;
@@ -583,7 +605,7 @@ k_g2_p1(const float* __restrict__ boxes, long long batch_stride, int n2_total, I
         }
         if (im.pf && im.pf_where == 2) prefetch_next();
         // ---- last y stage, times w_n1^(yl ky_a), to HBM in tile order: runs of T consecutive rows
-        const int slot = (yl ^ (x & (g.R2 - 1)));
+        const int slot = yl ^ sw_of_x(x, g.swshift, g.R2);
         const long long inner = ((long long)x * g.R2 + slot) << g.lgT;
         // A CTA that has the SM to itself (512^3 units) runs the last y stage in two halves of sub-blocks: after the
         // first half (one more barrier) its buffer rows are dead and ALL warps issue the copies of those rows of the
@@ -648,7 +670,7 @@ __device__ __forceinline__ void p2_first_stage(uint32_t tile32, const G2Dev& g, 
     constexpr int T = 32 / R2;
     constexpr int lgT = (T == 16) ? 4 : (T == 8) ? 3 : (T == 4) ? 2 : 1;
     constexpr int SH = lgT + 3;
-    const int q0 = g.n0 / R0;
+    const int q0 = g.n0 / R0, swshift = g.swshift;
     const int ntasks = q0 * T;
     for (int task = threadIdx.x; task < ntasks; task += blockDim.x) {
         const int t = task & (T - 1), o = task >> lgT;
@@ -657,7 +679,7 @@ __device__ __forceinline__ void p2_first_stage(uint32_t tile32, const G2Dev& g, 
 #pragma unroll
         for (int m = 0; m < R0; ++m) {
             const int x = o + m * q0;
-            row[m] = (tile32 + x * 256 + (t << 3)) ^ ((x & (R2 - 1)) << SH);
+            row[m] = (tile32 + x * 256 + (t << 3)) ^ (sw_of_x(x, swshift, R2) << SH);
 #pragma unroll
             for (int yl = 0; yl < R2; ++yl) v[m][yl] = lds64(row[m] ^ (yl << SH));
         }
@@ -739,16 +761,21 @@ __device__ __forceinline__ void p2_last_stage(const uint8_t* __restrict__ lutb,
     constexpr int NW = (RL + 3) / 4;
     const int ntasks = (g.n0 / RL) * 32;   // EARLY: == blockDim.x, the loop body runs once in every thread
     for (int task = threadIdx.x; task < ntasks; task += blockDim.x) {
-        const int c = task & 31, bf = task >> 5;
+        constexpr int lgR2 = (R2 == 16) ? 4 : (R2 == 8) ? 3 : 2;
+        int c, bf;
+        last_task_map(task, g.mapb, 5 - lgR2, lgR2, c, bf);
         float2 v[RL];
         uint32_t lw[NW];
         {   // x = bf RL + m: the XOR term of the address depends on x & (R2 - 1) only -> R2 row-relative offsets,
-            // rotated by (bf RL) & (R2 - 1), and compile-time displacements m * 256
+            // rotated by (bf RL) & (R2 - 1), and compile-time displacements m * 256.  (With the block index folded into
+            // the swizzle -- swshift < 31, RL a multiple of R2 -- the rotation is 0 and the term is XOR-ed with bf.)
             const uint32_t base = addr.base + (uint32_t)(bf * RL) * 256u;
             const int rot = (bf * RL) & (R2 - 1);
+            const int bx = (addr.swshift < 31) ? (bf & (R2 - 1)) : 0;
             uint32_t off[R2];
 #pragma unroll
-            for (int k = 0; k < R2; ++k) off[k] = base + (uint32_t)((c << 3) ^ (((k + rot) & (R2 - 1)) << addr.sh));
+            for (int k = 0; k < R2; ++k)
+                off[k] = base + (uint32_t)((c << 3) ^ ((((k + rot) & (R2 - 1)) ^ bx) << addr.sh));
 #pragma unroll
             for (int m = 0; m < RL; ++m) v[m] = lds64(off[m & (R2 - 1)] + m * 256);
         }
@@ -836,7 +863,7 @@ k_g2_p2(const float2* __restrict__ scratch, ItemMap im, const ChunkDev* __restri
             if (nx) bulk_prefetch_l2(nx, (uint32_t)tile_elems * 8u);
         }
     };
-    const AddrTile addr{smem_u32(tile), R2 - 1, lgT + 3};
+    const AddrTile addr{smem_u32(tile), R2 - 1, lgT + 3, g.swshift};
     FastDiv div32;
     div32.mul = 1u << 11;   // x / 32 for x < 65536: (x * 2^11) >> 16
     div32.shift = 16;
@@ -1156,6 +1183,16 @@ int g2_try_setup(ps21_plan* p, ShapePlan& sp) {
         break;
     }
     if (!R0) return no("sky-plane size does not split into the x radices");
+    {   // lane mapping of the last x stage (see last_task_map): needs whole groups of R2 butterflies, and a slot swizzle
+        // that separates their rows: x & (R2 - 1) does for odd radices; for the power-of-two ones the block index is
+        // folded in (RL a multiple of R2)
+        const int RL = rx.back(), nbf = n0 / RL;
+        g.lgR2 = (R2 == 16) ? 4 : (R2 == 8) ? 3 : 2;
+        g.mapb = (nbf % R2 == 0 && (RL % 2 == 1 || RL % R2 == 0) && !std::getenv("PS21_G2_NOMAPB")) ? 1 : 0;
+        g.swshift = 31;
+        if (g.mapb && RL % 2 == 0)
+            for (g.swshift = 0; (1 << g.swshift) < RL; ++g.swshift) {}
+    }
     if ((long long)g.R1 * g.M >= 65536 || (long long)g.R1 * g.nh >= 65536 || (long long)(g.M / 2 + 1) * g.R1 >= 65536 ||
         (long long)g.R1 * g.Lc >= 65536)
         return no("unit too large for the index arithmetic");
