@@ -41,6 +41,8 @@ constexpr int FLUSH_EVERY = 4;        // tiles between two fp32 -> fp64 flushes
 
 struct IpStage {
     int radix, q, twmul;   // q = butterflies per sub-block (L / radix); twiddle of output m' at offset o: tw[o m' twmul]
+    int nbf;               // butterflies of the stage per column (n / radix): from the host, a division per stage and unit
+                           // and thread was 2.5 % of the pass-1 instructions (ncu)
     FastDiv div_q;
 };
 struct IpFft {
@@ -183,7 +185,8 @@ __device__ __forceinline__ void ip_stage_T(const IpStage st, int nbf, int ncols,
 template <bool BIG, bool TRANSPOSED = false, class Addr, class Pre>
 __device__ __forceinline__ void ip_stage_any(const IpStage st, int n, int ncols, FastDiv div_cols,
                                              const Addr addr, const float2* tw, const Pre pre) {
-    const int nbf = n / st.radix;
+    const int nbf = st.nbf;
+    (void)n;
 #define PS21_IP_CASE(R)                                                        \
     case R:                                                                    \
         if (TRANSPOSED) ip_stage_T<R>(st, nbf, ncols, div_cols, addr, tw, pre);      \
@@ -439,7 +442,7 @@ k_g2_p1(const float* __restrict__ boxes, long long batch_stride, int n2_total, I
     // coalesced reads, contiguous writes.  `load_rows` is called by whole warps: rows j0 .. j1-1 of unit u, one row
     // per warp turn starting at `w0` of `nw` warps.
     auto load_rows = [&](int u, uint32_t buf32, int j0, int j1, int w0, int nw) {
-        const int x = x0 + u / g.R2, yl = u - (u / g.R2) * g.R2;
+        const int x = x0 + (u >> g.lgR2), yl = u & (g.R2 - 1);
         const float* slab = spec + (long long)x * g.n1 * n2_total + (long long)yl * n2_total;
         const int lane = tid & 31;
         const long long rstride = (long long)g.R2 * n2_total;
@@ -448,7 +451,11 @@ k_g2_p1(const float* __restrict__ boxes, long long batch_stride, int n2_total, I
                 const float* src = slab + j * rstride + 2 * lane;
                 uint32_t d = buf32 + (uint32_t)j * ldb + (uint32_t)lane * 8u;
                 if (aligned8) {
-                    for (int zc = lane; zc < M; zc += 32, d += 256u, src += 64) cp_async8_s32(d, src);
+                    // M / 32 whole warp turns (uniform trip count: no divergence bookkeeping, unrollable) + one partial
+                    // (ncu: the per-lane `zc < M` loop was 9 % of the pass-1 instructions on 200^3)
+#pragma unroll 1
+                    for (int i = 0; i < (M >> 5); ++i, d += 256u, src += 64) cp_async8_s32(d, src);
+                    if (lane < (M & 31)) cp_async8_s32(d, src);
                 } else {
                     for (int zc = lane; zc < M; zc += 32, d += 256u, src += 64) {
                         cp_async4_s32(d, src);
@@ -470,11 +477,11 @@ k_g2_p1(const float* __restrict__ boxes, long long batch_stride, int n2_total, I
     const int nunits = g.slabs * g.R2;
     issue_unit(0, smem32);
     for (int u = 0; u < nunits; ++u) {
-        float2* buf = smem + (u % g.nbuf) * bufstride;
-        const uint32_t buf32 = smem32 + (uint32_t)(u % g.nbuf) * (uint32_t)bufstride * 8u;
+        float2* buf = smem + (u & (g.nbuf - 1)) * bufstride;   // nbuf is 1 or 2
+        const uint32_t buf32 = smem32 + (uint32_t)(u & (g.nbuf - 1)) * (uint32_t)bufstride * 8u;
         const AddrStrided az{buf32, 8u, ldb};    // z transform: index = z pair / k_z slot, column = j
         const AddrRows ay{buf32, ldb, g.pair ? prow : nullptr};   // y transform: index = j, column = row
-        const int x = x0 + u / g.R2, yl = u - (u / g.R2) * g.R2;
+        const int x = x0 + (u >> g.lgR2), yl = u & (g.R2 - 1);
         cp_async_wait<0>();
         __syncthreads();   // unit u has landed; everybody is done with unit u - 1 (tables ready on the first turn)
         if (g.nbuf == 2 && u + 1 < nunits) issue_unit(u + 1, smem32 + (uint32_t)((u + 1) % 2) * (uint32_t)bufstride * 8u);
@@ -486,7 +493,7 @@ k_g2_p1(const float* __restrict__ boxes, long long batch_stride, int n2_total, I
             const int un = u + g.nbuf;
             const float* nslab = nullptr;
             if (un < nunits) {
-                const int xn = x0 + un / g.R2, yn = un - (un / g.R2) * g.R2;
+                const int xn = x0 + (un >> g.lgR2), yn = un & (g.R2 - 1);
                 nslab = spec + (long long)xn * g.n1 * n2_total + (long long)yn * n2_total;
             } else if ((im.pf & 2) && un == nunits) {
                 const long long n = (long long)blockIdx.y * gridDim.x + blockIdx.x + im.pf_ahead;
@@ -615,7 +622,7 @@ k_g2_p1(const float* __restrict__ boxes, long long batch_stride, int n2_total, I
         // counter per sub-block, the warp that completes it issues the copies -- measured slower still:
         // profiles/r02_g2_experiments.md.)
         const int RL = g.fy.st[ylast].radix;
-        const int nsub = R1 / RL;
+        const int nsub = g.fy.st[ylast].nbf;   // R1 / RL
         const bool halves = MINB == 1 && g.fuse_last && g.nbuf == 1 && !g.pair && nsub >= 2 && u + 1 < nunits &&
                             !(g.dbg_skip & 16);
         if (g.fuse_last) {
@@ -876,7 +883,13 @@ k_g2_p2(const float2* __restrict__ scratch, ItemMap im, const ChunkDev* __restri
     if (tid == 0 && tl < g.ntiles) issue_tile(tl);
     uint32_t phase = 0;
     int it = 0;
-    for (; tl < g.ntiles; tl += g.slots, ++it) {
+    // loop invariants (ncu: the two integer divisions below, redone for every tile, were 4 % of the 200^3 instructions):
+    // one task per thread and whole warps busy or idle together (the group bin mode votes per warp) -> early hand-over
+    const int ntasks_last = (g.n0 / RLk) * 32;
+    const bool early = ntasks_last == nthr;
+    int zt = tl % g.nzt;                  // z tile of `tl`, advanced with it
+    const int zt_step = g.slots % g.nzt;
+    for (; tl < g.ntiles; tl += g.slots, ++it, zt = (zt + zt_step >= g.nzt) ? zt + zt_step - g.nzt : zt + zt_step) {
         mbar_wait(bar, phase);
         phase ^= 1;
         p2_first_stage<R0, R2>(addr.base, g, twx);
@@ -886,13 +899,9 @@ k_g2_p2(const float2* __restrict__ scratch, ItemMap im, const ChunkDev* __restri
             __syncthreads();
         }
         {
-            const int zt = tl % g.nzt;
             bw.mult = (float)g.zmult[zt * T + (tid & (T - 1))];
             float2* dc_out = (tl == 0) ? dc + (box * nchunks + cid) : nullptr;
             const bool have_next = tl + g.slots < g.ntiles;
-            // one task per thread and whole warps busy or idle together (the group bin mode votes per warp)
-            const int ntasks_last = (g.n0 / RLk) * 32;
-            const bool early = ntasks_last == nthr;
             auto release = [&]() {   // warps 1.. signal without waiting, warp 0 waits for them and starts the copy
                 if (!have_next) return;
                 if (tid >= 32) {
@@ -1007,6 +1016,7 @@ static void make_ipfft(int n, const std::vector<int>& radices, int twscale, IpFf
         st.radix = r;
         st.q = L / r;
         st.twmul = (n / L) * twscale;
+        st.nbf = n / r;
         st.div_q = make_fastdiv(st.q);
         L = st.q;
     }
