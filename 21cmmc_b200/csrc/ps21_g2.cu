@@ -63,6 +63,7 @@ struct G2Dev {
     int slabs;                  // pass 1: consecutive x slabs per CTA
     int fuse_first, fuse_last;  // pass 1: untangle inside the first y stage / HBM store inside the last y stage
     int parts;                  // pass 1, units alone on an SM: pieces the last y stage is cut into for the row reload
+    int lgMpad;                 // pass 1: log2 of M rounded up to a multiple of 32 when that is a power of two, else 0
     int mapb, lgR2, swshift;    // pass 2, last stage: lanes = (k_z, R2 consecutive x blocks) instead of (k_z, ky_b) so that
                                 // the lanes of a warp meet their bin changes together; swshift: the ky_b slot of row x is
                                 // XOR-ed with (x ^ (x >> swshift)) & (R2 - 1) (31: plain x & (R2 - 1))
@@ -446,7 +447,23 @@ k_g2_p1(const float* __restrict__ boxes, long long batch_stride, int n2_total, I
         const float* slab = spec + (long long)x * g.n1 * n2_total + (long long)yl * n2_total;
         const int lane = tid & 31;
         const long long rstride = (long long)g.R2 * n2_total;
-        if (!g.pair) {
+        if (!g.pair && aligned8 == 2 && g.lgMpad > 0 && (1 << g.lgMpad) <= nthr) {
+            // a row padded to Mpad = 2^lgMpad pair slots: thread -> (row jr of the turn, slot zc); zc is fixed for a thread,
+            // only the row advances -- one LDGSTS + two pointer steps per copy, no per-row set-up (the warp-per-row
+            // loop below was still 15 % of the pass-1 instructions on 200^3 after its first trimming).  Only for rows that
+            // start on 32-byte sectors (aligned8 == 2): the 256-byte pieces of a row are then fetched by different warps,
+            // and on 8-byte aligned rows their shared boundary sectors cost more than the instructions save
+            // (250-slice chunks: pass 1 +7 %; 200^3: -2.3 %)
+            const int zc = tid & ((1 << g.lgMpad) - 1), jr = tid >> g.lgMpad, rpt = nthr >> g.lgMpad;
+            if (zc < M) {
+                const float* src = slab + (long long)(j0 + jr) * rstride + 2 * zc;
+                uint32_t d = buf32 + (uint32_t)(j0 + jr) * ldb + (uint32_t)zc * 8u;
+                const long long sstep = (long long)rpt * rstride;
+                const uint32_t dstep = (uint32_t)rpt * ldb;
+#pragma unroll 4
+                for (int j = j0 + jr; j < j1; j += rpt, src += sstep, d += dstep) cp_async8_s32(d, src);
+            }
+        } else if (!g.pair) {
             for (int j = j0 + w0; j < j1; j += nw) {
                 const float* src = slab + j * rstride + 2 * lane;
                 uint32_t d = buf32 + (uint32_t)j * ldb + (uint32_t)lane * 8u;
@@ -1212,6 +1229,12 @@ int g2_try_setup(ps21_plan* p, ShapePlan& sp) {
     make_ipfft(n0, rx, 1, g.fx);
     g.div_M = make_fastdiv(g.M); g.div_R1 = make_fastdiv(g.R1); g.div_nh = make_fastdiv(g.nh);
     g.div_zcols = make_fastdiv(g.zcols);
+    {
+        const int Mpad = ((g.M + 31) / 32) * 32;
+        g.lgMpad = 0;
+        if ((Mpad & (Mpad - 1)) == 0 && !std::getenv("PS21_G2_NOFLATLOAD"))
+            while ((1 << g.lgMpad) < Mpad) ++g.lgMpad;
+    }
     g.nzt = (g.nh + g.T - 1) / g.T;
     g.ntiles = g.R1 * g.nzt;
     {   // pass-2 CTAs per spectrum: about 12 tiles each
@@ -1390,6 +1413,11 @@ int g2_forward(ps21_plan* p, ShapePlan& sp, const float* d_boxes, long long batc
     int aligned8 = ((reinterpret_cast<uintptr_t>(d_boxes) & 7) == 0 && batch_stride % 2 == 0 && p->n2_total % 2 == 0) ? 1 : 0;
     for (int c : sp.chunks)
         if (p->chunks[c].start % 2) aligned8 = 0;
+    if (aligned8 && (reinterpret_cast<uintptr_t>(d_boxes) & 31) == 0 && batch_stride % 8 == 0 && p->n2_total % 8 == 0) {
+        aligned8 = 2;   // every row starts on a 32-byte sector
+        for (int c : sp.chunks)
+            if (p->chunks[c].start % 8) aligned8 = 1;
+    }
     {
         ProfScope ps(p, KK_PASS1, st);
         const int minb = gs->p1_threads != 256 ? 1
