@@ -307,7 +307,7 @@ __device__ __forceinline__ float2 zfix(float2 v, const float2* __restrict__ chir
 
 template <int R, bool BLU>
 __device__ __forceinline__ void p1_y_first(uint32_t buf, const G2Dev& g, const float2* __restrict__ twz,
-                                           const float2* __restrict__ twy, const uint16_t* __restrict__ rowz,
+                                           const float2* __restrict__ twf, const uint16_t* __restrict__ rowz,
                                            const float2* __restrict__ chirp) {
     // first y stage (radix R over j = o + m q) of the row pair (p, M - p), with the untangle of that pair done on
     // the values as they are read: one pass over shared memory and one barrier instead of two
@@ -350,12 +350,9 @@ __device__ __forceinline__ void p1_y_first(uint32_t buf, const G2Dev& g, const f
         small_dft<R>(a1);
         small_dft<R>(a2);
         if (q > 1) {
-            const int step = o * st.twmul;
-            int idx = step;
 #pragma unroll
             for (int m = 1; m < R; ++m) {
-                const float2 w = twy[idx];
-                idx += step;
+                const float2 w = twf[(m - 1) * q + o];   // w_n1^(o m twmul), lanes along o: contiguous
                 a1[m] = cmul_w2(a1[m], w);
                 a2[m] = cmul_w2(a2[m], w);
             }
@@ -414,7 +411,8 @@ k_g2_p1(const float* __restrict__ boxes, long long batch_stride, int n2_total, I
     float2* const chirp = twc + g.Lc;                                    // [M]   exp(-i pi n^2/M)  (Bluestein only)
     float2* const bhat = chirp + (g.bluestein ? M : 0);                  // [Lc]  chirp spectrum    (Bluestein only)
     float2* const twu = bhat + g.Lc;                                     // [R1]  w_n1^(yl ky_a) of the current unit
-    uint16_t* const rowz = reinterpret_cast<uint16_t*>(twu + R1);        // [M]   copy of G2Dev::rowz_of_k
+    float2* const twf = twu + R1;                                        // [(R-1) q] twiddles of the first y stage by (m, o)
+    uint16_t* const rowz = reinterpret_cast<uint16_t*>(twf + R1);        // [M]   copy of G2Dev::rowz_of_k
     uint16_t* const kya = rowz + M;                                      // [R1]  copy of G2Dev::kya_of_jp
     uint16_t* const prow = kya + R1;                                     // [nh]  copy of G2Dev::prow_of_row (pair mode)
     long long box;
@@ -428,6 +426,14 @@ k_g2_p1(const float* __restrict__ boxes, long long batch_stride, int n2_total, I
 
     for (int i = tid; i < g.nz; i += nthr) twz[i] = g.tw_z[i];
     for (int i = tid; i < g.n1; i += nthr) twy[i] = g.tw_y[i];
+    {   // first y stage: w_n1^(o m twmul) stored [m - 1][o]; its lanes run along o, and read straight from the w_n1^q table
+        // (stride m twmul) the R - 1 loads were 3- to 10-way bank conflicts: 15 % of all pass-1 wavefronts on 200^3 (ncu)
+        const IpStage st0 = g.fy.st[0];
+        for (int i = tid; i < (st0.radix - 1) * st0.q; i += nthr) {
+            const int m = i / st0.q + 1, o = i - (m - 1) * st0.q;
+            twf[i] = g.tw_y[o * m * st0.twmul];
+        }
+    }
     for (int i = tid; i < M; i += nthr) rowz[i] = g.rowz_of_k[i];
     for (int i = tid; i < R1; i += nthr) kya[i] = g.kya_of_jp[i];
     if (g.pair)
@@ -561,8 +567,8 @@ k_g2_p1(const float* __restrict__ boxes, long long batch_stride, int n2_total, I
         } else if (g.fuse_first) {
 #define PS21_G2_YFIRST(R)                                                        \
     do {                                                                         \
-        if (g.bluestein) p1_y_first<R, true>(buf32, g, twz, twy, rowz, chirp);   \
-        else p1_y_first<R, false>(buf32, g, twz, twy, rowz, chirp);              \
+        if (g.bluestein) p1_y_first<R, true>(buf32, g, twz, twf, rowz, chirp);   \
+        else p1_y_first<R, false>(buf32, g, twz, twf, rowz, chirp);              \
     } while (0)
             switch (g.fy.st[0].radix) {
                 case 2: PS21_G2_YFIRST(2); break;
@@ -1065,7 +1071,7 @@ static int upload(const std::vector<T>& v, T** d) {
 
 static size_t p1_smem(const G2Dev& g) {
     return (size_t)g.nbuf * g.R1 * g.ld * sizeof(float2) +
-           (size_t)(g.nz + g.n1 + g.R1 + 2 * g.Lc + (g.bluestein ? g.M : 0)) * sizeof(float2) +
+           (size_t)(g.nz + g.n1 + 2 * g.R1 + 2 * g.Lc + (g.bluestein ? g.M : 0)) * sizeof(float2) +
            (size_t)(g.M + g.R1 + g.nh + 2) * 2 + 64;
 }
 static size_t p2_smem(const G2Dev& g, int nbins, int nshare) {
@@ -1137,7 +1143,7 @@ int g2_try_setup(ps21_plan* p, ShapePlan& sp) {
     if (const char* e = std::getenv("PS21_G2_R2")) force_r2 = std::atoi(e);
     if (const char* e = std::getenv("PS21_G2_NBUF")) force_nbuf = std::atoi(e);
     auto extra1 = [&](int R1) {
-        return (size_t)(nz + n1 + R1 + 2 * g.Lc + (g.bluestein ? g.M : 0)) * sizeof(float2) +
+        return (size_t)(nz + n1 + 2 * R1 + 2 * g.Lc + (g.bluestein ? g.M : 0)) * sizeof(float2) +
                (size_t)(g.M + R1 + g.nh + 2) * 2 + 64;
     };
     auto buf1 = [&](int R1) { return (size_t)R1 * (g.zrows | 1) * sizeof(float2); };
